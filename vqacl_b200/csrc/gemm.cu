@@ -1,0 +1,188 @@
+// Host side of the tcgen05 GEMM: TMA tensor-map construction (cuTensorMapEncodeTiled through the
+// runtime's driver entry point, so the library does not link libcuda), tile-shape selection and launch.
+#include "gemm.h"
+
+#include <cudaTypedefs.h>
+#include <mutex>
+#include <stdarg.h>
+#include <string.h>
+#include <unordered_map>
+
+// ------------------------------------------------------------------------------------------
+// error channel shared by the whole library
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+void vq_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+extern "C" const char* vqacl_last_error() { return g_err; }
+
+namespace vq {
+
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  });
+  return fn;
+}
+
+struct TmKey {
+  const void* ptr;
+  uint64_t d0, d1, ld;
+  uint32_t b0, b1;
+  bool operator==(const TmKey& o) const {
+    return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && ld == o.ld && b0 == o.b0 && b1 == o.b1;
+  }
+};
+struct TmHash {
+  size_t operator()(const TmKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    h = h * 1000003u ^ k.d0;
+    h = h * 1000003u ^ k.d1;
+    h = h * 1000003u ^ k.ld;
+    h = h * 1000003u ^ (((uint64_t)k.b0 << 32) | k.b1);
+    return h;
+  }
+};
+static std::unordered_map<TmKey, CUtensorMap, TmHash> g_tm_cache;
+static std::mutex g_tm_mutex;
+
+// 2-D bf16 tensor, inner (contiguous) extent d0, outer extent d1, outer pitch ld elements; box b0 x b1, 128 B swizzle.
+static int make_tmap(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t ld, uint32_t b0, uint32_t b1) {
+  TmKey key{ptr, d0, d1, ld, b0, b1};
+  {
+    std::lock_guard<std::mutex> g(g_tm_mutex);
+    auto it = g_tm_cache.find(key);
+    if (it != g_tm_cache.end()) {
+      *out = it->second;
+      return 0;
+    }
+  }
+  auto fn = get_encode_fn();
+  VQ_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point not available (driver too old / no GPU)");
+  VQ_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA operand base %p is not 16-byte aligned", ptr);
+  VQ_CHECK((ld * 2) % 16 == 0, "TMA operand pitch %llu elements is not a multiple of 16 bytes", (unsigned long long)ld);
+  cuuint64_t dims[2] = {d0, d1};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {b0, b1};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VQ_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (dims %llu x %llu, ld %llu, box %u x %u)",
+           (int)r, (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)ld, b0, b1);
+  {
+    std::lock_guard<std::mutex> g(g_tm_mutex);
+    if (g_tm_cache.size() > 65536) g_tm_cache.clear();
+    g_tm_cache.emplace(key, *out);
+  }
+  return 0;
+}
+
+void gemm_tmap_cache_clear() {
+  std::lock_guard<std::mutex> g(g_tm_mutex);
+  g_tm_cache.clear();
+}
+
+static int g_num_sms = 0;
+int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  auto kern = gemm_bf16_tcgen05_kernel<BN, A_MN, B_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = ((args.M + GEMM_BM - 1) / GEMM_BM) * ((args.N + BN - 1) / BN) * args.splits;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, args);
+  VQ_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int BN>
+static int dispatch_major(const GemmOperand& A, const GemmOperand& B, const GemmArgs& args, cudaStream_t stream) {
+  CUtensorMap ta, tb;
+  if (!A.mn_major) {
+    if (make_tmap(&ta, A.ptr, args.K, args.M, A.ld, GEMM_BK, GEMM_BM)) return 1;
+  } else {
+    if (make_tmap(&ta, A.ptr, args.M, args.K, A.ld, 64, GEMM_BK)) return 1;
+  }
+  if (!B.mn_major) {
+    if (make_tmap(&tb, B.ptr, args.K, args.N, B.ld, GEMM_BK, BN)) return 1;
+  } else {
+    if (make_tmap(&tb, B.ptr, args.N, args.K, B.ld, 64, GEMM_BK)) return 1;
+  }
+  if (!A.mn_major && !B.mn_major) return launch<BN, false, false>(ta, tb, args, stream);
+  if (!A.mn_major && B.mn_major) return launch<BN, false, true>(ta, tb, args, stream);
+  if (A.mn_major && B.mn_major) return launch<BN, true, true>(ta, tb, args, stream);
+  VQ_CHECK(false, "gemm: A MN-major with B K-major is not instantiated");
+}
+
+int gemm_bf16(const GemmOperand& A, const GemmOperand& B, GemmArgs args, int force_bn, cudaStream_t stream) {
+  VQ_CHECK(args.M > 0 && args.N > 0 && args.K > 0, "gemm: empty problem %d x %d x %d", args.M, args.N, args.K);
+  VQ_CHECK(args.N % 8 == 0, "gemm: N=%d must be a multiple of 8", args.N);
+  VQ_CHECK(args.ldc % 8 == 0, "gemm: ldc=%d must be a multiple of 8", args.ldc);
+  if (args.splits < 1) args.splits = 1;
+  VQ_CHECK(args.splits == 1 || args.epi == EPI_ATOMIC_F32, "gemm: split-K needs the atomic epilogue");
+  const int kblocks = (args.K + GEMM_BK - 1) / GEMM_BK;
+  if (args.splits > kblocks) args.splits = kblocks;
+  // make sure no split is empty
+  {
+    int per = (kblocks + args.splits - 1) / args.splits;
+    args.splits = (kblocks + per - 1) / per;
+  }
+  int bn = force_bn;
+  if (bn == 0) {
+    const int tiles_m = (args.M + GEMM_BM - 1) / GEMM_BM;
+    const int sms = num_sms();
+    bn = 64;
+    if (args.N >= 256 && tiles_m * ((args.N + 255) / 256) * args.splits >= sms) bn = 256;
+    else if (args.N >= 128 && tiles_m * ((args.N + 127) / 128) * args.splits >= sms) bn = 128;
+  }
+  switch (bn) {
+    case 256: return dispatch_major<256>(A, B, args, stream);
+    case 128: return dispatch_major<128>(A, B, args, stream);
+    case 64: return dispatch_major<64>(A, B, args, stream);
+    default: VQ_CHECK(false, "gemm: unsupported BN %d", bn);
+  }
+}
+
+}  // namespace vq
+
+// ------------------------------------------------------------------------------------------
+// C-ABI entry (see include/vqacl_b200.h)
+// ------------------------------------------------------------------------------------------
+extern "C" int vqacl_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major, void* C,
+                               int ldc, const void* R, int ldr, int M, int N, int K, int epi, float alpha, int splits,
+                               int force_bn, void* stream) {
+  vq::GemmOperand a{A, lda, a_mn_major != 0}, b{B, ldb, b_mn_major != 0};
+  vq::GemmArgs g{};
+  g.epi = epi;
+  g.M = M; g.N = N; g.K = K;
+  g.C = C; g.ldc = ldc;
+  g.R = R; g.ldr = ldr;
+  g.alpha = alpha;
+  g.splits = splits;
+  return vq::gemm_bf16(a, b, g, force_bn, reinterpret_cast<cudaStream_t>(stream));
+}
