@@ -1,0 +1,128 @@
+/* vqacl_b200 — C-ABI of the B200-native VQACL hot path (VL-T5 train step + SI prototype bank + greedy decode).
+ *
+ * The reference (zhangxi1997/VQACL) is pure Python: its "FFI" for this path is the Python model-class API
+ *   VLT5VQA.train_step / test_step      VL-T5/src/vqa_model.py:18-121
+ *   VLT5.forward / prototype methods    VL-T5/src/modeling_t5_our.py:434-713
+ *   Trainer.train_step tail             VL-T5/src/vqacl.py:429-509
+ * which `vqacl_b200/` mirrors in Python on top of the entry points below (ctypes).
+ * Conventions: every function returns 0 on success; on failure it returns non-zero and vqacl_last_error() holds the
+ * message (the Python host raises). All data pointers are DEVICE pointers unless stated; `stream` is a cudaStream_t.
+ * No torch types cross this boundary. There is no CPU fallback.
+ */
+#ifndef VQACL_B200_H
+#define VQACL_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* vqacl_last_error(void);
+
+/* ---- model configuration (trainer_base.py:57-89 + t5-base hyper-parameters) ---- */
+typedef struct vqacl_config {
+  int vocab_size;       /* 32200 (tokenization.py:58-60, vqacl.py:98-99) */
+  int d_model;          /* 768 (kernels are specialised for it) */
+  int d_kv;             /* 64 */
+  int n_heads;          /* 12 */
+  int d_ff;             /* 3072 */
+  int n_enc_layers;     /* 12 */
+  int n_dec_layers;     /* 12 */
+  int n_buckets;        /* 32 */
+  int feat_dim;         /* 2048 */
+  int n_images;         /* 2 */
+  int n_ques;           /* 10 question-type prototypes */
+  int n_cate;           /* 80 object-category prototypes */
+  int split_L;          /* 20: VLT5.L, the hard-coded Q/V split (modeling_t5_our.py:381) */
+  int pad_id, eos_id, start_id; /* 0, 1, 0 */
+  float eps;            /* 1e-6 */
+  float dropout;        /* dropout_rate (param.py --dropout) */
+} vqacl_config;
+
+/* one step's inputs: what VLT5VQA.train_step moves to the device (vqa_model.py:20-27) */
+typedef struct vqacl_batch {
+  int B, L, N, T;              /* batch, text width, boxes per image, target width */
+  const float* vis_feats;      /* [B,N,feat_dim] fp32 */
+  const float* boxes;          /* [B,N,4] fp32 */
+  const int64_t* input_ids;    /* [B,L] */
+  const int64_t* labels;       /* [B,T], -100 = ignore (train only) */
+  const float* cate_labels;    /* [B,n_cate] one-hot fp32 (train only) */
+  const float* ques_labels;    /* [B,n_ques] one-hot fp32 (train only) */
+} vqacl_batch;
+
+/* SI prototype bank state (the reference keeps these as Python attributes of VLT5, modeling_t5_our.py:391-396) */
+typedef struct vqacl_proto_state {
+  float* Q_prototype;          /* [n_ques, d] persistent bank (== Q_task_mem_proto[t] storage for t > 0) */
+  float* V_prototype;          /* [n_cate, d] */
+  float* Q_num;                /* [n_ques] running counts */
+  float* V_num;                /* [n_cate] */
+  int proto_update;            /* kwargs['proto_update'] (train) */
+  int task_id;                 /* current_task_id */
+  int first_step_of_task;      /* current_task_id not in Q_task_cur_proto */
+  int has_mem;                 /* current_task_id in Q_task_mem_proto */
+  float alpha, beta;           /* --proto_alpha / --proto_beta */
+} vqacl_proto_state;
+
+/* ---- engine lifecycle ---- */
+int vqacl_engine_create(const vqacl_config* cfg, void** engine);
+void vqacl_engine_destroy(void* engine);
+/* parameter arena: one flat fp32 buffer; the reference's state_dict tensors are views at these offsets */
+int vqacl_param_count(void* engine);
+int vqacl_param_info(void* engine, int i, char* name, int name_cap, int64_t* offset, int* rows, int* cols, int* group);
+int64_t vqacl_arena_elems(void* engine, int64_t* n_decay, int64_t* n_train);
+int vqacl_bind_arena(void* engine, float* params, float* grads, void* params_bf16);
+/* relative-position bucket maps, int32[127] each: bucket of (key - query + 63); computed by the host with the HF formula */
+int vqacl_set_rel_buckets(void* engine, const int32_t* enc_bidirectional, const int32_t* dec_unidirectional);
+int vqacl_refresh_bf16(void* engine, void* stream);                 /* params fp32 -> bf16 GEMM copies */
+/* activation workspace: allocated by the host (torch caching allocator), carved by the engine */
+int64_t vqacl_workspace_bytes(void* engine, int B, int L, int N, int T);
+int vqacl_bind_workspace(void* engine, void* ws, int64_t bytes, int B, int L, int N, int T);
+int64_t vqacl_ws_offset(void* engine, const char* name);            /* byte offset of a named output, -1 if unknown */
+
+/* ---- hot path: VLT5.forward with labels (modeling_t5_our.py:514-713), split where the multi-GPU SI exchange sits ---- */
+int vqacl_forward_encoder(void* engine, const vqacl_batch* batch, const vqacl_proto_state* proto, uint32_t seed, int training, void* stream);
+int vqacl_forward_decoder(void* engine, const vqacl_batch* batch, const vqacl_proto_state* proto, void* stream);
+/* backward of sum_r w[r] * loss_row[r]; fills the gradient arena (zeroed first unless accumulate != 0) */
+int vqacl_backward(void* engine, const float* w_rows, int accumulate, void* stream);
+/* fused loss tail of VLT5VQA.train_step (vqa_model.py:46-54) */
+int vqacl_loss_tail(const float* loss_rows, const int64_t* labels, const float* scores, int B, int T, float* loss_out, float* w_rows, void* stream);
+/* clip_grad_norm_ + HF AdamW + bf16 refresh (vqacl.py:475-482, trainer_base.py:130-198) */
+int vqacl_clip_adamw(void* engine, float* exp_avg, float* exp_avg_sq, float lr, float beta1, float beta2, float eps,
+                     float weight_decay, int step, float max_grad_norm, float* grad_norm_out, void* stream);
+/* greedy generation (vqa_model.py:112-116; HF 4.2.1 greedy_search): out_tokens [B, max_len] int64, returns steps taken */
+int vqacl_generate(void* engine, const vqacl_batch* batch, const vqacl_proto_state* proto, int max_len, int64_t* out_tokens,
+                   int* out_len, void* stream);
+
+/* ---- individual operators (unit-test / building-block surface) ---- */
+int vqacl_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major, void* C, int ldc,
+                    const void* R, int ldr, int M, int N, int K, int epi, float alpha, int splits, int force_bn, void* stream);
+int vqacl_rmsnorm_fwd(const float* x, const float* w, void* y_bf16, float* y_f32, int M, float eps, float scale, void* stream);
+int vqacl_rmsnorm_bwd(const void* dn_bf16, const float* x, const float* w, const float* g_in, float* g_out, void* gb_out,
+                      float* dw, int M, float eps, float scale, void* stream);
+int vqacl_attention_fwd(const void* q, const void* k, const void* v, int ldq, int ldk, int ldv, void* o, int ldo, float* lse,
+                        int B, int H, int Sq, int Sk, const float* rel_table, const int32_t* rel_bucket, int rel_mode, int Lt,
+                        const float* keymask, int causal, void* stream);
+int vqacl_attention_bwd(const void* q, const void* k, const void* v, int ldq, int ldk, int ldv, const void* dO, int ldo,
+                        const float* lse, void* dq, void* dk, void* dv, int lddq, int lddk, int lddv, int B, int H, int Sq, int Sk,
+                        const float* rel_table, const int32_t* rel_bucket, int rel_mode, int Lt, const float* keymask, int causal,
+                        float* d_rel_table, void* stream);
+int vqacl_proto_means(const float* h, int B, int S, int split, float* meanQ, float* meanV, void* stream);
+int vqacl_proto_scatter_mean(const float* mean, const float* labels, int B, int C, float* proto, float* cnt, void* stream);
+int vqacl_proto_update(const float* curQ, const float* curV, const float* cntQ, const float* cntV, float* Qproto, float* Vproto,
+                       float* numQ, float* numV, int CQ, int CV, int task_id, int first_step_of_task, int has_mem, float alpha,
+                       float beta, void* stream);
+int vqacl_proto_retrieve(const float* P, int C, const float* x, int B, void* out_bf16, int out_pitch_rows, int out_row,
+                         int64_t* idx, float* out_f32, void* stream);
+int vqacl_ce_fwd(const void* logits_bf16, int ld, int M, int V, const int64_t* labels, float* lse, float* loss, void* stream);
+int vqacl_ce_bwd(void* logits_bf16, int ld, int M, int V, const int64_t* labels, const float* lse, const float* w, void* stream);
+int vqacl_visual_embed_fwd(const float* featpre, const float* boxes, const float* bf, const float* wf, const float* Wp,
+                           const float* bp, const float* wp, const float* img_emb, const float* shared, int V, int B, int N,
+                           int S, int L, float eps, float* x, void* stream);
+int vqacl_adamw_hf(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, int64_t n_decay, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, int step, const float* sumsq, float max_norm, void* stream);
+int vqacl_grad_sumsq(const float* g, int64_t n, float* partials, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VQACL_B200_H */

@@ -1,0 +1,437 @@
+// HBM-bound row kernels of the VL-T5 hot path: T5 RMSNorm fwd/bwd (hf5.5 modeling_t5.py:46-68), token-embedding
+// gather / scatter-add, the VisualEmbedding tail (modeling_t5_our.py:93-143), mask construction and casts.
+// One warp owns one 768-wide row: lane l holds the float4 chunks {l, l+32, ..., l+160} -> fully coalesced 512 B
+// wavefronts, warp-shuffle reductions, no shared memory on the forward paths.
+#include "ops.h"
+
+namespace vq {
+
+constexpr int RW_CHUNKS = DM / 4 / 32;  // 6 float4 chunks per lane
+constexpr int ROW_WARPS = 8;            // warps per CTA for the row kernels
+
+VQ_DEVINL int out_row_of(int r, int in_rpb, int out_rpb) { return in_rpb > 0 ? (r / in_rpb) * out_rpb + r % in_rpb : r; }
+
+VQ_DEVINL void load_row_f32(float (&v)[RW_CHUNKS][4], const float* row, int lane) {
+#pragma unroll
+  for (int j = 0; j < RW_CHUNKS; ++j) {
+    const float4 t = *reinterpret_cast<const float4*>(row + (lane + 32 * j) * 4);
+    v[j][0] = t.x; v[j][1] = t.y; v[j][2] = t.z; v[j][3] = t.w;
+  }
+}
+VQ_DEVINL void load_row_bf16(float (&v)[RW_CHUNKS][4], const __nv_bfloat16* row, int lane) {
+#pragma unroll
+  for (int j = 0; j < RW_CHUNKS; ++j) {
+    const uint2 t = *reinterpret_cast<const uint2*>(row + (lane + 32 * j) * 4);
+    const float2 a = unpack_bf16(t.x), b = unpack_bf16(t.y);
+    v[j][0] = a.x; v[j][1] = a.y; v[j][2] = b.x; v[j][3] = b.y;
+  }
+}
+VQ_DEVINL void store_row_f32(float* row, const float (&v)[RW_CHUNKS][4], int lane) {
+#pragma unroll
+  for (int j = 0; j < RW_CHUNKS; ++j)
+    *reinterpret_cast<float4*>(row + (lane + 32 * j) * 4) = make_float4(v[j][0], v[j][1], v[j][2], v[j][3]);
+}
+VQ_DEVINL void store_row_bf16(__nv_bfloat16* row, const float (&v)[RW_CHUNKS][4], int lane) {
+#pragma unroll
+  for (int j = 0; j < RW_CHUNKS; ++j)
+    *reinterpret_cast<uint2*>(row + (lane + 32 * j) * 4) = make_uint2(pack_bf16(v[j][0], v[j][1]), pack_bf16(v[j][2], v[j][3]));
+}
+VQ_DEVINL float row_sumsq(const float (&v)[RW_CHUNKS][4]) {
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < RW_CHUNKS; ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s += v[j][i] * v[j][i];
+  return warp_sum(s);
+}
+VQ_DEVINL void apply_dropout(float (&v)[RW_CHUNKS][4], const Dropout& d, uint64_t row_elem0, int lane) {
+  if (!d.thr) return;
+#pragma unroll
+  for (int j = 0; j < RW_CHUNKS; ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      v[j][i] *= vq_dropout_scale(d.seed, d.site, row_elem0 + (lane + 32 * j) * 4 + i, d.thr, d.inv_keep);
+}
+
+// ------------------------------------------------------------------------------------------------ cast
+__global__ void cast_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n8) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 a = reinterpret_cast<const float4*>(src)[2 * i], b = reinterpret_cast<const float4*>(src)[2 * i + 1];
+    reinterpret_cast<uint4*>(dst)[i] = make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
+  }
+}
+int cast_f32_to_bf16(const float* src, __nv_bfloat16* dst, size_t n, cudaStream_t stream) {
+  VQ_CHECK(n % 8 == 0, "cast: n=%zu must be a multiple of 8", n);
+  if (n == 0) return 0;
+  const size_t n8 = n / 8;
+  const int blocks = (int)((n8 + 255) / 256 < (size_t)num_sms() * 8 ? (n8 + 255) / 256 : (size_t)num_sms() * 8);
+  cast_kernel<<<blocks, 256, 0, stream>>>(src, dst, n8);
+  VQ_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ RMSNorm fwd
+__global__ void __launch_bounds__(ROW_WARPS * 32) rmsnorm_fwd_kernel(const RmsFwdArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  if (r >= a.M) return;
+  float v[RW_CHUNKS][4], w[RW_CHUNKS][4];
+  load_row_f32(v, a.x + (size_t)r * DM, lane);
+  load_row_f32(w, a.w, lane);
+  const float rstd = rsqrtf(row_sumsq(v) / DM + a.eps) * a.scale;
+#pragma unroll
+  for (int j = 0; j < RW_CHUNKS; ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[j][i] = v[j][i] * rstd * w[j][i];
+  apply_dropout(v, a.drop, (uint64_t)r * DM, lane);
+  const int ro = out_row_of(r, a.in_rpb, a.out_rpb);
+  if (a.y_bf16) store_row_bf16(a.y_bf16 + (size_t)ro * a.ld_bf16, v, lane);
+  if (a.y_f32) store_row_f32(a.y_f32 + (size_t)r * a.ld_f32, v, lane);
+}
+int rmsnorm_fwd(const RmsFwdArgs& a, cudaStream_t stream) {
+  if (a.M <= 0) return 0;
+  rmsnorm_fwd_kernel<<<(a.M + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, stream>>>(a);
+  VQ_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ RMSNorm bwd
+__global__ void __launch_bounds__(ROW_WARPS * 32) rmsnorm_bwd_kernel(const RmsBwdArgs a) {
+  __shared__ float s_dw[ROW_WARPS][DM];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float w[RW_CHUNKS][4], dwacc[RW_CHUNKS][4];
+  load_row_f32(w, a.w, lane);
+#pragma unroll
+  for (int j = 0; j < RW_CHUNKS; ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dwacc[j][i] = 0.f;
+  for (int r = blockIdx.x * ROW_WARPS + warp; r < a.M; r += gridDim.x * ROW_WARPS) {
+    float x[RW_CHUNKS][4], dy[RW_CHUNKS][4];
+    load_row_f32(x, a.x + (size_t)r * DM, lane);
+    const int rd = out_row_of(r, a.in_rpb, a.out_rpb);
+    load_row_bf16(dy, a.dn + (size_t)rd * a.ld_dn, lane);
+    if (a.dn2) {
+      float d2[RW_CHUNKS][4];
+      load_row_bf16(d2, a.dn2 + (size_t)rd * a.ld_dn2, lane);
+#pragma unroll
+      for (int j = 0; j < RW_CHUNKS; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dy[j][i] += d2[j][i];
+    }
+    apply_dropout(dy, a.own, (uint64_t)r * DM, lane);
+    const float rstd = rsqrtf(row_sumsq(x) / DM + a.eps);
+    float dot = 0.f;
+#pragma unroll
+    for (int j = 0; j < RW_CHUNKS; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        x[j][i] *= rstd;                      // xhat
+        dy[j][i] *= a.scale;                  // d(y / scale)
+        dwacc[j][i] += dy[j][i] * x[j][i];
+        dy[j][i] *= w[j][i];                  // dxhat
+        dot += dy[j][i] * x[j][i];
+      }
+    dot = warp_sum(dot) / DM;
+    float gout[RW_CHUNKS][4];
+    if (a.g_in) load_row_f32(gout, a.g_in + (size_t)r * DM, lane);
+#pragma unroll
+    for (int j = 0; j < RW_CHUNKS; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float dx = rstd * (dy[j][i] - x[j][i] * dot);
+        gout[j][i] = a.g_in ? gout[j][i] + dx : dx;
+      }
+    if (a.g_out) store_row_f32(a.g_out + (size_t)r * DM, gout, lane);
+    if (a.gb_out) {
+      apply_dropout(gout, a.consumer, (uint64_t)r * a.consumer_cols, lane);
+      store_row_bf16(a.gb_out + (size_t)r * DM, gout, lane);
+    }
+  }
+  if (a.dw) {
+#pragma unroll
+    for (int j = 0; j < RW_CHUNKS; ++j)
+      *reinterpret_cast<float4*>(&s_dw[warp][(lane + 32 * j) * 4]) = make_float4(dwacc[j][0], dwacc[j][1], dwacc[j][2], dwacc[j][3]);
+    __syncthreads();
+    for (int c = threadIdx.x; c < DM; c += ROW_WARPS * 32) {
+      float s = 0.f;
+#pragma unroll
+      for (int wv = 0; wv < ROW_WARPS; ++wv) s += s_dw[wv][c];
+      atomicAdd(&a.dw[c], s);
+    }
+  }
+}
+int rmsnorm_bwd(const RmsBwdArgs& a, cudaStream_t stream) {
+  if (a.M <= 0) return 0;
+  int blocks = (a.M + ROW_WARPS - 1) / ROW_WARPS;
+  const int cap = num_sms() * 2;
+  if (blocks > cap) blocks = cap;
+  rmsnorm_bwd_kernel<<<blocks, ROW_WARPS * 32, 0, stream>>>(a);
+  VQ_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ embeddings
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+embed_fwd_kernel(const int64_t* __restrict__ ids, int B, int L, const float* __restrict__ table, float* __restrict__ x, int S,
+                 int row0, Dropout drop) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  if (r >= B * L) return;
+  const int b = r / L, i = r % L;
+  float v[RW_CHUNKS][4];
+  load_row_f32(v, table + (size_t)ids[r] * DM, lane);
+  const size_t orow = (size_t)b * S + row0 + i;
+  apply_dropout(v, drop, orow * DM, lane);
+  store_row_f32(x + orow * DM, v, lane);
+}
+int embed_fwd(const int64_t* ids, int B, int L, const float* table, float* x, int S, int row0, Dropout drop, cudaStream_t stream) {
+  if (B * L <= 0) return 0;
+  embed_fwd_kernel<<<(B * L + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, stream>>>(ids, B, L, table, x, S, row0, drop);
+  VQ_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+embed_bwd_kernel(const int64_t* __restrict__ ids, int B, int L, const float* __restrict__ g, int S, int row0,
+                 float* __restrict__ dtable, Dropout drop) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  if (r >= B * L) return;
+  const int b = r / L, i = r % L;
+  const size_t grow = (size_t)b * S + row0 + i;
+  float v[RW_CHUNKS][4];
+  load_row_f32(v, g + grow * DM, lane);
+  apply_dropout(v, drop, grow * DM, lane);
+  float* dst = dtable + (size_t)ids[r] * DM;
+#pragma unroll
+  for (int j = 0; j < RW_CHUNKS; ++j)
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + (lane + 32 * j) * 4), "f"(v[j][0]), "f"(v[j][1]),
+                 "f"(v[j][2]), "f"(v[j][3])
+                 : "memory");
+}
+int embed_bwd(const int64_t* ids, int B, int L, const float* g, int S, int row0, float* dtable, Dropout drop, cudaStream_t stream) {
+  if (B * L <= 0) return 0;
+  embed_bwd_kernel<<<(B * L + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, stream>>>(ids, B, L, g, S, row0, dtable, drop);
+  VQ_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void shift_right_kernel(const int64_t* __restrict__ labels, int64_t* __restrict__ dec, int B, int T, int start_id, int pad_id) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * T) return;
+  const int t = i % T;
+  int64_t v = t == 0 ? (int64_t)start_id : labels[i - 1];
+  if (v == -100) v = pad_id;
+  dec[i] = v;
+}
+int shift_right(const int64_t* labels, int64_t* dec_ids, int B, int T, int start_id, int pad_id, cudaStream_t stream) {
+  if (B * T <= 0) return 0;
+  shift_right_kernel<<<(B * T + 255) / 256, 256, 0, stream>>>(labels, dec_ids, B, T, start_id, pad_id);
+  VQ_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void keymask_kernel(const int64_t* __restrict__ ids, int B, int L, int S, int pad_id, float* __restrict__ enc,
+                               float* __restrict__ cross) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * (S + 2)) return;
+  const int b = i / (S + 2), j = i % (S + 2);
+  const bool pad = j < L && ids[b * L + j] == pad_id;
+  if (cross) cross[i] = pad ? -1e9f : 0.f;
+  if (enc && j < S) enc[b * S + j] = pad ? -10000.0f : 0.f;
+}
+int build_keymasks(const int64_t* ids, int B, int L, int S, int pad_id, float* enc_mask, float* cross_mask, cudaStream_t stream) {
+  const int n = B * (S + 2);
+  if (n <= 0) return 0;
+  keymask_kernel<<<(n + 255) / 256, 256, 0, stream>>>(ids, B, L, S, pad_id, enc_mask, cross_mask);
+  VQ_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ VisualEmbedding
+VQ_DEVINL void vis_pos5(const float* boxes, int row, float (&p5)[5]) {
+  const float4 bx = *reinterpret_cast<const float4*>(boxes + (size_t)row * 4);
+  p5[0] = bx.x; p5[1] = bx.y; p5[2] = bx.z; p5[3] = bx.w;
+  // get_area as written (modeling_t5_our.py:78-90): (pos[3] - pos[2]) * (pos[1] - pos[0])
+  p5[4] = (bx.w - bx.z) * (bx.y - bx.x);
+}
+
+__global__ void __launch_bounds__(ROW_WARPS * 32) vis_embed_fwd_kernel(const VisArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  if (r >= a.B * a.N) return;
+  const int b = r / a.N, n = r % a.N;
+  float u[RW_CHUNKS][4], t[RW_CHUNKS][4], out[RW_CHUNKS][4];
+  // feature branch: RMSNorm(feats Wf^T + bf) * wf
+  load_row_f32(u, a.featpre + (size_t)r * DM, lane);
+  load_row_f32(t, a.bf, lane);
+#pragma unroll
+  for (int j = 0; j < RW_CHUNKS; ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) u[j][i] += t[j][i];
+  float rstd = rsqrtf(row_sumsq(u) / DM + a.eps);
+  load_row_f32(t, a.wf, lane);
+#pragma unroll
+  for (int j = 0; j < RW_CHUNKS; ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) out[j][i] = u[j][i] * rstd * t[j][i];
+  // position branch: RMSNorm([box, area] Wp^T + bp) * wp
+  float p5[5];
+  vis_pos5(a.boxes, r, p5);
+  load_row_f32(u, a.bp, lane);
+#pragma unroll
+  for (int j = 0; j < RW_CHUNKS; ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float* wrow = a.Wp + (size_t)((lane + 32 * j) * 4 + i) * 5;
+      float acc = u[j][i];
+#pragma unroll
+      for (int k = 0; k < 5; ++k) acc += wrow[k] * p5[k];
+      u[j][i] = acc;
+    }
+  rstd = rsqrtf(row_sumsq(u) / DM + a.eps);
+  load_row_f32(t, a.wp, lane);
+#pragma unroll
+  for (int j = 0; j < RW_CHUNKS; ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) out[j][i] += u[j][i] * rstd * t[j][i];
+  // + img_order_embedding[0] + shared[V - 1 - n]
+  load_row_f32(t, a.img_emb, lane);
+  load_row_f32(u, a.shared + (size_t)(a.V - 1 - n) * DM, lane);
+#pragma unroll
+  for (int j = 0; j < RW_CHUNKS; ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) out[j][i] += t[j][i] + u[j][i];
+  const size_t orow = (size_t)b * a.S + a.L + n;
+  apply_dropout(out, a.drop, orow * DM, lane);
+  store_row_f32(a.x + orow * DM, out, lane);
+}
+int vis_embed_fwd(const VisArgs& a, cudaStream_t stream) {
+  const int rows = a.B * a.N;
+  if (rows <= 0) return 0;
+  vis_embed_fwd_kernel<<<(rows + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, stream>>>(a);
+  VQ_LAUNCH_CHECK();
+  return 0;
+}
+
+// column-sum accumulators kept in shared memory per CTA, flushed once with global atomics
+enum { VA_DIMG = 0, VA_DWF, VA_DBF, VA_DWP, VA_DBP, VA_DWP0, VA_COUNT = VA_DWP0 + 5 };
+
+__global__ void __launch_bounds__(ROW_WARPS * 32) vis_embed_bwd_kernel(const VisArgs a) {
+  extern __shared__ float s_acc[];  // [VA_COUNT][DM]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < VA_COUNT * DM; i += ROW_WARPS * 32) s_acc[i] = 0.f;
+  __syncthreads();
+  const int rows = a.B * a.N;
+  for (int r = blockIdx.x * ROW_WARPS + warp; r < rows; r += gridDim.x * ROW_WARPS) {
+    const int b = r / a.N, n = r % a.N;
+    const size_t grow = (size_t)b * a.S + a.L + n;
+    float g[RW_CHUNKS][4], u[RW_CHUNKS][4], t[RW_CHUNKS][4];
+    load_row_f32(g, a.g + grow * DM, lane);
+    apply_dropout(g, a.drop, grow * DM, lane);
+    // image-order embedding row 0 and object-order (shared) row V-1-n
+    float* dsh = a.dshared + (size_t)(a.V - 1 - n) * DM;
+#pragma unroll
+    for (int j = 0; j < RW_CHUNKS; ++j) {
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dsh + (lane + 32 * j) * 4), "f"(g[j][0]), "f"(g[j][1]),
+                   "f"(g[j][2]), "f"(g[j][3])
+                   : "memory");
+#pragma unroll
+      for (int i = 0; i < 4; ++i) atomicAdd(&s_acc[VA_DIMG * DM + (lane + 32 * j) * 4 + i], g[j][i]);
+    }
+    // ---- feature branch
+    load_row_f32(u, a.featpre + (size_t)r * DM, lane);
+    load_row_f32(t, a.bf, lane);
+#pragma unroll
+    for (int j = 0; j < RW_CHUNKS; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) u[j][i] += t[j][i];
+    float rstd = rsqrtf(row_sumsq(u) / DM + a.eps);
+    load_row_f32(t, a.wf, lane);
+    float dot = 0.f;
+    float dx[RW_CHUNKS][4];
+#pragma unroll
+    for (int j = 0; j < RW_CHUNKS; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        u[j][i] *= rstd;  // uhat
+        atomicAdd(&s_acc[VA_DWF * DM + (lane + 32 * j) * 4 + i], g[j][i] * u[j][i]);
+        dx[j][i] = g[j][i] * t[j][i];
+        dot += dx[j][i] * u[j][i];
+      }
+    dot = warp_sum(dot) / DM;
+#pragma unroll
+    for (int j = 0; j < RW_CHUNKS; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        dx[j][i] = rstd * (dx[j][i] - u[j][i] * dot);
+        atomicAdd(&s_acc[VA_DBF * DM + (lane + 32 * j) * 4 + i], dx[j][i]);
+      }
+    store_row_bf16(a.dfeatpre + (size_t)r * DM, dx, lane);
+    // ---- position branch
+    float p5[5];
+    vis_pos5(a.boxes, r, p5);
+    load_row_f32(u, a.bp, lane);
+#pragma unroll
+    for (int j = 0; j < RW_CHUNKS; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float* wrow = a.Wp + (size_t)((lane + 32 * j) * 4 + i) * 5;
+        float acc = u[j][i];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) acc += wrow[k] * p5[k];
+        u[j][i] = acc;
+      }
+    rstd = rsqrtf(row_sumsq(u) / DM + a.eps);
+    load_row_f32(t, a.wp, lane);
+    dot = 0.f;
+#pragma unroll
+    for (int j = 0; j < RW_CHUNKS; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        u[j][i] *= rstd;
+        atomicAdd(&s_acc[VA_DWP * DM + (lane + 32 * j) * 4 + i], g[j][i] * u[j][i]);
+        dx[j][i] = g[j][i] * t[j][i];
+        dot += dx[j][i] * u[j][i];
+      }
+    dot = warp_sum(dot) / DM;
+#pragma unroll
+    for (int j = 0; j < RW_CHUNKS; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float dv = rstd * (dx[j][i] - u[j][i] * dot);
+        const int c = (lane + 32 * j) * 4 + i;
+        atomicAdd(&s_acc[VA_DBP * DM + c], dv);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) atomicAdd(&s_acc[(VA_DWP0 + k) * DM + c], dv * p5[k]);
+      }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < DM; c += ROW_WARPS * 32) {
+    atomicAdd(&a.dimg[c], s_acc[VA_DIMG * DM + c]);
+    atomicAdd(&a.dwf[c], s_acc[VA_DWF * DM + c]);
+    atomicAdd(&a.dbf[c], s_acc[VA_DBF * DM + c]);
+    atomicAdd(&a.dwp[c], s_acc[VA_DWP * DM + c]);
+    atomicAdd(&a.dbp[c], s_acc[VA_DBP * DM + c]);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) atomicAdd(&a.dWp[(size_t)c * 5 + k], s_acc[(VA_DWP0 + k) * DM + c]);
+  }
+}
+int vis_embed_bwd(const VisArgs& a, cudaStream_t stream) {
+  const int rows = a.B * a.N;
+  if (rows <= 0) return 0;
+  const int smem = VA_COUNT * DM * (int)sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    VQ_CUDA(cudaFuncSetAttribute(vis_embed_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = true;
+  }
+  int blocks = (rows + ROW_WARPS - 1) / ROW_WARPS;
+  const int cap = num_sms() * 2;
+  if (blocks > cap) blocks = cap;
+  vis_embed_bwd_kernel<<<blocks, ROW_WARPS * 32, smem, stream>>>(a);
+  VQ_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace vq

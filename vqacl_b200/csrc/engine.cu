@@ -1,0 +1,715 @@
+// VL-T5 / VQACL train step on B200: forward (VLT5.forward with labels, modeling_t5_our.py:514-713), backward and the
+// clip + AdamW tail (vqacl.py:461-487), issued kernel by kernel from C++.
+//
+// Data layout in HBM
+//   parameter arena  : one flat fp32 buffer (master weights), a same-shaped fp32 gradient arena and a bf16 copy that feeds
+//                      the tensor cores. Fused weights are adjacent so one GEMM covers them: per layer [Wq;Wk;Wv] (N = 2304),
+//                      and the cross-attention [Wk;Wv] of ALL decoder layers ([18432, 768]) so that the K/V projection of the
+//                      [B,58,768] decoder memory is a single GEMM (62 % of the decoder's FLOPs).
+//                      Order: decoder | cross-KV | encoder | visual | shared | no-decay group | never-trained group, i.e.
+//                      the order in which backward finishes gradients (bucketed all-reduce) and the AdamW decay boundary.
+//   residual stream  : fp32 snapshots x_k (one per sub-layer) so RMSNorm backward re-reads its exact input.
+//   GEMM operands    : bf16, row-major [rows, features]; attention reads heads in place from the packed [rows, 2304] QKV.
+#include "engine.h"
+
+#include <math.h>
+#include <string.h>
+
+namespace vq {
+
+// dropout site ids (the keep-mask of element i at site s is hash(seed, s, i); recomputed in backward, never stored)
+enum : uint32_t { SITE_ENC_EMB = 1, SITE_ENC_FINAL = 2, SITE_DEC_EMB = 3, SITE_DEC_FINAL = 4 };
+static inline uint32_t site_enc(int l, int k) { return 100u + (uint32_t)l * 4u + (uint32_t)k; }   // 0 probs 1 attn-out 2 ffn-inner 3 ffn-out
+static inline uint32_t site_dec(int l, int k) { return 300u + (uint32_t)l * 8u + (uint32_t)k; }   // 0 self probs 1 self out 2 cross probs 3 cross out 4 ffn inner 5 ffn out
+
+Dropout Engine::drop(uint32_t site) const {
+  Dropout d;
+  if (training && cfg.dropout > 0.f) {
+    d.thr = (uint32_t)fmin(4294967295.0, (double)cfg.dropout * 4294967296.0);
+    d.inv_keep = 1.f / (1.f - cfg.dropout);
+    d.seed = seed;
+    d.site = site;
+  }
+  return d;
+}
+
+// --------------------------------------------------------------------------------------------------- layout
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+int engine_build_layout(Engine& e) {
+  const vqacl_config& c = e.cfg;
+  VQ_CHECK(c.d_model == DM, "engine: kernels are specialised for d_model = %d (got %d)", DM, c.d_model);
+  VQ_CHECK(c.d_kv == 64 && c.n_heads * c.d_kv == c.d_model, "engine: needs d_kv = 64 and n_heads * d_kv = d_model");
+  VQ_CHECK(c.n_buckets <= 64, "engine: at most 64 relative-position buckets");
+  VQ_CHECK(c.vocab_size % 8 == 0 && c.d_ff % 8 == 0 && c.feat_dim % 8 == 0, "engine: vocab, d_ff, feat_dim must be multiples of 8");
+  const int d = c.d_model, f = c.d_ff;
+  size_t off = 0;
+  auto add = [&](const std::string& name, int rows, int cols, int group) {
+    off = align_up(off, 64);
+    e.params.push_back({name, off, rows, cols, group});
+    const size_t o = off;
+    off += (size_t)rows * cols;
+    return o;
+  };
+  e.dec.resize(c.n_dec_layers);
+  e.enc.resize(c.n_enc_layers);
+  char b[256];
+  // ---- weight-decay group -------------------------------------------------------------------------------
+  for (int l = 0; l < c.n_dec_layers; ++l) {
+    DecLayer& L = e.dec[l];
+    snprintf(b, sizeof b, "decoder.block.%d.layer.0.layer_norm.weight", l); L.ln0 = add(b, 1, d, 0);
+    snprintf(b, sizeof b, "decoder.block.%d.layer.0.SelfAttention.q.weight", l); L.qkv = add(b, d, d, 0);
+    snprintf(b, sizeof b, "decoder.block.%d.layer.0.SelfAttention.k.weight", l); add(b, d, d, 0);
+    snprintf(b, sizeof b, "decoder.block.%d.layer.0.SelfAttention.v.weight", l); add(b, d, d, 0);
+    snprintf(b, sizeof b, "decoder.block.%d.layer.0.SelfAttention.o.weight", l); L.o = add(b, d, d, 0);
+    snprintf(b, sizeof b, "decoder.block.%d.layer.1.layer_norm.weight", l); L.ln1 = add(b, 1, d, 0);
+    snprintf(b, sizeof b, "decoder.block.%d.layer.1.EncDecAttention.q.weight", l); L.cq = add(b, d, d, 0);
+    snprintf(b, sizeof b, "decoder.block.%d.layer.1.EncDecAttention.o.weight", l); L.co = add(b, d, d, 0);
+    snprintf(b, sizeof b, "decoder.block.%d.layer.2.layer_norm.weight", l); L.ln2 = add(b, 1, d, 0);
+    snprintf(b, sizeof b, "decoder.block.%d.layer.2.DenseReluDense.wi.weight", l); L.wi = add(b, f, d, 0);
+    snprintf(b, sizeof b, "decoder.block.%d.layer.2.DenseReluDense.wo.weight", l); L.wo = add(b, d, f, 0);
+  }
+  e.o_dec_final = add("decoder.final_layer_norm.weight", 1, d, 0);
+  for (int l = 0; l < c.n_dec_layers; ++l) {
+    snprintf(b, sizeof b, "decoder.block.%d.layer.1.EncDecAttention.k.weight", l);
+    const size_t o = add(b, d, d, 0);
+    if (l == 0) e.o_ckv = o;
+    snprintf(b, sizeof b, "decoder.block.%d.layer.1.EncDecAttention.v.weight", l); add(b, d, d, 0);
+  }
+  for (int l = 0; l < c.n_enc_layers; ++l) {
+    EncLayer& L = e.enc[l];
+    snprintf(b, sizeof b, "encoder.block.%d.layer.0.layer_norm.weight", l); L.ln0 = add(b, 1, d, 0);
+    snprintf(b, sizeof b, "encoder.block.%d.layer.0.SelfAttention.q.weight", l); L.qkv = add(b, d, d, 0);
+    snprintf(b, sizeof b, "encoder.block.%d.layer.0.SelfAttention.k.weight", l); add(b, d, d, 0);
+    snprintf(b, sizeof b, "encoder.block.%d.layer.0.SelfAttention.v.weight", l); add(b, d, d, 0);
+    snprintf(b, sizeof b, "encoder.block.%d.layer.0.SelfAttention.o.weight", l); L.o = add(b, d, d, 0);
+    snprintf(b, sizeof b, "encoder.block.%d.layer.1.layer_norm.weight", l); L.ln1 = add(b, 1, d, 0);
+    snprintf(b, sizeof b, "encoder.block.%d.layer.1.DenseReluDense.wi.weight", l); L.wi = add(b, f, d, 0);
+    snprintf(b, sizeof b, "encoder.block.%d.layer.1.DenseReluDense.wo.weight", l); L.wo = add(b, d, f, 0);
+  }
+  e.o_enc_final = add("encoder.final_layer_norm.weight", 1, d, 0);
+  e.o_Wf = add("encoder.visual_embedding.feat_embedding.0.weight", d, c.feat_dim, 0);
+  e.o_wf = add("encoder.visual_embedding.feat_embedding.1.weight", 1, d, 0);
+  e.o_Wp = add("encoder.visual_embedding.absolute_vis_pos_embedding.0.weight", d, 5, 0);
+  e.o_wp = add("encoder.visual_embedding.absolute_vis_pos_embedding.1.weight", 1, d, 0);
+  e.o_img = add("encoder.visual_embedding.img_order_embedding.weight", c.n_images, d, 0);
+  e.o_shared = add("shared.weight", c.vocab_size, d, 0);
+  off = align_up(off, 64);
+  e.n_decay = off;
+  // ---- no-decay group: names containing "bias" (trainer_base.py:148-160) ----------------------------------
+  e.o_bf = add("encoder.visual_embedding.feat_embedding.0.bias", 1, d, 1);
+  e.o_bp = add("encoder.visual_embedding.absolute_vis_pos_embedding.0.bias", 1, d, 1);
+  e.o_enc_rel = add("encoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight", c.n_buckets, c.n_heads, 1);
+  e.o_dec_rel = add("decoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight", c.n_buckets, c.n_heads, 1);
+  off = align_up(off, 64);
+  e.n_train = off;
+  // ---- never receive a gradient (modeling_t5_our.py:379-380 are unused) -------------------------------------
+  add("prototype_fc1.weight", d, d, 2);
+  add("prototype_fc1.bias", 1, d, 2);
+  add("prototype_fc2.weight", d, d, 2);
+  add("prototype_fc2.bias", 1, d, 2);
+  off = align_up(off, 64);
+  e.n_total = off;
+  // q,k,v of one layer must be adjacent (no alignment gap): d*d is a multiple of 64
+  VQ_CHECK(((size_t)d * d) % 64 == 0, "engine: d*d must be a multiple of 64");
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------------------- workspace
+struct Bump {
+  uint8_t* base;
+  int64_t off = 0;
+  std::map<std::string, int64_t>* names;
+  template <typename Tp>
+  Tp* take(size_t count, const char* name = nullptr) {
+    off = (off + 255) / 256 * 256;
+    Tp* p = base ? reinterpret_cast<Tp*>(base + off) : nullptr;
+    if (name && names) (*names)[name] = off;
+    off += (int64_t)(count * sizeof(Tp));
+    return p;
+  }
+};
+
+int64_t engine_carve(Engine& e, uint8_t* base, int B, int L, int N, int T) {
+  const vqacl_config& c = e.cfg;
+  const int d = c.d_model, f = c.d_ff, H = c.n_heads;
+  const int S = L + N, S2 = S + 2;
+  const size_t M = (size_t)B * S, Md = (size_t)B * T, M2 = (size_t)B * S2;
+  const int Le = c.n_enc_layers, Ld = c.n_dec_layers;
+  Workspace w;
+  std::map<std::string, int64_t> names;
+  Bump bp{base, 0, &names};
+  const int ldv = (c.vocab_size + 255) / 256 * 256;
+  w.feats_bf16 = bp.take<bf16>((size_t)B * N * c.feat_dim);
+  w.featpre = bp.take<float>((size_t)B * N * d);
+  w.x.resize(2 * Le + 1);
+  for (auto& p : w.x) p = bp.take<float>(M * d);
+  w.n1.resize(Le); w.qkv.resize(Le); w.ao.resize(Le); w.n2.resize(Le); w.h.resize(Le); w.lse_e.resize(Le);
+  for (int l = 0; l < Le; ++l) {
+    w.n1[l] = bp.take<bf16>(M * d);
+    w.qkv[l] = bp.take<bf16>(M * 3 * d);
+    w.ao[l] = bp.take<bf16>(M * d);
+    w.n2[l] = bp.take<bf16>(M * d);
+    w.h[l] = bp.take<bf16>(M * f);
+    w.lse_e[l] = bp.take<float>((size_t)B * H * S);
+  }
+  w.enc_hidden = bp.take<float>(M * d, "encoder_hidden_states");
+  w.mem = bp.take<bf16>(M2 * d, "decoder_memory");
+  w.enc_mask = bp.take<float>((size_t)B * S);
+  w.cross_mask = bp.take<float>((size_t)B * S2, "cross_mask");
+  w.meanQ = bp.take<float>((size_t)B * d, "meanQ");
+  w.meanV = bp.take<float>((size_t)B * d, "meanV");
+  w.curQ = bp.take<float>((size_t)c.n_ques * d, "curQ");
+  w.curV = bp.take<float>((size_t)c.n_cate * d, "curV");
+  w.cntQ = bp.take<float>(c.n_ques, "cntQ");
+  w.cntV = bp.take<float>(c.n_cate, "cntV");
+  w.idxQ = bp.take<int64_t>(B, "idxQ");
+  w.idxV = bp.take<int64_t>(B, "idxV");
+  w.dec_ids = bp.take<int64_t>(Md, "decoder_input_ids");
+  w.y.resize(3 * Ld + 1);
+  for (auto& p : w.y) p = bp.take<float>(Md * d);
+  w.dn1.resize(Ld); w.dqkv.resize(Ld); w.dao.resize(Ld); w.dn2.resize(Ld); w.cq.resize(Ld); w.cao.resize(Ld); w.dn3.resize(Ld);
+  w.dh.resize(Ld); w.lse_s.resize(Ld); w.lse_c.resize(Ld);
+  for (int l = 0; l < Ld; ++l) {
+    w.dn1[l] = bp.take<bf16>(Md * d);
+    w.dqkv[l] = bp.take<bf16>(Md * 3 * d);
+    w.dao[l] = bp.take<bf16>(Md * d);
+    w.dn2[l] = bp.take<bf16>(Md * d);
+    w.cq[l] = bp.take<bf16>(Md * d);
+    w.cao[l] = bp.take<bf16>(Md * d);
+    w.dn3[l] = bp.take<bf16>(Md * d);
+    w.dh[l] = bp.take<bf16>(Md * f);
+    w.lse_s[l] = bp.take<float>((size_t)B * H * T);
+    w.lse_c[l] = bp.take<float>((size_t)B * H * T);
+  }
+  w.kv_all = bp.take<bf16>(M2 * (size_t)Ld * 2 * d);
+  w.yfin = bp.take<bf16>(Md * d);
+  w.logits = bp.take<bf16>(Md * (size_t)ldv, "logits");
+  w.lse_ce = bp.take<float>(Md);
+  w.loss_rows = bp.take<float>(Md, "loss_rows");
+  w.w_rows = bp.take<float>(Md, "w_rows");
+  w.loss = bp.take<float>(4, "loss");
+  // backward
+  w.gd = bp.take<float>(Md * d);
+  w.gdb = bp.take<bf16>(Md * d);
+  w.t_d768 = bp.take<bf16>(Md * d);
+  w.t_dqkv = bp.take<bf16>(Md * 3 * d);
+  w.t_dh = bp.take<bf16>(Md * f);
+  w.t_dcq = bp.take<bf16>(Md * d);
+  w.ge = bp.take<float>(M * d);
+  w.geb = bp.take<bf16>(M * d);
+  w.t_e768 = bp.take<bf16>(M * d);
+  w.t_eqkv = bp.take<bf16>(M * 3 * d);
+  w.t_eh = bp.take<bf16>(M * f);
+  w.dkv_all = bp.take<bf16>(M2 * (size_t)Ld * 2 * d);
+  w.dmem = bp.take<bf16>(M2 * d);
+  w.dfeatpre = bp.take<bf16>((size_t)B * N * d);
+  w.sumsq_partials = bp.take<float>(2048);
+  w.sumsq = bp.take<float>(4, "grad_sumsq");
+  const int64_t total = (bp.off + 255) / 256 * 256;
+  if (base) {
+    e.w = w;
+    e.ws_names = names;
+    e.ws_base = base;
+    e.ws_bytes = total;
+    e.B = B; e.L = L; e.N = N; e.T = T;
+    e.ldv = ldv;
+    e.fwd_valid = false;
+  }
+  return total;
+}
+
+// --------------------------------------------------------------------------------------------------- GEMM helpers
+static int gemm_fwd(const bf16* A, int lda, const bf16* Wt, int K, void* C, int ldc, int M, int N, int epi, cudaStream_t st,
+                    const void* R = nullptr, int ldr = 0, Dropout dr = Dropout(), float alpha = 1.f) {
+  GemmArgs g{};
+  g.epi = epi; g.M = M; g.N = N; g.K = K; g.C = C; g.ldc = ldc; g.R = R; g.ldr = ldr; g.alpha = alpha; g.splits = 1;
+  g.drop_thr = dr.thr; g.drop_inv_keep = dr.inv_keep; g.seed = dr.seed; g.site = dr.site;
+  return gemm_bf16(GemmOperand{A, lda, false}, GemmOperand{Wt, K, false}, g, 0, st);
+}
+// dX[rows, n_in] = dY[rows, n_out] * W[n_out, n_in]      (W stored row-major -> MN-major B operand)
+static int gemm_dx(const bf16* dY, int lddy, const bf16* Wt, int n_out, int n_in, void* C, int ldc, int rows, int epi, cudaStream_t st,
+                   const void* R = nullptr, int ldr = 0, float alpha = 1.f) {
+  GemmArgs g{};
+  g.epi = epi; g.M = rows; g.N = n_in; g.K = n_out; g.C = C; g.ldc = ldc; g.R = R; g.ldr = ldr; g.alpha = alpha; g.splits = 1;
+  return gemm_bf16(GemmOperand{dY, lddy, false}, GemmOperand{Wt, n_in, true}, g, 0, st);
+}
+// dW[n_out, n_in] += dY[rows, n_out]^T * X[rows, n_in]    (both operands MN-major, split-K over rows, fp32 red.add)
+static int gemm_dw(const bf16* dY, int lddy, const bf16* X, int ldx, float* dWt, int n_out, int n_in, int rows, cudaStream_t st) {
+  GemmArgs g{};
+  g.epi = EPI_ATOMIC_F32; g.M = n_out; g.N = n_in; g.K = rows; g.C = dWt; g.ldc = n_in; g.alpha = 1.f;
+  const int tiles = ((n_out + 127) / 128) * ((n_in + 255) / 256);
+  const int kblocks = (rows + 63) / 64;
+  int splits = (2 * num_sms()) / (tiles > 0 ? tiles : 1);
+  if (splits > kblocks / 8) splits = kblocks / 8;
+  if (splits < 1) splits = 1;
+  g.splits = splits;
+  return gemm_bf16(GemmOperand{dY, lddy, true}, GemmOperand{X, ldx, true}, g, 0, st);
+}
+
+#define VQ_TRY(expr) do { if ((expr) != 0) return 1; } while (0)
+
+// --------------------------------------------------------------------------------------------------- forward
+static int check_batch(const Engine& e, const vqacl_batch* b, bool need_labels) {
+  VQ_CHECK(e.P && e.W, "engine: parameter arena not bound");
+  VQ_CHECK(e.ws_base, "engine: workspace not bound");
+  VQ_CHECK(e.enc_bucket && e.dec_bucket, "engine: relative-position bucket maps not set");
+  VQ_CHECK(b->B == e.B && b->L == e.L && b->N == e.N && (!need_labels || b->T == e.T),
+           "engine: batch shape (B=%d L=%d N=%d T=%d) does not match the bound workspace (B=%d L=%d N=%d T=%d)", b->B, b->L,
+           b->N, b->T, e.B, e.L, e.N, e.T);
+  VQ_CHECK(b->L + b->N <= 64 && b->L >= 1 && b->N >= 1, "engine: encoder length L+N=%d must be in [2,64]", b->L + b->N);
+  VQ_CHECK(!need_labels || (b->T >= 1 && b->T <= 64), "engine: target width T=%d must be in [1,64]", b->T);
+  VQ_CHECK(b->vis_feats && b->boxes && b->input_ids, "engine: missing batch pointers");
+  return 0;
+}
+
+static int encoder_forward(Engine& e, const vqacl_batch* b, cudaStream_t st) {
+  const vqacl_config& c = e.cfg;
+  Workspace& w = e.w;
+  const int d = c.d_model, f = c.d_ff, H = c.n_heads;
+  const int B = b->B, L = b->L, N = b->N, S = L + N, S2 = S + 2;
+  const int M = B * S;
+  VQ_TRY(build_keymasks(b->input_ids, B, L, S, c.pad_id, w.enc_mask, w.cross_mask, st));
+  // embeddings: text rows [0,L), visual rows [L,S)   (modeling_t5_our.py:196-214, :247)
+  VQ_TRY(embed_fwd(b->input_ids, B, L, e.P + e.o_shared, w.x[0], S, 0, e.drop(SITE_ENC_EMB), st));
+  VQ_TRY(cast_f32_to_bf16(b->vis_feats, w.feats_bf16, (size_t)B * N * c.feat_dim, st));
+  VQ_TRY(gemm_fwd(w.feats_bf16, c.feat_dim, e.W + e.o_Wf, c.feat_dim, w.featpre, d, B * N, d, EPI_F32, st));
+  VisArgs va{};
+  va.featpre = w.featpre; va.boxes = b->boxes; va.bf = e.P + e.o_bf; va.wf = e.P + e.o_wf; va.Wp = e.P + e.o_Wp;
+  va.bp = e.P + e.o_bp; va.wp = e.P + e.o_wp; va.img_emb = e.P + e.o_img; va.shared = e.P + e.o_shared;
+  va.V = c.vocab_size; va.B = B; va.N = N; va.S = S; va.L = L; va.eps = c.eps; va.x = w.x[0]; va.drop = e.drop(SITE_ENC_EMB);
+  VQ_TRY(vis_embed_fwd(va, st));
+  for (int l = 0; l < c.n_enc_layers; ++l) {
+    const EncLayer& P = e.enc[l];
+    RmsFwdArgs r{};
+    r.x = w.x[2 * l]; r.w = e.P + P.ln0; r.y_bf16 = w.n1[l]; r.ld_bf16 = d; r.M = M; r.eps = c.eps; r.scale = 1.f;
+    VQ_TRY(rmsnorm_fwd(r, st));
+    VQ_TRY(gemm_fwd(w.n1[l], d, e.W + P.qkv, d, w.qkv[l], 3 * d, M, 3 * d, EPI_BF16, st));
+    AttnArgs a{};
+    a.q = w.qkv[l]; a.k = w.qkv[l] + d; a.v = w.qkv[l] + 2 * d; a.ldq = a.ldk = a.ldv = 3 * d;
+    a.o = w.ao[l]; a.ldo = d; a.lse = w.lse_e[l]; a.B = B; a.H = H; a.Sq = S; a.Sk = S;
+    a.rel_table = e.P + e.o_enc_rel; a.rel_bucket = e.enc_bucket; a.rel_mode = 1; a.Lt = L; a.keymask = w.enc_mask; a.causal = 0;
+    const Dropout dp = e.drop(site_enc(l, 0));
+    a.drop_thr = dp.thr; a.drop_inv_keep = dp.inv_keep; a.seed = dp.seed; a.site = dp.site;
+    VQ_TRY(attn_fwd(a, st));
+    VQ_TRY(gemm_fwd(w.ao[l], d, e.W + P.o, d, w.x[2 * l + 1], d, M, d, EPI_RESID_F32, st, w.x[2 * l], d, e.drop(site_enc(l, 1))));
+    r.x = w.x[2 * l + 1]; r.w = e.P + P.ln1; r.y_bf16 = w.n2[l];
+    VQ_TRY(rmsnorm_fwd(r, st));
+    VQ_TRY(gemm_fwd(w.n2[l], d, e.W + P.wi, d, w.h[l], f, M, f, EPI_RELU_BF16, st, nullptr, 0, e.drop(site_enc(l, 2))));
+    VQ_TRY(gemm_fwd(w.h[l], f, e.W + P.wo, f, w.x[2 * l + 2], d, M, d, EPI_RESID_F32, st, w.x[2 * l + 1], d, e.drop(site_enc(l, 3))));
+  }
+  // final norm + dropout (:314-315): fp32 copy for the SI path / caller, bf16 straight into the [B,S+2,d] decoder memory
+  RmsFwdArgs r{};
+  r.x = w.x[2 * c.n_enc_layers]; r.w = e.P + e.o_enc_final; r.y_bf16 = w.mem; r.ld_bf16 = d; r.y_f32 = w.enc_hidden; r.ld_f32 = d;
+  r.M = M; r.eps = c.eps; r.scale = 1.f; r.in_rpb = S; r.out_rpb = S2; r.drop = e.drop(SITE_ENC_FINAL);
+  VQ_TRY(rmsnorm_fwd(r, st));
+  // SI path, part 1: token means (+ per-class sums for the update)   (:585-588, :601-611)
+  VQ_TRY(proto_means(w.enc_hidden, B, S, c.split_L, w.meanQ, w.meanV, st));
+  return 0;
+}
+
+static int si_path(Engine& e, const vqacl_batch* b, const vqacl_proto_state* ps, bool sums_ready, cudaStream_t st) {
+  const vqacl_config& c = e.cfg;
+  Workspace& w = e.w;
+  const int B = b->B, S2 = b->L + b->N + 2, S = b->L + b->N;
+  VQ_CHECK(ps && ps->Q_prototype && ps->V_prototype, "engine: prototype banks missing (Q_prototype / V_prototype)");
+  if (ps->proto_update) {
+    VQ_CHECK(b->cate_labels && b->ques_labels, "engine: proto_update needs cate_labels and ques_labels");
+    VQ_CHECK(ps->Q_num && ps->V_num, "engine: proto_update needs the count buffers");
+    if (!sums_ready) {
+      VQ_TRY(proto_scatter_mean(w.meanQ, b->ques_labels, B, c.n_ques, w.curQ, w.cntQ, st));
+      VQ_TRY(proto_scatter_mean(w.meanV, b->cate_labels, B, c.n_cate, w.curV, w.cntV, st));
+    } else {
+      VQ_TRY(proto_div(w.curQ, w.cntQ, c.n_ques, st));
+      VQ_TRY(proto_div(w.curV, w.cntV, c.n_cate, st));
+    }
+    ProtoUpdateArgs u{};
+    u.curQ = w.curQ; u.curV = w.curV; u.cntQ = w.cntQ; u.cntV = w.cntV;
+    u.Qproto = ps->Q_prototype; u.Vproto = ps->V_prototype; u.numQ = ps->Q_num; u.numV = ps->V_num;
+    u.CQ = c.n_ques; u.CV = c.n_cate; u.task_id = ps->task_id; u.first_step_of_task = ps->first_step_of_task;
+    u.has_mem = ps->has_mem; u.alpha = ps->alpha; u.beta = ps->beta;
+    VQ_TRY(proto_update(u, st));
+  }
+  // retrieval + feature mix (:601-615): rows S and S+1 of the decoder memory
+  VQ_TRY(proto_retrieve(ps->Q_prototype, c.n_ques, w.meanQ, B, w.mem, S2, S, w.idxQ, nullptr, st));
+  VQ_TRY(proto_retrieve(ps->V_prototype, c.n_cate, w.meanV, B, w.mem, S2, S + 1, w.idxV, nullptr, st));
+  return 0;
+}
+
+static int decoder_forward(Engine& e, const vqacl_batch* b, cudaStream_t st) {
+  const vqacl_config& c = e.cfg;
+  Workspace& w = e.w;
+  const int d = c.d_model, f = c.d_ff, H = c.n_heads, Ld = c.n_dec_layers;
+  const int B = b->B, T = b->T, S2 = b->L + b->N + 2;
+  const int Md = B * T, M2 = B * S2;
+  const int ldkv = Ld * 2 * d;
+  VQ_TRY(shift_right(b->labels, w.dec_ids, B, T, c.start_id, c.pad_id, st));                      // :620
+  VQ_TRY(embed_fwd(w.dec_ids, B, T, e.P + e.o_shared, w.y[0], T, 0, e.drop(SITE_DEC_EMB), st));
+  // cross-attention K/V of every decoder layer in one GEMM over the decoder memory
+  VQ_TRY(gemm_fwd(w.mem, d, e.W + e.o_ckv, d, w.kv_all, ldkv, M2, ldkv, EPI_BF16, st));
+  for (int l = 0; l < Ld; ++l) {
+    const DecLayer& P = e.dec[l];
+    RmsFwdArgs r{};
+    r.x = w.y[3 * l]; r.w = e.P + P.ln0; r.y_bf16 = w.dn1[l]; r.ld_bf16 = d; r.M = Md; r.eps = c.eps; r.scale = 1.f;
+    VQ_TRY(rmsnorm_fwd(r, st));
+    VQ_TRY(gemm_fwd(w.dn1[l], d, e.W + P.qkv, d, w.dqkv[l], 3 * d, Md, 3 * d, EPI_BF16, st));
+    AttnArgs a{};
+    a.q = w.dqkv[l]; a.k = w.dqkv[l] + d; a.v = w.dqkv[l] + 2 * d; a.ldq = a.ldk = a.ldv = 3 * d;
+    a.o = w.dao[l]; a.ldo = d; a.lse = w.lse_s[l]; a.B = B; a.H = H; a.Sq = T; a.Sk = T;
+    a.rel_table = e.P + e.o_dec_rel; a.rel_bucket = e.dec_bucket; a.rel_mode = 2; a.keymask = nullptr; a.causal = 1;
+    Dropout dp = e.drop(site_dec(l, 0));
+    a.drop_thr = dp.thr; a.drop_inv_keep = dp.inv_keep; a.seed = dp.seed; a.site = dp.site;
+    VQ_TRY(attn_fwd(a, st));
+    VQ_TRY(gemm_fwd(w.dao[l], d, e.W + P.o, d, w.y[3 * l + 1], d, Md, d, EPI_RESID_F32, st, w.y[3 * l], d, e.drop(site_dec(l, 1))));
+    // cross attention to the [B,S+2,d] memory: zero position bias, (1-mask)*-1e9 on text pads
+    r.x = w.y[3 * l + 1]; r.w = e.P + P.ln1; r.y_bf16 = w.dn2[l];
+    VQ_TRY(rmsnorm_fwd(r, st));
+    VQ_TRY(gemm_fwd(w.dn2[l], d, e.W + P.cq, d, w.cq[l], d, Md, d, EPI_BF16, st));
+    AttnArgs x{};
+    x.q = w.cq[l]; x.ldq = d; x.k = w.kv_all + (size_t)l * 2 * d; x.v = x.k + d; x.ldk = x.ldv = ldkv;
+    x.o = w.cao[l]; x.ldo = d; x.lse = w.lse_c[l]; x.B = B; x.H = H; x.Sq = T; x.Sk = S2;
+    x.rel_mode = 0; x.keymask = w.cross_mask; x.causal = 0;
+    dp = e.drop(site_dec(l, 2));
+    x.drop_thr = dp.thr; x.drop_inv_keep = dp.inv_keep; x.seed = dp.seed; x.site = dp.site;
+    VQ_TRY(attn_fwd(x, st));
+    VQ_TRY(gemm_fwd(w.cao[l], d, e.W + P.co, d, w.y[3 * l + 2], d, Md, d, EPI_RESID_F32, st, w.y[3 * l + 1], d, e.drop(site_dec(l, 3))));
+    r.x = w.y[3 * l + 2]; r.w = e.P + P.ln2; r.y_bf16 = w.dn3[l];
+    VQ_TRY(rmsnorm_fwd(r, st));
+    VQ_TRY(gemm_fwd(w.dn3[l], d, e.W + P.wi, d, w.dh[l], f, Md, f, EPI_RELU_BF16, st, nullptr, 0, e.drop(site_dec(l, 4))));
+    VQ_TRY(gemm_fwd(w.dh[l], f, e.W + P.wo, f, w.y[3 * l + 3], d, Md, d, EPI_RESID_F32, st, w.y[3 * l + 2], d, e.drop(site_dec(l, 5))));
+  }
+  // final norm, dropout, x d^-1/2 (:666), tied LM head (:671), CE with reduction='none' (:683-686)
+  RmsFwdArgs r{};
+  r.x = w.y[3 * Ld]; r.w = e.P + e.o_dec_final; r.y_bf16 = w.yfin; r.ld_bf16 = d; r.M = Md; r.eps = c.eps;
+  r.scale = 1.f / sqrtf((float)d); r.drop = e.drop(SITE_DEC_FINAL);
+  VQ_TRY(rmsnorm_fwd(r, st));
+  VQ_TRY(gemm_fwd(w.yfin, d, e.W + e.o_shared, d, w.logits, e.ldv, Md, c.vocab_size, EPI_BF16, st));
+  VQ_TRY(ce_fwd(w.logits, e.ldv, Md, c.vocab_size, b->labels, w.lse_ce, w.loss_rows, st));
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------------------- backward
+struct SavedBatch {
+  vqacl_batch b;
+  bool valid = false;
+};
+static std::map<Engine*, SavedBatch> g_saved;
+
+static int backward(Engine& e, const float* w_rows, int accumulate, cudaStream_t st) {
+  VQ_CHECK(e.fwd_valid, "engine: backward called without a preceding training forward");
+  VQ_CHECK(e.G, "engine: gradient arena not bound");
+  const vqacl_config& c = e.cfg;
+  Workspace& w = e.w;
+  const vqacl_batch& b = g_saved[&e].b;
+  const int d = c.d_model, f = c.d_ff, H = c.n_heads, Ld = c.n_dec_layers, Le = c.n_enc_layers;
+  const int B = b.B, L = b.L, N = b.N, T = b.T, S = L + N, S2 = S + 2;
+  const int M = B * S, Md = B * T, M2 = B * S2;
+  const int ldkv = Ld * 2 * d, V = c.vocab_size;
+  if (!accumulate) VQ_CUDA(cudaMemsetAsync(e.G, 0, e.n_train * sizeof(float), st));
+  // ---- LM head + CE
+  VQ_TRY(ce_bwd(w.logits, e.ldv, Md, V, b.labels, w.lse_ce, w_rows, st));
+  VQ_TRY(gemm_dx(w.logits, e.ldv, e.W + e.o_shared, V, d, w.t_d768, d, Md, EPI_BF16, st));
+  VQ_TRY(gemm_dw(w.logits, e.ldv, w.yfin, d, e.G + e.o_shared, V, d, Md, st));
+  RmsBwdArgs r{};
+  r.dn = w.t_d768; r.ld_dn = d; r.x = w.y[3 * Ld]; r.w = e.P + e.o_dec_final; r.g_in = nullptr; r.g_out = w.gd; r.gb_out = w.gdb;
+  r.dw = e.G + e.o_dec_final; r.M = Md; r.eps = c.eps; r.scale = 1.f / sqrtf((float)d); r.own = e.drop(SITE_DEC_FINAL);
+  r.consumer = e.drop(site_dec(Ld - 1, 5)); r.consumer_cols = d;
+  VQ_TRY(rmsnorm_bwd(r, st));
+  for (int l = Ld - 1; l >= 0; --l) {
+    const DecLayer& P = e.dec[l];
+    // FFN
+    VQ_TRY(gemm_dw(w.gdb, d, w.dh[l], f, e.G + P.wo, d, f, Md, st));
+    VQ_TRY(gemm_dx(w.gdb, d, e.W + P.wo, d, f, w.t_dh, f, Md, EPI_RELUBWD_BF16, st, w.dh[l], f, e.drop(site_dec(l, 4)).inv_keep));
+    VQ_TRY(gemm_dw(w.t_dh, f, w.dn3[l], d, e.G + P.wi, f, d, Md, st));
+    VQ_TRY(gemm_dx(w.t_dh, f, e.W + P.wi, f, d, w.t_d768, d, Md, EPI_BF16, st));
+    RmsBwdArgs q{};
+    q.dn = w.t_d768; q.ld_dn = d; q.x = w.y[3 * l + 2]; q.w = e.P + P.ln2; q.g_in = w.gd; q.g_out = w.gd; q.gb_out = w.gdb;
+    q.dw = e.G + P.ln2; q.M = Md; q.eps = c.eps; q.scale = 1.f; q.consumer = e.drop(site_dec(l, 3)); q.consumer_cols = d;
+    VQ_TRY(rmsnorm_bwd(q, st));
+    // cross attention
+    VQ_TRY(gemm_dw(w.gdb, d, w.cao[l], d, e.G + P.co, d, d, Md, st));
+    VQ_TRY(gemm_dx(w.gdb, d, e.W + P.co, d, d, w.t_d768, d, Md, EPI_BF16, st));
+    AttnArgs x{};
+    x.q = w.cq[l]; x.ldq = d; x.k = w.kv_all + (size_t)l * 2 * d; x.v = x.k + d; x.ldk = x.ldv = ldkv;
+    x.ldo = d; x.lse = w.lse_c[l]; x.B = B; x.H = H; x.Sq = T; x.Sk = S2; x.rel_mode = 0; x.keymask = w.cross_mask; x.causal = 0;
+    Dropout dp = e.drop(site_dec(l, 2));
+    x.drop_thr = dp.thr; x.drop_inv_keep = dp.inv_keep; x.seed = dp.seed; x.site = dp.site;
+    x.dO = w.t_d768; x.dq = w.t_dcq; x.lddq = d; x.dk = w.dkv_all + (size_t)l * 2 * d; x.dv = x.dk + d; x.lddk = x.lddv = ldkv;
+    VQ_TRY(attn_bwd(x, st));
+    VQ_TRY(gemm_dw(w.t_dcq, d, w.dn2[l], d, e.G + P.cq, d, d, Md, st));
+    VQ_TRY(gemm_dx(w.t_dcq, d, e.W + P.cq, d, d, w.t_d768, d, Md, EPI_BF16, st));
+    q.x = w.y[3 * l + 1]; q.w = e.P + P.ln1; q.dw = e.G + P.ln1; q.consumer = e.drop(site_dec(l, 1));
+    VQ_TRY(rmsnorm_bwd(q, st));
+    // self attention
+    VQ_TRY(gemm_dw(w.gdb, d, w.dao[l], d, e.G + P.o, d, d, Md, st));
+    VQ_TRY(gemm_dx(w.gdb, d, e.W + P.o, d, d, w.t_d768, d, Md, EPI_BF16, st));
+    AttnArgs a{};
+    a.q = w.dqkv[l]; a.k = w.dqkv[l] + d; a.v = w.dqkv[l] + 2 * d; a.ldq = a.ldk = a.ldv = 3 * d;
+    a.ldo = d; a.lse = w.lse_s[l]; a.B = B; a.H = H; a.Sq = T; a.Sk = T;
+    a.rel_table = e.P + e.o_dec_rel; a.rel_bucket = e.dec_bucket; a.rel_mode = 2; a.causal = 1;
+    dp = e.drop(site_dec(l, 0));
+    a.drop_thr = dp.thr; a.drop_inv_keep = dp.inv_keep; a.seed = dp.seed; a.site = dp.site;
+    a.dO = w.t_d768; a.dq = w.t_dqkv; a.dk = w.t_dqkv + d; a.dv = w.t_dqkv + 2 * d; a.lddq = a.lddk = a.lddv = 3 * d;
+    a.d_rel_table = e.G + e.o_dec_rel;
+    VQ_TRY(attn_bwd(a, st));
+    VQ_TRY(gemm_dw(w.t_dqkv, 3 * d, w.dn1[l], d, e.G + P.qkv, 3 * d, d, Md, st));
+    VQ_TRY(gemm_dx(w.t_dqkv, 3 * d, e.W + P.qkv, 3 * d, d, w.t_d768, d, Md, EPI_BF16, st));
+    q.x = w.y[3 * l]; q.w = e.P + P.ln0; q.dw = e.G + P.ln0;
+    q.consumer = l > 0 ? e.drop(site_dec(l - 1, 5)) : Dropout();
+    VQ_TRY(rmsnorm_bwd(q, st));
+  }
+  // decoder token embedding (tied `shared`)
+  VQ_TRY(embed_bwd(w.dec_ids, B, T, w.gd, T, 0, e.G + e.o_shared, e.drop(SITE_DEC_EMB), st));
+  // cross-attention K/V projection of all layers: dW and the gradient flowing into the decoder memory
+  VQ_TRY(gemm_dw(w.dkv_all, ldkv, w.mem, d, e.G + e.o_ckv, ldkv, d, M2, st));
+  VQ_TRY(gemm_dx(w.dkv_all, ldkv, e.W + e.o_ckv, ldkv, d, w.dmem, d, M2, EPI_BF16, st));
+  // ---- encoder: final norm (rows S, S+1 of each memory slab are the detached prototypes -> dropped by the row map)
+  RmsBwdArgs en{};
+  en.dn = w.dmem; en.ld_dn = d; en.in_rpb = S; en.out_rpb = S2; en.x = w.x[2 * Le]; en.w = e.P + e.o_enc_final;
+  en.g_in = nullptr; en.g_out = w.ge; en.gb_out = w.geb; en.dw = e.G + e.o_enc_final; en.M = M; en.eps = c.eps; en.scale = 1.f;
+  en.own = e.drop(SITE_ENC_FINAL); en.consumer = e.drop(site_enc(Le - 1, 3)); en.consumer_cols = d;
+  VQ_TRY(rmsnorm_bwd(en, st));
+  for (int l = Le - 1; l >= 0; --l) {
+    const EncLayer& P = e.enc[l];
+    VQ_TRY(gemm_dw(w.geb, d, w.h[l], f, e.G + P.wo, d, f, M, st));
+    VQ_TRY(gemm_dx(w.geb, d, e.W + P.wo, d, f, w.t_eh, f, M, EPI_RELUBWD_BF16, st, w.h[l], f, e.drop(site_enc(l, 2)).inv_keep));
+    VQ_TRY(gemm_dw(w.t_eh, f, w.n2[l], d, e.G + P.wi, f, d, M, st));
+    VQ_TRY(gemm_dx(w.t_eh, f, e.W + P.wi, f, d, w.t_e768, d, M, EPI_BF16, st));
+    RmsBwdArgs q{};
+    q.dn = w.t_e768; q.ld_dn = d; q.x = w.x[2 * l + 1]; q.w = e.P + P.ln1; q.g_in = w.ge; q.g_out = w.ge; q.gb_out = w.geb;
+    q.dw = e.G + P.ln1; q.M = M; q.eps = c.eps; q.scale = 1.f; q.consumer = e.drop(site_enc(l, 1)); q.consumer_cols = d;
+    VQ_TRY(rmsnorm_bwd(q, st));
+    VQ_TRY(gemm_dw(w.geb, d, w.ao[l], d, e.G + P.o, d, d, M, st));
+    VQ_TRY(gemm_dx(w.geb, d, e.W + P.o, d, d, w.t_e768, d, M, EPI_BF16, st));
+    AttnArgs a{};
+    a.q = w.qkv[l]; a.k = w.qkv[l] + d; a.v = w.qkv[l] + 2 * d; a.ldq = a.ldk = a.ldv = 3 * d;
+    a.ldo = d; a.lse = w.lse_e[l]; a.B = B; a.H = H; a.Sq = S; a.Sk = S;
+    a.rel_table = e.P + e.o_enc_rel; a.rel_bucket = e.enc_bucket; a.rel_mode = 1; a.Lt = L; a.keymask = w.enc_mask; a.causal = 0;
+    const Dropout dp = e.drop(site_enc(l, 0));
+    a.drop_thr = dp.thr; a.drop_inv_keep = dp.inv_keep; a.seed = dp.seed; a.site = dp.site;
+    a.dO = w.t_e768; a.dq = w.t_eqkv; a.dk = w.t_eqkv + d; a.dv = w.t_eqkv + 2 * d; a.lddq = a.lddk = a.lddv = 3 * d;
+    a.d_rel_table = e.G + e.o_enc_rel;
+    VQ_TRY(attn_bwd(a, st));
+    VQ_TRY(gemm_dw(w.t_eqkv, 3 * d, w.n1[l], d, e.G + P.qkv, 3 * d, d, M, st));
+    VQ_TRY(gemm_dx(w.t_eqkv, 3 * d, e.W + P.qkv, 3 * d, d, w.t_e768, d, M, EPI_BF16, st));
+    q.x = w.x[2 * l]; q.w = e.P + P.ln0; q.dw = e.G + P.ln0;
+    q.consumer = l > 0 ? e.drop(site_enc(l - 1, 3)) : Dropout();
+    if (l == 0) q.gb_out = nullptr;
+    VQ_TRY(rmsnorm_bwd(q, st));
+  }
+  // ---- embeddings: text tokens (tied shared) and the VisualEmbedding
+  VQ_TRY(embed_bwd(b.input_ids, B, L, w.ge, S, 0, e.G + e.o_shared, e.drop(SITE_ENC_EMB), st));
+  VisArgs va{};
+  va.featpre = w.featpre; va.boxes = b.boxes; va.bf = e.P + e.o_bf; va.wf = e.P + e.o_wf; va.Wp = e.P + e.o_Wp;
+  va.bp = e.P + e.o_bp; va.wp = e.P + e.o_wp; va.img_emb = e.P + e.o_img; va.shared = e.P + e.o_shared;
+  va.V = V; va.B = B; va.N = N; va.S = S; va.L = L; va.eps = c.eps; va.drop = e.drop(SITE_ENC_EMB);
+  va.g = w.ge; va.dfeatpre = w.dfeatpre; va.dbf = e.G + e.o_bf; va.dwf = e.G + e.o_wf; va.dWp = e.G + e.o_Wp;
+  va.dbp = e.G + e.o_bp; va.dwp = e.G + e.o_wp; va.dimg = e.G + e.o_img; va.dshared = e.G + e.o_shared;
+  VQ_TRY(vis_embed_bwd(va, st));
+  VQ_TRY(gemm_dw(w.dfeatpre, d, w.feats_bf16, c.feat_dim, e.G + e.o_Wf, d, c.feat_dim, B * N, st));
+  return 0;
+}
+
+}  // namespace vq
+
+// ===================================================================================================== C-ABI
+using namespace vq;
+#define ENG(p) (*reinterpret_cast<Engine*>(p))
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" int vqacl_engine_create(const vqacl_config* cfg, void** engine) {
+  VQ_CHECK(cfg && engine, "engine_create: null argument");
+  Engine* e = new Engine();
+  e->cfg = *cfg;
+  if (engine_build_layout(*e)) {
+    delete e;
+    return 1;
+  }
+  *engine = e;
+  return 0;
+}
+extern "C" void vqacl_engine_destroy(void* engine) {
+  if (!engine) return;
+  g_saved.erase(reinterpret_cast<Engine*>(engine));
+  delete reinterpret_cast<Engine*>(engine);
+}
+extern "C" int vqacl_param_count(void* engine) { return (int)ENG(engine).params.size(); }
+extern "C" int vqacl_param_info(void* engine, int i, char* name, int name_cap, int64_t* offset, int* rows, int* cols, int* group) {
+  Engine& e = ENG(engine);
+  VQ_CHECK(i >= 0 && i < (int)e.params.size(), "param_info: index %d out of range", i);
+  const ParamInfo& p = e.params[i];
+  if (name && name_cap > 0) {
+    strncpy(name, p.name.c_str(), name_cap - 1);
+    name[name_cap - 1] = 0;
+  }
+  if (offset) *offset = (int64_t)p.off;
+  if (rows) *rows = p.rows;
+  if (cols) *cols = p.cols;
+  if (group) *group = p.group;
+  return 0;
+}
+extern "C" int64_t vqacl_arena_elems(void* engine, int64_t* n_decay, int64_t* n_train) {
+  Engine& e = ENG(engine);
+  if (n_decay) *n_decay = (int64_t)e.n_decay;
+  if (n_train) *n_train = (int64_t)e.n_train;
+  return (int64_t)e.n_total;
+}
+extern "C" int vqacl_bind_arena(void* engine, float* params, float* grads, void* params_bf16) {
+  Engine& e = ENG(engine);
+  VQ_CHECK(params && params_bf16, "bind_arena: null arena");
+  VQ_CHECK(((uintptr_t)params & 255) == 0 && ((uintptr_t)params_bf16 & 255) == 0 && ((uintptr_t)grads & 255) == 0,
+           "bind_arena: arenas must be 256-byte aligned");
+  e.P = params; e.G = grads; e.W = reinterpret_cast<bf16*>(params_bf16);
+  gemm_tmap_cache_clear();
+  return 0;
+}
+extern "C" int vqacl_set_rel_buckets(void* engine, const int32_t* enc_b, const int32_t* dec_b) {
+  ENG(engine).enc_bucket = enc_b;
+  ENG(engine).dec_bucket = dec_b;
+  return 0;
+}
+extern "C" int vqacl_refresh_bf16(void* engine, void* stream) {
+  Engine& e = ENG(engine);
+  VQ_CHECK(e.P && e.W, "refresh_bf16: arena not bound");
+  return cast_f32_to_bf16(e.P, e.W, e.n_total, ST(stream));
+}
+extern "C" int64_t vqacl_workspace_bytes(void* engine, int B, int L, int N, int T) { return engine_carve(ENG(engine), nullptr, B, L, N, T); }
+extern "C" int vqacl_bind_workspace(void* engine, void* ws, int64_t bytes, int B, int L, int N, int T) {
+  Engine& e = ENG(engine);
+  VQ_CHECK(ws && ((uintptr_t)ws & 255) == 0, "bind_workspace: workspace must be 256-byte aligned");
+  const int64_t need = engine_carve(e, nullptr, B, L, N, T);
+  VQ_CHECK(bytes >= need, "bind_workspace: %lld bytes given, %lld needed", (long long)bytes, (long long)need);
+  engine_carve(e, reinterpret_cast<uint8_t*>(ws), B, L, N, T);
+  gemm_tmap_cache_clear();
+  return 0;
+}
+extern "C" int64_t vqacl_ws_offset(void* engine, const char* name) {
+  Engine& e = ENG(engine);
+  auto it = e.ws_names.find(name);
+  return it == e.ws_names.end() ? -1 : it->second;
+}
+
+extern "C" int vqacl_forward_encoder(void* engine, const vqacl_batch* batch, const vqacl_proto_state* proto, uint32_t seed,
+                                     int training, void* stream) {
+  Engine& e = ENG(engine);
+  (void)proto;
+  if (check_batch(e, batch, training != 0)) return 1;
+  e.seed = seed;
+  e.training = training != 0;
+  e.fwd_valid = false;
+  return encoder_forward(e, batch, ST(stream));
+}
+extern "C" int vqacl_forward_decoder(void* engine, const vqacl_batch* batch, const vqacl_proto_state* proto, void* stream) {
+  Engine& e = ENG(engine);
+  if (check_batch(e, batch, true)) return 1;
+  VQ_CHECK(batch->labels, "forward_decoder: labels required");
+  if (si_path(e, batch, proto, false, ST(stream))) return 1;
+  if (decoder_forward(e, batch, ST(stream))) return 1;
+  g_saved[&e].b = *batch;
+  e.fwd_valid = true;
+  return 0;
+}
+extern "C" int vqacl_backward(void* engine, const float* w_rows, int accumulate, void* stream) {
+  return backward(ENG(engine), w_rows, accumulate, ST(stream));
+}
+extern "C" int vqacl_loss_tail(const float* loss_rows, const int64_t* labels, const float* scores, int B, int T, float* loss_out,
+                               float* w_rows, void* stream) {
+  return loss_tail(loss_rows, labels, scores, B, T, loss_out, w_rows, ST(stream));
+}
+extern "C" int vqacl_clip_adamw(void* engine, float* exp_avg, float* exp_avg_sq, float lr, float beta1, float beta2, float eps,
+                                float weight_decay, int step, float max_grad_norm, float* grad_norm_out, void* stream) {
+  Engine& e = ENG(engine);
+  VQ_CHECK(e.P && e.G && e.W && e.ws_base, "clip_adamw: arena / workspace not bound");
+  VQ_TRY(grad_sumsq(e.G, e.n_train, e.w.sumsq_partials, e.w.sumsq, ST(stream)));
+  AdamArgs a{};
+  a.p = e.P; a.g = e.G; a.m = exp_avg; a.v = exp_avg_sq; a.p_bf16 = e.W; a.n = e.n_train; a.n_decay = e.n_decay;
+  a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay; a.step = step;
+  a.sumsq = e.w.sumsq; a.max_norm = max_grad_norm;
+  VQ_TRY(adamw_hf(a, ST(stream)));
+  if (grad_norm_out) VQ_CUDA(cudaMemcpyAsync(grad_norm_out, e.w.sumsq, sizeof(float), cudaMemcpyDeviceToDevice, ST(stream)));
+  return 0;
+}
+
+// ---- individual operators
+extern "C" int vqacl_rmsnorm_fwd(const float* x, const float* w, void* y_bf16, float* y_f32, int M, float eps, float scale, void* stream) {
+  RmsFwdArgs r{};
+  r.x = x; r.w = w; r.y_bf16 = reinterpret_cast<bf16*>(y_bf16); r.ld_bf16 = DM; r.y_f32 = y_f32; r.ld_f32 = DM; r.M = M; r.eps = eps; r.scale = scale;
+  return rmsnorm_fwd(r, ST(stream));
+}
+extern "C" int vqacl_rmsnorm_bwd(const void* dn_bf16, const float* x, const float* w, const float* g_in, float* g_out, void* gb_out,
+                                 float* dw, int M, float eps, float scale, void* stream) {
+  RmsBwdArgs r{};
+  r.dn = reinterpret_cast<const bf16*>(dn_bf16); r.ld_dn = DM; r.x = x; r.w = w; r.g_in = g_in; r.g_out = g_out;
+  r.gb_out = reinterpret_cast<bf16*>(gb_out); r.dw = dw; r.M = M; r.eps = eps; r.scale = scale; r.consumer_cols = DM;
+  return rmsnorm_bwd(r, ST(stream));
+}
+static AttnArgs make_attn(const void* q, const void* k, const void* v, int ldq, int ldk, int ldv, int ldo, float* lse, int B, int H,
+                          int Sq, int Sk, const float* rel_table, const int32_t* rel_bucket, int rel_mode, int Lt,
+                          const float* keymask, int causal) {
+  AttnArgs a{};
+  a.q = reinterpret_cast<const bf16*>(q); a.k = reinterpret_cast<const bf16*>(k); a.v = reinterpret_cast<const bf16*>(v);
+  a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.ldo = ldo; a.lse = lse; a.B = B; a.H = H; a.Sq = Sq; a.Sk = Sk;
+  a.rel_table = rel_table; a.rel_bucket = rel_bucket; a.rel_mode = rel_mode; a.Lt = Lt; a.keymask = keymask; a.causal = causal;
+  return a;
+}
+extern "C" int vqacl_attention_fwd(const void* q, const void* k, const void* v, int ldq, int ldk, int ldv, void* o, int ldo, float* lse,
+                                   int B, int H, int Sq, int Sk, const float* rel_table, const int32_t* rel_bucket, int rel_mode,
+                                   int Lt, const float* keymask, int causal, void* stream) {
+  AttnArgs a = make_attn(q, k, v, ldq, ldk, ldv, ldo, lse, B, H, Sq, Sk, rel_table, rel_bucket, rel_mode, Lt, keymask, causal);
+  a.o = reinterpret_cast<bf16*>(o);
+  return attn_fwd(a, ST(stream));
+}
+extern "C" int vqacl_attention_bwd(const void* q, const void* k, const void* v, int ldq, int ldk, int ldv, const void* dO, int ldo,
+                                   const float* lse, void* dq, void* dk, void* dv, int lddq, int lddk, int lddv, int B, int H, int Sq,
+                                   int Sk, const float* rel_table, const int32_t* rel_bucket, int rel_mode, int Lt,
+                                   const float* keymask, int causal, float* d_rel_table, void* stream) {
+  AttnArgs a = make_attn(q, k, v, ldq, ldk, ldv, ldo, const_cast<float*>(lse), B, H, Sq, Sk, rel_table, rel_bucket, rel_mode, Lt,
+                         keymask, causal);
+  a.dO = reinterpret_cast<const bf16*>(dO);
+  a.dq = reinterpret_cast<bf16*>(dq); a.dk = reinterpret_cast<bf16*>(dk); a.dv = reinterpret_cast<bf16*>(dv);
+  a.lddq = lddq; a.lddk = lddk; a.lddv = lddv; a.d_rel_table = d_rel_table;
+  return attn_bwd(a, ST(stream));
+}
+extern "C" int vqacl_proto_means(const float* h, int B, int S, int split, float* meanQ, float* meanV, void* stream) {
+  return proto_means(h, B, S, split, meanQ, meanV, ST(stream));
+}
+extern "C" int vqacl_proto_scatter_mean(const float* mean, const float* labels, int B, int C, float* proto, float* cnt, void* stream) {
+  return proto_scatter_mean(mean, labels, B, C, proto, cnt, ST(stream));
+}
+extern "C" int vqacl_proto_update(const float* curQ, const float* curV, const float* cntQ, const float* cntV, float* Qproto,
+                                  float* Vproto, float* numQ, float* numV, int CQ, int CV, int task_id, int first_step_of_task,
+                                  int has_mem, float alpha, float beta, void* stream) {
+  ProtoUpdateArgs u{};
+  u.curQ = curQ; u.curV = curV; u.cntQ = cntQ; u.cntV = cntV; u.Qproto = Qproto; u.Vproto = Vproto; u.numQ = numQ; u.numV = numV;
+  u.CQ = CQ; u.CV = CV; u.task_id = task_id; u.first_step_of_task = first_step_of_task; u.has_mem = has_mem; u.alpha = alpha; u.beta = beta;
+  return proto_update(u, ST(stream));
+}
+extern "C" int vqacl_proto_retrieve(const float* P, int C, const float* x, int B, void* out_bf16, int out_pitch_rows, int out_row,
+                                    int64_t* idx, float* out_f32, void* stream) {
+  return proto_retrieve(P, C, x, B, reinterpret_cast<bf16*>(out_bf16), out_pitch_rows, out_row, idx, out_f32, ST(stream));
+}
+extern "C" int vqacl_ce_fwd(const void* logits, int ld, int M, int V, const int64_t* labels, float* lse, float* loss, void* stream) {
+  return ce_fwd(reinterpret_cast<const bf16*>(logits), ld, M, V, labels, lse, loss, ST(stream));
+}
+extern "C" int vqacl_ce_bwd(void* logits, int ld, int M, int V, const int64_t* labels, const float* lse, const float* w, void* stream) {
+  return ce_bwd(reinterpret_cast<bf16*>(logits), ld, M, V, labels, lse, w, ST(stream));
+}
+extern "C" int vqacl_visual_embed_fwd(const float* featpre, const float* boxes, const float* bf, const float* wf, const float* Wp,
+                                      const float* bp, const float* wp, const float* img_emb, const float* shared, int V, int B,
+                                      int N, int S, int L, float eps, float* x, void* stream) {
+  VisArgs va{};
+  va.featpre = featpre; va.boxes = boxes; va.bf = bf; va.wf = wf; va.Wp = Wp; va.bp = bp; va.wp = wp; va.img_emb = img_emb;
+  va.shared = shared; va.V = V; va.B = B; va.N = N; va.S = S; va.L = L; va.eps = eps; va.x = x;
+  return vis_embed_fwd(va, ST(stream));
+}
+extern "C" int vqacl_adamw_hf(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, int64_t n_decay, float lr,
+                              float beta1, float beta2, float eps, float weight_decay, int step, const float* sumsq, float max_norm,
+                              void* stream) {
+  AdamArgs a{};
+  a.p = p; a.g = g; a.m = m; a.v = v; a.p_bf16 = reinterpret_cast<bf16*>(p_bf16); a.n = (size_t)n; a.n_decay = (size_t)n_decay;
+  a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay; a.step = step; a.sumsq = sumsq; a.max_norm = max_norm;
+  return adamw_hf(a, ST(stream));
+}
+extern "C" int vqacl_grad_sumsq(const float* g, int64_t n, float* partials, float* out, void* stream) {
+  return grad_sumsq(g, (size_t)n, partials, out, ST(stream));
+}

@@ -1,0 +1,82 @@
+// The VL-T5 / VQACL step engine: owns the parameter-arena layout and the activation workspace carve-up and issues
+// every kernel of forward, backward, optimizer and greedy decode from C++ (no Python between launches).
+#pragma once
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/vqacl_b200.h"
+#include "gemm.h"
+#include "ops.h"
+
+namespace vq {
+
+typedef __nv_bfloat16 bf16;
+
+struct ParamInfo {
+  std::string name;
+  size_t off;
+  int rows, cols;
+  int group;  // 0 = weight-decay group, 1 = no-decay group ("bias" in the name), 2 = never receives a gradient
+};
+
+struct EncLayer { size_t ln0, qkv, o, ln1, wi, wo; };
+struct DecLayer { size_t ln0, qkv, o, ln1, cq, co, ln2, wi, wo; };
+
+struct Workspace {
+  // encoder (M = B*S rows)
+  bf16* feats_bf16; float* featpre;
+  std::vector<float*> x;          // residual stream snapshots, 2*Le + 1
+  std::vector<bf16*> n1, qkv, ao, n2, h;
+  std::vector<float*> lse_e;
+  float* enc_hidden;              // [B,S,d] fp32 (post final norm/dropout) -> encoder_hidden_states
+  bf16* mem;                      // [B,S+2,d] decoder memory
+  float *enc_mask, *cross_mask;
+  // SI path
+  float *meanQ, *meanV, *curQ, *curV, *cntQ, *cntV;
+  int64_t *idxQ, *idxV;
+  // decoder (Md = B*T rows)
+  int64_t* dec_ids;
+  std::vector<float*> y;          // 3*Ld + 1
+  std::vector<bf16*> dn1, dqkv, dao, dn2, cq, cao, dn3, dh;
+  std::vector<float*> lse_s, lse_c;
+  bf16* kv_all;                   // [B*(S+2), Ld*2*d]
+  bf16* yfin;                     // [Md, d]
+  bf16* logits;                   // [Md, ldv]
+  float *lse_ce, *loss_rows, *w_rows, *loss;
+  // backward scratch
+  float *gd, *ge;                 // fp32 residual-stream gradients (decoder / encoder)
+  bf16 *gdb, *geb;                // bf16 copies (masked for the consuming branch)
+  bf16 *t_d768, *t_dqkv, *t_dh, *t_dcq;       // decoder temporaries
+  bf16 *t_e768, *t_eqkv, *t_eh;               // encoder temporaries
+  bf16* dkv_all; bf16* dmem; bf16* dfeatpre;
+  float* sumsq_partials; float* sumsq;
+};
+
+struct Engine {
+  vqacl_config cfg;
+  std::vector<ParamInfo> params;
+  size_t n_decay = 0, n_train = 0, n_total = 0;
+  std::vector<EncLayer> enc;
+  std::vector<DecLayer> dec;
+  size_t o_dec_final = 0, o_ckv = 0, o_enc_final = 0, o_Wf = 0, o_wf = 0, o_Wp = 0, o_wp = 0, o_img = 0, o_shared = 0;
+  size_t o_bf = 0, o_bp = 0, o_enc_rel = 0, o_dec_rel = 0;
+  float* P = nullptr; float* G = nullptr; bf16* W = nullptr;
+  const int* enc_bucket = nullptr; const int* dec_bucket = nullptr;
+  // workspace
+  uint8_t* ws_base = nullptr; int64_t ws_bytes = 0;
+  int B = 0, L = 0, N = 0, T = 0;
+  Workspace w;
+  std::map<std::string, int64_t> ws_names;
+  int ldv = 0;  // logits pitch
+  // step state
+  uint32_t seed = 0; bool training = false; bool fwd_valid = false;
+  // decode workspace (separate carve, see decode.cu)
+  Dropout drop(uint32_t site) const;
+  int S() const { return L + N; }
+};
+
+int engine_build_layout(Engine& e);
+int64_t engine_carve(Engine& e, uint8_t* base, int B, int L, int N, int T);  // base == nullptr: size query only
+
+}  // namespace vq

@@ -1,0 +1,102 @@
+// Step tail of Trainer.train_step (vqacl.py:461-487): clip_grad_norm_(5.0) + HF-4.2.1 AdamW over the flat parameter
+// arena, fused with the bf16 refresh of the GEMM weight copies. HBM-bound: per element it reads p, g, m, v (16 B) and
+// writes p, m, v, bf16(p) (14 B).
+//   HF AdamW (transformers 4.2.1 optimization.py, correct_bias=True), per element:
+//     m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  p -= lr*sqrt(1-b2^t)/(1-b1^t) * m / (sqrt(v) + eps);
+//     then p -= lr * wd * p          (decay after the step, with lr, on the decayed group only)
+#include "ops.h"
+
+namespace vq {
+
+constexpr int SQ_THREADS = 256;
+constexpr int SQ_MAX_BLOCKS = 1184;  // 148 * 8
+
+__global__ void __launch_bounds__(SQ_THREADS) sumsq_partial_kernel(const float* __restrict__ g, size_t n4, size_t n, float* __restrict__ partials) {
+  __shared__ float s_w[SQ_THREADS / 32];
+  float acc = 0.f;
+  for (size_t i = blockIdx.x * (size_t)SQ_THREADS + threadIdx.x; i < n4; i += (size_t)gridDim.x * SQ_THREADS) {
+    const float4 t = reinterpret_cast<const float4*>(g)[i];
+    acc += t.x * t.x + t.y * t.y + t.z * t.z + t.w * t.w;
+  }
+  if (blockIdx.x == 0)
+    for (size_t i = n4 * 4 + threadIdx.x; i < n; i += SQ_THREADS) acc += g[i] * g[i];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < SQ_THREADS / 32; ++w) s += s_w[w];
+    partials[blockIdx.x] = s;
+  }
+}
+__global__ void __launch_bounds__(256) sumsq_final_kernel(const float* __restrict__ partials, int n, float* __restrict__ out) {
+  __shared__ double s_p[256];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) acc += (double)partials[i];
+  s_p[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) s_p[threadIdx.x] += s_p[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = (float)s_p[0];
+}
+int grad_sumsq(const float* g, size_t n, float* partials, float* out, cudaStream_t stream) {
+  VQ_CHECK((reinterpret_cast<uintptr_t>(g) & 15) == 0, "grad_sumsq: gradient arena must be 16-byte aligned");
+  const size_t n4 = n / 4;
+  size_t want = (n4 + SQ_THREADS - 1) / SQ_THREADS;
+  const int blocks = (int)(want < 1 ? 1 : (want > SQ_MAX_BLOCKS ? SQ_MAX_BLOCKS : want));
+  sumsq_partial_kernel<<<blocks, SQ_THREADS, 0, stream>>>(g, n4, n, partials);
+  VQ_LAUNCH_CHECK();
+  sumsq_final_kernel<<<1, 256, 0, stream>>>(partials, blocks, out);
+  VQ_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) adamw_kernel(const AdamArgs a, float step_size, float clip_max) {
+  float coef = 1.f;
+  if (a.sumsq && clip_max > 0.f) {
+    const float c = clip_max / (sqrtf(*a.sumsq) + 1e-6f);  // torch clip_grad_norm_: clip_coef = max_norm / (total_norm + 1e-6)
+    coef = c < 1.f ? c : 1.f;
+  }
+  const float b1 = a.beta1, b2 = a.beta2;
+  const size_t n4 = a.n / 4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 p = reinterpret_cast<float4*>(a.p)[i];
+    const float4 g4 = reinterpret_cast<const float4*>(a.g)[i];
+    float4 m = reinterpret_cast<float4*>(a.m)[i];
+    float4 v = reinterpret_cast<float4*>(a.v)[i];
+    const float wd = (i * 4 < a.n_decay) ? a.lr * a.weight_decay : 0.f;  // n_decay is a multiple of 4 (host-checked)
+    float* pp = &p.x; const float* gg = &g4.x; float* mm = &m.x; float* vv = &v.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float g = gg[k] * coef;
+      mm[k] = b1 * mm[k] + (1.f - b1) * g;
+      vv[k] = b2 * vv[k] + (1.f - b2) * g * g;
+      float x = pp[k] - step_size * (mm[k] / (sqrtf(vv[k]) + a.eps));
+      x = x - wd * x;
+      pp[k] = x;
+    }
+    reinterpret_cast<float4*>(a.p)[i] = p;
+    reinterpret_cast<float4*>(a.m)[i] = m;
+    reinterpret_cast<float4*>(a.v)[i] = v;
+    if (a.p_bf16) reinterpret_cast<uint2*>(a.p_bf16)[i] = make_uint2(pack_bf16(p.x, p.y), pack_bf16(p.z, p.w));
+  }
+}
+int adamw_hf(const AdamArgs& a, cudaStream_t stream) {
+  VQ_CHECK(a.n % 4 == 0 && a.n_decay % 4 == 0, "adamw: arena sizes must be multiples of 4 (n=%zu n_decay=%zu)", a.n, a.n_decay);
+  VQ_CHECK(a.step >= 1, "adamw: step must be >= 1");
+  if (a.n == 0) return 0;
+  const double bc1 = 1.0 - pow((double)a.beta1, (double)a.step);
+  const double bc2 = 1.0 - pow((double)a.beta2, (double)a.step);
+  const float step_size = (float)((double)a.lr * sqrt(bc2) / bc1);
+  const size_t n4 = a.n / 4;
+  size_t want = (n4 + 255) / 256;
+  const size_t cap = (size_t)num_sms() * 16;
+  const int blocks = (int)(want > cap ? cap : want);
+  adamw_kernel<<<blocks, 256, 0, stream>>>(a, step_size, a.max_norm);
+  VQ_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace vq
