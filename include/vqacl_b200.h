@@ -81,17 +81,30 @@ int64_t vqacl_ws_offset(void* engine, const char* name);            /* byte offs
 
 /* ---- hot path: VLT5.forward with labels (modeling_t5_our.py:514-713), split where the multi-GPU SI exchange sits ---- */
 int vqacl_forward_encoder(void* engine, const vqacl_batch* batch, const vqacl_proto_state* proto, uint32_t seed, int training, void* stream);
-int vqacl_forward_decoder(void* engine, const vqacl_batch* batch, const vqacl_proto_state* proto, void* stream);
-/* backward of sum_r w[r] * loss_row[r]; fills the gradient arena (zeroed first unless accumulate != 0) */
-int vqacl_backward(void* engine, const float* w_rows, int accumulate, void* stream);
+/* multi-GPU SI exchange: after forward_encoder, write the UN-divided per-class feature sums and counts of
+ * this rank's batch into the workspace regions "curQ" [n_ques,d], "curV" [n_cate,d], "cntQ", "cntV"; the host all-reduces
+ * (sum) them and passes sums_ready = 1 to forward_decoder, which then divides instead of recomputing. */
+int vqacl_proto_sums(void* engine, const vqacl_batch* batch, void* stream);
+int vqacl_forward_decoder(void* engine, const vqacl_batch* batch, const vqacl_proto_state* proto, int sums_ready, void* stream);
+/* backward of sum_r w[r] * loss_row[r] (loss.backward(), vqacl.py:461); fills the gradient arena (zeroed in stage 0 unless
+ * accumulate != 0). Runs stages [stage_begin, stage_end) (stage_end < 0: to the end) so that the host can overlap the NCCL
+ * all-reduce of a finished arena range (vqacl_backward_stage_range) with the remaining stages. */
+int vqacl_backward(void* engine, const float* w_rows, int accumulate, int stage_begin, int stage_end, void* stream);
+int vqacl_backward_stages(void* engine);
+int vqacl_backward_stage_range(void* engine, int stage, int64_t* begin, int64_t* end);
 /* fused loss tail of VLT5VQA.train_step (vqa_model.py:46-54) */
 int vqacl_loss_tail(const float* loss_rows, const int64_t* labels, const float* scores, int B, int T, float* loss_out, float* w_rows, void* stream);
 /* clip_grad_norm_ + HF AdamW + bf16 refresh (vqacl.py:475-482, trainer_base.py:130-198) */
 int vqacl_clip_adamw(void* engine, float* exp_avg, float* exp_avg_sq, float lr, float beta1, float beta2, float eps,
                      float weight_decay, int step, float max_grad_norm, float* grad_norm_out, void* stream);
-/* greedy generation (vqa_model.py:112-116; HF 4.2.1 greedy_search): out_tokens [B, max_len] int64, returns steps taken */
+/* greedy generation (vqa_model.py:112-116; HF 4.2.1 generate/greedy_search with max_length 20):
+ * out_tokens [B, max_len] int64 (column 0 = start token, finished rows emit pad); *out_len = columns produced.
+ * Synchronises the stream once per generated token (the all-rows-finished test, as HF does). */
+int64_t vqacl_generate_workspace_bytes(void* engine, int B, int L, int N, int max_len);
 int vqacl_generate(void* engine, const vqacl_batch* batch, const vqacl_proto_state* proto, int max_len, int64_t* out_tokens,
-                   int* out_len, void* stream);
+                   void* workspace, int64_t workspace_bytes, int* out_len, void* stream);
+/* number of kernels this library has launched so far in this process (bench.py's gpu_launches) */
+long long vqacl_launch_count(void);
 
 /* ---- individual operators (unit-test / building-block surface) ---- */
 int vqacl_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major, void* C, int ldc,

@@ -97,13 +97,13 @@ VQ_DEVINL void scores_tile(float (&s)[8][4], const __nv_bfloat16 (*sq)[AT_P], co
   for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int qi = m0 + g + (i >> 1) * 8;
+      const int qi = m0 + g + (i >> 1) * 8 + p.q_off;   // absolute query position
       const int kj = nt * 8 + 2 * t + (i & 1);
       float x = s[nt][i];
       if (kj >= p.Sk) {
         x = -INFINITY;
       } else {
-        if (p.rel_mode == 2 || (p.rel_mode == 1 && qi < p.Lt && kj < p.Lt)) x += sbias[kj - qi + (AT_S - 1)];
+        if (p.rel_mode == 2 || (p.rel_mode == 1 && qi < p.Lt && kj < p.Lt)) x += sbias[min(max(kj - qi, -(AT_S - 1)), AT_S - 1) + (AT_S - 1)];
         x += skmask[kj];
         if (p.causal && kj > qi) x += -10000.0f;
       }
@@ -116,9 +116,9 @@ __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const AttnArgs p) 
   AttnSmemFwd& sm = *reinterpret_cast<AttnSmemFwd*>(at_smem_raw);
   const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  load_head(sm.q, p.q + (size_t)b * p.Sq * p.ldq + h * AT_D, p.ldq, p.Sq);
-  load_head(sm.k, p.k + (size_t)b * p.Sk * p.ldk + h * AT_D, p.ldk, p.Sk);
-  load_head(sm.v, p.v + (size_t)b * p.Sk * p.ldv + h * AT_D, p.ldv, p.Sk);
+  load_head(sm.q, p.q + (size_t)b * (p.q_bstride ? p.q_bstride : (long long)p.Sq * p.ldq) + h * AT_D, p.ldq, p.Sq);
+  load_head(sm.k, p.k + (size_t)b * (p.k_bstride ? p.k_bstride : (long long)p.Sk * p.ldk) + h * AT_D, p.ldk, p.Sk);
+  load_head(sm.v, p.v + (size_t)b * (p.v_bstride ? p.v_bstride : (long long)p.Sk * p.ldv) + h * AT_D, p.ldv, p.Sk);
   for (int r = threadIdx.x; r < 2 * AT_S - 1; r += AT_THREADS)
     sm.bias[r] = p.rel_mode ? p.rel_table[p.rel_bucket[r] * p.H + h] : 0.f;
   for (int j = threadIdx.x; j < AT_S; j += AT_THREADS) sm.kmask[j] = (p.keymask && j < p.Sk) ? p.keymask[(size_t)b * p.Sk + j] : 0.f;
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const AttnArgs p) 
   for (int r = 0; r < 2; ++r) {
     const int qi = m0 + g + r * 8;
     if (qi < p.Sq) {
-      __nv_bfloat16* dst = p.o + ((size_t)b * p.Sq + qi) * p.ldo + h * AT_D + 2 * t;
+      __nv_bfloat16* dst = p.o + (size_t)b * (p.o_bstride ? p.o_bstride : (long long)p.Sq * p.ldo) + (size_t)qi * p.ldo + h * AT_D + 2 * t;
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) *reinterpret_cast<uint32_t*>(dst + nt * 8) = pack_bf16(o[nt][2 * r], o[nt][2 * r + 1]);
     }
@@ -385,6 +385,7 @@ int attn_fwd(const AttnArgs& a, cudaStream_t stream) {
 int attn_bwd(const AttnArgs& a, cudaStream_t stream) {
   if (check_args(a)) return 1;
   VQ_CHECK(a.lse && a.dO && a.dq && a.dk && a.dv, "attention bwd: missing pointers");
+  VQ_CHECK(!a.q_bstride && !a.k_bstride && !a.v_bstride && !a.o_bstride && !a.q_off, "attention bwd: strided / offset form is forward-only");
   VQ_CHECK(a.lddq % 8 == 0 && a.lddk % 8 == 0 && a.lddv % 8 == 0, "attention bwd: pitches must be multiples of 8");
   static bool attr = false;
   if (!attr) {

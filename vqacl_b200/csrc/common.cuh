@@ -34,7 +34,13 @@ void vq_set_error(const char* fmt, ...);
     }                                                                              \
   } while (0)
 
-#define VQ_LAUNCH_CHECK() VQ_CUDA(cudaGetLastError())
+// every kernel launch of the library goes through this: counts launches (bench.py reports them) and surfaces errors
+extern long long g_vq_launches;
+#define VQ_LAUNCH_CHECK()            \
+  do {                               \
+    ++g_vq_launches;                 \
+    VQ_CUDA(cudaGetLastError());     \
+  } while (0)
 
 // ---------------------------------------------------------------------------------------------
 // small device utilities

@@ -220,13 +220,6 @@ int64_t engine_carve(Engine& e, uint8_t* base, int B, int L, int N, int T) {
 }
 
 // --------------------------------------------------------------------------------------------------- GEMM helpers
-static int gemm_fwd(const bf16* A, int lda, const bf16* Wt, int K, void* C, int ldc, int M, int N, int epi, cudaStream_t st,
-                    const void* R = nullptr, int ldr = 0, Dropout dr = Dropout(), float alpha = 1.f) {
-  GemmArgs g{};
-  g.epi = epi; g.M = M; g.N = N; g.K = K; g.C = C; g.ldc = ldc; g.R = R; g.ldr = ldr; g.alpha = alpha; g.splits = 1;
-  g.drop_thr = dr.thr; g.drop_inv_keep = dr.inv_keep; g.seed = dr.seed; g.site = dr.site;
-  return gemm_bf16(GemmOperand{A, lda, false}, GemmOperand{Wt, K, false}, g, 0, st);
-}
 // dX[rows, n_in] = dY[rows, n_out] * W[n_out, n_in]      (W stored row-major -> MN-major B operand)
 static int gemm_dx(const bf16* dY, int lddy, const bf16* Wt, int n_out, int n_in, void* C, int ldc, int rows, int epi, cudaStream_t st,
                    const void* R = nullptr, int ldr = 0, float alpha = 1.f) {
@@ -247,10 +240,9 @@ static int gemm_dw(const bf16* dY, int lddy, const bf16* X, int ldx, float* dWt,
   return gemm_bf16(GemmOperand{dY, lddy, true}, GemmOperand{X, ldx, true}, g, 0, st);
 }
 
-#define VQ_TRY(expr) do { if ((expr) != 0) return 1; } while (0)
 
 // --------------------------------------------------------------------------------------------------- forward
-static int check_batch(const Engine& e, const vqacl_batch* b, bool need_labels) {
+int check_batch(const Engine& e, const vqacl_batch* b, bool need_labels) {
   VQ_CHECK(e.P && e.W, "engine: parameter arena not bound");
   VQ_CHECK(e.ws_base, "engine: workspace not bound");
   VQ_CHECK(e.enc_bucket && e.dec_bucket, "engine: relative-position bucket maps not set");
@@ -263,7 +255,7 @@ static int check_batch(const Engine& e, const vqacl_batch* b, bool need_labels) 
   return 0;
 }
 
-static int encoder_forward(Engine& e, const vqacl_batch* b, cudaStream_t st) {
+int encoder_forward(Engine& e, const vqacl_batch* b, cudaStream_t st) {
   const vqacl_config& c = e.cfg;
   Workspace& w = e.w;
   const int d = c.d_model, f = c.d_ff, H = c.n_heads;
@@ -308,7 +300,7 @@ static int encoder_forward(Engine& e, const vqacl_batch* b, cudaStream_t st) {
   return 0;
 }
 
-static int si_path(Engine& e, const vqacl_batch* b, const vqacl_proto_state* ps, bool sums_ready, cudaStream_t st) {
+int si_path(Engine& e, const vqacl_batch* b, const vqacl_proto_state* ps, bool sums_ready, cudaStream_t st) {
   const vqacl_config& c = e.cfg;
   Workspace& w = e.w;
   const int B = b->B, S2 = b->L + b->N + 2, S = b->L + b->N;
@@ -395,7 +387,37 @@ struct SavedBatch {
 };
 static std::map<Engine*, SavedBatch> g_saved;
 
-static int backward(Engine& e, const float* w_rows, int accumulate, cudaStream_t st) {
+// Backward runs in stages so that the host can start the gradient all-reduce of a finished arena range while later
+// stages still compute:
+//   stage 0            : CE + LM head + decoder final norm
+//   stage 1 .. Ld      : decoder layer Ld - stage
+//   stage Ld+1         : decoder token embedding, cross-attention K/V projection (all layers), encoder final norm
+//   stage Ld+2 .. Ld+1+Le : encoder layer Le - (stage - Ld - 1)
+//   stage Ld+Le+2      : text / visual embeddings
+static int n_backward_stages(const Engine& e) { return e.cfg.n_dec_layers + e.cfg.n_enc_layers + 3; }
+
+// arena range [*a, *b) whose gradients are final once `stage` has run (possibly empty)
+static void backward_stage_range(const Engine& e, int stage, int64_t* a, int64_t* b) {
+  const int Ld = e.cfg.n_dec_layers, Le = e.cfg.n_enc_layers;
+  *a = *b = 0;
+  if (stage >= 1 && stage <= Ld) {
+    const int l = Ld - stage;
+    *a = (int64_t)e.dec[l].ln0;
+    *b = (int64_t)(l + 1 < Ld ? e.dec[l + 1].ln0 : e.o_dec_final);
+  } else if (stage == Ld + 1) {
+    *a = (int64_t)e.o_dec_final;
+    *b = (int64_t)(Le > 0 ? e.enc[0].ln0 : e.o_enc_final);
+  } else if (stage >= Ld + 2 && stage <= Ld + 1 + Le) {
+    const int l = Le - (stage - Ld - 1);
+    *a = (int64_t)e.enc[l].ln0;
+    *b = (int64_t)(l + 1 < Le ? e.enc[l + 1].ln0 : e.o_enc_final);
+  } else if (stage == Ld + Le + 2) {
+    *a = (int64_t)e.o_enc_final;
+    *b = (int64_t)e.n_train;
+  }
+}
+
+static int backward(Engine& e, const float* w_rows, int accumulate, int stage_begin, int stage_end, cudaStream_t st) {
   VQ_CHECK(e.fwd_valid, "engine: backward called without a preceding training forward");
   VQ_CHECK(e.G, "engine: gradient arena not bound");
   const vqacl_config& c = e.cfg;
@@ -405,8 +427,14 @@ static int backward(Engine& e, const float* w_rows, int accumulate, cudaStream_t
   const int B = b.B, L = b.L, N = b.N, T = b.T, S = L + N, S2 = S + 2;
   const int M = B * S, Md = B * T, M2 = B * S2;
   const int ldkv = Ld * 2 * d, V = c.vocab_size;
+  const int n_stages = n_backward_stages(e);
+  if (stage_end < 0 || stage_end > n_stages) stage_end = n_stages;
+  VQ_CHECK(stage_begin >= 0 && stage_begin <= stage_end, "backward: bad stage range [%d, %d)", stage_begin, stage_end);
+  auto on = [&](int s) { return s >= stage_begin && s < stage_end; };
+  if (on(0)) {
   if (!accumulate) VQ_CUDA(cudaMemsetAsync(e.G, 0, e.n_train * sizeof(float), st));
   // ---- LM head + CE
+  VQ_CHECK(w_rows, "backward: w_rows (dL/dloss_row) required");
   VQ_TRY(ce_bwd(w.logits, e.ldv, Md, V, b.labels, w.lse_ce, w_rows, st));
   VQ_TRY(gemm_dx(w.logits, e.ldv, e.W + e.o_shared, V, d, w.t_d768, d, Md, EPI_BF16, st));
   VQ_TRY(gemm_dw(w.logits, e.ldv, w.yfin, d, e.G + e.o_shared, V, d, Md, st));
@@ -415,7 +443,9 @@ static int backward(Engine& e, const float* w_rows, int accumulate, cudaStream_t
   r.dw = e.G + e.o_dec_final; r.M = Md; r.eps = c.eps; r.scale = 1.f / sqrtf((float)d); r.own = e.drop(SITE_DEC_FINAL);
   r.consumer = e.drop(site_dec(Ld - 1, 5)); r.consumer_cols = d;
   VQ_TRY(rmsnorm_bwd(r, st));
+  }
   for (int l = Ld - 1; l >= 0; --l) {
+    if (!on(Ld - l)) continue;
     const DecLayer& P = e.dec[l];
     // FFN
     VQ_TRY(gemm_dw(w.gdb, d, w.dh[l], f, e.G + P.wo, d, f, Md, st));
@@ -458,6 +488,7 @@ static int backward(Engine& e, const float* w_rows, int accumulate, cudaStream_t
     q.consumer = l > 0 ? e.drop(site_dec(l - 1, 5)) : Dropout();
     VQ_TRY(rmsnorm_bwd(q, st));
   }
+  if (on(Ld + 1)) {
   // decoder token embedding (tied `shared`)
   VQ_TRY(embed_bwd(w.dec_ids, B, T, w.gd, T, 0, e.G + e.o_shared, e.drop(SITE_DEC_EMB), st));
   // cross-attention K/V projection of all layers: dW and the gradient flowing into the decoder memory
@@ -469,7 +500,9 @@ static int backward(Engine& e, const float* w_rows, int accumulate, cudaStream_t
   en.g_in = nullptr; en.g_out = w.ge; en.gb_out = w.geb; en.dw = e.G + e.o_enc_final; en.M = M; en.eps = c.eps; en.scale = 1.f;
   en.own = e.drop(SITE_ENC_FINAL); en.consumer = e.drop(site_enc(Le - 1, 3)); en.consumer_cols = d;
   VQ_TRY(rmsnorm_bwd(en, st));
+  }
   for (int l = Le - 1; l >= 0; --l) {
+    if (!on(Ld + 1 + Le - l)) continue;
     const EncLayer& P = e.enc[l];
     VQ_TRY(gemm_dw(w.geb, d, w.h[l], f, e.G + P.wo, d, f, M, st));
     VQ_TRY(gemm_dx(w.geb, d, e.W + P.wo, d, f, w.t_eh, f, M, EPI_RELUBWD_BF16, st, w.h[l], f, e.drop(site_enc(l, 2)).inv_keep));
@@ -497,6 +530,7 @@ static int backward(Engine& e, const float* w_rows, int accumulate, cudaStream_t
     if (l == 0) q.gb_out = nullptr;
     VQ_TRY(rmsnorm_bwd(q, st));
   }
+  if (!on(Ld + Le + 2)) return 0;
   // ---- embeddings: text tokens (tied shared) and the VisualEmbedding
   VQ_TRY(embed_bwd(b.input_ids, B, L, w.ge, S, 0, e.G + e.o_shared, e.drop(SITE_ENC_EMB), st));
   VisArgs va{};
@@ -599,18 +633,34 @@ extern "C" int vqacl_forward_encoder(void* engine, const vqacl_batch* batch, con
   e.fwd_valid = false;
   return encoder_forward(e, batch, ST(stream));
 }
-extern "C" int vqacl_forward_decoder(void* engine, const vqacl_batch* batch, const vqacl_proto_state* proto, void* stream) {
+extern "C" int vqacl_proto_sums(void* engine, const vqacl_batch* batch, void* stream) {
+  Engine& e = ENG(engine);
+  if (check_batch(e, batch, false)) return 1;
+  VQ_CHECK(batch->cate_labels && batch->ques_labels, "proto_sums: needs cate_labels and ques_labels");
+  VQ_TRY(proto_scatter_sum(e.w.meanQ, batch->ques_labels, batch->B, e.cfg.n_ques, e.w.curQ, e.w.cntQ, ST(stream)));
+  VQ_TRY(proto_scatter_sum(e.w.meanV, batch->cate_labels, batch->B, e.cfg.n_cate, e.w.curV, e.w.cntV, ST(stream)));
+  return 0;
+}
+extern "C" int vqacl_forward_decoder(void* engine, const vqacl_batch* batch, const vqacl_proto_state* proto, int sums_ready,
+                                     void* stream) {
   Engine& e = ENG(engine);
   if (check_batch(e, batch, true)) return 1;
   VQ_CHECK(batch->labels, "forward_decoder: labels required");
-  if (si_path(e, batch, proto, false, ST(stream))) return 1;
+  if (si_path(e, batch, proto, sums_ready != 0, ST(stream))) return 1;
   if (decoder_forward(e, batch, ST(stream))) return 1;
   g_saved[&e].b = *batch;
   e.fwd_valid = true;
   return 0;
 }
-extern "C" int vqacl_backward(void* engine, const float* w_rows, int accumulate, void* stream) {
-  return backward(ENG(engine), w_rows, accumulate, ST(stream));
+extern "C" int vqacl_backward(void* engine, const float* w_rows, int accumulate, int stage_begin, int stage_end, void* stream) {
+  return backward(ENG(engine), w_rows, accumulate, stage_begin, stage_end, ST(stream));
+}
+extern "C" int vqacl_backward_stages(void* engine) { return n_backward_stages(ENG(engine)); }
+extern "C" int vqacl_backward_stage_range(void* engine, int stage, int64_t* begin, int64_t* end) {
+  Engine& e = ENG(engine);
+  VQ_CHECK(stage >= 0 && stage < n_backward_stages(e) && begin && end, "backward_stage_range: bad arguments");
+  backward_stage_range(e, stage, begin, end);
+  return 0;
 }
 extern "C" int vqacl_loss_tail(const float* loss_rows, const int64_t* labels, const float* scores, int B, int T, float* loss_out,
                                float* w_rows, void* stream) {

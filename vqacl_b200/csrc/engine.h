@@ -76,6 +76,21 @@ struct Engine {
   int S() const { return L + N; }
 };
 
+#define VQ_TRY(expr) do { if ((expr) != 0) return 1; } while (0)
+
+// Y[M,N] = epilogue(X[M,K] * W[N,K]^T): both operands K-major (nn.Linear forward)
+inline int gemm_fwd(const bf16* A, int lda, const bf16* Wt, int K, void* C, int ldc, int M, int N, int epi, cudaStream_t st,
+                    const void* R = nullptr, int ldr = 0, Dropout dr = Dropout(), float alpha = 1.f) {
+  GemmArgs g{};
+  g.epi = epi; g.M = M; g.N = N; g.K = K; g.C = C; g.ldc = ldc; g.R = R; g.ldr = ldr; g.alpha = alpha; g.splits = 1;
+  g.drop_thr = dr.thr; g.drop_inv_keep = dr.inv_keep; g.seed = dr.seed; g.site = dr.site;
+  return gemm_bf16(GemmOperand{A, lda, false}, GemmOperand{Wt, K, false}, g, 0, st);
+}
+
+int check_batch(const Engine& e, const vqacl_batch* b, bool need_labels);
+int encoder_forward(Engine& e, const vqacl_batch* b, cudaStream_t st);
+int si_path(Engine& e, const vqacl_batch* b, const vqacl_proto_state* ps, bool sums_ready, cudaStream_t st);
+
 int engine_build_layout(Engine& e);
 int64_t engine_carve(Engine& e, uint8_t* base, int B, int L, int N, int T);  // base == nullptr: size query only
 

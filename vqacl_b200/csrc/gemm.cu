@@ -19,6 +19,8 @@ void vq_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 extern "C" const char* vqacl_last_error() { return g_err; }
+long long g_vq_launches = 0;
+extern "C" long long vqacl_launch_count() { return g_vq_launches; }
 
 namespace vq {
 

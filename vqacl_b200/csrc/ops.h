@@ -36,6 +36,10 @@ struct AttnArgs {
   __nv_bfloat16 *dq, *dk, *dv;
   int lddq, lddk, lddv;
   float* d_rel_table;       // [num_buckets, H] accumulated with atomics, or null
+  // KV-cached decoding (forward only): element strides between batch entries (0 = S * ld, i.e. densely packed) and the
+  // absolute position of query row 0 (the relative-position bias of HF's position_bias[:, :, -seq_length:, :])
+  long long q_bstride, k_bstride, v_bstride, o_bstride;
+  int q_off;
 };
 int attn_fwd(const AttnArgs& a, cudaStream_t stream);
 int attn_bwd(const AttnArgs& a, cudaStream_t stream);
