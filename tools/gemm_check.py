@@ -38,7 +38,7 @@ def run_case(M, N, K, a_mn, b_mn, epi, bn, splits=1):
     elif epi == EPI_ATOMIC:
         ref = ref + 0.5
     elif epi == EPI_RELUBWD:
-        R = torch.randn(M, N, device="cuda", generator=g).bfloat16()
+        R = torch.randn(M, N, device="cuda", generator=g).relu().bfloat16()  # saved relu output: >= 0
         ref = ref * (R.float() > 0)
     gemm(A, a_mn, B, b_mn, C, R, M, N, K, epi, 1.0, splits, bn)
     torch.cuda.synchronize()

@@ -37,9 +37,11 @@ VQ_DEVINL void mma16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
-// load a [rows<=64, 64] bf16 head slice into smem (zero padded), 16-byte vectors
+// load a [rows<=64, 64] bf16 head slice into smem, 16-byte vectors; rows [rows, round_up(rows,16)) are zero-filled and
+// rows beyond that are left untouched (every consumer loop is bounded by the same round-up)
 VQ_DEVINL void load_head(__nv_bfloat16 (*dst)[AT_P], const __nv_bfloat16* src, int ld, int rows) {
-  for (int idx = threadIdx.x; idx < AT_S * (AT_D / 8); idx += AT_THREADS) {
+  const int rows16 = (rows + 15) & ~15;
+  for (int idx = threadIdx.x; idx < rows16 * (AT_D / 8); idx += AT_THREADS) {
     const int r = idx >> 3, c = (idx & 7) * 8;
     uint4 v = make_uint4(0, 0, 0, 0);
     if (r < rows) v = *reinterpret_cast<const uint4*>(src + (size_t)r * ld + c);
@@ -68,15 +70,20 @@ VQ_DEVINL void frag_b_t(uint32_t (&b)[2], const __nv_bfloat16 (*X)[AT_P], int n0
   ldsm_x2_t(b, &X[k0 + mi * 8 + r][n0]);
 }
 
+// dropout pair index of probabilities (q, k), (q, k+1) of problem `blk` (k even)
+VQ_DEVINL uint32_t attn_pair_idx(uint32_t blk, int q, int k) { return ((blk * AT_S + (uint32_t)q) * AT_S + (uint32_t)k) >> 1; }
+
 struct AttnSmemFwd {
   __nv_bfloat16 q[AT_S][AT_P], k[AT_S][AT_P], v[AT_S][AT_P];
   float bias[2 * AT_S];
   float kmask[AT_S];
 };
 
-// scores for the warp's 16 query rows vs all 64 keys, bias/mask applied; keys >= Sk get -inf
+// scores for the warp's 16 query rows vs the keys, bias/mask applied; keys >= Sk get -inf.
+// Only the ceil(Sk/8) key tiles that exist are multiplied (decoder self-attention has Sk = T <= 10).
 VQ_DEVINL void scores_tile(float (&s)[8][4], const __nv_bfloat16 (*sq)[AT_P], const __nv_bfloat16 (*sk)[AT_P],
                            const float* sbias, const float* skmask, const AttnArgs& p, int m0, int lane) {
+  const int nkt = (p.Sk + 7) >> 3;
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
@@ -87,9 +94,11 @@ VQ_DEVINL void scores_tile(float (&s)[8][4], const __nv_bfloat16 (*sq)[AT_P], co
     frag_a(a, sq, m0, kk * 16, lane);
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      uint32_t b[2];
-      frag_b(b, sk, nt * 8, kk * 16, lane);
-      mma16816(s[nt], a, b);
+      if (nt < nkt) {
+        uint32_t b[2];
+        frag_b(b, sk, nt * 8, kk * 16, lane);
+        mma16816(s[nt], a, b);
+      }
     }
   }
   const int g = lane >> 2, t = lane & 3;
@@ -111,7 +120,13 @@ VQ_DEVINL void scores_tile(float (&s)[8][4], const __nv_bfloat16 (*sq)[AT_P], co
     }
 }
 
-__global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const AttnArgs p) {
+VQ_DEVINL void load_bias_mask(float* sbias, float* skmask, const AttnArgs& p, int b, int h) {
+  if (p.rel_mode)
+    for (int r = threadIdx.x; r < 2 * AT_S - 1; r += AT_THREADS) sbias[r] = p.rel_table[p.rel_bucket[r] * p.H + h];
+  for (int j = threadIdx.x; j < AT_S; j += AT_THREADS) skmask[j] = (p.keymask && j < p.Sk) ? p.keymask[(size_t)b * p.Sk + j] : 0.f;
+}
+
+__global__ void __launch_bounds__(AT_THREADS, 4) attn_fwd_kernel(const AttnArgs p) {
   extern __shared__ uint8_t at_smem_raw[];
   AttnSmemFwd& sm = *reinterpret_cast<AttnSmemFwd*>(at_smem_raw);
   const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
@@ -119,9 +134,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const AttnArgs p) 
   load_head(sm.q, p.q + (size_t)b * (p.q_bstride ? p.q_bstride : (long long)p.Sq * p.ldq) + h * AT_D, p.ldq, p.Sq);
   load_head(sm.k, p.k + (size_t)b * (p.k_bstride ? p.k_bstride : (long long)p.Sk * p.ldk) + h * AT_D, p.ldk, p.Sk);
   load_head(sm.v, p.v + (size_t)b * (p.v_bstride ? p.v_bstride : (long long)p.Sk * p.ldv) + h * AT_D, p.ldv, p.Sk);
-  for (int r = threadIdx.x; r < 2 * AT_S - 1; r += AT_THREADS)
-    sm.bias[r] = p.rel_mode ? p.rel_table[p.rel_bucket[r] * p.H + h] : 0.f;
-  for (int j = threadIdx.x; j < AT_S; j += AT_THREADS) sm.kmask[j] = (p.keymask && j < p.Sk) ? p.keymask[(size_t)b * p.Sk + j] : 0.f;
+  load_bias_mask(sm.bias, sm.kmask, p, b, h);
   __syncthreads();
   const int m0 = warp * 16;
   if (m0 >= p.Sq) return;
@@ -164,15 +177,18 @@ __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const AttnArgs p) 
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float pr = s[nt][i] * inv[i >> 1];
+    for (int r = 0; r < 2; ++r) {
+      float s0 = inv[r], s1 = inv[r];
       if (p.drop_thr) {
-        const int qi = m0 + g + (i >> 1) * 8, kj = nt * 8 + 2 * t + (i & 1);
-        pr *= vq_dropout_scale(p.seed, p.site, ((uint64_t)blockIdx.x * AT_S + qi) * AT_S + kj, p.drop_thr, p.drop_inv_keep);
+        float d0, d1;
+        vq_dropout_pair(p.seed, attn_pair_idx(blockIdx.x, m0 + g + r * 8, nt * 8 + 2 * t), p.drop_thr, p.drop_inv_keep, d0, d1);
+        s0 *= d0; s1 *= d1;
       }
-      s[nt][i] = pr;
+      s[nt][2 * r] *= s0;
+      s[nt][2 * r + 1] *= s1;
     }
-  // O = P V
+  // O = P V over the ceil(Sk/16) key blocks that exist
+  const int nkk = (p.Sk + 15) >> 4;
   float o[8][4];
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt)
@@ -180,16 +196,18 @@ __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const AttnArgs p) 
     for (int i = 0; i < 4; ++i) o[nt][i] = 0.f;
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk) {
-    uint32_t a[4];
-    a[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
-    a[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
-    a[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-    a[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+    if (kk < nkk) {
+      uint32_t a[4];
+      a[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
+      a[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
+      a[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+      a[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      uint32_t bb[2];
-      frag_b_t(bb, sm.v, nt * 8, kk * 16, lane);
-      mma16816(o[nt], a, bb);
+      for (int nt = 0; nt < 8; ++nt) {
+        uint32_t bb[2];
+        frag_b_t(bb, sm.v, nt * 8, kk * 16, lane);
+        mma16816(o[nt], a, bb);
+      }
     }
   }
 #pragma unroll
@@ -210,7 +228,7 @@ struct AttnSmemBwd {
   float dbucket[64];
 };
 
-__global__ void __launch_bounds__(AT_THREADS) attn_bwd_kernel(const AttnArgs p) {
+__global__ void __launch_bounds__(AT_THREADS, 3) attn_bwd_kernel(const AttnArgs p) {
   extern __shared__ uint8_t at_smem_raw[];
   AttnSmemBwd& sm = *reinterpret_cast<AttnSmemBwd*>(at_smem_raw);
   const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
@@ -220,15 +238,16 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_kernel(const AttnArgs p) 
   load_head(sm.k, p.k + (size_t)b * p.Sk * p.ldk + h * AT_D, p.ldk, p.Sk);
   load_head(sm.v, p.v + (size_t)b * p.Sk * p.ldv + h * AT_D, p.ldv, p.Sk);
   load_head(sm.dO, p.dO + (size_t)b * p.Sq * p.ldo + h * AT_D, p.ldo, p.Sq);
-  for (int r = threadIdx.x; r < 2 * AT_S - 1; r += AT_THREADS)
-    sm.bias[r] = p.rel_mode ? p.rel_table[p.rel_bucket[r] * p.H + h] : 0.f;
-  for (int j = threadIdx.x; j < AT_S; j += AT_THREADS) sm.kmask[j] = (p.keymask && j < p.Sk) ? p.keymask[(size_t)b * p.Sk + j] : 0.f;
+  load_bias_mask(sm.bias, sm.kmask, p, b, h);
   if (threadIdx.x < 64) sm.dbucket[threadIdx.x] = 0.f;
   __syncthreads();
 
-  // ---- phase 1: this warp owns 16 query rows ----
+  const int nkt = (p.Sk + 7) >> 3;    // key tiles of 8 that exist
+  const int nkk = (p.Sk + 15) >> 4;   // key blocks of 16
+  const int nqk = (p.Sq + 15) >> 4;   // query blocks of 16
+  // ---- phase 1: this warp owns 16 query rows (warps past the last query block only take part in phase 2) ----
   const int m0 = warp * 16;
-  {
+  if (m0 < p.Sq) {
     float s[8][4];
     scores_tile(s, sm.q, sm.k, sm.bias, sm.kmask, p, m0, lane);
     float lse[2];
@@ -249,29 +268,27 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_kernel(const AttnArgs p) 
       frag_a(a, sm.dO, m0, kk * 16, lane);
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
-        uint32_t bb[2];
-        frag_b(bb, sm.v, nt * 8, kk * 16, lane);
-        mma16816(dp[nt], a, bb);
+        if (nt < nkt) {
+          uint32_t bb[2];
+          frag_b(bb, sm.v, nt * 8, kk * 16, lane);
+          mma16816(dp[nt], a, bb);
+        }
       }
     }
     float dsum[2] = {0.f, 0.f};
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float pr = __expf(s[nt][i] - lse[i >> 1]);  // exp(-inf) = 0 for masked keys / padded rows
-        float sc = 1.f;
-        if (p.drop_thr) {
-          const int qi = m0 + g + (i >> 1) * 8, kj = nt * 8 + 2 * t + (i & 1);
-          sc = vq_dropout_scale(p.seed, p.site, ((uint64_t)blockIdx.x * AT_S + qi) * AT_S + kj, p.drop_thr, p.drop_inv_keep);
-        }
-        const float dpp = dp[nt][i] * sc;  // dP
-        s[nt][i] = pr;
-        dp[nt][i] = dpp;
-        dsum[i >> 1] += pr * dpp;
-        // dropped P for dV
-        const float pd = pr * sc;
-        sm.P[m0 + g + (i >> 1) * 8][nt * 8 + 2 * t + (i & 1)] = __float2bfloat16_rn(pd);
+      for (int r = 0; r < 2; ++r) {
+        const int qi = m0 + g + r * 8, kj = nt * 8 + 2 * t;
+        float sc0 = 1.f, sc1 = 1.f;
+        if (p.drop_thr) vq_dropout_pair(p.seed, attn_pair_idx(blockIdx.x, qi, kj), p.drop_thr, p.drop_inv_keep, sc0, sc1);
+        const float p0 = __expf(s[nt][2 * r] - lse[r]), p1 = __expf(s[nt][2 * r + 1] - lse[r]);  // exp(-inf) = 0: masked keys / padded rows
+        const float d0 = dp[nt][2 * r] * sc0, d1 = dp[nt][2 * r + 1] * sc1;                          // dP
+        s[nt][2 * r] = p0; s[nt][2 * r + 1] = p1;
+        dp[nt][2 * r] = d0; dp[nt][2 * r + 1] = d1;
+        dsum[r] += p0 * d0 + p1 * d1;
+        *reinterpret_cast<uint32_t*>(&sm.P[qi][kj]) = pack_bf16(p0 * sc0, p1 * sc1);                  // dropped P, for dV
       }
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -281,23 +298,20 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_kernel(const AttnArgs p) 
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float ds = s[nt][i] * (dp[nt][i] - dsum[i >> 1]);
-        s[nt][i] = ds;
-        const int qi = m0 + g + (i >> 1) * 8, kj = nt * 8 + 2 * t + (i & 1);
-        sm.dS[qi][kj] = __float2bfloat16_rn(ds);
-        if (p.d_rel_table && qi < p.Sq && kj < p.Sk && (p.rel_mode == 2 || (p.rel_mode == 1 && qi < p.Lt && kj < p.Lt)))
-          atomicAdd(&sm.dbucket[p.rel_bucket[kj - qi + (AT_S - 1)]], ds);
+      for (int r = 0; r < 2; ++r) {
+        const float ds0 = s[nt][2 * r] * (dp[nt][2 * r] - dsum[r]), ds1 = s[nt][2 * r + 1] * (dp[nt][2 * r + 1] - dsum[r]);
+        s[nt][2 * r] = ds0; s[nt][2 * r + 1] = ds1;
+        *reinterpret_cast<uint32_t*>(&sm.dS[m0 + g + r * 8][nt * 8 + 2 * t]) = pack_bf16(ds0, ds1);
       }
     // dQ = dS K   (B[k=key][n=d] stored [key][d] -> transposed fragment loads)
-    if (m0 < p.Sq) {
-      float dq[8][4];
+    float dq[8][4];
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt)
+    for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) dq[nt][i] = 0.f;
+      for (int i = 0; i < 4; ++i) dq[nt][i] = 0.f;
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
+    for (int kk = 0; kk < 4; ++kk) {
+      if (kk < nkk) {
         uint32_t a[4];
         a[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
         a[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
@@ -310,19 +324,32 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_kernel(const AttnArgs p) 
           mma16816(dq[nt], a, bb);
         }
       }
+    }
 #pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const int qi = m0 + g + r * 8;
-        if (qi < p.Sq) {
-          __nv_bfloat16* dst = p.dq + ((size_t)b * p.Sq + qi) * p.lddq + h * AT_D + 2 * t;
+    for (int r = 0; r < 2; ++r) {
+      const int qi = m0 + g + r * 8;
+      if (qi < p.Sq) {
+        __nv_bfloat16* dst = p.dq + ((size_t)b * p.Sq + qi) * p.lddq + h * AT_D + 2 * t;
 #pragma unroll
-          for (int nt = 0; nt < 8; ++nt) *reinterpret_cast<uint32_t*>(dst + nt * 8) = pack_bf16(dq[nt][2 * r], dq[nt][2 * r + 1]);
-        }
+        for (int nt = 0; nt < 8; ++nt) *reinterpret_cast<uint32_t*>(dst + nt * 8) = pack_bf16(dq[nt][2 * r], dq[nt][2 * r + 1]);
       }
     }
   }
   __syncthreads();
-  // ---- phase 2: this warp owns 16 key rows: dV = Pd^T dO, dK = dS^T Q (contraction over the 64 query slots) ----
+  // ---- relative-position-bias gradient: d table[bucket(k - q)] += dS[q][k]; one thread per diagonal of the biased
+  //      region sums its <= 64 entries from smem, then one smem atomic per diagonal and one global atomic per bucket ----
+  if (p.d_rel_table) {
+    const int nq = p.rel_mode == 1 ? min(p.Sq, p.Lt) : p.Sq;
+    const int nk = p.rel_mode == 1 ? min(p.Sk, p.Lt) : p.Sk;
+    const int ndiag = nq + nk - 1;
+    for (int dgi = threadIdx.x; dgi < ndiag; dgi += AT_THREADS) {
+      const int rel = dgi - (nq - 1);   // k - q
+      float acc = 0.f;
+      for (int qi = max(0, -rel); qi < nq && qi + rel < nk; ++qi) acc += __bfloat162float(sm.dS[qi][qi + rel]);
+      atomicAdd(&sm.dbucket[p.rel_bucket[rel + (AT_S - 1)]], acc);
+    }
+  }
+  // ---- phase 2: this warp owns 16 key rows: dV = Pd^T dO, dK = dS^T Q (contraction over the query blocks that exist) ----
   if (m0 < p.Sk) {
     float dv[8][4], dk[8][4];
 #pragma unroll
@@ -331,16 +358,18 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_kernel(const AttnArgs p) 
       for (int i = 0; i < 4; ++i) dv[nt][i] = dk[nt][i] = 0.f;
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
-      uint32_t ap[4], as[4];
-      frag_a_t(ap, sm.P, m0, kk * 16, lane);
-      frag_a_t(as, sm.dS, m0, kk * 16, lane);
+      if (kk < nqk) {
+        uint32_t ap[4], as[4];
+        frag_a_t(ap, sm.P, m0, kk * 16, lane);
+        frag_a_t(as, sm.dS, m0, kk * 16, lane);
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        uint32_t b1[2], b2[2];
-        frag_b_t(b1, sm.dO, nt * 8, kk * 16, lane);
-        frag_b_t(b2, sm.q, nt * 8, kk * 16, lane);
-        mma16816(dv[nt], ap, b1);
-        mma16816(dk[nt], as, b2);
+        for (int nt = 0; nt < 8; ++nt) {
+          uint32_t b1[2], b2[2];
+          frag_b_t(b1, sm.dO, nt * 8, kk * 16, lane);
+          frag_b_t(b2, sm.q, nt * 8, kk * 16, lane);
+          mma16816(dv[nt], ap, b1);
+          mma16816(dk[nt], as, b2);
+        }
       }
     }
 #pragma unroll
@@ -357,9 +386,12 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_kernel(const AttnArgs p) 
       }
     }
   }
-  if (p.d_rel_table && threadIdx.x < 64) {
-    const float v = sm.dbucket[threadIdx.x];
-    if (v != 0.f) atomicAdd(&p.d_rel_table[threadIdx.x * p.H + h], v);
+  if (p.d_rel_table) {
+    __syncthreads();
+    if (threadIdx.x < 64) {
+      const float v = sm.dbucket[threadIdx.x];
+      if (v != 0.f) atomicAdd(&p.d_rel_table[threadIdx.x * p.H + h], v);
+    }
   }
 }
 

@@ -70,18 +70,27 @@ VQ_DEVINL float2 unpack_bf16(uint32_t u) {
 }
 VQ_DEVINL float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
-// Counter-based dropout hash (keep-mask is recomputed in backward from the same key, nothing is
-// stored). key = (seed, site, element index). Returns a uniform u32.
-VQ_DEVINL uint32_t vq_hash32(uint32_t seed, uint32_t site, uint64_t idx) {
-  uint64_t x = idx * 0x9E3779B97F4A7C15ull + (((uint64_t)seed << 32) | site);
-  x ^= x >> 32; x *= 0xD6E8FEB86659FD93ull;
-  x ^= x >> 32; x *= 0xD6E8FEB86659FD93ull;
-  x ^= x >> 32;
-  return (uint32_t)x;
+// Counter-based dropout (the keep-mask is recomputed in backward from the same key, nothing is stored).
+// One 32-bit hash (murmur3 finaliser over key + pair index) decides TWO adjacent elements, 16 bits each:
+// element e is kept iff its 16-bit lane >= thr16, thr16 = round(p * 65536)  (p is quantised to 1/65536).
+// key = mix(seed, site) is computed on the host once per launch.
+VQ_DEVINL uint32_t vq_hash_pair(uint32_t key, uint32_t pair_idx) {
+  uint32_t x = pair_idx * 0x9E3779B1u + key;
+  x ^= x >> 16; x *= 0x85EBCA6Bu;
+  x ^= x >> 13; x *= 0xC2B2AE35u;
+  x ^= x >> 16;
+  return x;
 }
-// dropout scale for element idx: 0 if dropped else 1/(1-p). thr = p * 2^32.
-VQ_DEVINL float vq_dropout_scale(uint32_t seed, uint32_t site, uint64_t idx, uint32_t thr, float inv_keep) {
-  return vq_hash32(seed, site, idx) >= thr ? inv_keep : 0.0f;
+// scales (0 or 1/keep) of elements 2*pair_idx and 2*pair_idx + 1
+VQ_DEVINL void vq_dropout_pair(uint32_t key, uint32_t pair_idx, uint32_t thr16, float inv_keep, float& s0, float& s1) {
+  const uint32_t h = vq_hash_pair(key, pair_idx);
+  s0 = (h & 0xFFFFu) >= thr16 ? inv_keep : 0.0f;
+  s1 = (h >> 16) >= thr16 ? inv_keep : 0.0f;
+}
+// scale of a single element (slow path for odd layouts)
+VQ_DEVINL float vq_dropout_scale(uint32_t key, uint64_t idx, uint32_t thr16, float inv_keep) {
+  const uint32_t h = vq_hash_pair(key, (uint32_t)(idx >> 1));
+  return ((idx & 1) ? (h >> 16) : (h & 0xFFFFu)) >= thr16 ? inv_keep : 0.0f;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -46,11 +46,15 @@ VQ_DEVINL float row_sumsq(const float (&v)[RW_CHUNKS][4]) {
 }
 VQ_DEVINL void apply_dropout(float (&v)[RW_CHUNKS][4], const Dropout& d, uint64_t row_elem0, int lane) {
   if (!d.thr) return;
+  const uint32_t pair0 = (uint32_t)(row_elem0 >> 1);   // row_elem0 is a multiple of 4
 #pragma unroll
-  for (int j = 0; j < RW_CHUNKS; ++j)
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-      v[j][i] *= vq_dropout_scale(d.seed, d.site, row_elem0 + (lane + 32 * j) * 4 + i, d.thr, d.inv_keep);
+  for (int j = 0; j < RW_CHUNKS; ++j) {
+    const uint32_t pi = pair0 + (uint32_t)(lane + 32 * j) * 2u;
+    float s0, s1, s2, s3;
+    vq_dropout_pair(d.seed, pi, d.thr, d.inv_keep, s0, s1);
+    vq_dropout_pair(d.seed, pi + 1, d.thr, d.inv_keep, s2, s3);
+    v[j][0] *= s0; v[j][1] *= s1; v[j][2] *= s2; v[j][3] *= s3;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ cast
@@ -109,7 +113,8 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) rmsnorm_bwd_kernel(const RmsBw
     float x[RW_CHUNKS][4], dy[RW_CHUNKS][4];
     load_row_f32(x, a.x + (size_t)r * DM, lane);
     const int rd = out_row_of(r, a.in_rpb, a.out_rpb);
-    load_row_bf16(dy, a.dn + (size_t)rd * a.ld_dn, lane);
+    if (a.dn_f32) load_row_f32(dy, a.dn_f32 + (size_t)rd * a.ld_dn, lane);
+    else load_row_bf16(dy, a.dn + (size_t)rd * a.ld_dn, lane);
     if (a.dn2) {
       float d2[RW_CHUNKS][4];
       load_row_bf16(d2, a.dn2 + (size_t)rd * a.ld_dn2, lane);

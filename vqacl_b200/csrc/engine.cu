@@ -25,9 +25,14 @@ static inline uint32_t site_dec(int l, int k) { return 300u + (uint32_t)l * 8u +
 Dropout Engine::drop(uint32_t site) const {
   Dropout d;
   if (training && cfg.dropout > 0.f) {
-    d.thr = (uint32_t)fmin(4294967295.0, (double)cfg.dropout * 4294967296.0);
-    d.inv_keep = 1.f / (1.f - cfg.dropout);
-    d.seed = seed;
+    double t = floor((double)cfg.dropout * 65536.0 + 0.5);
+    if (t < 1.0) t = 1.0;
+    if (t > 65535.0) t = 65535.0;
+    d.thr = (uint32_t)t;                                   // 16-bit threshold: p is quantised to 1/65536
+    d.inv_keep = (float)(65536.0 / (65536.0 - t));
+    uint64_t k = ((uint64_t)seed << 32 | site) * 0x9E3779B97F4A7C15ull;   // key = mix(seed, site), once per launch
+    k ^= k >> 29; k *= 0xBF58476D1CE4E5B9ull; k ^= k >> 32;
+    d.seed = (uint32_t)k;
     d.site = site;
   }
   return d;
@@ -193,6 +198,7 @@ int64_t engine_carve(Engine& e, uint8_t* base, int B, int L, int N, int T) {
   w.gd = bp.take<float>(Md * d);
   w.gdb = bp.take<bf16>(Md * d);
   w.t_d768 = bp.take<bf16>(Md * d);
+  w.t_d768_f32 = bp.take<float>(Md * d);
   w.t_dqkv = bp.take<bf16>(Md * 3 * d);
   w.t_dh = bp.take<bf16>(Md * f);
   w.t_dcq = bp.take<bf16>(Md * d);
@@ -222,9 +228,9 @@ int64_t engine_carve(Engine& e, uint8_t* base, int B, int L, int N, int T) {
 // --------------------------------------------------------------------------------------------------- GEMM helpers
 // dX[rows, n_in] = dY[rows, n_out] * W[n_out, n_in]      (W stored row-major -> MN-major B operand)
 static int gemm_dx(const bf16* dY, int lddy, const bf16* Wt, int n_out, int n_in, void* C, int ldc, int rows, int epi, cudaStream_t st,
-                   const void* R = nullptr, int ldr = 0, float alpha = 1.f) {
+                   const void* R = nullptr, int ldr = 0, float alpha = 1.f, int splits = 1) {
   GemmArgs g{};
-  g.epi = epi; g.M = rows; g.N = n_in; g.K = n_out; g.C = C; g.ldc = ldc; g.R = R; g.ldr = ldr; g.alpha = alpha; g.splits = 1;
+  g.epi = epi; g.M = rows; g.N = n_in; g.K = n_out; g.C = C; g.ldc = ldc; g.R = R; g.ldr = ldr; g.alpha = alpha; g.splits = splits;
   return gemm_bf16(GemmOperand{dY, lddy, false}, GemmOperand{Wt, n_in, true}, g, 0, st);
 }
 // dW[n_out, n_in] += dY[rows, n_out]^T * X[rows, n_in]    (both operands MN-major, split-K over rows, fp32 red.add)
@@ -436,10 +442,18 @@ static int backward(Engine& e, const float* w_rows, int accumulate, int stage_be
   // ---- LM head + CE
   VQ_CHECK(w_rows, "backward: w_rows (dL/dloss_row) required");
   VQ_TRY(ce_bwd(w.logits, e.ldv, Md, V, b.labels, w.lse_ce, w_rows, st));
-  VQ_TRY(gemm_dx(w.logits, e.ldv, e.W + e.o_shared, V, d, w.t_d768, d, Md, EPI_BF16, st));
+  // dY_fin[Md, d] = dLogits[Md, V] * E[V, d]: few output tiles but a 32 200-deep contraction -> split-K into an fp32 buffer
+  {
+    const int tiles = ((Md + 127) / 128) * ((d + 255) / 256);
+    int splits = num_sms() / (tiles > 0 ? tiles : 1);
+    if (splits < 1) splits = 1;
+    if (splits > 16) splits = 16;
+    VQ_CUDA(cudaMemsetAsync(w.t_d768_f32, 0, (size_t)Md * d * sizeof(float), st));
+    VQ_TRY(gemm_dx(w.logits, e.ldv, e.W + e.o_shared, V, d, w.t_d768_f32, d, Md, EPI_ATOMIC_F32, st, nullptr, 0, 1.f, splits));
+  }
   VQ_TRY(gemm_dw(w.logits, e.ldv, w.yfin, d, e.G + e.o_shared, V, d, Md, st));
   RmsBwdArgs r{};
-  r.dn = w.t_d768; r.ld_dn = d; r.x = w.y[3 * Ld]; r.w = e.P + e.o_dec_final; r.g_in = nullptr; r.g_out = w.gd; r.gb_out = w.gdb;
+  r.dn_f32 = w.t_d768_f32; r.ld_dn = d; r.x = w.y[3 * Ld]; r.w = e.P + e.o_dec_final; r.g_in = nullptr; r.g_out = w.gd; r.gb_out = w.gdb;
   r.dw = e.G + e.o_dec_final; r.M = Md; r.eps = c.eps; r.scale = 1.f / sqrtf((float)d); r.own = e.drop(SITE_DEC_FINAL);
   r.consumer = e.drop(site_dec(Ld - 1, 5)); r.consumer_cols = d;
   VQ_TRY(rmsnorm_bwd(r, st));

@@ -48,6 +48,7 @@ struct Workspace {
   float *gd, *ge;                 // fp32 residual-stream gradients (decoder / encoder)
   bf16 *gdb, *geb;                // bf16 copies (masked for the consuming branch)
   bf16 *t_d768, *t_dqkv, *t_dh, *t_dcq;       // decoder temporaries
+  float* t_d768_f32;                          // split-K target of the LM-head dX GEMM
   bf16 *t_e768, *t_eqkv, *t_eh;               // encoder temporaries
   bf16* dkv_all; bf16* dmem; bf16* dfeatpre;
   float* sumsq_partials; float* sumsq;

@@ -156,11 +156,21 @@ int gemm_bf16(const GemmOperand& A, const GemmOperand& B, GemmArgs args, int for
   }
   int bn = force_bn;
   if (bn == 0) {
+    // pick the tile width that minimises waves x per-tile MMA time. Cycles per 64-deep k-block of a 128 x BN tile:
+    // 4 MMAs of max(128*BN/256, smem operand read time) cycles (the narrow tiles are bound by re-reading A from smem).
     const int tiles_m = (args.M + GEMM_BM - 1) / GEMM_BM;
     const int sms = num_sms();
-    bn = 64;
-    if (args.N >= 256 && tiles_m * ((args.N + 255) / 256) * args.splits >= sms) bn = 256;
-    else if (args.N >= 128 && tiles_m * ((args.N + 127) / 128) * args.splits >= sms) bn = 128;
+    const int kb_split = (kblocks + args.splits - 1) / args.splits;
+    const int cand[3] = {256, 128, 64};
+    const int cyc[3] = {512, 272, 176};
+    long best = -1;
+    for (int i = 0; i < 3; ++i) {
+      if (cand[i] > 64 && args.N < cand[i] / 2 + 8) continue;   // mostly-empty tile
+      const long work = (long)tiles_m * ((args.N + cand[i] - 1) / cand[i]) * args.splits;
+      const long waves = (work + sms - 1) / sms;
+      const long cost = waves * ((long)kb_split * cyc[i] + 600 + cand[i] * 4);   // + pipeline fill and epilogue drain
+      if (best < 0 || cost < best) { best = cost; bn = cand[i]; }
+    }
   }
   switch (bn) {
     case 256: return dispatch_major<256>(A, B, args, stream);

@@ -3,7 +3,8 @@
 //   warp 0  : TMA producer            (one elected lane)
 //   warp 1  : tcgen05.mma issuer      (one elected lane)
 //   warp 2  : TMEM allocator
-//   warps 4-7: epilogue (TMEM -> registers -> fused epilogue -> global)
+//   warps 4-11: epilogue (TMEM -> registers -> fused math -> swizzled smem transposition -> coalesced global), two warps
+//              per TMEM lane quarter working on alternate 32-column chunks
 // Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
 //
 // Replaces, for the VL-T5 hot path, every cuBLAS sgemm the reference reaches through nn.Linear
@@ -16,12 +17,11 @@ namespace vq {
 
 enum GemmEpi : int {
   EPI_BF16 = 0,          // C(bf16) = alpha * acc
-  EPI_RELU_BF16 = 1,     // C(bf16) = dropout(relu(acc))
+  EPI_RELU_BF16 = 1,     // C(bf16) = dropout(relu(alpha * acc))
   EPI_RESID_F32 = 2,     // C(f32)  = R(f32) + dropout(alpha * acc)
   EPI_ATOMIC_F32 = 3,    // C(f32) += alpha * acc (red.global.add; split-K capable)
-  EPI_RELUBWD_BF16 = 4,  // C(bf16) = acc * (R(bf16) > 0 ? alpha : 0)   R = saved relu(+dropout) output
-  EPI_F32 = 5,           // C(f32)  = alpha * acc
-  EPI_BF16_ROWMASK = 6   // C(bf16) = alpha * acc for rows with (row % rowmod) < rowkeep, else skipped
+  EPI_RELUBWD_BF16 = 4,  // C(bf16) = R(bf16) != 0 ? alpha * acc : 0      R = saved relu(+dropout) output (>= 0)
+  EPI_F32 = 5            // C(f32)  = alpha * acc
 };
 
 struct GemmArgs {
@@ -33,15 +33,16 @@ struct GemmArgs {
   int ldr;            // elements
   float alpha;
   int splits;         // split-K factor (EPI_ATOMIC_F32 only)
-  uint32_t drop_thr;  // p * 2^32 (0 = no dropout)
+  uint32_t drop_thr;  // 16-bit keep threshold (0 = no dropout), see vq_dropout_pair
   float drop_inv_keep;
-  uint32_t seed, site;
-  int rowmod, rowkeep;
+  uint32_t seed, site;  // seed = per-launch dropout key (already mixed with the site id); site is informational
 };
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_EPI_WARPS = 8;
+constexpr int GEMM_THREADS = 128 + GEMM_EPI_WARPS * 32;
+constexpr int EPI_TILE_BYTES = 4096;                         // one 32x32 fp32 (or 32x32 bf16 in half of it) tile per epilogue warp
 
 template <int BN>
 struct GemmCfg {
@@ -50,8 +51,146 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int TMEM_COLS = 2 * BN;  // two accumulator stages
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + GEMM_EPI_WARPS * EPI_TILE_BYTES;
 };
+
+VQ_DEVINL void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+VQ_DEVINL uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+// One 128 x BN accumulator tile: this warp owns TMEM lanes [32q, 32q+32) (= tile rows) and the 32-column chunks
+// c = half, half+2, ... tcgen05.ld 32x32b gives thread = row, registers = 32 consecutive columns; a global access from that
+// layout is 32 row-strided 16-byte requests per instruction. The fused math therefore runs in the row layout, the result is
+// transposed through a private XOR-swizzled smem tile (conflict-free 16-byte writes and reads, no padding), and global
+// memory is touched with 4 (bf16: 8) full rows of 128 (64) contiguous bytes per instruction. Extra operands (residual R,
+// saved activations H) are fetched with the same coalesced pattern before the accumulator wait.
+template <int EPI, int BN>
+VQ_DEVINL void gemm_epilogue_tile(const GemmArgs& p, uint32_t t_base, uint32_t stg, int row_base, int n_base, int half, int lane,
+                                  bool has_k, uint64_t* tfull, uint32_t aphase) {
+  constexpr bool OUT_BF16 = (EPI == EPI_BF16 || EPI == EPI_RELU_BF16 || EPI == EPI_RELUBWD_BF16);
+  const int M = p.M, N = p.N, ldc = p.ldc, ldr = p.ldr;
+  const float alpha = p.alpha;
+  bool waited = false;
+#pragma unroll 1
+  for (int c = half; c < BN / 32; c += 2) {
+    const int col0 = n_base + c * 32;
+    if (col0 >= N) break;
+    // ---- coalesced prefetch of the extra operand ----
+    float4 rres[8];
+    uint4 rh[4];
+    if (EPI == EPI_RESID_F32) {
+      const int gcol = col0 + (lane & 7) * 4;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int grow = row_base + it * 4 + (lane >> 3);
+        rres[it] = (grow < M && gcol < N) ? *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.R) + (size_t)grow * ldr + gcol)
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    if (EPI == EPI_RELUBWD_BF16) {
+      const int gcol = col0 + (lane & 3) * 8;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int grow = row_base + it * 8 + (lane >> 2);
+        rh[it] = (grow < M && gcol < N) ? *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.R) + (size_t)grow * ldr + gcol)
+                                        : make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+    if (!waited) {
+      mbar_wait(tfull, aphase);
+      tc_fence_after();
+      waited = true;
+    }
+    uint32_t r[32];
+    tmem_ld_32x32(t_base + c * 32, r);
+    tmem_ld_wait();
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * alpha;
+    if (EPI == EPI_RELU_BF16) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+    }
+    if ((EPI == EPI_RELU_BF16 || EPI == EPI_RESID_F32) && p.drop_thr) {
+      const uint32_t pi = (uint32_t)(((size_t)(row_base + lane) * N + col0) >> 1);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float s0, s1;
+        vq_dropout_pair(p.seed, pi + j, p.drop_thr, p.drop_inv_keep, s0, s1);
+        v[2 * j] *= s0;
+        v[2 * j + 1] *= s1;
+      }
+    }
+    if (OUT_BF16) {
+      // stage 32 rows x 64 B; 16-byte piece j of row l lives at slot j ^ ((l >> 1) & 3)
+      const uint32_t wrow = stg + lane * 64;
+      const int sw = (lane >> 1) & 3;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        sts128(wrow + ((j ^ sw) << 4), pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+               pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+      __syncwarp();
+      const int piece = lane & 3;
+      const int gcol = col0 + piece * 8;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int rr = it * 8 + (lane >> 2);
+        const int grow = row_base + rr;
+        uint4 o = lds128(stg + rr * 64 + ((piece ^ ((rr >> 1) & 3)) << 4));
+        if (EPI == EPI_RELUBWD_BF16) {
+          const uint32_t hh[4] = {rh[it].x, rh[it].y, rh[it].z, rh[it].w};
+          uint32_t oo[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t m = ((hh[k] & 0x00007FFFu) ? 0x0000FFFFu : 0u) | ((hh[k] & 0x7FFF0000u) ? 0xFFFF0000u : 0u);
+            oo[k] &= m;
+          }
+          o = make_uint4(oo[0], oo[1], oo[2], oo[3]);
+        }
+        if (has_k && grow < M && gcol < N) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)grow * ldc + gcol) = o;
+      }
+    } else {
+      // stage 32 rows x 128 B; 16-byte piece j of row l lives at slot j ^ (l & 7)
+      const uint32_t wrow = stg + lane * 128;
+      const int sw = lane & 7;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        sts128(wrow + ((j ^ sw) << 4), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
+               __float_as_uint(v[4 * j + 3]));
+      __syncwarp();
+      const int piece = lane & 7;
+      const int gcol = col0 + piece * 4;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int rr = it * 4 + (lane >> 3);
+        const int grow = row_base + rr;
+        const uint4 u = lds128(stg + rr * 128 + ((piece ^ (rr & 7)) << 4));
+        float4 o = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
+        if (has_k && grow < M && gcol < N) {
+          float* dst = reinterpret_cast<float*>(p.C) + (size_t)grow * ldc + gcol;
+          if (EPI == EPI_RESID_F32) {
+            o.x += rres[it].x; o.y += rres[it].y; o.z += rres[it].z; o.w += rres[it].w;
+            *reinterpret_cast<float4*>(dst) = o;
+          } else if (EPI == EPI_ATOMIC_F32) {
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
+          } else {
+            *reinterpret_cast<float4*>(dst) = o;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+  if (!waited) {
+    mbar_wait(tfull, aphase);
+    tc_fence_after();
+  }
+}
 
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -59,13 +198,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                          const GemmArgs p) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // the 128-byte swizzle needs 1024-byte aligned stage bases; do not rely on the attribute alone
+  const uint32_t raw_u32 = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_u32 + 1023u) & ~1023u) - raw_u32);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint8_t* epi_stage = smem + STAGES * Cfg::STAGE_BYTES + 256;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -88,7 +230,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);
+      mbar_init(&tempty_bar[i], GEMM_EPI_WARPS);
     }
     mbar_fence_init();
   }
@@ -172,116 +314,26 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
   } else if (warp >= 4) {
     // ------------------------------ epilogue ----------------------------------
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int half = (warp - 4) >> 2;  // which alternate 32-column chunks it handles
+    const uint32_t stg = smem_u32(epi_stage) + (warp - 4) * EPI_TILE_BYTES;
     int astage = 0;
     uint32_t aphase = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
       const int split = w / tiles_mn;
       const int t = w - split * tiles_mn;
       const int m_blk = t / tiles_n, n_blk = t - m_blk * tiles_n;
-      const int kb0 = split * kb_per_split;
-      const bool has_k = kb0 < kblocks;
-      mbar_wait(&tfull_bar[astage], aphase);
-      tc_fence_after();
-      const int row = m_blk * GEMM_BM + q * 32 + lane;
-      const bool row_ok = row < p.M && has_k &&
-                          (p.rowmod <= 0 || (row % p.rowmod) < p.rowkeep);
+      const bool has_k = split * kb_per_split < kblocks;
+      const int row_base = m_blk * GEMM_BM + q * 32;
       const uint32_t t_base = tmem_base + astage * BN + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(t_base + c * 32, r);
-        tmem_ld_wait();
-        const int col0 = n_blk * BN + c * 32;
-        if (row_ok && col0 < p.N) {
-          float v[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
-          const int ncols = min(32, p.N - col0);  // multiple of 8 (host-checked)
-          const size_t coff = (size_t)row * p.ldc + col0;
-          const int epi = p.epi;
-          if (epi == EPI_BF16 || epi == EPI_BF16_ROWMASK) {
-            __nv_bfloat16* C = reinterpret_cast<__nv_bfloat16*>(p.C) + coff;
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-              if (g * 8 < ncols) {
-                uint4 o;
-                o.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]);
-                o.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
-                o.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]);
-                o.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
-                *reinterpret_cast<uint4*>(C + g * 8) = o;
-              }
-          } else if (epi == EPI_RELU_BF16) {
-            __nv_bfloat16* C = reinterpret_cast<__nv_bfloat16*>(p.C) + coff;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              float x = fmaxf(v[i], 0.0f);
-              if (p.drop_thr) x *= vq_dropout_scale(p.seed, p.site, (uint64_t)row * p.N + col0 + i, p.drop_thr, p.drop_inv_keep);
-              v[i] = x;
-            }
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-              if (g * 8 < ncols) {
-                uint4 o;
-                o.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]);
-                o.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
-                o.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]);
-                o.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
-                *reinterpret_cast<uint4*>(C + g * 8) = o;
-              }
-          } else if (epi == EPI_RESID_F32) {
-            float* C = reinterpret_cast<float*>(p.C) + coff;
-            const float* R = reinterpret_cast<const float*>(p.R) + (size_t)row * p.ldr + col0;
-#pragma unroll
-            for (int g = 0; g < 8; ++g)
-              if (g * 4 < ncols) {
-                float4 rr = *reinterpret_cast<const float4*>(R + g * 4);
-                float a0 = v[g * 4 + 0], a1 = v[g * 4 + 1], a2 = v[g * 4 + 2], a3 = v[g * 4 + 3];
-                if (p.drop_thr) {
-                  const uint64_t e = (uint64_t)row * p.N + col0 + g * 4;
-                  a0 *= vq_dropout_scale(p.seed, p.site, e + 0, p.drop_thr, p.drop_inv_keep);
-                  a1 *= vq_dropout_scale(p.seed, p.site, e + 1, p.drop_thr, p.drop_inv_keep);
-                  a2 *= vq_dropout_scale(p.seed, p.site, e + 2, p.drop_thr, p.drop_inv_keep);
-                  a3 *= vq_dropout_scale(p.seed, p.site, e + 3, p.drop_thr, p.drop_inv_keep);
-                }
-                rr.x += a0; rr.y += a1; rr.z += a2; rr.w += a3;
-                *reinterpret_cast<float4*>(C + g * 4) = rr;
-              }
-          } else if (epi == EPI_ATOMIC_F32) {
-            float* C = reinterpret_cast<float*>(p.C) + coff;
-#pragma unroll
-            for (int g = 0; g < 8; ++g)
-              if (g * 4 < ncols) {
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(C + g * 4), "f"(v[g * 4 + 0]),
-                             "f"(v[g * 4 + 1]), "f"(v[g * 4 + 2]), "f"(v[g * 4 + 3])
-                             : "memory");
-              }
-          } else if (epi == EPI_RELUBWD_BF16) {
-            __nv_bfloat16* C = reinterpret_cast<__nv_bfloat16*>(p.C) + coff;
-            const __nv_bfloat16* H = reinterpret_cast<const __nv_bfloat16*>(p.R) + (size_t)row * p.ldr + col0;
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-              if (g * 8 < ncols) {
-                uint4 h = *reinterpret_cast<const uint4*>(H + g * 8);
-                const uint32_t hh[4] = {h.x, h.y, h.z, h.w};
-                uint32_t oo[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  float2 hv = unpack_bf16(hh[j]);
-                  // v already carries alpha (= 1/keep of the inner dropout)
-                  oo[j] = pack_bf16(hv.x > 0.0f ? v[g * 8 + 2 * j] : 0.0f, hv.y > 0.0f ? v[g * 8 + 2 * j + 1] : 0.0f);
-                }
-                *reinterpret_cast<uint4*>(C + g * 8) = make_uint4(oo[0], oo[1], oo[2], oo[3]);
-              }
-          } else {  // EPI_F32
-            float* C = reinterpret_cast<float*>(p.C) + coff;
-#pragma unroll
-            for (int g = 0; g < 8; ++g)
-              if (g * 4 < ncols)
-                *reinterpret_cast<float4*>(C + g * 4) = make_float4(v[g * 4 + 0], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
-          }
-        }
+      uint64_t* tf = &tfull_bar[astage];
+      switch (p.epi) {
+        case EPI_BF16: gemm_epilogue_tile<EPI_BF16, BN>(p, t_base, stg, row_base, n_blk * BN, half, lane, has_k, tf, aphase); break;
+        case EPI_RELU_BF16: gemm_epilogue_tile<EPI_RELU_BF16, BN>(p, t_base, stg, row_base, n_blk * BN, half, lane, has_k, tf, aphase); break;
+        case EPI_RESID_F32: gemm_epilogue_tile<EPI_RESID_F32, BN>(p, t_base, stg, row_base, n_blk * BN, half, lane, has_k, tf, aphase); break;
+        case EPI_ATOMIC_F32: gemm_epilogue_tile<EPI_ATOMIC_F32, BN>(p, t_base, stg, row_base, n_blk * BN, half, lane, has_k, tf, aphase); break;
+        case EPI_RELUBWD_BF16: gemm_epilogue_tile<EPI_RELUBWD_BF16, BN>(p, t_base, stg, row_base, n_blk * BN, half, lane, has_k, tf, aphase); break;
+        default: gemm_epilogue_tile<EPI_F32, BN>(p, t_base, stg, row_base, n_blk * BN, half, lane, has_k, tf, aphase); break;
       }
       tc_fence_before();
       __syncwarp();
