@@ -71,7 +71,8 @@ int vqacl_param_count(void* engine);
 int vqacl_param_info(void* engine, int i, char* name, int name_cap, int64_t* offset, int* rows, int* cols, int* group);
 int64_t vqacl_arena_elems(void* engine, int64_t* n_decay, int64_t* n_train);
 int vqacl_bind_arena(void* engine, float* params, float* grads, void* params_bf16);
-/* relative-position bucket maps, int32[127] each: bucket of (key - query + 63); computed by the host with the HF formula */
+/* relative-position bucket maps, HOST int32[127] each: bucket of (key - query + 63); computed by the host with the HF formula
+ * (T5Attention._relative_position_bucket); they are copied and passed to the attention kernels as kernel parameters */
 int vqacl_set_rel_buckets(void* engine, const int32_t* enc_bidirectional, const int32_t* dec_unidirectional);
 int vqacl_refresh_bf16(void* engine, void* stream);                 /* params fp32 -> bf16 GEMM copies */
 /* activation workspace: allocated by the host (torch caching allocator), carved by the engine */
@@ -106,7 +107,7 @@ int vqacl_generate(void* engine, const vqacl_batch* batch, const vqacl_proto_sta
 /* number of kernels this library has launched so far in this process (bench.py's gpu_launches) */
 long long vqacl_launch_count(void);
 
-/* ---- individual operators (unit-test / building-block surface) ---- */
+/* ---- individual operators (unit-test / building-block surface); `rel_bucket` is a HOST int32[127] table ---- */
 int vqacl_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major, void* C, int ldc,
                     const void* R, int ldr, int M, int N, int K, int epi, float alpha, int splits, int force_bn, void* stream);
 int vqacl_rmsnorm_fwd(const float* x, const float* w, void* y_bf16, float* y_f32, int M, float eps, float scale, void* stream);
@@ -125,7 +126,7 @@ int vqacl_proto_update(const float* curQ, const float* curV, const float* cntQ, 
                        float* numQ, float* numV, int CQ, int CV, int task_id, int first_step_of_task, int has_mem, float alpha,
                        float beta, void* stream);
 int vqacl_proto_retrieve(const float* P, int C, const float* x, int B, void* out_bf16, int out_pitch_rows, int out_row,
-                         int64_t* idx, float* out_f32, void* stream);
+                         int64_t* idx, float* out_f32, float* scratch /* [C,768] fp32 */, void* stream);
 int vqacl_ce_fwd(const void* logits_bf16, int ld, int M, int V, const int64_t* labels, float* lse, float* loss, void* stream);
 int vqacl_ce_bwd(void* logits_bf16, int ld, int M, int V, const int64_t* labels, const float* lse, const float* w, void* stream);
 int vqacl_visual_embed_fwd(const float* featpre, const float* boxes, const float* bf, const float* wf, const float* Wp,

@@ -20,7 +20,7 @@ def _L():
         L.vqacl_proto_means.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]
         L.vqacl_proto_scatter_mean.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]
         L.vqacl_proto_update.argtypes = [c_void_p] * 8 + [c_int] * 5 + [F, F, c_void_p]
-        L.vqacl_proto_retrieve.argtypes = [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]
+        L.vqacl_proto_retrieve.argtypes = [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
         L.vqacl_ce_fwd.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
         L.vqacl_ce_bwd.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
         L.vqacl_loss_tail.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]
@@ -93,7 +93,8 @@ def proto_retrieve(P, x):
     B = x.shape[0]
     out = torch.empty(B, 768, device=x.device)
     idx = torch.empty(B, dtype=torch.int64, device=x.device)
-    check(_L().vqacl_proto_retrieve(ptr(P), P.shape[0], ptr(x), B, None, 0, 0, ptr(idx), ptr(out), cur_stream()))
+    scratch = torch.empty(P.shape[0], 768, device=x.device)
+    check(_L().vqacl_proto_retrieve(ptr(P), P.shape[0], ptr(x), B, None, 0, 0, ptr(idx), ptr(out), ptr(scratch), cur_stream()))
     return out, idx
 
 

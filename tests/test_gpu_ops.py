@@ -63,7 +63,7 @@ def test_attention_fwd_bwd_vs_torch(mode):
     keymask = None
     kw = {}
     if mode == "enc":
-        bucket = rel_bucket_table(True).to(DEV)
+        bucket = rel_bucket_table(True)          # host table
         att = O.T5Attention(O.VLT5Config(), False, True).to(DEV)
         att.relative_attention_bias.weight = torch.nn.Parameter(table.detach().clone())
         tb = att.compute_bias(Lt, Lt)
@@ -76,7 +76,7 @@ def test_attention_fwd_bwd_vs_torch(mode):
         bias = full + pad[:, None, None, :]
         kw = dict(rel_table=table.detach(), rel_bucket=bucket, rel_mode=1, Lt=Lt, keymask=keymask)
     elif mode == "dec_self":
-        bucket = rel_bucket_table(False).to(DEV)
+        bucket = rel_bucket_table(False)
         att = O.T5Attention(O.VLT5Config(), True, True).to(DEV)
         att.relative_attention_bias.weight = torch.nn.Parameter(table.detach().clone())
         causal = torch.tril(torch.ones(Sq, Sk, device=DEV))

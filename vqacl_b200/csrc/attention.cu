@@ -10,6 +10,8 @@
 #include "common.cuh"
 #include "ops.h"
 
+#include <string.h>
+
 namespace vq {
 
 constexpr int AT_S = 64;      // max queries / keys per problem
@@ -37,15 +39,40 @@ VQ_DEVINL void mma16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
-// load a [rows<=64, 64] bf16 head slice into smem, 16-byte vectors; rows [rows, round_up(rows,16)) are zero-filled and
-// rows beyond that are left untouched (every consumer loop is bounded by the same round-up)
-VQ_DEVINL void load_head(__nv_bfloat16 (*dst)[AT_P], const __nv_bfloat16* src, int ld, int rows) {
-  const int rows16 = (rows + 15) & ~15;
-  for (int idx = threadIdx.x; idx < rows16 * (AT_D / 8); idx += AT_THREADS) {
-    const int r = idx >> 3, c = (idx & 7) * 8;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (r < rows) v = *reinterpret_cast<const uint4*>(src + (size_t)r * ld + c);
-    *reinterpret_cast<uint4*>(&dst[r][c]) = v;
+typedef __nv_bfloat16 (*AttnTile)[AT_P];
+
+struct AttnBuckets { int8_t b[2 * AT_S]; };   // rel -> bucket map, passed by value (constant bank)
+
+// Load NM [rows<=64, 64] bf16 head slices into smem with 16-byte vectors. All global loads of a batch (4 per matrix and
+// thread) are issued before the first shared store so that NM*4 requests per thread are in flight.
+template <int NW, int NM>
+VQ_DEVINL void load_heads(AttnTile const (&dst)[NM], const __nv_bfloat16* const (&src)[NM], const int (&ld)[NM], const int (&rows)[NM],
+                          const int (&fill)[NM], int tid) {
+  constexpr int T = NW * 32;
+  int total[NM], maxtotal = 0;
+#pragma unroll
+  for (int m = 0; m < NM; ++m) {
+    total[m] = fill[m] * (AT_D / 8);   // rows [rows, fill) are zero-filled: every tile row a consumer can touch is defined
+    maxtotal = max(maxtotal, total[m]);
+  }
+  for (int base = 0; base < maxtotal; base += 4 * T) {
+    uint4 v[NM][4];
+#pragma unroll
+    for (int m = 0; m < NM; ++m)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int idx = base + u * T + tid;
+        const int r = idx >> 3, c = (idx & 7) * 8;
+        v[m][u] = make_uint4(0, 0, 0, 0);
+        if (idx < total[m] && r < rows[m]) v[m][u] = *reinterpret_cast<const uint4*>(src[m] + (size_t)r * ld[m] + c);
+      }
+#pragma unroll
+    for (int m = 0; m < NM; ++m)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int idx = base + u * T + tid;
+        if (idx < total[m]) *reinterpret_cast<uint4*>(&dst[m][idx >> 3][(idx & 7) * 8]) = v[m][u];
+      }
   }
 }
 
@@ -73,19 +100,41 @@ VQ_DEVINL void frag_b_t(uint32_t (&b)[2], const __nv_bfloat16 (*X)[AT_P], int n0
 // dropout pair index of probabilities (q, k), (q, k+1) of problem `blk` (k even)
 VQ_DEVINL uint32_t attn_pair_idx(uint32_t blk, int q, int k) { return ((blk * AT_S + (uint32_t)q) * AT_S + (uint32_t)k) >> 1; }
 
-struct AttnSmemFwd {
-  __nv_bfloat16 q[AT_S][AT_P], k[AT_S][AT_P], v[AT_S][AT_P];
-  float bias[2 * AT_S];
-  float kmask[AT_S];
-};
+// Shared memory is carved per launch for the rows that exist (rounded up to 16), and the CTA has one warp per 16 query
+// rows (backward: per 16 query or key rows), so the decoder's tiny problems (Sq = T <= 10) run as 1-warp CTAs with 7-21 KB
+// of smem and many CTAs per SM instead of idling three warps and 28-56 KB.
+constexpr int AT_HDR_BYTES = (2 * AT_S + AT_S + 64) * 4;   // bias[128] | kmask[64] | dbucket[64] (floats)
+VQ_DEVINL int rows16(int n) { return (n + 15) & ~15; }
+// query-side tiles hold round_up(Sq, 16) rows, key-side tiles NKT * 8 rows (16 or 64)
+static inline int attn_smem_fwd(int Sq, int krows) { return AT_HDR_BYTES + (((Sq + 15) & ~15) + 2 * krows) * AT_P * 2; }
+static inline int attn_smem_bwd(int Sq, int krows) { return AT_HDR_BYTES + (4 * ((Sq + 15) & ~15) + 2 * krows) * AT_P * 2; }
 
-// scores for the warp's 16 query rows vs the keys, bias/mask applied; keys >= Sk get -inf.
-// Only the ceil(Sk/8) key tiles that exist are multiplied (decoder self-attention has Sk = T <= 10).
-VQ_DEVINL void scores_tile(float (&s)[8][4], const __nv_bfloat16 (*sq)[AT_P], const __nv_bfloat16 (*sk)[AT_P],
+// two adjacent B fragments (k16 x n16) at once; B[k][n] stored as X[n][k] row-major: regs {b(n0)[0], b(n0)[1], b(n0+8)[0], b(n0+8)[1]}
+VQ_DEVINL void frag_b2(uint32_t (&b)[4], const __nv_bfloat16 (*X)[AT_P], int n0, int k0, int lane) {
+  const int mi = lane >> 3, r = lane & 7;
+  ldsm_x4(b, &X[n0 + (mi >> 1) * 8 + r][k0 + (mi & 1) * 8]);
+}
+// same for B[k][n] stored as X[k][n] row-major
+VQ_DEVINL void frag_b2_t(uint32_t (&b)[4], const __nv_bfloat16 (*X)[AT_P], int n0, int k0, int lane) {
+  const int mi = lane >> 3, r = lane & 7;
+  ldsm_x4_t(b, &X[k0 + (mi & 1) * 8 + r][n0 + (mi >> 1) * 8]);
+}
+VQ_DEVINL void mma2(float (&d0)[4], float (&d1)[4], const uint32_t (&a)[4], const uint32_t (&b)[4]) {
+  const uint32_t b0[2] = {b[0], b[1]}, b1[2] = {b[2], b[3]};
+  mma16816(d0, a, b0);
+  mma16816(d1, a, b1);
+}
+
+// scores for the warp's 16 query rows vs NKT key tiles of 8 (NKT = 2: decoder self-attention, Sk <= 16; NKT = 8: up to
+// 64 keys), bias/mask applied; keys >= Sk get -inf. The additive terms are organised so that the common case costs one
+// FADD per score: the key-side term (padding mask, -inf beyond Sk) comes from smem as float2, the relative-position bias
+// is only visited for the tiles that intersect the biased region (encoder: the text x text corner), the causal term only
+// for decoder self-attention.
+template <int NKT>
+VQ_DEVINL void scores_tile(float (&s)[NKT][4], const __nv_bfloat16 (*sq)[AT_P], const __nv_bfloat16 (*sk)[AT_P],
                            const float* sbias, const float* skmask, const AttnArgs& p, int m0, int lane) {
-  const int nkt = (p.Sk + 7) >> 3;
 #pragma unroll
-  for (int nt = 0; nt < 8; ++nt)
+  for (int nt = 0; nt < NKT; ++nt)
 #pragma unroll
     for (int i = 0; i < 4; ++i) s[nt][i] = 0.f;
 #pragma unroll
@@ -93,58 +142,113 @@ VQ_DEVINL void scores_tile(float (&s)[8][4], const __nv_bfloat16 (*sq)[AT_P], co
     uint32_t a[4];
     frag_a(a, sq, m0, kk * 16, lane);
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      if (nt < nkt) {
-        uint32_t b[2];
-        frag_b(b, sk, nt * 8, kk * 16, lane);
-        mma16816(s[nt], a, b);
-      }
+    for (int nt = 0; nt < NKT; nt += 2) {
+      uint32_t b[4];
+      frag_b2(b, sk, nt * 8, kk * 16, lane);
+      mma2(s[nt], s[nt + 1], a, b);
     }
   }
   const int g = lane >> 2, t = lane & 3;
+  // key-side term: skmask[] already holds -inf for keys >= Sk (load_bias_mask)
 #pragma unroll
-  for (int nt = 0; nt < 8; ++nt)
+  for (int nt = 0; nt < NKT; ++nt) {
+    const float2 ka = *reinterpret_cast<const float2*>(skmask + nt * 8 + 2 * t);
+    s[nt][0] += ka.x; s[nt][1] += ka.y; s[nt][2] += ka.x; s[nt][3] += ka.y;
+  }
+  const int q0 = m0 + g + p.q_off;   // absolute position of this thread's first query row (second is q0 + 8)
+  if (p.rel_mode == 2) {
+    // bias everywhere (decoder self-attention); rel = key - query is within +-63 by construction
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int qi = m0 + g + (i >> 1) * 8 + p.q_off;   // absolute query position
-      const int kj = nt * 8 + 2 * t + (i & 1);
-      float x = s[nt][i];
-      if (kj >= p.Sk) {
-        x = -INFINITY;
-      } else {
-        if (p.rel_mode == 2 || (p.rel_mode == 1 && qi < p.Lt && kj < p.Lt)) x += sbias[min(max(kj - qi, -(AT_S - 1)), AT_S - 1) + (AT_S - 1)];
-        x += skmask[kj];
-        if (p.causal && kj > qi) x += -10000.0f;
-      }
-      s[nt][i] = x;
+    for (int nt = 0; nt < NKT; ++nt) {
+      const float* bp = sbias + (nt * 8 + 2 * t - q0 + (AT_S - 1));
+      s[nt][0] += bp[0]; s[nt][1] += bp[1]; s[nt][2] += bp[-8]; s[nt][3] += bp[-7];
     }
+  } else if (p.rel_mode == 1 && m0 < p.Lt) {
+    // bias on the text x text corner only (encoder): rows / key tiles beyond Lt are skipped warp-uniformly
+    const bool r0 = q0 < p.Lt, r1 = q0 + 8 < p.Lt;
+#pragma unroll
+    for (int nt = 0; nt < NKT; ++nt)
+      if (nt * 8 < p.Lt) {
+        const int kj = nt * 8 + 2 * t;
+        const float* bp = sbias + (kj - q0 + (AT_S - 1));
+        const bool c0 = kj < p.Lt, c1 = kj + 1 < p.Lt;
+        if (r0 && c0) s[nt][0] += bp[0];
+        if (r0 && c1) s[nt][1] += bp[1];
+        if (r1 && c0) s[nt][2] += bp[-8];
+        if (r1 && c1) s[nt][3] += bp[-7];
+      }
+  }
+  if (p.causal) {
+#pragma unroll
+    for (int nt = 0; nt < NKT; ++nt) {
+      const int kj = nt * 8 + 2 * t;
+      if (kj > q0) s[nt][0] += -10000.0f;
+      if (kj + 1 > q0) s[nt][1] += -10000.0f;
+      if (kj > q0 + 8) s[nt][2] += -10000.0f;
+      if (kj + 1 > q0 + 8) s[nt][3] += -10000.0f;
+    }
+  }
 }
 
-VQ_DEVINL void load_bias_mask(float* sbias, float* skmask, const AttnArgs& p, int b, int h) {
-  if (p.rel_mode)
-    for (int r = threadIdx.x; r < 2 * AT_S - 1; r += AT_THREADS) sbias[r] = p.rel_table[p.rel_bucket[r] * p.H + h];
-  for (int j = threadIdx.x; j < AT_S; j += AT_THREADS) skmask[j] = (p.keymask && j < p.Sk) ? p.keymask[(size_t)b * p.Sk + j] : 0.f;
+template <int NW>
+VQ_DEVINL void load_bias_mask(float* sbias, float* skmask, const AttnArgs& p, const AttnBuckets& bk, int b, int h, int tid) {
+  constexpr int T = NW * 32;
+  if (p.rel_mode) {
+#pragma unroll
+    for (int it = 0; it < (2 * AT_S + T - 1) / T; ++it) {
+      const int r = it * T + tid;
+      if (r < 2 * AT_S - 1) sbias[r] = p.rel_table[(int)bk.b[r] * p.H + h];
+    }
+  }
+  // key-side additive term: padding mask for existing keys, -inf beyond Sk
+#pragma unroll
+  for (int it = 0; it < (AT_S + T - 1) / T; ++it) {
+    const int j = it * T + tid;
+    if (j < AT_S) skmask[j] = j < p.Sk ? (p.keymask ? p.keymask[(size_t)b * p.Sk + j] : 0.f) : -INFINITY;
+  }
 }
 
-__global__ void __launch_bounds__(AT_THREADS, 4) attn_fwd_kernel(const AttnArgs p) {
-  extern __shared__ uint8_t at_smem_raw[];
-  AttnSmemFwd& sm = *reinterpret_cast<AttnSmemFwd*>(at_smem_raw);
-  const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  load_head(sm.q, p.q + (size_t)b * (p.q_bstride ? p.q_bstride : (long long)p.Sq * p.ldq) + h * AT_D, p.ldq, p.Sq);
-  load_head(sm.k, p.k + (size_t)b * (p.k_bstride ? p.k_bstride : (long long)p.Sk * p.ldk) + h * AT_D, p.ldk, p.Sk);
-  load_head(sm.v, p.v + (size_t)b * (p.v_bstride ? p.v_bstride : (long long)p.Sk * p.ldv) + h * AT_D, p.ldv, p.Sk);
-  load_bias_mask(sm.bias, sm.kmask, p, b, h);
-  __syncthreads();
+// HPC > 1 (only with NW == 1): the CTA holds HPC independent single-warp problems (consecutive (batch, head) pairs), each
+// with its own smem slice — the decoder's 3840 tiny problems are otherwise bound by the CTA dispatch rate.
+template <int NW, int NKT, int HPC>
+__global__ void __launch_bounds__(NW * 32 * HPC, NW == 4 ? 6 : 16 / (NW * HPC)) attn_fwd_kernel(const AttnArgs p, const __grid_constant__ AttnBuckets bk) {
+  static_assert(HPC == 1 || NW == 1, "several problems per CTA only for single-warp problems");
+  vq_pdl_trigger();
+  vq_pdl_wait();
+  extern __shared__ __align__(16) uint8_t at_smem_base[];
+  const int vblk = HPC == 1 ? (int)blockIdx.x : (int)blockIdx.x * HPC + (int)(threadIdx.x >> 5);   // problem index = b * H + h
+  if (vblk >= p.B * p.H) return;
+  const int tid = HPC == 1 ? (int)threadIdx.x : (int)(threadIdx.x & 31);
+  uint8_t* at_smem_raw = at_smem_base + (HPC == 1 ? 0 : (threadIdx.x >> 5) * (AT_HDR_BYTES + (rows16(p.Sq) + 2 * NKT * 8) * AT_P * 2));
+  struct { float* bias; float* kmask; AttnTile q, k, v; } sm;
+  sm.bias = reinterpret_cast<float*>(at_smem_raw);
+  sm.kmask = sm.bias + 2 * AT_S;
+  sm.q = reinterpret_cast<AttnTile>(at_smem_raw + AT_HDR_BYTES);
+  sm.k = sm.q + rows16(p.Sq);
+  sm.v = sm.k + NKT * 8;
+  const int b = vblk / p.H, h = vblk % p.H;
+  const int warp = tid >> 5, lane = tid & 31;
+  {
+    const AttnTile dst[3] = {sm.q, sm.k, sm.v};
+    const __nv_bfloat16* const src[3] = {p.q + (size_t)b * (p.q_bstride ? p.q_bstride : (long long)p.Sq * p.ldq) + h * AT_D,
+                                         p.k + (size_t)b * (p.k_bstride ? p.k_bstride : (long long)p.Sk * p.ldk) + h * AT_D,
+                                         p.v + (size_t)b * (p.v_bstride ? p.v_bstride : (long long)p.Sk * p.ldv) + h * AT_D};
+    const int ld[3] = {p.ldq, p.ldk, p.ldv};
+    const int rows[3] = {p.Sq, p.Sk, p.Sk};
+    const int fill[3] = {rows16(p.Sq), NKT * 8, NKT * 8};
+    load_bias_mask<NW>(sm.bias, sm.kmask, p, bk, b, h, tid);
+    load_heads<NW, 3>(dst, src, ld, rows, fill, tid);
+  }
+  if (NW == 1) __syncwarp(); else __syncthreads();
   const int m0 = warp * 16;
   if (m0 >= p.Sq) return;
-  float s[8][4];
-  scores_tile(s, sm.q, sm.k, sm.bias, sm.kmask, p, m0, lane);
+  float s[NKT][4];
+  scores_tile<NKT>(s, sm.q, sm.k, sm.bias, sm.kmask, p, m0, lane);
   const int g = lane >> 2, t = lane & 3;
   // row-wise softmax (rows g and g+8 of this warp's tile), fp32
   float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
-  for (int nt = 0; nt < 8; ++nt)
+  for (int nt = 0; nt < NKT; ++nt)
 #pragma unroll
     for (int i = 0; i < 4; ++i) mx[i >> 1] = fmaxf(mx[i >> 1], s[nt][i]);
 #pragma unroll
@@ -154,7 +258,7 @@ __global__ void __launch_bounds__(AT_THREADS, 4) attn_fwd_kernel(const AttnArgs 
   }
   float sum[2] = {0.f, 0.f};
 #pragma unroll
-  for (int nt = 0; nt < 8; ++nt)
+  for (int nt = 0; nt < NKT; ++nt)
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float e = __expf(s[nt][i] - mx[i >> 1]);
@@ -175,39 +279,36 @@ __global__ void __launch_bounds__(AT_THREADS, 4) attn_fwd_kernel(const AttnArgs 
     }
   }
 #pragma unroll
-  for (int nt = 0; nt < 8; ++nt)
+  for (int nt = 0; nt < NKT; ++nt)
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       float s0 = inv[r], s1 = inv[r];
       if (p.drop_thr) {
         float d0, d1;
-        vq_dropout_pair(p.seed, attn_pair_idx(blockIdx.x, m0 + g + r * 8, nt * 8 + 2 * t), p.drop_thr, p.drop_inv_keep, d0, d1);
+        vq_dropout_pair(p.seed, attn_pair_idx(vblk, m0 + g + r * 8, nt * 8 + 2 * t), p.drop_thr, p.drop_inv_keep, d0, d1);
         s0 *= d0; s1 *= d1;
       }
       s[nt][2 * r] *= s0;
       s[nt][2 * r + 1] *= s1;
     }
-  // O = P V over the ceil(Sk/16) key blocks that exist
-  const int nkk = (p.Sk + 15) >> 4;
+  // O = P V
   float o[8][4];
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
     for (int i = 0; i < 4; ++i) o[nt][i] = 0.f;
 #pragma unroll
-  for (int kk = 0; kk < 4; ++kk) {
-    if (kk < nkk) {
-      uint32_t a[4];
-      a[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
-      a[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
-      a[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-      a[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+  for (int kk = 0; kk < NKT / 2; ++kk) {
+    uint32_t a[4];
+    a[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
+    a[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
+    a[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+    a[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        uint32_t bb[2];
-        frag_b_t(bb, sm.v, nt * 8, kk * 16, lane);
-        mma16816(o[nt], a, bb);
-      }
+    for (int nt = 0; nt < 8; nt += 2) {
+      uint32_t bb[4];
+      frag_b2_t(bb, sm.v, nt * 8, kk * 16, lane);
+      mma2(o[nt], o[nt + 1], a, bb);
     }
   }
 #pragma unroll
@@ -221,35 +322,48 @@ __global__ void __launch_bounds__(AT_THREADS, 4) attn_fwd_kernel(const AttnArgs 
   }
 }
 
-struct AttnSmemBwd {
-  __nv_bfloat16 q[AT_S][AT_P], k[AT_S][AT_P], v[AT_S][AT_P], dO[AT_S][AT_P], P[AT_S][AT_P], dS[AT_S][AT_P];
-  float bias[2 * AT_S];
-  float kmask[AT_S];
-  float dbucket[64];
-};
-
-__global__ void __launch_bounds__(AT_THREADS, 3) attn_bwd_kernel(const AttnArgs p) {
-  extern __shared__ uint8_t at_smem_raw[];
-  AttnSmemBwd& sm = *reinterpret_cast<AttnSmemBwd*>(at_smem_raw);
-  const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+template <int NW, int NKT, int HPC>
+__global__ void __launch_bounds__(NW * 32 * HPC, NW == 4 ? 4 : 8 / HPC) attn_bwd_kernel(const AttnArgs p, const __grid_constant__ AttnBuckets bk) {
+  static_assert(HPC == 1 || NW == 1, "several problems per CTA only for single-warp problems");
+  vq_pdl_trigger();
+  vq_pdl_wait();
+  extern __shared__ __align__(16) uint8_t at_smem_base[];
+  const int vblk = HPC == 1 ? (int)blockIdx.x : (int)blockIdx.x * HPC + (int)(threadIdx.x >> 5);   // problem index = b * H + h
+  if (vblk >= p.B * p.H) return;
+  const int tid = HPC == 1 ? (int)threadIdx.x : (int)(threadIdx.x & 31);
+  uint8_t* at_smem_raw = at_smem_base + (HPC == 1 ? 0 : (threadIdx.x >> 5) * (AT_HDR_BYTES + (4 * rows16(p.Sq) + 2 * NKT * 8) * AT_P * 2));
+  struct { float* bias; float* kmask; float* dbucket; AttnTile q, dO, P, dS, k, v; } sm;
+  sm.bias = reinterpret_cast<float*>(at_smem_raw);
+  sm.kmask = sm.bias + 2 * AT_S;
+  sm.dbucket = sm.kmask + AT_S;
+  sm.q = reinterpret_cast<AttnTile>(at_smem_raw + AT_HDR_BYTES);
+  sm.dO = sm.q + rows16(p.Sq);
+  sm.P = sm.dO + rows16(p.Sq);
+  sm.dS = sm.P + rows16(p.Sq);
+  sm.k = sm.dS + rows16(p.Sq);
+  sm.v = sm.k + NKT * 8;
+  const int b = vblk / p.H, h = vblk % p.H;
+  const int warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
-  load_head(sm.q, p.q + (size_t)b * p.Sq * p.ldq + h * AT_D, p.ldq, p.Sq);
-  load_head(sm.k, p.k + (size_t)b * p.Sk * p.ldk + h * AT_D, p.ldk, p.Sk);
-  load_head(sm.v, p.v + (size_t)b * p.Sk * p.ldv + h * AT_D, p.ldv, p.Sk);
-  load_head(sm.dO, p.dO + (size_t)b * p.Sq * p.ldo + h * AT_D, p.ldo, p.Sq);
-  load_bias_mask(sm.bias, sm.kmask, p, b, h);
-  if (threadIdx.x < 64) sm.dbucket[threadIdx.x] = 0.f;
-  __syncthreads();
+  {
+    const AttnTile dst[4] = {sm.q, sm.k, sm.v, sm.dO};
+    const __nv_bfloat16* const src[4] = {p.q + (size_t)b * p.Sq * p.ldq + h * AT_D, p.k + (size_t)b * p.Sk * p.ldk + h * AT_D,
+                                         p.v + (size_t)b * p.Sk * p.ldv + h * AT_D, p.dO + (size_t)b * p.Sq * p.ldo + h * AT_D};
+    const int ld[4] = {p.ldq, p.ldk, p.ldv, p.ldo};
+    const int rows[4] = {p.Sq, p.Sk, p.Sk, p.Sq};
+    const int fill[4] = {rows16(p.Sq), NKT * 8, NKT * 8, rows16(p.Sq)};
+    load_bias_mask<NW>(sm.bias, sm.kmask, p, bk, b, h, tid);
+    load_heads<NW, 4>(dst, src, ld, rows, fill, tid);
+  }
+  for (int i = tid; i < 64; i += NW * 32) sm.dbucket[i] = 0.f;
+  if (NW == 1) __syncwarp(); else __syncthreads();
 
-  const int nkt = (p.Sk + 7) >> 3;    // key tiles of 8 that exist
-  const int nkk = (p.Sk + 15) >> 4;   // key blocks of 16
   const int nqk = (p.Sq + 15) >> 4;   // query blocks of 16
   // ---- phase 1: this warp owns 16 query rows (warps past the last query block only take part in phase 2) ----
   const int m0 = warp * 16;
   if (m0 < p.Sq) {
-    float s[8][4];
-    scores_tile(s, sm.q, sm.k, sm.bias, sm.kmask, p, m0, lane);
+    float s[NKT][4];
+    scores_tile<NKT>(s, sm.q, sm.k, sm.bias, sm.kmask, p, m0, lane);
     float lse[2];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -257,9 +371,9 @@ __global__ void __launch_bounds__(AT_THREADS, 3) attn_bwd_kernel(const AttnArgs 
       lse[r] = qi < p.Sq ? p.lse[((size_t)b * p.H + h) * p.Sq + qi] : INFINITY;  // rows >= Sq -> P = 0
     }
     // dPd = dO V^T
-    float dp[8][4];
+    float dp[NKT][4];
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
+    for (int nt = 0; nt < NKT; ++nt)
 #pragma unroll
       for (int i = 0; i < 4; ++i) dp[nt][i] = 0.f;
 #pragma unroll
@@ -267,22 +381,20 @@ __global__ void __launch_bounds__(AT_THREADS, 3) attn_bwd_kernel(const AttnArgs 
       uint32_t a[4];
       frag_a(a, sm.dO, m0, kk * 16, lane);
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        if (nt < nkt) {
-          uint32_t bb[2];
-          frag_b(bb, sm.v, nt * 8, kk * 16, lane);
-          mma16816(dp[nt], a, bb);
-        }
+      for (int nt = 0; nt < NKT; nt += 2) {
+        uint32_t bb[4];
+        frag_b2(bb, sm.v, nt * 8, kk * 16, lane);
+        mma2(dp[nt], dp[nt + 1], a, bb);
       }
     }
     float dsum[2] = {0.f, 0.f};
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
+    for (int nt = 0; nt < NKT; ++nt)
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
         const int qi = m0 + g + r * 8, kj = nt * 8 + 2 * t;
         float sc0 = 1.f, sc1 = 1.f;
-        if (p.drop_thr) vq_dropout_pair(p.seed, attn_pair_idx(blockIdx.x, qi, kj), p.drop_thr, p.drop_inv_keep, sc0, sc1);
+        if (p.drop_thr) vq_dropout_pair(p.seed, attn_pair_idx(vblk, qi, kj), p.drop_thr, p.drop_inv_keep, sc0, sc1);
         const float p0 = __expf(s[nt][2 * r] - lse[r]), p1 = __expf(s[nt][2 * r + 1] - lse[r]);  // exp(-inf) = 0: masked keys / padded rows
         const float d0 = dp[nt][2 * r] * sc0, d1 = dp[nt][2 * r + 1] * sc1;                          // dP
         s[nt][2 * r] = p0; s[nt][2 * r + 1] = p1;
@@ -296,7 +408,7 @@ __global__ void __launch_bounds__(AT_THREADS, 3) attn_bwd_kernel(const AttnArgs 
       dsum[r] += __shfl_xor_sync(0xffffffffu, dsum[r], 2);
     }
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
+    for (int nt = 0; nt < NKT; ++nt)
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
         const float ds0 = s[nt][2 * r] * (dp[nt][2 * r] - dsum[r]), ds1 = s[nt][2 * r + 1] * (dp[nt][2 * r + 1] - dsum[r]);
@@ -310,19 +422,17 @@ __global__ void __launch_bounds__(AT_THREADS, 3) attn_bwd_kernel(const AttnArgs 
 #pragma unroll
       for (int i = 0; i < 4; ++i) dq[nt][i] = 0.f;
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-      if (kk < nkk) {
-        uint32_t a[4];
-        a[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
-        a[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
-        a[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-        a[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+    for (int kk = 0; kk < NKT / 2; ++kk) {
+      uint32_t a[4];
+      a[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
+      a[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
+      a[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+      a[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-          uint32_t bb[2];
-          frag_b_t(bb, sm.k, nt * 8, kk * 16, lane);
-          mma16816(dq[nt], a, bb);
-        }
+      for (int nt = 0; nt < 8; nt += 2) {
+        uint32_t bb[4];
+        frag_b2_t(bb, sm.k, nt * 8, kk * 16, lane);
+        mma2(dq[nt], dq[nt + 1], a, bb);
       }
     }
 #pragma unroll
@@ -335,18 +445,18 @@ __global__ void __launch_bounds__(AT_THREADS, 3) attn_bwd_kernel(const AttnArgs 
       }
     }
   }
-  __syncthreads();
+  if (NW == 1) __syncwarp(); else __syncthreads();
   // ---- relative-position-bias gradient: d table[bucket(k - q)] += dS[q][k]; one thread per diagonal of the biased
   //      region sums its <= 64 entries from smem, then one smem atomic per diagonal and one global atomic per bucket ----
   if (p.d_rel_table) {
     const int nq = p.rel_mode == 1 ? min(p.Sq, p.Lt) : p.Sq;
     const int nk = p.rel_mode == 1 ? min(p.Sk, p.Lt) : p.Sk;
     const int ndiag = nq + nk - 1;
-    for (int dgi = threadIdx.x; dgi < ndiag; dgi += AT_THREADS) {
+    for (int dgi = tid; dgi < ndiag; dgi += NW * 32) {
       const int rel = dgi - (nq - 1);   // k - q
       float acc = 0.f;
       for (int qi = max(0, -rel); qi < nq && qi + rel < nk; ++qi) acc += __bfloat162float(sm.dS[qi][qi + rel]);
-      atomicAdd(&sm.dbucket[p.rel_bucket[rel + (AT_S - 1)]], acc);
+      atomicAdd(&sm.dbucket[(int)bk.b[rel + (AT_S - 1)]], acc);
     }
   }
   // ---- phase 2: this warp owns 16 key rows: dV = Pd^T dO, dK = dS^T Q (contraction over the query blocks that exist) ----
@@ -357,18 +467,18 @@ __global__ void __launch_bounds__(AT_THREADS, 3) attn_bwd_kernel(const AttnArgs 
 #pragma unroll
       for (int i = 0; i < 4; ++i) dv[nt][i] = dk[nt][i] = 0.f;
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
+    for (int kk = 0; kk < NW; ++kk) {
       if (kk < nqk) {
         uint32_t ap[4], as[4];
         frag_a_t(ap, sm.P, m0, kk * 16, lane);
         frag_a_t(as, sm.dS, m0, kk * 16, lane);
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-          uint32_t b1[2], b2[2];
-          frag_b_t(b1, sm.dO, nt * 8, kk * 16, lane);
-          frag_b_t(b2, sm.q, nt * 8, kk * 16, lane);
-          mma16816(dv[nt], ap, b1);
-          mma16816(dk[nt], as, b2);
+        for (int nt = 0; nt < 8; nt += 2) {
+          uint32_t b1[4], b2[4];
+          frag_b2_t(b1, sm.dO, nt * 8, kk * 16, lane);
+          frag_b2_t(b2, sm.q, nt * 8, kk * 16, lane);
+          mma2(dv[nt], dv[nt + 1], ap, b1);
+          mma2(dk[nt], dk[nt + 1], as, b2);
         }
       }
     }
@@ -387,10 +497,10 @@ __global__ void __launch_bounds__(AT_THREADS, 3) attn_bwd_kernel(const AttnArgs 
     }
   }
   if (p.d_rel_table) {
-    __syncthreads();
-    if (threadIdx.x < 64) {
-      const float v = sm.dbucket[threadIdx.x];
-      if (v != 0.f) atomicAdd(&p.d_rel_table[threadIdx.x * p.H + h], v);
+    if (NW == 1) __syncwarp(); else __syncthreads();
+    for (int i = tid; i < 64; i += NW * 32) {
+      const float v = sm.dbucket[i];
+      if (v != 0.f) atomicAdd(&p.d_rel_table[i * p.H + h], v);
     }
   }
 }
@@ -402,16 +512,55 @@ static int check_args(const AttnArgs& a) {
   return 0;
 }
 
-int attn_fwd(const AttnArgs& a, cudaStream_t stream) {
-  if (check_args(a)) return 1;
+static int make_buckets(const AttnArgs& a, AttnBuckets* bk) {
+  memset(bk, 0, sizeof(*bk));
+  if (a.rel_mode)
+    for (int r = 0; r < 2 * AT_S - 1; ++r) {
+      VQ_CHECK(a.rel_bucket[r] >= 0 && a.rel_bucket[r] < 64, "attention: bucket %d out of range", a.rel_bucket[r]);
+      bk->b[r] = (int8_t)a.rel_bucket[r];
+    }
+  return 0;
+}
+
+constexpr int AT_HPC = 4;   // single-warp problems per CTA
+template <int NW, int NKT>
+static int launch_fwd(const AttnArgs& a, const AttnBuckets& bk, cudaStream_t stream) {
+  constexpr int HPC = NW == 1 ? AT_HPC : 1;
   static bool attr = false;
   if (!attr) {
-    VQ_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AttnSmemFwd)));
+    VQ_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<NW, NKT, HPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, HPC * attn_smem_fwd(NW * 16, NKT * 8)));
+    VQ_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<NW, NKT, HPC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     attr = true;
   }
-  attn_fwd_kernel<<<a.B * a.H, AT_THREADS, sizeof(AttnSmemFwd), stream>>>(a);
+  (void)vq_launch(attn_fwd_kernel<NW, NKT, HPC>, dim3((a.B * a.H + HPC - 1) / HPC), dim3(32 * NW * HPC),
+                  (size_t)HPC * attn_smem_fwd(a.Sq, NKT * 8), stream, a, bk);
   VQ_LAUNCH_CHECK();
   return 0;
+}
+template <int NW, int NKT>
+static int launch_bwd(const AttnArgs& a, const AttnBuckets& bk, cudaStream_t stream) {
+  constexpr int HPC = NW == 1 ? AT_HPC : 1;
+  static bool attr = false;
+  if (!attr) {
+    VQ_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<NW, NKT, HPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, HPC * attn_smem_bwd(AT_S, NKT * 8)));
+    VQ_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<NW, NKT, HPC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    attr = true;
+  }
+  (void)vq_launch(attn_bwd_kernel<NW, NKT, HPC>, dim3((a.B * a.H + HPC - 1) / HPC), dim3(32 * NW * HPC),
+                  (size_t)HPC * attn_smem_bwd(a.Sq, NKT * 8), stream, a, bk);
+  VQ_LAUNCH_CHECK();
+  return 0;
+}
+
+int attn_fwd(const AttnArgs& a, cudaStream_t stream) {
+  if (check_args(a)) return 1;
+  AttnBuckets bk;
+  if (make_buckets(a, &bk)) return 1;
+  const int warps = (a.Sq + 15) / 16;   // one warp per 16 query rows
+  if (warps == 1 && a.Sk <= 16) return launch_fwd<1, 2>(a, bk, stream);   // decoder self-attention / decode steps
+  if (warps == 1) return launch_fwd<1, 8>(a, bk, stream);                  // cross-attention
+  if (warps == 2) return launch_fwd<2, 8>(a, bk, stream);
+  return launch_fwd<4, 8>(a, bk, stream);                                  // encoder
 }
 
 int attn_bwd(const AttnArgs& a, cudaStream_t stream) {
@@ -419,14 +568,12 @@ int attn_bwd(const AttnArgs& a, cudaStream_t stream) {
   VQ_CHECK(a.lse && a.dO && a.dq && a.dk && a.dv, "attention bwd: missing pointers");
   VQ_CHECK(!a.q_bstride && !a.k_bstride && !a.v_bstride && !a.o_bstride && !a.q_off, "attention bwd: strided / offset form is forward-only");
   VQ_CHECK(a.lddq % 8 == 0 && a.lddk % 8 == 0 && a.lddv % 8 == 0, "attention bwd: pitches must be multiples of 8");
-  static bool attr = false;
-  if (!attr) {
-    VQ_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AttnSmemBwd)));
-    attr = true;
-  }
-  attn_bwd_kernel<<<a.B * a.H, AT_THREADS, sizeof(AttnSmemBwd), stream>>>(a);
-  VQ_LAUNCH_CHECK();
-  return 0;
+  AttnBuckets bk;
+  if (make_buckets(a, &bk)) return 1;
+  const int warps = (max(a.Sq, a.Sk) + 15) / 16;   // phase 1: 16 query rows per warp, phase 2: 16 key rows per warp
+  if (warps == 1) return launch_bwd<1, 2>(a, bk, stream);
+  if (warps == 2) return launch_bwd<2, 8>(a, bk, stream);
+  return launch_bwd<4, 8>(a, bk, stream);
 }
 
 }  // namespace vq

@@ -43,6 +43,31 @@ extern long long g_vq_launches;
   } while (0)
 
 // ---------------------------------------------------------------------------------------------
+// launches: every kernel of the library is launched with programmatic stream serialization (PDL) so that the prologue of
+// kernel i+1 (barrier init, TMEM allocation, descriptor prefetch, block scheduling) overlaps the tail of kernel i. Each
+// kernel calls vq_pdl_trigger() first and vq_pdl_wait() before it touches global memory; the wait returns only when every
+// preceding grid has completed and flushed, so ordering is exactly that of a plain stream.
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+static inline cudaError_t vq_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<Args&&>(args)...);
+}
+__device__ __forceinline__ void vq_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void vq_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
+// ---------------------------------------------------------------------------------------------
 // small device utilities
 // ---------------------------------------------------------------------------------------------
 VQ_DEVINL uint32_t smem_u32(const void* p) {

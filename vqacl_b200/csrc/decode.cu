@@ -41,6 +41,8 @@ static int64_t decode_carve(const Engine& e, uint8_t* base, int B, int max_len, 
 
 __global__ void decode_init_kernel(int64_t* __restrict__ out, int max_len, int64_t* __restrict__ cur, int* __restrict__ unfinished,
                                    int B, int start_id) {
+  vq_pdl_trigger();
+  vq_pdl_wait();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   out[(size_t)b * max_len] = start_id;
@@ -52,6 +54,8 @@ __global__ void decode_init_kernel(int64_t* __restrict__ out, int max_len, int64
 __global__ void decode_advance_kernel(const int64_t* __restrict__ next, int64_t* __restrict__ out, int max_len, int col,
                                       int64_t* __restrict__ cur, int* __restrict__ unfinished, int* __restrict__ n_unfinished, int B,
                                       int pad_id, int eos_id) {
+  vq_pdl_trigger();
+  vq_pdl_wait();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const int u = unfinished[b];
@@ -141,7 +145,7 @@ extern "C" int vqacl_generate(void* engine, const vqacl_batch* batch, const vqac
   ps.proto_update = 0;                                     // modeling_t5_our.py:607-612: frozen banks at test time
   VQ_TRY(si_path(e, batch, &ps, false, st));
   VQ_TRY(gemm_fwd(e.w.mem, d, e.W + e.o_ckv, d, e.w.kv_all, Ld * 2 * d, B * S2, Ld * 2 * d, EPI_BF16, st));
-  decode_init_kernel<<<(B + 255) / 256, 256, 0, st>>>(out_tokens, max_len, dw.cur, dw.unfinished, B, c.start_id);
+  (void)vq_launch(decode_init_kernel, dim3((B + 255) / 256), dim3(256), 0, st, out_tokens, max_len, dw.cur, dw.unfinished, B, c.start_id);
   VQ_LAUNCH_CHECK();
   static int* h_flag = nullptr;
   if (!h_flag) VQ_CUDA(cudaMallocHost(&h_flag, sizeof(int)));
@@ -149,7 +153,7 @@ extern "C" int vqacl_generate(void* engine, const vqacl_batch* batch, const vqac
   for (int t = 0; t + 1 < max_len; ++t) {
     VQ_TRY(decode_step(e, dw, B, S2, max_len, t, st));
     VQ_CUDA(cudaMemsetAsync(dw.n_unfinished, 0, sizeof(int), st));
-    decode_advance_kernel<<<(B + 255) / 256, 256, 0, st>>>(dw.next, out_tokens, max_len, t + 1, dw.cur, dw.unfinished,
+    (void)vq_launch(decode_advance_kernel, dim3((B + 255) / 256), dim3(256), 0, st, dw.next, out_tokens, max_len, t + 1, dw.cur, dw.unfinished,
                                                            dw.n_unfinished, B, c.pad_id, c.eos_id);
     VQ_LAUNCH_CHECK();
     len = t + 2;

@@ -59,6 +59,8 @@ VQ_DEVINL void apply_dropout(float (&v)[RW_CHUNKS][4], const Dropout& d, uint64_
 
 // ------------------------------------------------------------------------------------------------ cast
 __global__ void cast_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n8) {
+  vq_pdl_trigger();
+  vq_pdl_wait();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
     const float4 a = reinterpret_cast<const float4*>(src)[2 * i], b = reinterpret_cast<const float4*>(src)[2 * i + 1];
     reinterpret_cast<uint4*>(dst)[i] = make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
@@ -69,13 +71,15 @@ int cast_f32_to_bf16(const float* src, __nv_bfloat16* dst, size_t n, cudaStream_
   if (n == 0) return 0;
   const size_t n8 = n / 8;
   const int blocks = (int)((n8 + 255) / 256 < (size_t)num_sms() * 8 ? (n8 + 255) / 256 : (size_t)num_sms() * 8);
-  cast_kernel<<<blocks, 256, 0, stream>>>(src, dst, n8);
+  (void)vq_launch(cast_kernel, dim3(blocks), dim3(256), 0, stream, src, dst, n8);
   VQ_LAUNCH_CHECK();
   return 0;
 }
 
 // ------------------------------------------------------------------------------------------------ RMSNorm fwd
 __global__ void __launch_bounds__(ROW_WARPS * 32) rmsnorm_fwd_kernel(const RmsFwdArgs a) {
+  vq_pdl_trigger();
+  vq_pdl_wait();
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   if (r >= a.M) return;
@@ -94,13 +98,15 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) rmsnorm_fwd_kernel(const RmsFw
 }
 int rmsnorm_fwd(const RmsFwdArgs& a, cudaStream_t stream) {
   if (a.M <= 0) return 0;
-  rmsnorm_fwd_kernel<<<(a.M + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, stream>>>(a);
+  (void)vq_launch(rmsnorm_fwd_kernel, dim3((a.M + ROW_WARPS - 1) / ROW_WARPS), dim3(ROW_WARPS * 32), 0, stream, a);
   VQ_LAUNCH_CHECK();
   return 0;
 }
 
 // ------------------------------------------------------------------------------------------------ RMSNorm bwd
 __global__ void __launch_bounds__(ROW_WARPS * 32) rmsnorm_bwd_kernel(const RmsBwdArgs a) {
+  vq_pdl_trigger();
+  vq_pdl_wait();
   __shared__ float s_dw[ROW_WARPS][DM];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float w[RW_CHUNKS][4], dwacc[RW_CHUNKS][4];
@@ -170,7 +176,7 @@ int rmsnorm_bwd(const RmsBwdArgs& a, cudaStream_t stream) {
   int blocks = (a.M + ROW_WARPS - 1) / ROW_WARPS;
   const int cap = num_sms() * 2;
   if (blocks > cap) blocks = cap;
-  rmsnorm_bwd_kernel<<<blocks, ROW_WARPS * 32, 0, stream>>>(a);
+  (void)vq_launch(rmsnorm_bwd_kernel, dim3(blocks), dim3(ROW_WARPS * 32), 0, stream, a);
   VQ_LAUNCH_CHECK();
   return 0;
 }
@@ -179,6 +185,8 @@ int rmsnorm_bwd(const RmsBwdArgs& a, cudaStream_t stream) {
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 embed_fwd_kernel(const int64_t* __restrict__ ids, int B, int L, const float* __restrict__ table, float* __restrict__ x, int S,
                  int row0, Dropout drop) {
+  vq_pdl_trigger();
+  vq_pdl_wait();
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   if (r >= B * L) return;
@@ -191,7 +199,7 @@ embed_fwd_kernel(const int64_t* __restrict__ ids, int B, int L, const float* __r
 }
 int embed_fwd(const int64_t* ids, int B, int L, const float* table, float* x, int S, int row0, Dropout drop, cudaStream_t stream) {
   if (B * L <= 0) return 0;
-  embed_fwd_kernel<<<(B * L + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, stream>>>(ids, B, L, table, x, S, row0, drop);
+  (void)vq_launch(embed_fwd_kernel, dim3((B * L + ROW_WARPS - 1) / ROW_WARPS), dim3(ROW_WARPS * 32), 0, stream, ids, B, L, table, x, S, row0, drop);
   VQ_LAUNCH_CHECK();
   return 0;
 }
@@ -199,6 +207,8 @@ int embed_fwd(const int64_t* ids, int B, int L, const float* table, float* x, in
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 embed_bwd_kernel(const int64_t* __restrict__ ids, int B, int L, const float* __restrict__ g, int S, int row0,
                  float* __restrict__ dtable, Dropout drop) {
+  vq_pdl_trigger();
+  vq_pdl_wait();
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   if (r >= B * L) return;
@@ -216,12 +226,14 @@ embed_bwd_kernel(const int64_t* __restrict__ ids, int B, int L, const float* __r
 }
 int embed_bwd(const int64_t* ids, int B, int L, const float* g, int S, int row0, float* dtable, Dropout drop, cudaStream_t stream) {
   if (B * L <= 0) return 0;
-  embed_bwd_kernel<<<(B * L + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, stream>>>(ids, B, L, g, S, row0, dtable, drop);
+  (void)vq_launch(embed_bwd_kernel, dim3((B * L + ROW_WARPS - 1) / ROW_WARPS), dim3(ROW_WARPS * 32), 0, stream, ids, B, L, g, S, row0, dtable, drop);
   VQ_LAUNCH_CHECK();
   return 0;
 }
 
 __global__ void shift_right_kernel(const int64_t* __restrict__ labels, int64_t* __restrict__ dec, int B, int T, int start_id, int pad_id) {
+  vq_pdl_trigger();
+  vq_pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * T) return;
   const int t = i % T;
@@ -231,13 +243,15 @@ __global__ void shift_right_kernel(const int64_t* __restrict__ labels, int64_t* 
 }
 int shift_right(const int64_t* labels, int64_t* dec_ids, int B, int T, int start_id, int pad_id, cudaStream_t stream) {
   if (B * T <= 0) return 0;
-  shift_right_kernel<<<(B * T + 255) / 256, 256, 0, stream>>>(labels, dec_ids, B, T, start_id, pad_id);
+  (void)vq_launch(shift_right_kernel, dim3((B * T + 255) / 256), dim3(256), 0, stream, labels, dec_ids, B, T, start_id, pad_id);
   VQ_LAUNCH_CHECK();
   return 0;
 }
 
 __global__ void keymask_kernel(const int64_t* __restrict__ ids, int B, int L, int S, int pad_id, float* __restrict__ enc,
                                float* __restrict__ cross) {
+  vq_pdl_trigger();
+  vq_pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * (S + 2)) return;
   const int b = i / (S + 2), j = i % (S + 2);
@@ -248,7 +262,7 @@ __global__ void keymask_kernel(const int64_t* __restrict__ ids, int B, int L, in
 int build_keymasks(const int64_t* ids, int B, int L, int S, int pad_id, float* enc_mask, float* cross_mask, cudaStream_t stream) {
   const int n = B * (S + 2);
   if (n <= 0) return 0;
-  keymask_kernel<<<(n + 255) / 256, 256, 0, stream>>>(ids, B, L, S, pad_id, enc_mask, cross_mask);
+  (void)vq_launch(keymask_kernel, dim3((n + 255) / 256), dim3(256), 0, stream, ids, B, L, S, pad_id, enc_mask, cross_mask);
   VQ_LAUNCH_CHECK();
   return 0;
 }
@@ -262,6 +276,8 @@ VQ_DEVINL void vis_pos5(const float* boxes, int row, float (&p5)[5]) {
 }
 
 __global__ void __launch_bounds__(ROW_WARPS * 32) vis_embed_fwd_kernel(const VisArgs a) {
+  vq_pdl_trigger();
+  vq_pdl_wait();
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   if (r >= a.B * a.N) return;
@@ -314,7 +330,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) vis_embed_fwd_kernel(const Vis
 int vis_embed_fwd(const VisArgs& a, cudaStream_t stream) {
   const int rows = a.B * a.N;
   if (rows <= 0) return 0;
-  vis_embed_fwd_kernel<<<(rows + ROW_WARPS - 1) / ROW_WARPS, ROW_WARPS * 32, 0, stream>>>(a);
+  (void)vq_launch(vis_embed_fwd_kernel, dim3((rows + ROW_WARPS - 1) / ROW_WARPS), dim3(ROW_WARPS * 32), 0, stream, a);
   VQ_LAUNCH_CHECK();
   return 0;
 }
@@ -323,6 +339,8 @@ int vis_embed_fwd(const VisArgs& a, cudaStream_t stream) {
 enum { VA_DIMG = 0, VA_DWF, VA_DBF, VA_DWP, VA_DBP, VA_DWP0, VA_COUNT = VA_DWP0 + 5 };
 
 __global__ void __launch_bounds__(ROW_WARPS * 32) vis_embed_bwd_kernel(const VisArgs a) {
+  vq_pdl_trigger();
+  vq_pdl_wait();
   extern __shared__ float s_acc[];  // [VA_COUNT][DM]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < VA_COUNT * DM; i += ROW_WARPS * 32) s_acc[i] = 0.f;
@@ -434,7 +452,7 @@ int vis_embed_bwd(const VisArgs& a, cudaStream_t stream) {
   int blocks = (rows + ROW_WARPS - 1) / ROW_WARPS;
   const int cap = num_sms() * 2;
   if (blocks > cap) blocks = cap;
-  vis_embed_bwd_kernel<<<blocks, ROW_WARPS * 32, smem, stream>>>(a);
+  (void)vq_launch(vis_embed_bwd_kernel, dim3(blocks), dim3(ROW_WARPS * 32), smem, stream, a);
   VQ_LAUNCH_CHECK();
   return 0;
 }

@@ -168,6 +168,7 @@ int64_t engine_carve(Engine& e, uint8_t* base, int B, int L, int N, int T) {
   w.curV = bp.take<float>((size_t)c.n_cate * d, "curV");
   w.cntQ = bp.take<float>(c.n_ques, "cntQ");
   w.cntV = bp.take<float>(c.n_cate, "cntV");
+  w.pnorm = bp.take<float>((size_t)(c.n_ques > c.n_cate ? c.n_ques : c.n_cate) * d);
   w.idxQ = bp.take<int64_t>(B, "idxQ");
   w.idxV = bp.take<int64_t>(B, "idxV");
   w.dec_ids = bp.take<int64_t>(Md, "decoder_input_ids");
@@ -196,17 +197,21 @@ int64_t engine_carve(Engine& e, uint8_t* base, int B, int L, int N, int T) {
   w.loss = bp.take<float>(4, "loss");
   // backward
   w.gd = bp.take<float>(Md * d);
-  w.gdb = bp.take<bf16>(Md * d);
+  for (auto& p : w.gdb_ring) p = bp.take<bf16>(Md * d);
   w.t_d768 = bp.take<bf16>(Md * d);
   w.t_d768_f32 = bp.take<float>(Md * d);
-  w.t_dqkv = bp.take<bf16>(Md * 3 * d);
-  w.t_dh = bp.take<bf16>(Md * f);
-  w.t_dcq = bp.take<bf16>(Md * d);
+  for (int i = 0; i < Workspace::RING; ++i) {
+    w.t_dqkv[i] = bp.take<bf16>(Md * 3 * d);
+    w.t_dh[i] = bp.take<bf16>(Md * f);
+    w.t_dcq[i] = bp.take<bf16>(Md * d);
+  }
   w.ge = bp.take<float>(M * d);
-  w.geb = bp.take<bf16>(M * d);
+  for (auto& p : w.geb_ring) p = bp.take<bf16>(M * d);
   w.t_e768 = bp.take<bf16>(M * d);
-  w.t_eqkv = bp.take<bf16>(M * 3 * d);
-  w.t_eh = bp.take<bf16>(M * f);
+  for (int i = 0; i < Workspace::RING; ++i) {
+    w.t_eqkv[i] = bp.take<bf16>(M * 3 * d);
+    w.t_eh[i] = bp.take<bf16>(M * f);
+  }
   w.dkv_all = bp.take<bf16>(M2 * (size_t)Ld * 2 * d);
   w.dmem = bp.take<bf16>(M2 * d);
   w.dfeatpre = bp.take<bf16>((size_t)B * N * d);
@@ -329,8 +334,8 @@ int si_path(Engine& e, const vqacl_batch* b, const vqacl_proto_state* ps, bool s
     VQ_TRY(proto_update(u, st));
   }
   // retrieval + feature mix (:601-615): rows S and S+1 of the decoder memory
-  VQ_TRY(proto_retrieve(ps->Q_prototype, c.n_ques, w.meanQ, B, w.mem, S2, S, w.idxQ, nullptr, st));
-  VQ_TRY(proto_retrieve(ps->V_prototype, c.n_cate, w.meanV, B, w.mem, S2, S + 1, w.idxV, nullptr, st));
+  VQ_TRY(proto_retrieve(ps->Q_prototype, c.n_ques, w.meanQ, B, w.mem, S2, S, w.idxQ, nullptr, w.pnorm, st));
+  VQ_TRY(proto_retrieve(ps->V_prototype, c.n_cate, w.meanV, B, w.mem, S2, S + 1, w.idxV, nullptr, w.pnorm, st));
   return 0;
 }
 
@@ -423,9 +428,26 @@ static void backward_stage_range(const Engine& e, int stage, int64_t* a, int64_t
   }
 }
 
+static int ensure_side_stream(Engine& e) {
+  if (e.side) return 0;
+  VQ_CUDA(cudaStreamCreateWithFlags(&e.side, cudaStreamNonBlocking));
+  VQ_CUDA(cudaEventCreateWithFlags(&e.ev_fork, cudaEventDisableTiming));
+  VQ_CUDA(cudaEventCreateWithFlags(&e.ev_join, cudaEventDisableTiming));
+  for (auto& ev : e.ev_layer) VQ_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  return 0;
+}
+
+// Two streams: `st` carries the dependency chain (dX GEMMs, attention and norm backward); every weight-gradient GEMM
+// goes to the side stream `sd` right after the kernel that produced its dY operand (fork event). Nothing reads a dW
+// before the optimizer, so the side stream fills the SMs the chain leaves idle — whole SMs for the decoder's small
+// launches (M = B*T rows: 78-117 CTAs), wave tails for the encoder's. Write-after-read safety: every dY buffer the side
+// stream reads comes from a ring 3 layers deep, and the main stream starts a layer only after the side stream has
+// finished the layer two above it (ev_layer).
 static int backward(Engine& e, const float* w_rows, int accumulate, int stage_begin, int stage_end, cudaStream_t st) {
   VQ_CHECK(e.fwd_valid, "engine: backward called without a preceding training forward");
   VQ_CHECK(e.G, "engine: gradient arena not bound");
+  if (ensure_side_stream(e)) return 1;
+  cudaStream_t sd = e.side;
   const vqacl_config& c = e.cfg;
   Workspace& w = e.w;
   const vqacl_batch& b = g_saved[&e].b;
@@ -433,128 +455,180 @@ static int backward(Engine& e, const float* w_rows, int accumulate, int stage_be
   const int B = b.B, L = b.L, N = b.N, T = b.T, S = L + N, S2 = S + 2;
   const int M = B * S, Md = B * T, M2 = B * S2;
   const int ldkv = Ld * 2 * d, V = c.vocab_size;
+  constexpr int RING = Workspace::RING;
   const int n_stages = n_backward_stages(e);
   if (stage_end < 0 || stage_end > n_stages) stage_end = n_stages;
   VQ_CHECK(stage_begin >= 0 && stage_begin <= stage_end, "backward: bad stage range [%d, %d)", stage_begin, stage_end);
   auto on = [&](int s) { return s >= stage_begin && s < stage_end; };
+  // side stream picks up everything the main stream has issued so far
+  auto fork = [&]() -> int {
+    VQ_CUDA(cudaEventRecord(e.ev_fork, st));
+    VQ_CUDA(cudaStreamWaitEvent(sd, e.ev_fork, 0));
+    return 0;
+  };
+  int layer_no = 0;   // layers processed in this call (for the 2-layer lag)
+  auto layer_begin = [&]() -> int {
+    // the side stream must be done with the layer two above before its ring slots are rewritten
+    if (layer_no >= 2) VQ_CUDA(cudaStreamWaitEvent(st, e.ev_layer[(layer_no - 2) & 3], 0));
+    return 0;
+  };
+  auto layer_end = [&]() -> int {
+    VQ_CUDA(cudaEventRecord(e.ev_layer[layer_no & 3], sd));
+    ++layer_no;
+    return 0;
+  };
   if (on(0)) {
-  if (!accumulate) VQ_CUDA(cudaMemsetAsync(e.G, 0, e.n_train * sizeof(float), st));
-  // ---- LM head + CE
-  VQ_CHECK(w_rows, "backward: w_rows (dL/dloss_row) required");
-  VQ_TRY(ce_bwd(w.logits, e.ldv, Md, V, b.labels, w.lse_ce, w_rows, st));
-  // dY_fin[Md, d] = dLogits[Md, V] * E[V, d]: few output tiles but a 32 200-deep contraction -> split-K into an fp32 buffer
-  {
-    const int tiles = ((Md + 127) / 128) * ((d + 255) / 256);
-    int splits = num_sms() / (tiles > 0 ? tiles : 1);
-    if (splits < 1) splits = 1;
-    if (splits > 16) splits = 16;
-    VQ_CUDA(cudaMemsetAsync(w.t_d768_f32, 0, (size_t)Md * d * sizeof(float), st));
-    VQ_TRY(gemm_dx(w.logits, e.ldv, e.W + e.o_shared, V, d, w.t_d768_f32, d, Md, EPI_ATOMIC_F32, st, nullptr, 0, 1.f, splits));
-  }
-  VQ_TRY(gemm_dw(w.logits, e.ldv, w.yfin, d, e.G + e.o_shared, V, d, Md, st));
-  RmsBwdArgs r{};
-  r.dn_f32 = w.t_d768_f32; r.ld_dn = d; r.x = w.y[3 * Ld]; r.w = e.P + e.o_dec_final; r.g_in = nullptr; r.g_out = w.gd; r.gb_out = w.gdb;
-  r.dw = e.G + e.o_dec_final; r.M = Md; r.eps = c.eps; r.scale = 1.f / sqrtf((float)d); r.own = e.drop(SITE_DEC_FINAL);
-  r.consumer = e.drop(site_dec(Ld - 1, 5)); r.consumer_cols = d;
-  VQ_TRY(rmsnorm_bwd(r, st));
+    if (!accumulate) VQ_CUDA(cudaMemsetAsync(e.G, 0, e.n_train * sizeof(float), st));
+    // ---- LM head + CE
+    VQ_CHECK(w_rows, "backward: w_rows (dL/dloss_row) required");
+    VQ_TRY(ce_bwd(w.logits, e.ldv, Md, V, b.labels, w.lse_ce, w_rows, st));
+    VQ_TRY(fork());
+    VQ_TRY(gemm_dw(w.logits, e.ldv, w.yfin, d, e.G + e.o_shared, V, d, Md, sd));
+    // dY_fin[Md, d] = dLogits[Md, V] * E[V, d]: few output tiles but a 32 200-deep contraction -> split-K into an fp32 buffer
+    {
+      const int tiles = ((Md + 127) / 128) * ((d + 255) / 256);
+      int splits = num_sms() / (tiles > 0 ? tiles : 1);
+      if (splits < 1) splits = 1;
+      if (splits > 16) splits = 16;
+      VQ_CUDA(cudaMemsetAsync(w.t_d768_f32, 0, (size_t)Md * d * sizeof(float), st));
+      VQ_TRY(gemm_dx(w.logits, e.ldv, e.W + e.o_shared, V, d, w.t_d768_f32, d, Md, EPI_ATOMIC_F32, st, nullptr, 0, 1.f, splits));
+    }
+    e.gdb_i = 0;
+    RmsBwdArgs r{};
+    r.dn_f32 = w.t_d768_f32; r.ld_dn = d; r.x = w.y[3 * Ld]; r.w = e.P + e.o_dec_final; r.g_in = nullptr; r.g_out = w.gd;
+    r.gb_out = w.gdb_ring[e.gdb_i];
+    r.dw = e.G + e.o_dec_final; r.M = Md; r.eps = c.eps; r.scale = 1.f / sqrtf((float)d); r.own = e.drop(SITE_DEC_FINAL);
+    r.consumer = e.drop(site_dec(Ld - 1, 5)); r.consumer_cols = d;
+    VQ_TRY(rmsnorm_bwd(r, st));
   }
   for (int l = Ld - 1; l >= 0; --l) {
     if (!on(Ld - l)) continue;
     const DecLayer& P = e.dec[l];
+    VQ_TRY(layer_begin());
+    const int ri = l % RING;
+    bf16* gdb_in = w.gdb_ring[e.gdb_i];
+    bf16* gdb_1 = w.gdb_ring[(e.gdb_i + 1) % (3 * RING)];
+    bf16* gdb_2 = w.gdb_ring[(e.gdb_i + 2) % (3 * RING)];
+    bf16* gdb_out = w.gdb_ring[(e.gdb_i + 3) % (3 * RING)];
+    e.gdb_i = (e.gdb_i + 3) % (3 * RING);
     // FFN
-    VQ_TRY(gemm_dw(w.gdb, d, w.dh[l], f, e.G + P.wo, d, f, Md, st));
-    VQ_TRY(gemm_dx(w.gdb, d, e.W + P.wo, d, f, w.t_dh, f, Md, EPI_RELUBWD_BF16, st, w.dh[l], f, e.drop(site_dec(l, 4)).inv_keep));
-    VQ_TRY(gemm_dw(w.t_dh, f, w.dn3[l], d, e.G + P.wi, f, d, Md, st));
-    VQ_TRY(gemm_dx(w.t_dh, f, e.W + P.wi, f, d, w.t_d768, d, Md, EPI_BF16, st));
+    VQ_TRY(fork());
+    VQ_TRY(gemm_dw(gdb_in, d, w.dh[l], f, e.G + P.wo, d, f, Md, sd));
+    VQ_TRY(gemm_dx(gdb_in, d, e.W + P.wo, d, f, w.t_dh[ri], f, Md, EPI_RELUBWD_BF16, st, w.dh[l], f, e.drop(site_dec(l, 4)).inv_keep));
+    VQ_TRY(fork());
+    VQ_TRY(gemm_dw(w.t_dh[ri], f, w.dn3[l], d, e.G + P.wi, f, d, Md, sd));
+    VQ_TRY(gemm_dx(w.t_dh[ri], f, e.W + P.wi, f, d, w.t_d768, d, Md, EPI_BF16, st));
     RmsBwdArgs q{};
-    q.dn = w.t_d768; q.ld_dn = d; q.x = w.y[3 * l + 2]; q.w = e.P + P.ln2; q.g_in = w.gd; q.g_out = w.gd; q.gb_out = w.gdb;
+    q.dn = w.t_d768; q.ld_dn = d; q.x = w.y[3 * l + 2]; q.w = e.P + P.ln2; q.g_in = w.gd; q.g_out = w.gd; q.gb_out = gdb_1;
     q.dw = e.G + P.ln2; q.M = Md; q.eps = c.eps; q.scale = 1.f; q.consumer = e.drop(site_dec(l, 3)); q.consumer_cols = d;
     VQ_TRY(rmsnorm_bwd(q, st));
     // cross attention
-    VQ_TRY(gemm_dw(w.gdb, d, w.cao[l], d, e.G + P.co, d, d, Md, st));
-    VQ_TRY(gemm_dx(w.gdb, d, e.W + P.co, d, d, w.t_d768, d, Md, EPI_BF16, st));
+    VQ_TRY(fork());
+    VQ_TRY(gemm_dw(gdb_1, d, w.cao[l], d, e.G + P.co, d, d, Md, sd));
+    VQ_TRY(gemm_dx(gdb_1, d, e.W + P.co, d, d, w.t_d768, d, Md, EPI_BF16, st));
     AttnArgs x{};
     x.q = w.cq[l]; x.ldq = d; x.k = w.kv_all + (size_t)l * 2 * d; x.v = x.k + d; x.ldk = x.ldv = ldkv;
     x.ldo = d; x.lse = w.lse_c[l]; x.B = B; x.H = H; x.Sq = T; x.Sk = S2; x.rel_mode = 0; x.keymask = w.cross_mask; x.causal = 0;
     Dropout dp = e.drop(site_dec(l, 2));
     x.drop_thr = dp.thr; x.drop_inv_keep = dp.inv_keep; x.seed = dp.seed; x.site = dp.site;
-    x.dO = w.t_d768; x.dq = w.t_dcq; x.lddq = d; x.dk = w.dkv_all + (size_t)l * 2 * d; x.dv = x.dk + d; x.lddk = x.lddv = ldkv;
+    x.dO = w.t_d768; x.dq = w.t_dcq[ri]; x.lddq = d; x.dk = w.dkv_all + (size_t)l * 2 * d; x.dv = x.dk + d; x.lddk = x.lddv = ldkv;
     VQ_TRY(attn_bwd(x, st));
-    VQ_TRY(gemm_dw(w.t_dcq, d, w.dn2[l], d, e.G + P.cq, d, d, Md, st));
-    VQ_TRY(gemm_dx(w.t_dcq, d, e.W + P.cq, d, d, w.t_d768, d, Md, EPI_BF16, st));
-    q.x = w.y[3 * l + 1]; q.w = e.P + P.ln1; q.dw = e.G + P.ln1; q.consumer = e.drop(site_dec(l, 1));
+    VQ_TRY(fork());
+    VQ_TRY(gemm_dw(w.t_dcq[ri], d, w.dn2[l], d, e.G + P.cq, d, d, Md, sd));
+    VQ_TRY(gemm_dx(w.t_dcq[ri], d, e.W + P.cq, d, d, w.t_d768, d, Md, EPI_BF16, st));
+    q.x = w.y[3 * l + 1]; q.w = e.P + P.ln1; q.dw = e.G + P.ln1; q.consumer = e.drop(site_dec(l, 1)); q.gb_out = gdb_2;
     VQ_TRY(rmsnorm_bwd(q, st));
     // self attention
-    VQ_TRY(gemm_dw(w.gdb, d, w.dao[l], d, e.G + P.o, d, d, Md, st));
-    VQ_TRY(gemm_dx(w.gdb, d, e.W + P.o, d, d, w.t_d768, d, Md, EPI_BF16, st));
+    VQ_TRY(fork());
+    VQ_TRY(gemm_dw(gdb_2, d, w.dao[l], d, e.G + P.o, d, d, Md, sd));
+    VQ_TRY(gemm_dx(gdb_2, d, e.W + P.o, d, d, w.t_d768, d, Md, EPI_BF16, st));
     AttnArgs a{};
     a.q = w.dqkv[l]; a.k = w.dqkv[l] + d; a.v = w.dqkv[l] + 2 * d; a.ldq = a.ldk = a.ldv = 3 * d;
     a.ldo = d; a.lse = w.lse_s[l]; a.B = B; a.H = H; a.Sq = T; a.Sk = T;
     a.rel_table = e.P + e.o_dec_rel; a.rel_bucket = e.dec_bucket; a.rel_mode = 2; a.causal = 1;
     dp = e.drop(site_dec(l, 0));
     a.drop_thr = dp.thr; a.drop_inv_keep = dp.inv_keep; a.seed = dp.seed; a.site = dp.site;
-    a.dO = w.t_d768; a.dq = w.t_dqkv; a.dk = w.t_dqkv + d; a.dv = w.t_dqkv + 2 * d; a.lddq = a.lddk = a.lddv = 3 * d;
+    a.dO = w.t_d768; a.dq = w.t_dqkv[ri]; a.dk = w.t_dqkv[ri] + d; a.dv = w.t_dqkv[ri] + 2 * d; a.lddq = a.lddk = a.lddv = 3 * d;
     a.d_rel_table = e.G + e.o_dec_rel;
     VQ_TRY(attn_bwd(a, st));
-    VQ_TRY(gemm_dw(w.t_dqkv, 3 * d, w.dn1[l], d, e.G + P.qkv, 3 * d, d, Md, st));
-    VQ_TRY(gemm_dx(w.t_dqkv, 3 * d, e.W + P.qkv, 3 * d, d, w.t_d768, d, Md, EPI_BF16, st));
-    q.x = w.y[3 * l]; q.w = e.P + P.ln0; q.dw = e.G + P.ln0;
+    VQ_TRY(fork());
+    VQ_TRY(gemm_dw(w.t_dqkv[ri], 3 * d, w.dn1[l], d, e.G + P.qkv, 3 * d, d, Md, sd));
+    VQ_TRY(gemm_dx(w.t_dqkv[ri], 3 * d, e.W + P.qkv, 3 * d, d, w.t_d768, d, Md, EPI_BF16, st));
+    q.x = w.y[3 * l]; q.w = e.P + P.ln0; q.dw = e.G + P.ln0; q.gb_out = gdb_out;
     q.consumer = l > 0 ? e.drop(site_dec(l - 1, 5)) : Dropout();
     VQ_TRY(rmsnorm_bwd(q, st));
+    VQ_TRY(layer_end());
   }
   if (on(Ld + 1)) {
-  // decoder token embedding (tied `shared`)
-  VQ_TRY(embed_bwd(w.dec_ids, B, T, w.gd, T, 0, e.G + e.o_shared, e.drop(SITE_DEC_EMB), st));
-  // cross-attention K/V projection of all layers: dW and the gradient flowing into the decoder memory
-  VQ_TRY(gemm_dw(w.dkv_all, ldkv, w.mem, d, e.G + e.o_ckv, ldkv, d, M2, st));
-  VQ_TRY(gemm_dx(w.dkv_all, ldkv, e.W + e.o_ckv, ldkv, d, w.dmem, d, M2, EPI_BF16, st));
-  // ---- encoder: final norm (rows S, S+1 of each memory slab are the detached prototypes -> dropped by the row map)
-  RmsBwdArgs en{};
-  en.dn = w.dmem; en.ld_dn = d; en.in_rpb = S; en.out_rpb = S2; en.x = w.x[2 * Le]; en.w = e.P + e.o_enc_final;
-  en.g_in = nullptr; en.g_out = w.ge; en.gb_out = w.geb; en.dw = e.G + e.o_enc_final; en.M = M; en.eps = c.eps; en.scale = 1.f;
-  en.own = e.drop(SITE_ENC_FINAL); en.consumer = e.drop(site_enc(Le - 1, 3)); en.consumer_cols = d;
-  VQ_TRY(rmsnorm_bwd(en, st));
+    // decoder token embedding (tied `shared`)
+    VQ_TRY(embed_bwd(w.dec_ids, B, T, w.gd, T, 0, e.G + e.o_shared, e.drop(SITE_DEC_EMB), st));
+    // cross-attention K/V projection of all layers: dW and the gradient flowing into the decoder memory
+    VQ_TRY(fork());
+    VQ_TRY(gemm_dw(w.dkv_all, ldkv, w.mem, d, e.G + e.o_ckv, ldkv, d, M2, sd));
+    VQ_TRY(gemm_dx(w.dkv_all, ldkv, e.W + e.o_ckv, ldkv, d, w.dmem, d, M2, EPI_BF16, st));
+    // ---- encoder: final norm (rows S, S+1 of each memory slab are the detached prototypes -> dropped by the row map)
+    e.geb_i = 0;
+    RmsBwdArgs en{};
+    en.dn = w.dmem; en.ld_dn = d; en.in_rpb = S; en.out_rpb = S2; en.x = w.x[2 * Le]; en.w = e.P + e.o_enc_final;
+    en.g_in = nullptr; en.g_out = w.ge; en.gb_out = w.geb_ring[e.geb_i]; en.dw = e.G + e.o_enc_final; en.M = M; en.eps = c.eps; en.scale = 1.f;
+    en.own = e.drop(SITE_ENC_FINAL); en.consumer = e.drop(site_enc(Le - 1, 3)); en.consumer_cols = d;
+    VQ_TRY(rmsnorm_bwd(en, st));
   }
   for (int l = Le - 1; l >= 0; --l) {
     if (!on(Ld + 1 + Le - l)) continue;
     const EncLayer& P = e.enc[l];
-    VQ_TRY(gemm_dw(w.geb, d, w.h[l], f, e.G + P.wo, d, f, M, st));
-    VQ_TRY(gemm_dx(w.geb, d, e.W + P.wo, d, f, w.t_eh, f, M, EPI_RELUBWD_BF16, st, w.h[l], f, e.drop(site_enc(l, 2)).inv_keep));
-    VQ_TRY(gemm_dw(w.t_eh, f, w.n2[l], d, e.G + P.wi, f, d, M, st));
-    VQ_TRY(gemm_dx(w.t_eh, f, e.W + P.wi, f, d, w.t_e768, d, M, EPI_BF16, st));
+    VQ_TRY(layer_begin());
+    const int ri = l % RING;
+    bf16* geb_in = w.geb_ring[e.geb_i];
+    bf16* geb_1 = w.geb_ring[(e.geb_i + 1) % (2 * RING)];
+    bf16* geb_out = w.geb_ring[(e.geb_i + 2) % (2 * RING)];
+    e.geb_i = (e.geb_i + 2) % (2 * RING);
+    VQ_TRY(fork());
+    VQ_TRY(gemm_dw(geb_in, d, w.h[l], f, e.G + P.wo, d, f, M, sd));
+    VQ_TRY(gemm_dx(geb_in, d, e.W + P.wo, d, f, w.t_eh[ri], f, M, EPI_RELUBWD_BF16, st, w.h[l], f, e.drop(site_enc(l, 2)).inv_keep));
+    VQ_TRY(fork());
+    VQ_TRY(gemm_dw(w.t_eh[ri], f, w.n2[l], d, e.G + P.wi, f, d, M, sd));
+    VQ_TRY(gemm_dx(w.t_eh[ri], f, e.W + P.wi, f, d, w.t_e768, d, M, EPI_BF16, st));
     RmsBwdArgs q{};
-    q.dn = w.t_e768; q.ld_dn = d; q.x = w.x[2 * l + 1]; q.w = e.P + P.ln1; q.g_in = w.ge; q.g_out = w.ge; q.gb_out = w.geb;
+    q.dn = w.t_e768; q.ld_dn = d; q.x = w.x[2 * l + 1]; q.w = e.P + P.ln1; q.g_in = w.ge; q.g_out = w.ge; q.gb_out = geb_1;
     q.dw = e.G + P.ln1; q.M = M; q.eps = c.eps; q.scale = 1.f; q.consumer = e.drop(site_enc(l, 1)); q.consumer_cols = d;
     VQ_TRY(rmsnorm_bwd(q, st));
-    VQ_TRY(gemm_dw(w.geb, d, w.ao[l], d, e.G + P.o, d, d, M, st));
-    VQ_TRY(gemm_dx(w.geb, d, e.W + P.o, d, d, w.t_e768, d, M, EPI_BF16, st));
+    VQ_TRY(fork());
+    VQ_TRY(gemm_dw(geb_1, d, w.ao[l], d, e.G + P.o, d, d, M, sd));
+    VQ_TRY(gemm_dx(geb_1, d, e.W + P.o, d, d, w.t_e768, d, M, EPI_BF16, st));
     AttnArgs a{};
     a.q = w.qkv[l]; a.k = w.qkv[l] + d; a.v = w.qkv[l] + 2 * d; a.ldq = a.ldk = a.ldv = 3 * d;
     a.ldo = d; a.lse = w.lse_e[l]; a.B = B; a.H = H; a.Sq = S; a.Sk = S;
     a.rel_table = e.P + e.o_enc_rel; a.rel_bucket = e.enc_bucket; a.rel_mode = 1; a.Lt = L; a.keymask = w.enc_mask; a.causal = 0;
     const Dropout dp = e.drop(site_enc(l, 0));
     a.drop_thr = dp.thr; a.drop_inv_keep = dp.inv_keep; a.seed = dp.seed; a.site = dp.site;
-    a.dO = w.t_e768; a.dq = w.t_eqkv; a.dk = w.t_eqkv + d; a.dv = w.t_eqkv + 2 * d; a.lddq = a.lddk = a.lddv = 3 * d;
+    a.dO = w.t_e768; a.dq = w.t_eqkv[ri]; a.dk = w.t_eqkv[ri] + d; a.dv = w.t_eqkv[ri] + 2 * d; a.lddq = a.lddk = a.lddv = 3 * d;
     a.d_rel_table = e.G + e.o_enc_rel;
     VQ_TRY(attn_bwd(a, st));
-    VQ_TRY(gemm_dw(w.t_eqkv, 3 * d, w.n1[l], d, e.G + P.qkv, 3 * d, d, M, st));
-    VQ_TRY(gemm_dx(w.t_eqkv, 3 * d, e.W + P.qkv, 3 * d, d, w.t_e768, d, M, EPI_BF16, st));
-    q.x = w.x[2 * l]; q.w = e.P + P.ln0; q.dw = e.G + P.ln0;
+    VQ_TRY(fork());
+    VQ_TRY(gemm_dw(w.t_eqkv[ri], 3 * d, w.n1[l], d, e.G + P.qkv, 3 * d, d, M, sd));
+    VQ_TRY(gemm_dx(w.t_eqkv[ri], 3 * d, e.W + P.qkv, 3 * d, d, w.t_e768, d, M, EPI_BF16, st));
+    q.x = w.x[2 * l]; q.w = e.P + P.ln0; q.dw = e.G + P.ln0; q.gb_out = geb_out;
     q.consumer = l > 0 ? e.drop(site_enc(l - 1, 3)) : Dropout();
     if (l == 0) q.gb_out = nullptr;
     VQ_TRY(rmsnorm_bwd(q, st));
+    VQ_TRY(layer_end());
   }
-  if (!on(Ld + Le + 2)) return 0;
-  // ---- embeddings: text tokens (tied shared) and the VisualEmbedding
-  VQ_TRY(embed_bwd(b.input_ids, B, L, w.ge, S, 0, e.G + e.o_shared, e.drop(SITE_ENC_EMB), st));
-  VisArgs va{};
-  va.featpre = w.featpre; va.boxes = b.boxes; va.bf = e.P + e.o_bf; va.wf = e.P + e.o_wf; va.Wp = e.P + e.o_Wp;
-  va.bp = e.P + e.o_bp; va.wp = e.P + e.o_wp; va.img_emb = e.P + e.o_img; va.shared = e.P + e.o_shared;
-  va.V = V; va.B = B; va.N = N; va.S = S; va.L = L; va.eps = c.eps; va.drop = e.drop(SITE_ENC_EMB);
-  va.g = w.ge; va.dfeatpre = w.dfeatpre; va.dbf = e.G + e.o_bf; va.dwf = e.G + e.o_wf; va.dWp = e.G + e.o_Wp;
-  va.dbp = e.G + e.o_bp; va.dwp = e.G + e.o_wp; va.dimg = e.G + e.o_img; va.dshared = e.G + e.o_shared;
-  VQ_TRY(vis_embed_bwd(va, st));
-  VQ_TRY(gemm_dw(w.dfeatpre, d, w.feats_bf16, c.feat_dim, e.G + e.o_Wf, d, c.feat_dim, B * N, st));
+  if (on(Ld + Le + 2)) {
+    // ---- embeddings: text tokens (tied shared) and the VisualEmbedding
+    VQ_TRY(embed_bwd(b.input_ids, B, L, w.ge, S, 0, e.G + e.o_shared, e.drop(SITE_ENC_EMB), st));
+    VisArgs va{};
+    va.featpre = w.featpre; va.boxes = b.boxes; va.bf = e.P + e.o_bf; va.wf = e.P + e.o_wf; va.Wp = e.P + e.o_Wp;
+    va.bp = e.P + e.o_bp; va.wp = e.P + e.o_wp; va.img_emb = e.P + e.o_img; va.shared = e.P + e.o_shared;
+    va.V = V; va.B = B; va.N = N; va.S = S; va.L = L; va.eps = c.eps; va.drop = e.drop(SITE_ENC_EMB);
+    va.g = w.ge; va.dfeatpre = w.dfeatpre; va.dbf = e.G + e.o_bf; va.dwf = e.G + e.o_wf; va.dWp = e.G + e.o_Wp;
+    va.dbp = e.G + e.o_bp; va.dwp = e.G + e.o_wp; va.dimg = e.G + e.o_img; va.dshared = e.G + e.o_shared;
+    VQ_TRY(vis_embed_bwd(va, st));
+    VQ_TRY(gemm_dw(w.dfeatpre, d, w.feats_bf16, c.feat_dim, e.G + e.o_Wf, d, c.feat_dim, B * N, st));
+  }
+  // join: the caller's stream owns every gradient written by this call
+  VQ_CUDA(cudaEventRecord(e.ev_join, sd));
+  VQ_CUDA(cudaStreamWaitEvent(st, e.ev_join, 0));
   return 0;
 }
 
@@ -578,6 +652,16 @@ extern "C" int vqacl_engine_create(const vqacl_config* cfg, void** engine) {
 }
 extern "C" void vqacl_engine_destroy(void* engine) {
   if (!engine) return;
+  {
+    Engine& e = *reinterpret_cast<Engine*>(engine);
+    if (e.side) {
+      cudaStreamSynchronize(e.side);
+      cudaEventDestroy(e.ev_fork);
+      cudaEventDestroy(e.ev_join);
+      for (auto& ev : e.ev_layer) cudaEventDestroy(ev);
+      cudaStreamDestroy(e.side);
+    }
+  }
   g_saved.erase(reinterpret_cast<Engine*>(engine));
   delete reinterpret_cast<Engine*>(engine);
 }
@@ -612,8 +696,12 @@ extern "C" int vqacl_bind_arena(void* engine, float* params, float* grads, void*
   return 0;
 }
 extern "C" int vqacl_set_rel_buckets(void* engine, const int32_t* enc_b, const int32_t* dec_b) {
-  ENG(engine).enc_bucket = enc_b;
-  ENG(engine).dec_bucket = dec_b;
+  Engine& e = ENG(engine);
+  VQ_CHECK(enc_b && dec_b, "set_rel_buckets: null table");
+  memcpy(e.enc_bucket_h, enc_b, 127 * sizeof(int32_t));   // HOST pointers: the maps travel in kernel parameters
+  memcpy(e.dec_bucket_h, dec_b, 127 * sizeof(int32_t));
+  e.enc_bucket = e.enc_bucket_h;
+  e.dec_bucket = e.dec_bucket_h;
   return 0;
 }
 extern "C" int vqacl_refresh_bf16(void* engine, void* stream) {
@@ -749,8 +837,8 @@ extern "C" int vqacl_proto_update(const float* curQ, const float* curV, const fl
   return proto_update(u, ST(stream));
 }
 extern "C" int vqacl_proto_retrieve(const float* P, int C, const float* x, int B, void* out_bf16, int out_pitch_rows, int out_row,
-                                    int64_t* idx, float* out_f32, void* stream) {
-  return proto_retrieve(P, C, x, B, reinterpret_cast<bf16*>(out_bf16), out_pitch_rows, out_row, idx, out_f32, ST(stream));
+                                    int64_t* idx, float* out_f32, float* scratch, void* stream) {
+  return proto_retrieve(P, C, x, B, reinterpret_cast<bf16*>(out_bf16), out_pitch_rows, out_row, idx, out_f32, scratch, ST(stream));
 }
 extern "C" int vqacl_ce_fwd(const void* logits, int ld, int M, int V, const int64_t* labels, float* lse, float* loss, void* stream) {
   return ce_fwd(reinterpret_cast<const bf16*>(logits), ld, M, V, labels, lse, loss, ST(stream));

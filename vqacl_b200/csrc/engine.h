@@ -33,7 +33,7 @@ struct Workspace {
   bf16* mem;                      // [B,S+2,d] decoder memory
   float *enc_mask, *cross_mask;
   // SI path
-  float *meanQ, *meanV, *curQ, *curV, *cntQ, *cntV;
+  float *meanQ, *meanV, *curQ, *curV, *cntQ, *cntV, *pnorm;
   int64_t *idxQ, *idxV;
   // decoder (Md = B*T rows)
   int64_t* dec_ids;
@@ -46,10 +46,14 @@ struct Workspace {
   float *lse_ce, *loss_rows, *w_rows, *loss;
   // backward scratch
   float *gd, *ge;                 // fp32 residual-stream gradients (decoder / encoder)
-  bf16 *gdb, *geb;                // bf16 copies (masked for the consuming branch)
-  bf16 *t_d768, *t_dqkv, *t_dh, *t_dcq;       // decoder temporaries
-  float* t_d768_f32;                          // split-K target of the LM-head dX GEMM
-  bf16 *t_e768, *t_eqkv, *t_eh;               // encoder temporaries
+  // dY operands that the weight-gradient GEMMs read on the side stream live in small rings (3 layers deep) so that the
+  // main stream can run ahead without write-after-read hazards (see backward())
+  static constexpr int RING = 3;
+  bf16* gdb_ring[3 * RING]; bf16* geb_ring[2 * RING];     // bf16 residual-stream gradients (masked for the consuming branch)
+  bf16 *t_dqkv[RING], *t_dh[RING], *t_dcq[RING];          // decoder dY temporaries
+  bf16 *t_eqkv[RING], *t_eh[RING];                        // encoder dY temporaries
+  bf16 *t_d768, *t_e768;                                  // main-stream-only temporaries
+  float* t_d768_f32;                                      // split-K target of the LM-head dX GEMM
   bf16* dkv_all; bf16* dmem; bf16* dfeatpre;
   float* sumsq_partials; float* sumsq;
 };
@@ -63,6 +67,7 @@ struct Engine {
   size_t o_dec_final = 0, o_ckv = 0, o_enc_final = 0, o_Wf = 0, o_wf = 0, o_Wp = 0, o_wp = 0, o_img = 0, o_shared = 0;
   size_t o_bf = 0, o_bp = 0, o_enc_rel = 0, o_dec_rel = 0;
   float* P = nullptr; float* G = nullptr; bf16* W = nullptr;
+  int enc_bucket_h[128] = {0}, dec_bucket_h[128] = {0};   // host copies of the rel -> bucket maps (go into kernel params)
   const int* enc_bucket = nullptr; const int* dec_bucket = nullptr;
   // workspace
   uint8_t* ws_base = nullptr; int64_t ws_bytes = 0;
@@ -72,6 +77,10 @@ struct Engine {
   int ldv = 0;  // logits pitch
   // step state
   uint32_t seed = 0; bool training = false; bool fwd_valid = false;
+  // side stream for the weight-gradient GEMMs (nobody consumes dW before the optimizer, so they run beside the dX chain)
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_layer[4] = {nullptr, nullptr, nullptr, nullptr};
+  int gdb_i = 0, geb_i = 0;
   // decode workspace (separate carve, see decode.cu)
   Dropout drop(uint32_t site) const;
   int S() const { return L + N; }

@@ -117,7 +117,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& 
   }
   const int tiles = ((args.M + GEMM_BM - 1) / GEMM_BM) * ((args.N + BN - 1) / BN) * args.splits;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, args);
+  (void)vq_launch(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, ta, tb, args);
   VQ_LAUNCH_CHECK();
   return 0;
 }

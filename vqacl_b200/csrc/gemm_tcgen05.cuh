@@ -196,6 +196,7 @@ template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const GemmArgs p) {
+  vq_pdl_trigger();
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -239,6 +240,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  vq_pdl_wait();   // everything above overlapped the previous kernel's tail; global memory is touched only below
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------

@@ -20,6 +20,8 @@ VQ_DEVINL void lse_combine(float& m, float& s, float m2, float s2) {
 __global__ void __launch_bounds__(CE_THREADS)
 ce_fwd_kernel(const __nv_bfloat16* __restrict__ logits, int ld, int V, const int64_t* __restrict__ labels, float* __restrict__ lse,
               float* __restrict__ loss) {
+  vq_pdl_trigger();
+  vq_pdl_wait();
   __shared__ float s_m[CE_THREADS / 32], s_s[CE_THREADS / 32];
   const int r = blockIdx.x;
   const __nv_bfloat16* row = logits + (size_t)r * ld;
@@ -58,7 +60,7 @@ ce_fwd_kernel(const __nv_bfloat16* __restrict__ logits, int ld, int V, const int
 int ce_fwd(const __nv_bfloat16* logits, int ld, int M, int V, const int64_t* labels, float* lse, float* loss, cudaStream_t stream) {
   if (M <= 0) return 0;
   VQ_CHECK(ld % 8 == 0, "ce_fwd: logits pitch %d must be a multiple of 8", ld);
-  ce_fwd_kernel<<<M, CE_THREADS, 0, stream>>>(logits, ld, V, labels, lse, loss);
+  (void)vq_launch(ce_fwd_kernel, dim3(M), dim3(CE_THREADS), 0, stream, logits, ld, V, labels, lse, loss);
   VQ_LAUNCH_CHECK();
   return 0;
 }
@@ -66,6 +68,8 @@ int ce_fwd(const __nv_bfloat16* logits, int ld, int M, int V, const int64_t* lab
 __global__ void __launch_bounds__(CE_THREADS)
 ce_bwd_kernel(__nv_bfloat16* __restrict__ logits, int ld, int V, const int64_t* __restrict__ labels, const float* __restrict__ lse,
               const float* __restrict__ w) {
+  vq_pdl_trigger();
+  vq_pdl_wait();
   const int r = blockIdx.x;
   __nv_bfloat16* row = logits + (size_t)r * ld;
   const int64_t lab = labels[r];
@@ -92,7 +96,7 @@ ce_bwd_kernel(__nv_bfloat16* __restrict__ logits, int ld, int V, const int64_t* 
 int ce_bwd(__nv_bfloat16* logits, int ld, int M, int V, const int64_t* labels, const float* lse, const float* w, cudaStream_t stream) {
   if (M <= 0) return 0;
   VQ_CHECK(ld % 8 == 0, "ce_bwd: logits pitch %d must be a multiple of 8", ld);
-  ce_bwd_kernel<<<M, CE_THREADS, 0, stream>>>(logits, ld, V, labels, lse, w);
+  (void)vq_launch(ce_bwd_kernel, dim3(M), dim3(CE_THREADS), 0, stream, logits, ld, V, labels, lse, w);
   VQ_LAUNCH_CHECK();
   return 0;
 }
@@ -101,6 +105,8 @@ int ce_bwd(__nv_bfloat16* logits, int ld, int M, int V, const int64_t* labels, c
 __global__ void __launch_bounds__(256) loss_tail_kernel(const float* __restrict__ loss_rows, const int64_t* __restrict__ labels,
                                                         const float* __restrict__ scores, int B, int T, float* __restrict__ loss_out,
                                                         float* __restrict__ w_rows) {
+  vq_pdl_trigger();
+  vq_pdl_wait();
   __shared__ float s_part[256];
   float acc = 0.f;
   for (int b = threadIdx.x; b < B; b += 256) {
@@ -124,13 +130,15 @@ __global__ void __launch_bounds__(256) loss_tail_kernel(const float* __restrict_
 }
 int loss_tail(const float* loss_rows, const int64_t* labels, const float* scores, int B, int T, float* loss_out, float* w_rows,
               cudaStream_t stream) {
-  loss_tail_kernel<<<1, 256, 0, stream>>>(loss_rows, labels, scores, B, T, loss_out, w_rows);
+  (void)vq_launch(loss_tail_kernel, dim3(1), dim3(256), 0, stream, loss_rows, labels, scores, B, T, loss_out, w_rows);
   VQ_LAUNCH_CHECK();
   return 0;
 }
 
 __global__ void __launch_bounds__(CE_THREADS)
 argmax_rows_kernel(const __nv_bfloat16* __restrict__ logits, int ld, int V, int64_t* __restrict__ out) {
+  vq_pdl_trigger();
+  vq_pdl_wait();
   __shared__ float s_v[CE_THREADS / 32];
   __shared__ int s_i[CE_THREADS / 32];
   const int r = blockIdx.x;
@@ -157,7 +165,7 @@ argmax_rows_kernel(const __nv_bfloat16* __restrict__ logits, int ld, int V, int6
 }
 int argmax_rows(const __nv_bfloat16* logits, int ld, int M, int V, int64_t* out, cudaStream_t stream) {
   if (M <= 0) return 0;
-  argmax_rows_kernel<<<M, CE_THREADS, 0, stream>>>(logits, ld, V, out);
+  (void)vq_launch(argmax_rows_kernel, dim3(M), dim3(CE_THREADS), 0, stream, logits, ld, V, out);
   VQ_LAUNCH_CHECK();
   return 0;
 }

@@ -25,7 +25,8 @@ struct AttnArgs {
   float* lse;               // [B,H,Sq] fwd out / bwd in
   int B, H, Sq, Sk;
   const float* rel_table;   // [num_buckets, H] fp32 (relative_attention_bias.weight) or null
-  const int* rel_bucket;    // [127] bucket of (key - query + 63), host-precomputed with the HF formula
+  const int* rel_bucket;    // HOST pointer, int32[127]: bucket of (key - query + 63), precomputed with the HF formula;
+                            // copied into the kernel parameters (constant bank) so the bias table needs one global load per entry
   int rel_mode;             // 0 none, 1 bias on the text x text corner only (encoder), 2 bias everywhere (decoder self)
   int Lt;                   // text length for rel_mode 1
   const float* keymask;     // [B,Sk] additive key mask or null
@@ -131,8 +132,9 @@ struct ProtoUpdateArgs {
 };
 int proto_update(const ProtoUpdateArgs& a, cudaStream_t stream);
 // cosine_similarity_multi + feature mix: idx[b] = first argmax_c cos(tanh P_c, tanh x_b); out row = raw P[idx[b]] (bf16)
+// scratch: [C,768] fp32 (normalised tanh of the bank)
 int proto_retrieve(const float* P, int C, const float* x, int B, __nv_bfloat16* out, int out_pitch_rows, int out_row,
-                   int64_t* idx, float* out_f32, cudaStream_t stream);
+                   int64_t* idx, float* out_f32, float* scratch, cudaStream_t stream);
 
 // ---------------------------------------------------------------- lmhead_ce.cu
 // per-row log-sum-exp and CE loss over bf16 logits [M, V] (pitch ld); label -100 -> loss 0

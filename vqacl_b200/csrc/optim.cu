@@ -12,6 +12,8 @@ constexpr int SQ_THREADS = 256;
 constexpr int SQ_MAX_BLOCKS = 1184;  // 148 * 8
 
 __global__ void __launch_bounds__(SQ_THREADS) sumsq_partial_kernel(const float* __restrict__ g, size_t n4, size_t n, float* __restrict__ partials) {
+  vq_pdl_trigger();
+  vq_pdl_wait();
   __shared__ float s_w[SQ_THREADS / 32];
   float acc = 0.f;
   for (size_t i = blockIdx.x * (size_t)SQ_THREADS + threadIdx.x; i < n4; i += (size_t)gridDim.x * SQ_THREADS) {
@@ -30,6 +32,8 @@ __global__ void __launch_bounds__(SQ_THREADS) sumsq_partial_kernel(const float* 
   }
 }
 __global__ void __launch_bounds__(256) sumsq_final_kernel(const float* __restrict__ partials, int n, float* __restrict__ out) {
+  vq_pdl_trigger();
+  vq_pdl_wait();
   __shared__ double s_p[256];
   double acc = 0.0;
   for (int i = threadIdx.x; i < n; i += 256) acc += (double)partials[i];
@@ -46,14 +50,16 @@ int grad_sumsq(const float* g, size_t n, float* partials, float* out, cudaStream
   const size_t n4 = n / 4;
   size_t want = (n4 + SQ_THREADS - 1) / SQ_THREADS;
   const int blocks = (int)(want < 1 ? 1 : (want > SQ_MAX_BLOCKS ? SQ_MAX_BLOCKS : want));
-  sumsq_partial_kernel<<<blocks, SQ_THREADS, 0, stream>>>(g, n4, n, partials);
+  (void)vq_launch(sumsq_partial_kernel, dim3(blocks), dim3(SQ_THREADS), 0, stream, g, n4, n, partials);
   VQ_LAUNCH_CHECK();
-  sumsq_final_kernel<<<1, 256, 0, stream>>>(partials, blocks, out);
+  (void)vq_launch(sumsq_final_kernel, dim3(1), dim3(256), 0, stream, partials, blocks, out);
   VQ_LAUNCH_CHECK();
   return 0;
 }
 
 __global__ void __launch_bounds__(256) adamw_kernel(const AdamArgs a, float step_size, float clip_max) {
+  vq_pdl_trigger();
+  vq_pdl_wait();
   float coef = 1.f;
   if (a.sumsq && clip_max > 0.f) {
     const float c = clip_max / (sqrtf(*a.sumsq) + 1e-6f);  // torch clip_grad_norm_: clip_coef = max_norm / (total_norm + 1e-6)
@@ -94,7 +100,7 @@ int adamw_hf(const AdamArgs& a, cudaStream_t stream) {
   size_t want = (n4 + 255) / 256;
   const size_t cap = (size_t)num_sms() * 16;
   const int blocks = (int)(want > cap ? cap : want);
-  adamw_kernel<<<blocks, 256, 0, stream>>>(a, step_size, a.max_norm);
+  (void)vq_launch(adamw_kernel, dim3(blocks), dim3(256), 0, stream, a, step_size, a.max_norm);
   VQ_LAUNCH_CHECK();
   return 0;
 }

@@ -12,6 +12,8 @@ namespace vq {
 // one CTA per batch element, 192 threads x float4 = 768 columns
 __global__ void __launch_bounds__(192) proto_means_kernel(const float* __restrict__ h, int S, int split, float* __restrict__ mq,
                                                           float* __restrict__ mv) {
+  vq_pdl_trigger();
+  vq_pdl_wait();
   const int b = blockIdx.x, c = threadIdx.x * 4;
   const float* base = h + (size_t)b * S * DM + c;
   float4 aq = make_float4(0, 0, 0, 0), av = make_float4(0, 0, 0, 0);
@@ -30,44 +32,68 @@ __global__ void __launch_bounds__(192) proto_means_kernel(const float* __restric
 }
 int proto_means(const float* h, int B, int S, int split, float* meanQ, float* meanV, cudaStream_t stream) {
   if (B <= 0) return 0;
-  proto_means_kernel<<<B, 192, 0, stream>>>(h, S, split, meanQ, meanV);
+  (void)vq_launch(proto_means_kernel, dim3(B), dim3(192), 0, stream, h, S, split, meanQ, meanV);
   VQ_LAUNCH_CHECK();
   return 0;
 }
 
-// one CTA per class: proto[c] = sum_b labels[b,c] * mean[b]  (/ divisor when DIVIDE)
+// calculate_current_prototype: proto[c] = sum_b labels[b,c] * mean[b]  (/ divisor when DIVIDE); cnt[c] = sum_b labels[b,c].
+// grid (C, 768/128): a CTA owns 128 columns of one class; its 4 warp-groups each reduce a quarter of the batch with
+// unconditional FMAs (labels are one-hot weights, so the loads do not depend on them and pipeline 8 deep), then the four
+// partials are combined in a fixed order (deterministic; no atomics).
+constexpr int PS_COLS = 128, PS_GROUPS = 4;
 template <bool DIVIDE>
-__global__ void __launch_bounds__(192) proto_scatter_kernel(const float* __restrict__ mean, const float* __restrict__ labels, int B,
-                                                            int C, float* __restrict__ proto, float* __restrict__ cnt) {
-  const int c = blockIdx.x, col = threadIdx.x * 4;
-  float4 acc = make_float4(0, 0, 0, 0);
-  float n = 0.f;
-  for (int b = 0; b < B; ++b) {
-    const float l = labels[(size_t)b * C + c];
-    n += l;
-    if (l != 0.f) {
-      const float4 t = *reinterpret_cast<const float4*>(mean + (size_t)b * DM + col);
-      acc.x += l * t.x; acc.y += l * t.y; acc.z += l * t.z; acc.w += l * t.w;
-    }
+__global__ void __launch_bounds__(PS_COLS * PS_GROUPS) proto_scatter_kernel(const float* __restrict__ mean, const float* __restrict__ labels, int B,
+                                                                            int C, float* __restrict__ proto, float* __restrict__ cnt) {
+  vq_pdl_trigger();
+  vq_pdl_wait();
+  extern __shared__ float ps_smem[];          // wl[B] | part[PS_GROUPS][PS_COLS]
+  float* wl = ps_smem;
+  float* part = ps_smem + ((B + 3) & ~3);
+  const int c = blockIdx.x, col = blockIdx.y * PS_COLS + (threadIdx.x & (PS_COLS - 1)), grp = threadIdx.x / PS_COLS;
+  for (int b = threadIdx.x; b < B; b += PS_COLS * PS_GROUPS) wl[b] = labels[(size_t)b * C + c];
+  __syncthreads();
+  const int per = (B + PS_GROUPS - 1) / PS_GROUPS;
+  const int b0 = grp * per, b1 = min(B, b0 + per);
+  float acc = 0.f;
+  int b = b0;
+  for (; b + 8 <= b1; b += 8) {
+    float m[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) m[u] = mean[(size_t)(b + u) * DM + col];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc += wl[b + u] * m[u];
   }
-  if (DIVIDE) {
-    const float d = n <= 0.f ? 1.f : n;  // torch.where(div <= 0, ones, div)
-    acc.x /= d; acc.y /= d; acc.z /= d; acc.w /= d;
+  for (; b < b1; ++b) acc += wl[b] * mean[(size_t)b * DM + col];
+  part[grp * PS_COLS + (threadIdx.x & (PS_COLS - 1))] = acc;
+  __syncthreads();
+  if (grp == 0) {
+    float n = 0.f;
+    for (int i = 0; i < B; ++i) n += wl[i];            // exact: one-hot labels, integer-valued sums
+    float v = part[threadIdx.x] + part[PS_COLS + threadIdx.x] + part[2 * PS_COLS + threadIdx.x] + part[3 * PS_COLS + threadIdx.x];
+    if (DIVIDE) v /= (n <= 0.f ? 1.f : n);             // torch.where(div <= 0, ones, div)
+    proto[(size_t)c * DM + col] = v;
+    if (blockIdx.y == 0 && threadIdx.x == 0) cnt[c] = n;
   }
-  *reinterpret_cast<float4*>(proto + (size_t)c * DM + col) = acc;
-  if (threadIdx.x == 0) cnt[c] = n;
+}
+template <bool DIVIDE>
+static int proto_scatter_launch(const float* mean, const float* labels, int B, int C, float* proto, float* cnt, cudaStream_t stream) {
+  if (C <= 0) return 0;
+  const size_t smem = (((size_t)B + 3) & ~(size_t)3) * 4 + PS_GROUPS * PS_COLS * 4;
+  VQ_CHECK(smem <= 48 * 1024, "proto_scatter: batch %d too large for the label staging buffer", B);
+  (void)vq_launch(proto_scatter_kernel<DIVIDE>, dim3(C, DM / PS_COLS), dim3(PS_COLS * PS_GROUPS), smem, stream, mean, labels, B, C, proto, cnt);
+  VQ_LAUNCH_CHECK();
+  return 0;
 }
 int proto_scatter_mean(const float* mean, const float* labels, int B, int C, float* proto, float* cnt, cudaStream_t stream) {
-  proto_scatter_kernel<true><<<C, 192, 0, stream>>>(mean, labels, B, C, proto, cnt);
-  VQ_LAUNCH_CHECK();
-  return 0;
+  return proto_scatter_launch<true>(mean, labels, B, C, proto, cnt, stream);
 }
 int proto_scatter_sum(const float* mean, const float* labels, int B, int C, float* proto, float* cnt, cudaStream_t stream) {
-  proto_scatter_kernel<false><<<C, 192, 0, stream>>>(mean, labels, B, C, proto, cnt);
-  VQ_LAUNCH_CHECK();
-  return 0;
+  return proto_scatter_launch<false>(mean, labels, B, C, proto, cnt, stream);
 }
 __global__ void __launch_bounds__(192) proto_div_kernel(float* __restrict__ proto, const float* __restrict__ cnt) {
+  vq_pdl_trigger();
+  vq_pdl_wait();
   const int c = blockIdx.x, col = threadIdx.x * 4;
   const float n = cnt[c];
   const float d = n <= 0.f ? 1.f : n;
@@ -76,7 +102,7 @@ __global__ void __launch_bounds__(192) proto_div_kernel(float* __restrict__ prot
   *reinterpret_cast<float4*>(proto + (size_t)c * DM + col) = t;
 }
 int proto_div(float* proto_sums, const float* cnt, int C, cudaStream_t stream) {
-  proto_div_kernel<<<C, 192, 0, stream>>>(proto_sums, cnt);
+  (void)vq_launch(proto_div_kernel, dim3(C), dim3(192), 0, stream, proto_sums, cnt);
   VQ_LAUNCH_CHECK();
   return 0;
 }
@@ -91,6 +117,8 @@ int proto_div(float* proto_sums, const float* cnt, int C, cudaStream_t stream) {
 //         V = beta*V + (1-beta)*curV;  nums += counts
 // blocks [0,CQ) handle Q rows, [CQ, CQ+CV) handle V rows.
 __global__ void __launch_bounds__(192) proto_update_kernel(const ProtoUpdateArgs a) {
+  vq_pdl_trigger();
+  vq_pdl_wait();
   const int col = threadIdx.x * 4;
   if ((int)blockIdx.x < a.CQ) {
     const int c = blockIdx.x;
@@ -122,7 +150,7 @@ __global__ void __launch_bounds__(192) proto_update_kernel(const ProtoUpdateArgs
 }
 int proto_update(const ProtoUpdateArgs& a, cudaStream_t stream) {
   VQ_CHECK(a.task_id >= 0 && a.task_id < a.CQ, "proto_update: task id %d outside [0,%d)", a.task_id, a.CQ);
-  proto_update_kernel<<<a.CQ + a.CV, 192, 0, stream>>>(a);
+  (void)vq_launch(proto_update_kernel, dim3(a.CQ + a.CV), dim3(192), 0, stream, a);
   VQ_LAUNCH_CHECK();
   return 0;
 }
@@ -130,12 +158,40 @@ int proto_update(const ProtoUpdateArgs& a, cudaStream_t stream) {
 // cosine_similarity_multi (:434-462): a_n = normalize(tanh(P)), b_n = normalize(tanh(x)) (F.normalize eps 1e-12),
 // idx = first argmax_c <a_n[c], b_n>; output = RAW P[idx] written as bf16 into row `out_row` of each batch element's
 // [out_pitch_rows, 768] decoder-memory slab (the torch.cat of :615), and optionally as fp32.
-// One CTA per batch element; warp w scans classes w, w+8, ...
+// Step 1 (proto_normalize_kernel, one CTA per class): Pn[c] = tanh(P[c]) / max(||tanh(P[c])||, 1e-12), once per call
+// instead of once per batch element. Step 2 (proto_retrieve_kernel, one CTA per batch element): warp w scans classes
+// w, w+8, ... with warp-shuffle dot products.
 constexpr int PR_WARPS = 8;
+__global__ void __launch_bounds__(PR_WARPS * 32) proto_normalize_kernel(const float* __restrict__ P, float* __restrict__ Pn) {
+  vq_pdl_trigger();
+  vq_pdl_wait();
+  __shared__ float s_red[PR_WARPS];
+  const int c = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float t[DM / (PR_WARPS * 32)];
+  float ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < DM / (PR_WARPS * 32); ++j) {
+    t[j] = tanhf(P[(size_t)c * DM + threadIdx.x + j * PR_WARPS * 32]);
+    ss += t[j] * t[j];
+  }
+  ss = warp_sum(ss);
+  if (lane == 0) s_red[warp] = ss;
+  __syncthreads();
+  float n = 0.f;
+#pragma unroll
+  for (int w = 0; w < PR_WARPS; ++w) n += s_red[w];
+  n = fmaxf(sqrtf(n), 1e-12f);
+#pragma unroll
+  for (int j = 0; j < DM / (PR_WARPS * 32); ++j) Pn[(size_t)c * DM + threadIdx.x + j * PR_WARPS * 32] = t[j] / n;
+}
+
 __global__ void __launch_bounds__(PR_WARPS * 32)
-proto_retrieve_kernel(const float* __restrict__ P, int C, const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
-                      int out_pitch_rows, int out_row, int64_t* __restrict__ idx_out, float* __restrict__ out_f32) {
-  __shared__ float s_tx[DM];
+proto_retrieve_kernel(const float* __restrict__ P, const float* __restrict__ Pn, int C, const float* __restrict__ x,
+                      __nv_bfloat16* __restrict__ out, int out_pitch_rows, int out_row, int64_t* __restrict__ idx_out,
+                      float* __restrict__ out_f32) {
+  vq_pdl_trigger();
+  vq_pdl_wait();
+  __shared__ __align__(16) float s_tx[DM];
   __shared__ float s_best[PR_WARPS];
   __shared__ int s_besti[PR_WARPS];
   __shared__ float s_red[PR_WARPS];
@@ -155,19 +211,21 @@ proto_retrieve_kernel(const float* __restrict__ P, int C, const float* __restric
 #pragma unroll
   for (int w = 0; w < PR_WARPS; ++w) xn += s_red[w];
   xn = fmaxf(sqrtf(xn), 1e-12f);
+  for (int c = threadIdx.x; c < DM; c += PR_WARPS * 32) s_tx[c] /= xn;   // each thread rescales the elements it wrote
+  __syncthreads();
   float best = -INFINITY;
   int besti = 0x7fffffff;
   for (int c = warp; c < C; c += PR_WARPS) {
-    float dot = 0.f, pn = 0.f;
-    for (int k = lane; k < DM; k += 32) {
-      const float t = tanhf(P[(size_t)c * DM + k]);
-      pn += t * t;
-      dot += (t) * (s_tx[k] / xn);
+    float dot = 0.f;
+#pragma unroll
+    for (int j = 0; j < DM / 128; ++j) {
+      const int k = (lane + 32 * j) * 4;
+      const float4 a = *reinterpret_cast<const float4*>(Pn + (size_t)c * DM + k);
+      const float4 t = *reinterpret_cast<const float4*>(s_tx + k);
+      dot += a.x * t.x + a.y * t.y + a.z * t.z + a.w * t.w;
     }
     dot = warp_sum(dot);
-    pn = warp_sum(pn);
-    const float sim = dot / fmaxf(sqrtf(pn), 1e-12f);
-    if (sim > best) { best = sim; besti = c; }  // classes visited in increasing order per warp -> first max
+    if (dot > best) { best = dot; besti = c; }  // classes visited in increasing order per warp -> first max
   }
   if (lane == 0) { s_best[warp] = best; s_besti[warp] = besti; }
   __syncthreads();
@@ -176,6 +234,7 @@ proto_retrieve_kernel(const float* __restrict__ P, int C, const float* __restric
     int bi = s_besti[0];
     for (int w = 1; w < PR_WARPS; ++w)
       if (s_best[w] > bb || (s_best[w] == bb && s_besti[w] < bi)) { bb = s_best[w]; bi = s_besti[w]; }
+    if (bi < 0 || bi >= C) bi = 0;   // all similarities NaN: keep the access in range
     s_idx = bi;
     idx_out[b] = bi;
   }
@@ -188,10 +247,14 @@ proto_retrieve_kernel(const float* __restrict__ P, int C, const float* __restric
   }
 }
 int proto_retrieve(const float* P, int C, const float* x, int B, __nv_bfloat16* out, int out_pitch_rows, int out_row,
-                   int64_t* idx, float* out_f32, cudaStream_t stream) {
+                   int64_t* idx, float* out_f32, float* scratch, cudaStream_t stream) {
   if (B <= 0) return 0;
   VQ_CHECK(C >= 1, "proto_retrieve: empty bank");
-  proto_retrieve_kernel<<<B, PR_WARPS * 32, 0, stream>>>(P, C, x, out, out_pitch_rows, out_row, idx, out_f32);
+  VQ_CHECK(scratch, "proto_retrieve: scratch [C,768] fp32 required");
+  (void)vq_launch(proto_normalize_kernel, dim3(C), dim3(PR_WARPS * 32), 0, stream, P, scratch);
+  VQ_LAUNCH_CHECK();
+  (void)vq_launch(proto_retrieve_kernel, dim3(B), dim3(PR_WARPS * 32), 0, stream, P, (const float*)scratch, C, x, out, out_pitch_rows, out_row, idx,
+                  out_f32);
   VQ_LAUNCH_CHECK();
   return 0;
 }

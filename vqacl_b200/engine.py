@@ -145,8 +145,8 @@ class Engine:
             check(L.vqacl_bind_arena(h, ptr(self.P), ptr(self.G), ptr(self.W)))
             nb = cfg.relative_attention_num_buckets
             md = getattr(cfg, "relative_attention_max_distance", 128)
-            self.enc_bucket = rel_bucket_table(True, nb, md).to(self.device)
-            self.dec_bucket = rel_bucket_table(False, nb, md).to(self.device)
+            self.enc_bucket = rel_bucket_table(True, nb, md).contiguous()      # host tables (kernel parameters)
+            self.dec_bucket = rel_bucket_table(False, nb, md).contiguous()
             check(L.vqacl_set_rel_buckets(h, ptr(self.enc_bucket), ptr(self.dec_bucket)))
         self.ws = None
         self.ws_shape = None
