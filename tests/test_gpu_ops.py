@@ -235,7 +235,7 @@ def test_gemm_epilogues_ragged(epi):
     elif epi == 4:
         R = torch.randn(M, N, device=DEV).relu().bfloat16()
         ref = ref * (R.float() > 0)
-    for bn in (64, 128, 256):
+    for bn in (64, 128, 256, 512):        # 512 = 256 x 256 tiles on CTA pairs (cta_group::2)
         C.fill_(0.5)
         cabi.gemm(A, 0, Bm, 0, C, R, M, N, K, epi, bn=bn)
         torch.cuda.synchronize()

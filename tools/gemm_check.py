@@ -57,7 +57,7 @@ def bench(M, N, K, a_mn, b_mn, epi, bn, splits=1, iters=20):
     A = Al.t().contiguous() if a_mn else Al
     B = Bl.t().contiguous() if b_mn else Bl
     C = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16 if epi in (0, 1, 4) else torch.float32)
-    R = torch.zeros(M, N, device="cuda", dtype=torch.float32) if epi == EPI_RESID else None
+    R = torch.zeros(M, N, device="cuda", dtype=torch.float32) if epi == EPI_RESID else (torch.ones(M, N, device="cuda", dtype=torch.bfloat16) if epi == EPI_RELUBWD else None)
     for _ in range(3):
         gemm(A, a_mn, B, b_mn, C, R, M, N, K, epi, 1.0, splits, bn)
     e0 = torch.cuda.Event(enable_timing=True)
@@ -100,6 +100,18 @@ def main():
     ok &= run_case(1600, 32200, 768, False, False, EPI_BF16, 0)
     ok &= run_case(1600, 768, 32200, False, True, EPI_BF16, 0)
     ok &= run_case(32200, 768, 1600, True, True, EPI_ATOMIC, 0)
+    # CTA-pair kernel (bn = 512: 256 x 256 tiles on clusters of two CTAs)
+    if "--no-pair" not in sys.argv:
+        ok &= run_case(256, 256, 64, False, False, EPI_F32, 512)
+        ok &= run_case(256, 256, 256, False, False, EPI_F32, 512)
+        ok &= run_case(256, 256, 256, False, True, EPI_F32, 512)
+        ok &= run_case(256, 256, 256, True, True, EPI_F32, 512)
+        for (a_mn, b_mn) in ((False, False), (False, True), (True, True)):
+            ok &= run_case(1000, 776, 520, a_mn, b_mn, EPI_F32, 512)
+            ok &= run_case(4480, 2304, 768, a_mn, b_mn, EPI_BF16, 512)
+        for epi in (EPI_RELU, EPI_RESID, EPI_ATOMIC, EPI_RELUBWD):
+            ok &= run_case(17920 // 4, 768, 768, False, False, epi, 512)
+        ok &= run_case(3072, 768, 4480, True, True, EPI_ATOMIC, 512, splits=5)
     print("ALL OK" if ok else "FAILURES", flush=True)
     if "--bench" in sys.argv:
         bench(17920, 2304, 768, False, False, EPI_BF16, 0)
@@ -110,6 +122,15 @@ def main():
         bench(3072, 768, 17920, True, True, EPI_ATOMIC, 0, splits=4)
         bench(768, 768, 17920, True, True, EPI_ATOMIC, 0, splits=8)
         bench(8192, 8192, 8192, False, False, EPI_BF16, 256)
+        if "--no-pair" not in sys.argv:
+            bench(17920, 2304, 768, False, False, EPI_BF16, 512)
+            bench(17920, 768, 768, False, False, EPI_RESID, 512)
+            bench(17920, 3072, 768, False, False, EPI_RELU, 512)
+            bench(17920, 768, 3072, False, False, EPI_RESID, 512)
+            bench(17920, 768, 3072, False, True, EPI_BF16, 512)
+            bench(17920, 3072, 768, False, True, EPI_RELUBWD, 512)
+            bench(3072, 768, 17920, True, True, EPI_ATOMIC, 512, splits=4)
+            bench(8192, 8192, 8192, False, False, EPI_BF16, 512)
     return 0 if ok else 1
 
 

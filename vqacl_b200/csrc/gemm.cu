@@ -5,6 +5,7 @@
 #include <cudaTypedefs.h>
 #include <mutex>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include <unordered_map>
 
@@ -95,6 +96,7 @@ void gemm_tmap_cache_clear() {
   g_tm_cache.clear();
 }
 
+static int g_pair_enabled = 1;   // VQACL_GEMM_PAIR=0 disables the CTA-pair kernel (A/B measurements)
 static int g_num_sms = 0;
 int num_sms() {
   if (g_num_sms == 0) {
@@ -102,6 +104,8 @@ int num_sms() {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (g_num_sms <= 0) g_num_sms = 148;
+    const char* ev = getenv("VQACL_GEMM_PAIR");
+    if (ev && ev[0] == '0') g_pair_enabled = 0;
   }
   return g_num_sms;
 }
@@ -120,6 +124,55 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& 
   (void)vq_launch(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, ta, tb, args);
   VQ_LAUNCH_CHECK();
   return 0;
+}
+
+// CTA-pair kernel: clusters of 2 CTAs, 256 x 256 tiles (see gemm_tcgen05.cuh)
+template <bool A_MN, bool B_MN>
+static int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, cudaStream_t stream) {
+  auto kern = gemm_bf16_tcgen05_2cta_kernel<A_MN, B_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int work = ((args.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM)) * ((args.N + GEMM2_BN - 1) / GEMM2_BN) * args.splits;
+  const int max_pairs = num_sms() / 2;
+  const int pairs = work < max_pairs ? work : max_pairs;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Gemm2Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  VQ_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, args));
+  ++g_vq_launches;
+  return 0;
+}
+
+static int dispatch_pair(const GemmOperand& A, const GemmOperand& B, const GemmArgs& args, cudaStream_t stream) {
+  CUtensorMap ta, tb;
+  if (!A.mn_major) {
+    if (make_tmap(&ta, A.ptr, args.K, args.M, A.ld, GEMM_BK, GEMM_BM)) return 1;
+  } else {
+    if (make_tmap(&ta, A.ptr, args.M, args.K, A.ld, 64, GEMM_BK)) return 1;
+  }
+  if (!B.mn_major) {
+    if (make_tmap(&tb, B.ptr, args.K, args.N, B.ld, GEMM_BK, GEMM2_BN / 2)) return 1;   // each CTA loads half of the 256-wide B tile
+  } else {
+    if (make_tmap(&tb, B.ptr, args.N, args.K, B.ld, 64, GEMM_BK)) return 1;
+  }
+  if (!A.mn_major && !B.mn_major) return launch_pair<false, false>(ta, tb, args, stream);
+  if (!A.mn_major && B.mn_major) return launch_pair<false, true>(ta, tb, args, stream);
+  if (A.mn_major && B.mn_major) return launch_pair<true, true>(ta, tb, args, stream);
+  VQ_CHECK(false, "gemm: A MN-major with B K-major is not instantiated");
 }
 
 template <int BN>
@@ -156,13 +209,15 @@ int gemm_bf16(const GemmOperand& A, const GemmOperand& B, GemmArgs args, int for
   }
   int bn = force_bn;
   if (bn == 0) {
-    // pick the tile width that minimises waves x per-tile MMA time. Cycles per 64-deep k-block of a 128 x BN tile:
-    // 4 MMAs of max(128*BN/256, smem operand read time) cycles (the narrow tiles are bound by re-reading A from smem).
+    // pick the tile shape that minimises waves x per-tile MMA time. Cycles per 64-deep k-block:
+    //   128 x BN single-CTA tile: 4 MMAs, each bound by shared-memory traffic (TMA write + operand read) rather than the
+    //   tensor pipe — 128 x 256 runs at 2/3 of the MMA rate (measured), the narrow tiles re-read A even more often;
+    //   256 x 256 CTA-pair tile (bn = 512): 4 MMAs at the full rate on two SMs.
     const int tiles_m = (args.M + GEMM_BM - 1) / GEMM_BM;
     const int sms = num_sms();
     const int kb_split = (kblocks + args.splits - 1) / args.splits;
     const int cand[3] = {256, 128, 64};
-    const int cyc[3] = {512, 272, 176};
+    const int cyc[3] = {768, 400, 240};
     long best = -1;
     for (int i = 0; i < 3; ++i) {
       if (cand[i] > 64 && args.N < cand[i] / 2 + 8) continue;   // mostly-empty tile
@@ -171,7 +226,14 @@ int gemm_bf16(const GemmOperand& A, const GemmOperand& B, GemmArgs args, int for
       const long cost = waves * ((long)kb_split * cyc[i] + 600 + cand[i] * 4);   // + pipeline fill and epilogue drain
       if (best < 0 || cost < best) { best = cost; bn = cand[i]; }
     }
+    if (args.N >= 192 && args.M >= 192 && g_pair_enabled) {
+      const long work = (long)((args.M + 255) / 256) * ((args.N + 255) / 256) * args.splits;
+      const long waves = (work + sms / 2 - 1) / (sms / 2);
+      const long cost = waves * ((long)kb_split * 512 + 900 + 1024);
+      if (cost < best) { best = cost; bn = 512; }
+    }
   }
+  if (bn == 512) return dispatch_pair(A, B, args, stream);
   switch (bn) {
     case 256: return dispatch_major<256>(A, B, args, stream);
     case 128: return dispatch_major<128>(A, B, args, stream);

@@ -76,30 +76,47 @@ VQ_DEVINL void gemm_epilogue_tile(const GemmArgs& p, uint32_t t_base, uint32_t s
   const int M = p.M, N = p.N, ldc = p.ldc, ldr = p.ldr;
   const float alpha = p.alpha;
   bool waited = false;
+  // extra-operand registers are double-buffered in time: the operand of chunk c+2 (this warp's next chunk) is requested right
+  // after the accumulator of chunk c has been read, so its global-memory latency overlaps the math and stores of chunk c
+  float4 rres[8];
+  uint4 rh[4];
+  auto prefetch = [&](int cc) {
+    const int pcol0 = n_base + cc * 32;
+    if (EPI == EPI_RESID_F32) {
+      const int gcol = pcol0 + (lane & 7) * 4;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int grow = row_base + it * 4 + (lane >> 3);
+        rres[it] = (cc < BN / 32 && grow < M && gcol < N)
+                       ? *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.R) + (size_t)grow * ldr + gcol)
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    if (EPI == EPI_RELUBWD_BF16) {
+      const int gcol = pcol0 + (lane & 3) * 8;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int grow = row_base + it * 8 + (lane >> 2);
+        rh[it] = (cc < BN / 32 && grow < M && gcol < N)
+                     ? *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.R) + (size_t)grow * ldr + gcol)
+                     : make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+  };
+  prefetch(half);
 #pragma unroll 1
   for (int c = half; c < BN / 32; c += 2) {
     const int col0 = n_base + c * 32;
     if (col0 >= N) break;
-    // ---- coalesced prefetch of the extra operand ----
-    float4 rres[8];
-    uint4 rh[4];
+    float4 cres[8];
+    uint4 ch[4];
     if (EPI == EPI_RESID_F32) {
-      const int gcol = col0 + (lane & 7) * 4;
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int grow = row_base + it * 4 + (lane >> 3);
-        rres[it] = (grow < M && gcol < N) ? *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.R) + (size_t)grow * ldr + gcol)
-                                          : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+      for (int it = 0; it < 8; ++it) cres[it] = rres[it];
     }
     if (EPI == EPI_RELUBWD_BF16) {
-      const int gcol = col0 + (lane & 3) * 8;
 #pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        const int grow = row_base + it * 8 + (lane >> 2);
-        rh[it] = (grow < M && gcol < N) ? *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.R) + (size_t)grow * ldr + gcol)
-                                        : make_uint4(0u, 0u, 0u, 0u);
-      }
+      for (int it = 0; it < 4; ++it) ch[it] = rh[it];
     }
     if (!waited) {
       mbar_wait(tfull, aphase);
@@ -109,6 +126,7 @@ VQ_DEVINL void gemm_epilogue_tile(const GemmArgs& p, uint32_t t_base, uint32_t s
     uint32_t r[32];
     tmem_ld_32x32(t_base + c * 32, r);
     tmem_ld_wait();
+    prefetch(c + 2);
     float v[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * alpha;
@@ -143,7 +161,7 @@ VQ_DEVINL void gemm_epilogue_tile(const GemmArgs& p, uint32_t t_base, uint32_t s
         const int grow = row_base + rr;
         uint4 o = lds128(stg + rr * 64 + ((piece ^ ((rr >> 1) & 3)) << 4));
         if (EPI == EPI_RELUBWD_BF16) {
-          const uint32_t hh[4] = {rh[it].x, rh[it].y, rh[it].z, rh[it].w};
+          const uint32_t hh[4] = {ch[it].x, ch[it].y, ch[it].z, ch[it].w};
           uint32_t oo[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -174,7 +192,7 @@ VQ_DEVINL void gemm_epilogue_tile(const GemmArgs& p, uint32_t t_base, uint32_t s
         if (has_k && grow < M && gcol < N) {
           float* dst = reinterpret_cast<float*>(p.C) + (size_t)grow * ldc + gcol;
           if (EPI == EPI_RESID_F32) {
-            o.x += rres[it].x; o.y += rres[it].y; o.z += rres[it].z; o.w += rres[it].w;
+            o.x += cres[it].x; o.y += cres[it].y; o.z += cres[it].z; o.w += cres[it].w;
             *reinterpret_cast<float4*>(dst) = o;
           } else if (EPI == EPI_ATOMIC_F32) {
             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
@@ -349,6 +367,187 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2): a cluster of two CTAs computes 256 x 256 tiles. Each CTA stages its own 128 rows
+// of A and its half (128 of the 256 columns) of B per k-block, the leader CTA's elected lane issues one M = 256 MMA that
+// reads both CTAs' shared memory and writes rows 0-127 to the leader's TMEM and rows 128-255 to the peer's. Compared with
+// the single-CTA 128 x 256 tile this cuts shared-memory traffic per FLOP by a third (TMA writes + MMA reads: 128 instead of
+// 192 B/cycle/SM at full tensor rate — the single-CTA kernel saturates at 2/3 tensor-pipe utilisation, profiles/r01_*).
+//   full[s]   (leader's)        : 1 arrival (leader producer's expect_tx for BOTH CTAs' bytes) + the bytes of both CTAs' loads
+//   empty[s]  (one per CTA)     : tcgen05.commit multicast to both CTAs when the MMAs that read stage s are done
+//   tfull[a]  (one per CTA)     : tcgen05.commit multicast when a 256 x 256 accumulator is complete
+//   tempty[a] (leader's)        : 16 arrivals = 8 epilogue warps of each CTA (the peer arrives remotely)
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int GEMM2_BN = 256;
+struct Gemm2Cfg {
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;              // 128 rows of A
+  static constexpr int B_BYTES = (GEMM2_BN / 2) * GEMM_BK * 2;       // this CTA's half of the B tile
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;              // 32 KB
+  static constexpr int STAGES = 6;
+  static constexpr int TMEM_COLS = 2 * GEMM2_BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + GEMM_EPI_WARPS * EPI_TILE_BYTES;
+};
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs p) {
+  vq_pdl_trigger();
+  using Cfg = Gemm2Cfg;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int BN = GEMM2_BN;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t raw_u32 = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_u32 + 1023u) & ~1023u) - raw_u32);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint8_t* epi_stage = smem + STAGES * Cfg::STAGE_BYTES + 256;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();        // 0 = leader
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  const int tiles_m = (p.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
+  const int tiles_n = (p.N + BN - 1) / BN;
+  const int kblocks = (p.K + GEMM_BK - 1) / GEMM_BK;
+  const int kb_per_split = (kblocks + p.splits - 1) / p.splits;
+  const int tiles_mn = tiles_m * tiles_n;
+  const int total_work = tiles_mn * p.splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 2 * GEMM_EPI_WARPS);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc_2sm(tmem_holder, Cfg::TMEM_COLS);
+  tc_fence_before();
+  cluster_sync_all();          // barriers of both CTAs initialised, TMEM of both allocated
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+  vq_pdl_wait();
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer (both CTAs) ------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = pair; w < total_work; w += npairs) {
+        const int split = w / tiles_mn;
+        const int t = w - split * tiles_mn;
+        const int m_blk = t / tiles_n, n_blk = t - m_blk * tiles_n;
+        const int m0 = m_blk * 2 * GEMM_BM + (int)rank * GEMM_BM;        // this CTA's 128 rows of the 256-row tile
+        const int n0 = n_blk * BN + (int)rank * (BN / 2);                // this CTA's half of the B tile
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(kblocks, kb0 + kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);   // bytes of BOTH CTAs land on the leader's barrier
+          if (!A_MN) {
+            tma_load_2d_2sm(sa, &tmA, &full_bar[stage], kb * GEMM_BK, m0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < GEMM_BM / 64; ++j)
+              tma_load_2d_2sm(sa + j * (GEMM_BK * 128), &tmA, &full_bar[stage], m0 + j * 64, kb * GEMM_BK);
+          }
+          if (!B_MN) {
+            tma_load_2d_2sm(sb, &tmB, &full_bar[stage], kb * GEMM_BK, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < (BN / 2) / 64; ++j)
+              tma_load_2d_2sm(sb + j * (GEMM_BK * 128), &tmB, &full_bar[stage], n0 + j * 64, kb * GEMM_BK);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer (leader CTA only) --------------------------------
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * GEMM_BM, BN, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int astage = 0;
+      uint32_t aphase = 0;
+      for (int w = pair; w < total_work; w += npairs) {
+        const int split = w / tiles_mn;
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(kblocks, kb0 + kb_per_split);
+        mbar_wait(&tempty_bar[astage], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + astage * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            const uint64_t adesc = A_MN ? umma_smem_desc_sw128(sa + k * 2048, GEMM_BK * 128, 1024)
+                                        : umma_smem_desc_sw128(sa + k * 32, 16, 1024);
+            const uint64_t bdesc = B_MN ? umma_smem_desc_sw128(sb + k * 2048, GEMM_BK * 128, 1024)
+                                        : umma_smem_desc_sw128(sb + k * 32, 16, 1024);
+            umma_f16_2sm(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_2sm(&empty_bar[stage]);   // frees this stage in BOTH CTAs
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2sm(&tfull_bar[astage]);    // accumulator complete -> epilogue warps of both CTAs
+        if (++astage == 2) { astage = 0; aphase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------ epilogue (both CTAs, own 128 rows) ----------------------------------
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    const uint32_t stg = smem_u32(epi_stage) + (warp - 4) * EPI_TILE_BYTES;
+    int astage = 0;
+    uint32_t aphase = 0;
+    for (int w = pair; w < total_work; w += npairs) {
+      const int split = w / tiles_mn;
+      const int t = w - split * tiles_mn;
+      const int m_blk = t / tiles_n, n_blk = t - m_blk * tiles_n;
+      const bool has_k = split * kb_per_split < kblocks;
+      const int row_base = m_blk * 2 * GEMM_BM + (int)rank * GEMM_BM + q * 32;
+      const uint32_t t_base = tmem_base + astage * BN + ((uint32_t)(q * 32) << 16);
+      uint64_t* tf = &tfull_bar[astage];
+      switch (p.epi) {
+        case EPI_BF16: gemm_epilogue_tile<EPI_BF16, BN>(p, t_base, stg, row_base, n_blk * BN, half, lane, has_k, tf, aphase); break;
+        case EPI_RELU_BF16: gemm_epilogue_tile<EPI_RELU_BF16, BN>(p, t_base, stg, row_base, n_blk * BN, half, lane, has_k, tf, aphase); break;
+        case EPI_RESID_F32: gemm_epilogue_tile<EPI_RESID_F32, BN>(p, t_base, stg, row_base, n_blk * BN, half, lane, has_k, tf, aphase); break;
+        case EPI_ATOMIC_F32: gemm_epilogue_tile<EPI_ATOMIC_F32, BN>(p, t_base, stg, row_base, n_blk * BN, half, lane, has_k, tf, aphase); break;
+        case EPI_RELUBWD_BF16: gemm_epilogue_tile<EPI_RELUBWD_BF16, BN>(p, t_base, stg, row_base, n_blk * BN, half, lane, has_k, tf, aphase); break;
+        default: gemm_epilogue_tile<EPI_F32, BN>(p, t_base, stg, row_base, n_blk * BN, half, lane, has_k, tf, aphase); break;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&tempty_bar[astage], 0);   // the leader's MMA lane owns accumulator reuse
+      if (++astage == 2) { astage = 0; aphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();          // the peer's smem / TMEM must stay alive until the leader's last MMA and both epilogues are done
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
