@@ -224,7 +224,7 @@ def run_native(args):
             return r["loss"].item()
         return None
 
-    def timed(batches, steps, warmup, read_loss):
+    def timed(batches, steps, warmup, read_loss, prefetch=False):
         for i in range(warmup):
             step(batches[i % pool], read_loss)
         if world > 1:
@@ -233,8 +233,13 @@ def run_native(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = model._engine.launch_count()
         e0.record()
-        for i in range(steps):
-            step(batches[i % pool], read_loss)
+        if prefetch:
+            # the public input path: pinned host batches -> BatchPrefetcher (H2D of batch i+1 on a side stream during step i)
+            for b in V.BatchPrefetcher((batches[i % pool] for i in range(steps)), dev):
+                step(b, read_loss)
+        else:
+            for i in range(steps):
+                step(batches[i % pool], read_loss)
         e1.record()
         if world > 1:
             dist.barrier()
@@ -252,7 +257,7 @@ def run_native(args):
         clocks.start()
     ms, launches = timed(devb, args.steps, warm, False)
     ck = clocks.stop() if rank == 0 else None
-    ms_e2e, _ = timed(host, args.steps, 2, True)
+    ms_e2e, _ = timed(host, args.steps, 2, True, prefetch=True)
     value = world * B * args.steps / (ms / 1e3)
     e2e = world * B * args.steps / (ms_e2e / 1e3)
     if rank == 0:

@@ -4,6 +4,7 @@ from ._lib import VqaclError
 from .config import VLT5Config
 from .modeling import VLT5, VLT5VQA, VLSeq2SeqLMOutput
 from .optim import FusedAdamW, get_constant_schedule_with_warmup
+from .data import BatchPrefetcher
 
-__all__ = ["VqaclError", "VLT5Config", "VLT5", "VLT5VQA", "VLSeq2SeqLMOutput", "FusedAdamW",
+__all__ = ["VqaclError", "VLT5Config", "VLT5", "VLT5VQA", "VLSeq2SeqLMOutput", "FusedAdamW", "BatchPrefetcher",
            "get_constant_schedule_with_warmup"]
