@@ -97,7 +97,11 @@ int vqacl_backward_stage_range(void* engine, int stage, int64_t* begin, int64_t*
 int vqacl_loss_tail(const float* loss_rows, const int64_t* labels, const float* scores, int B, int T, float* loss_out, float* w_rows, void* stream);
 /* clip_grad_norm_ + HF AdamW + bf16 refresh (vqacl.py:475-482, trainer_base.py:130-198) */
 int vqacl_clip_adamw(void* engine, float* exp_avg, float* exp_avg_sq, float lr, float beta1, float beta2, float eps,
-                     float weight_decay, int step, float max_grad_norm, float* grad_norm_out, void* stream);
+                     float weight_decay, int step, float max_grad_norm, float* grad_norm_out, int overlap, void* stream);
+/* overlap != 0: the (HBM-bound) update runs on an internal stream in the order the next forward reads the parameters and
+ * vqacl_forward_encoder/decoder/generate wait chunk by chunk; any OTHER consumer of the parameters must call
+ * vqacl_param_sync(engine, its_stream) first. */
+int vqacl_param_sync(void* engine, void* stream);
 /* greedy generation (vqa_model.py:112-116; HF 4.2.1 generate/greedy_search with max_length 20):
  * out_tokens [B, max_len] int64 (column 0 = start token, finished rows emit pad); *out_len = columns produced.
  * Synchronises the stream once per generated token (the all-rows-finished test, as HF does). */

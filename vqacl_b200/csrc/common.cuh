@@ -48,9 +48,14 @@ extern long long g_vq_launches;
 // kernel calls vq_pdl_trigger() first and vq_pdl_wait() before it touches global memory; the wait returns only when every
 // preceding grid has completed and flushed, so ordering is exactly that of a plain stream.
 // ---------------------------------------------------------------------------------------------
+// All kernels ask for the SAME shared-memory carveout (maximum shared, what the GEMM needs): CTAs of two kernels can only
+// share an SM when their L1/shared split agrees, and the engine relies on that (optimizer and dW GEMMs on side streams
+// next to the dependency chain; the GEMM is capped at 128 registers/thread to leave room).
 #ifdef __CUDACC__
+void vq_kernel_first_use(const void* kern);   // gemm.cu: sets the carveout attribute once per kernel
 template <typename... KArgs, typename... Args>
 static inline cudaError_t vq_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  vq_kernel_first_use(reinterpret_cast<const void*>(kern));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;

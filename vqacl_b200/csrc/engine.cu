@@ -272,6 +272,7 @@ int encoder_forward(Engine& e, const vqacl_batch* b, cudaStream_t st) {
   const int d = c.d_model, f = c.d_ff, H = c.n_heads;
   const int B = b->B, L = b->L, N = b->N, S = L + N, S2 = S + 2;
   const int M = B * S;
+  VQ_TRY(wait_params(e, 0, st));   // embeddings + visual projection + final norms
   VQ_TRY(build_keymasks(b->input_ids, B, L, S, c.pad_id, w.enc_mask, w.cross_mask, st));
   // embeddings: text rows [0,L), visual rows [L,S)   (modeling_t5_our.py:196-214, :247)
   VQ_TRY(embed_fwd(b->input_ids, B, L, e.P + e.o_shared, w.x[0], S, 0, e.drop(SITE_ENC_EMB), st));
@@ -284,6 +285,7 @@ int encoder_forward(Engine& e, const vqacl_batch* b, cudaStream_t st) {
   VQ_TRY(vis_embed_fwd(va, st));
   for (int l = 0; l < c.n_enc_layers; ++l) {
     const EncLayer& P = e.enc[l];
+    VQ_TRY(wait_params(e, 1 + l, st));
     RmsFwdArgs r{};
     r.x = w.x[2 * l]; r.w = e.P + P.ln0; r.y_bf16 = w.n1[l]; r.ld_bf16 = d; r.M = M; r.eps = c.eps; r.scale = 1.f;
     VQ_TRY(rmsnorm_fwd(r, st));
@@ -346,6 +348,7 @@ static int decoder_forward(Engine& e, const vqacl_batch* b, cudaStream_t st) {
   const int B = b->B, T = b->T, S2 = b->L + b->N + 2;
   const int Md = B * T, M2 = B * S2;
   const int ldkv = Ld * 2 * d;
+  VQ_TRY(wait_params(e, 1 + c.n_enc_layers, st));   // decoder + cross-KV weights (last optimizer chunk)
   VQ_TRY(shift_right(b->labels, w.dec_ids, B, T, c.start_id, c.pad_id, st));                      // :620
   VQ_TRY(embed_fwd(w.dec_ids, B, T, e.P + e.o_shared, w.y[0], T, 0, e.drop(SITE_DEC_EMB), st));
   // cross-attention K/V of every decoder layer in one GEMM over the decoder memory
@@ -426,6 +429,14 @@ static void backward_stage_range(const Engine& e, int stage, int64_t* a, int64_t
     *a = (int64_t)e.o_enc_final;
     *b = (int64_t)e.n_train;
   }
+}
+
+int wait_params(Engine& e, int chunk, cudaStream_t st) {
+  if (!e.opt_pending) return 0;
+  VQ_CHECK(chunk >= 0 && chunk < (int)e.ev_opt.size(), "wait_params: chunk %d out of range", chunk);
+  VQ_CUDA(cudaStreamWaitEvent(st, e.ev_opt[chunk], 0));
+  if (chunk + 1 == (int)e.ev_opt.size()) e.opt_pending = false;   // everything the optimizer wrote is now ordered before `st`
+  return 0;
 }
 
 static int ensure_side_stream(Engine& e) {
@@ -654,6 +665,12 @@ extern "C" void vqacl_engine_destroy(void* engine) {
   if (!engine) return;
   {
     Engine& e = *reinterpret_cast<Engine*>(engine);
+    if (e.opt_stream) {
+      cudaStreamSynchronize(e.opt_stream);
+      for (auto& ev : e.ev_opt) cudaEventDestroy(ev);
+      cudaEventDestroy(e.ev_opt_fork);
+      cudaStreamDestroy(e.opt_stream);
+    }
     if (e.side) {
       cudaStreamSynchronize(e.side);
       cudaEventDestroy(e.ev_fork);
@@ -768,17 +785,60 @@ extern "C" int vqacl_loss_tail(const float* loss_rows, const int64_t* labels, co
                                float* w_rows, void* stream) {
   return loss_tail(loss_rows, labels, scores, B, T, loss_out, w_rows, ST(stream));
 }
-extern "C" int vqacl_clip_adamw(void* engine, float* exp_avg, float* exp_avg_sq, float lr, float beta1, float beta2, float eps,
-                                float weight_decay, int step, float max_grad_norm, float* grad_norm_out, void* stream) {
-  Engine& e = ENG(engine);
-  VQ_CHECK(e.P && e.G && e.W && e.ws_base, "clip_adamw: arena / workspace not bound");
-  VQ_TRY(grad_sumsq(e.G, e.n_train, e.w.sumsq_partials, e.w.sumsq, ST(stream)));
+static AdamArgs adam_range(const Engine& e, float* m, float* v, size_t b, size_t en, float lr, float beta1, float beta2, float eps,
+                           float weight_decay, int step, float max_norm) {
   AdamArgs a{};
-  a.p = e.P; a.g = e.G; a.m = exp_avg; a.v = exp_avg_sq; a.p_bf16 = e.W; a.n = e.n_train; a.n_decay = e.n_decay;
+  a.p = e.P + b; a.g = e.G + b; a.m = m + b; a.v = v + b; a.p_bf16 = e.W + b; a.n = en - b;
+  a.n_decay = e.n_decay > b ? (e.n_decay - b < a.n ? e.n_decay - b : a.n) : 0;
   a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay; a.step = step;
-  a.sumsq = e.w.sumsq; a.max_norm = max_grad_norm;
-  VQ_TRY(adamw_hf(a, ST(stream)));
-  if (grad_norm_out) VQ_CUDA(cudaMemcpyAsync(grad_norm_out, e.w.sumsq, sizeof(float), cudaMemcpyDeviceToDevice, ST(stream)));
+  a.sumsq = e.w.sumsq; a.max_norm = max_norm;
+  return a;
+}
+
+extern "C" int vqacl_clip_adamw(void* engine, float* exp_avg, float* exp_avg_sq, float lr, float beta1, float beta2, float eps,
+                                float weight_decay, int step, float max_grad_norm, float* grad_norm_out, int overlap, void* stream) {
+  Engine& e = ENG(engine);
+  cudaStream_t st = ST(stream);
+  VQ_CHECK(e.P && e.G && e.W && e.ws_base, "clip_adamw: arena / workspace not bound");
+  if (e.opt_pending) {   // a previous overlapped step that no forward consumed: order it before this one
+    VQ_CUDA(cudaStreamWaitEvent(st, e.ev_opt.back(), 0));
+    e.opt_pending = false;
+  }
+  VQ_TRY(grad_sumsq(e.G, e.n_train, e.w.sumsq_partials, e.w.sumsq, st));
+  if (grad_norm_out) VQ_CUDA(cudaMemcpyAsync(grad_norm_out, e.w.sumsq, sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (!overlap) {
+    VQ_TRY(adamw_hf(adam_range(e, exp_avg, exp_avg_sq, 0, e.n_train, lr, beta1, beta2, eps, weight_decay, step, max_grad_norm), st));
+    return 0;
+  }
+  // ---- overlapped: the update is HBM-bound (30 B/param), the next forward's encoder GEMMs are tensor-bound. Update the arena
+  //      in the order the forward reads it, on a separate stream; forward_encoder/decoder wait per chunk (wait_params).
+  const int Le = e.cfg.n_enc_layers;
+  if (!e.opt_stream) {
+    VQ_CUDA(cudaStreamCreateWithFlags(&e.opt_stream, cudaStreamNonBlocking));
+    VQ_CUDA(cudaEventCreateWithFlags(&e.ev_opt_fork, cudaEventDisableTiming));
+    e.ev_opt.resize(Le + 2);
+    for (auto& ev : e.ev_opt) VQ_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  }
+  VQ_CUDA(cudaEventRecord(e.ev_opt_fork, st));
+  VQ_CUDA(cudaStreamWaitEvent(e.opt_stream, e.ev_opt_fork, 0));
+  auto chunk = [&](int k, size_t b, size_t en) -> int {
+    if (en > b) VQ_TRY(adamw_hf(adam_range(e, exp_avg, exp_avg_sq, b, en, lr, beta1, beta2, eps, weight_decay, step, max_grad_norm), e.opt_stream));
+    VQ_CUDA(cudaEventRecord(e.ev_opt[k], e.opt_stream));
+    return 0;
+  };
+  VQ_TRY(chunk(0, e.o_enc_final, e.n_train));
+  for (int l = 0; l < Le; ++l) VQ_TRY(chunk(1 + l, e.enc[l].ln0, l + 1 < Le ? e.enc[l + 1].ln0 : e.o_enc_final));
+  VQ_TRY(chunk(1 + Le, 0, Le > 0 ? e.enc[0].ln0 : e.o_enc_final));
+  e.opt_pending = true;
+  return 0;
+}
+// order everything a pending overlapped optimizer step wrote before `stream` (state_dict(), evaluation, user code)
+extern "C" int vqacl_param_sync(void* engine, void* stream) {
+  Engine& e = ENG(engine);
+  if (e.opt_pending) {
+    VQ_CUDA(cudaStreamWaitEvent(ST(stream), e.ev_opt.back(), 0));
+    e.opt_pending = false;
+  }
   return 0;
 }
 

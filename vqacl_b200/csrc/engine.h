@@ -81,6 +81,12 @@ struct Engine {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_layer[4] = {nullptr, nullptr, nullptr, nullptr};
   int gdb_i = 0, geb_i = 0;
+  // optimizer overlapped with the next forward: chunks of the arena are updated on `opt_stream` in the order the forward
+  // uses them (embeddings+visual | encoder layer 0..Le-1 | decoder+cross-KV); ev_opt[k] marks chunk k ready
+  cudaStream_t opt_stream = nullptr;
+  std::vector<cudaEvent_t> ev_opt;
+  cudaEvent_t ev_opt_fork = nullptr;
+  bool opt_pending = false;
   // decode workspace (separate carve, see decode.cu)
   Dropout drop(uint32_t site) const;
   int S() const { return L + N; }
@@ -98,6 +104,8 @@ inline int gemm_fwd(const bf16* A, int lda, const bf16* Wt, int K, void* C, int 
 }
 
 int check_batch(const Engine& e, const vqacl_batch* b, bool need_labels);
+// make `st` wait until optimizer chunk k (see Engine::ev_opt) has been written; no-op when no overlapped step is pending
+int wait_params(Engine& e, int chunk, cudaStream_t st);
 int encoder_forward(Engine& e, const vqacl_batch* b, cudaStream_t st);
 int si_path(Engine& e, const vqacl_batch* b, const vqacl_proto_state* ps, bool sums_ready, cudaStream_t st);
 

@@ -21,6 +21,12 @@ void vq_set_error(const char* fmt, ...) {
 }
 extern "C" const char* vqacl_last_error() { return g_err; }
 long long g_vq_launches = 0;
+void vq_kernel_first_use(const void* kern) {
+  static std::mutex mu;
+  static std::unordered_map<const void*, bool> seen;
+  std::lock_guard<std::mutex> g(mu);
+  if (seen.emplace(kern, true).second) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
 extern "C" long long vqacl_launch_count() { return g_vq_launches; }
 
 namespace vq {

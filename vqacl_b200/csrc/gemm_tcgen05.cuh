@@ -42,6 +42,9 @@ constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_EPI_WARPS = 8;
 constexpr int GEMM_THREADS = 128 + GEMM_EPI_WARPS * 32;
+#ifndef GEMM_MAXREG
+#define GEMM_MAXREG 128   // 384 threads x 128 = 48 K registers: leaves room on the SM for a memory-bound kernel of another stream
+#endif
 constexpr int EPI_TILE_BYTES = 4096;                         // one 32x32 fp32 (or 32x32 bf16 in half of it) tile per epilogue warp
 
 template <int BN>
@@ -211,7 +214,7 @@ VQ_DEVINL void gemm_epilogue_tile(const GemmArgs& p, uint32_t t_base, uint32_t s
 }
 
 template <int BN, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __maxnreg__(GEMM_MAXREG)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const GemmArgs p) {
   vq_pdl_trigger();
@@ -392,7 +395,7 @@ struct Gemm2Cfg {
 };
 
 template <bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __maxnreg__(GEMM_MAXREG)
 gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs p) {
   vq_pdl_trigger();
   using Cfg = Gemm2Cfg;

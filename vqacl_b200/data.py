@@ -17,20 +17,43 @@ class BatchPrefetcher:
         self.device = torch.device(device)
         self.depth = max(1, int(depth))
         self.stream = torch.cuda.Stream(device=self.device)
+        # device staging buffers are allocated once per (key, shape, dtype) and reused round-robin: no allocator traffic
+        # (and no cudaMalloc synchronisation) in the steady state. depth + 2 slots: depth in flight + the one the step is
+        # reading + one the previous step may still be reading.
+        self._slots = {}
+        self._turn = 0
+        self._free_ev = [None] * (self.depth + 2)
+
+    def _buffer(self, key, like, slot):
+        k = (key, tuple(like.shape), like.dtype, slot)
+        buf = self._slots.get(k)
+        if buf is None:
+            buf = torch.empty(like.shape, dtype=like.dtype, device=self.device)
+            self._slots[k] = buf
+        return buf
 
     def _stage(self, batch):
         out = {}
+        slot = self._turn % (self.depth + 2)
+        self._turn += 1
+        if self._free_ev[slot] is not None:
+            self.stream.wait_event(self._free_ev[slot])      # the step that consumed this slot last has finished with it
         with torch.cuda.stream(self.stream):
             for k, v in batch.items():
                 if torch.is_tensor(v) and k in _TENSOR_KEYS:
-                    if not v.is_cuda and not v.is_pinned():
+                    if v.is_cuda:
+                        out[k] = v
+                        continue
+                    if not v.is_pinned():
                         v = v.pin_memory()
-                    out[k] = v.to(self.device, non_blocking=True)
+                    buf = self._buffer(k, v, slot)
+                    buf.copy_(v, non_blocking=True)
+                    out[k] = buf
                 else:
                     out[k] = v
             ev = torch.cuda.Event()
             ev.record(self.stream)
-        return out, ev
+        return out, ev, slot
 
     def __iter__(self):
         it = iter(self.loader)
@@ -40,12 +63,17 @@ class BatchPrefetcher:
                 q.append(self._stage(next(it)))
         except StopIteration:
             pass
+        prev_slot = None
         while q:
-            batch, ev = q.pop(0)
-            torch.cuda.current_stream(self.device).wait_event(ev)
-            for v in batch.values():
-                if torch.is_tensor(v) and v.is_cuda:
-                    v.record_stream(torch.cuda.current_stream(self.device))
+            batch, ev, slot = q.pop(0)
+            cur = torch.cuda.current_stream(self.device)
+            cur.wait_event(ev)
+            if prev_slot is not None:
+                # everything the consumer issued for the previous batch is now in the current stream: mark its slot reusable
+                fe = torch.cuda.Event()
+                fe.record(cur)
+                self._free_ev[prev_slot] = fe
+            prev_slot = slot
             try:
                 q.append(self._stage(next(it)))
             except StopIteration:

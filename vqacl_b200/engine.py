@@ -72,7 +72,8 @@ def _declare(L):
     L.vqacl_backward_stage_range.argtypes = [c_void_p, c_int, POINTER(c_int64), POINTER(c_int64)]
     L.vqacl_loss_tail.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]
     L.vqacl_clip_adamw.argtypes = [c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_float, c_float, c_int,
-                                   c_float, c_void_p, c_void_p]
+                                   c_float, c_void_p, c_int, c_void_p]
+    L.vqacl_param_sync.argtypes = [c_void_p, c_void_p]
     L.vqacl_generate.argtypes = [c_void_p, POINTER(CBatch), POINTER(CProtoState), c_int, c_void_p, c_void_p, c_int64,
                                  POINTER(c_int), c_void_p]
     L.vqacl_generate_workspace_bytes.argtypes = [c_void_p, c_int, c_int, c_int, c_int]
@@ -232,10 +233,15 @@ class Engine:
     def backward(self, w_rows, accumulate=False, stage_begin=0, stage_end=-1):
         check(self.L.vqacl_backward(self.h, ptr(w_rows), int(accumulate), stage_begin, stage_end, cur_stream()))
 
-    def clip_adamw(self, m, v, lr, beta1, beta2, eps, wd, step, max_norm, norm_out=None):
+    def clip_adamw(self, m, v, lr, beta1, beta2, eps, wd, step, max_norm, norm_out=None, overlap=False):
         """norm_out (fp32[1], device) receives the SQUARED global gradient norm."""
         check(self.L.vqacl_clip_adamw(self.h, ptr(m), ptr(v), lr, beta1, beta2, eps, wd, step, max_norm,
-                                      ptr(norm_out), cur_stream()))
+                                      ptr(norm_out), int(overlap), cur_stream()))
+
+    def param_sync(self):
+        """Order a pending overlapped optimizer step before the current stream (needed before touching parameters outside
+        the engine's own forward / generate calls)."""
+        check(self.L.vqacl_param_sync(self.h, cur_stream()))
         self.bf16_stale = False   # the optimizer kernel refreshes the bf16 copies itself
 
     def generate(self, cb, ps, max_len):

@@ -346,6 +346,15 @@ class VLT5(nn.Module):
         self._Q_prototype_num = torch.zeros(self.config.n_ques_classes, dtype=torch.float32, device=device)
         self._V_prototype_num = torch.zeros(self.config.n_cate_classes, dtype=torch.float32, device=device)
 
+    def param_sync(self):
+        """Make the current stream wait for a pending overlapped optimizer step (FusedAdamW(overlap_with_next_forward=True))."""
+        if getattr(self, "_engine", None) is not None:
+            self._engine.param_sync()
+
+    def state_dict(self, *a, **kw):
+        self.param_sync()
+        return super().state_dict(*a, **kw)
+
     def _mark_params_dirty(self):
         """fp32 masters were modified outside the fused optimizer -> bf16 GEMM copies must be refreshed before use."""
         if getattr(self, "_engine", None) is not None:

@@ -12,7 +12,11 @@ from ._lib import VqaclError
 
 
 class FusedAdamW(torch.optim.Optimizer):
-    def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.01, max_grad_norm=0.0):
+    def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.01, max_grad_norm=0.0,
+                 overlap_with_next_forward=False):
+        """overlap_with_next_forward: run the (HBM-bound) update on a side stream, in the order the next forward reads the
+        parameters; `train_step` / `forward` / `generate` / `state_dict` wait for exactly what they need. Code that reads
+        parameter tensors directly right after `step()` must call `model.param_sync()` first (off by default)."""
         model = getattr(model, "module", model)
         eng = model._need_engine()
         no_decay = ["bias", "LayerNorm.weight"]                     # trainer_base.py:148 (T5 'layer_norm.weight' does NOT match)
@@ -31,6 +35,7 @@ class FusedAdamW(torch.optim.Optimizer):
                 raise VqaclError(f"arena decay group of {n} disagrees with the reference's no_decay rule")
         self.model, self.eng = model, eng
         self.max_grad_norm = float(max_grad_norm)
+        self.overlap = bool(overlap_with_next_forward)
         self.exp_avg = torch.zeros(eng.n_train, dtype=torch.float32, device=eng.device)
         self.exp_avg_sq = torch.zeros(eng.n_train, dtype=torch.float32, device=eng.device)
         self.grad_sumsq = torch.zeros(1, dtype=torch.float32, device=eng.device)
@@ -49,7 +54,7 @@ class FusedAdamW(torch.optim.Optimizer):
         b1, b2 = g0["betas"]
         mg = self.max_grad_norm if max_grad_norm is None else float(max_grad_norm)
         self.eng.clip_adamw(self.exp_avg, self.exp_avg_sq, float(g0["lr"]), float(b1), float(b2), float(g0["eps"]),
-                            float(g0["weight_decay"]), self.t, mg, self.grad_sumsq)
+                            float(g0["weight_decay"]), self.t, mg, self.grad_sumsq, overlap=self.overlap)
         return None
 
     def zero_grad(self, set_to_none=True):
