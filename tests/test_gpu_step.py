@@ -170,3 +170,19 @@ def test_full_size_batch_properties():
     ra = m2.train_step(small, 0, 0.5, 0.3)
     assert torch.equal(ra["encoder_hidden_states"], enc_big)                 # same rows, bit-exact, whatever the batch size
     assert log_big.isfinite().all() and r2["loss"].isfinite()               # (logits differ: the bank holds other batch means)
+
+
+def test_nextqa_shapes():
+    """configs[3]: the NExT-QA variant's shapes — 16 visual tokens (nextqa_data.py:132-133), text width up to 23 (> the
+    hard-wired split at 20, so text tokens leak into the V mean), target width 6, 8 question types."""
+    import vqacl_b200 as V
+    ocfg = O.VLT5Config(num_layers=2, num_decoder_layers=2, dropout_rate=0.0, n_ques_classes=8)
+    om = O.VLT5VQA(ocfg).init_weights_like_reference(7).cuda()
+    cfg = V.VLT5Config(vocab_size=32200, num_layers=2, num_decoder_layers=2, dropout_rate=0.0, n_ques_classes=8)
+    m = V.VLT5VQA(cfg)
+    m.load_state_dict(om.state_dict())
+    m = m.cuda()
+    om.train(); m.train()
+    for i, (task, L) in enumerate(((0, 23), (0, 21), (1, 23))):
+        b = O.synthetic_batch(6, seed=40 + i, L=L, T=6, n_boxes=16, task_id=task, n_ques=8)
+        _check_step(om, m, b, task, alpha=0.3, beta=0.3, grads=(i == 2))
