@@ -123,7 +123,8 @@ int vqacl_attention_fwd(const void* q, const void* k, const void* v, int ldq, in
 int vqacl_attention_bwd(const void* q, const void* k, const void* v, int ldq, int ldk, int ldv, const void* dO, int ldo,
                         const float* lse, void* dq, void* dk, void* dv, int lddq, int lddk, int lddv, int B, int H, int Sq, int Sk,
                         const float* rel_table, const int32_t* rel_bucket, int rel_mode, int Lt, const float* keymask, int causal,
-                        float* d_rel_table, void* stream);
+                        float* d_rel_table, const void* o_saved /* forward output (pitch ldo) or NULL: enables the key-split
+                        backward for Sq <= 16 < Sk */, void* stream);
 int vqacl_proto_means(const float* h, int B, int S, int split, float* meanQ, float* meanV, void* stream);
 int vqacl_proto_scatter_mean(const float* mean, const float* labels, int B, int C, float* proto, float* cnt, void* stream);
 int vqacl_proto_update(const float* curQ, const float* curV, const float* cntQ, const float* cntV, float* Qproto, float* Vproto,

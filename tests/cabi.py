@@ -16,7 +16,7 @@ def _L():
         L.vqacl_rmsnorm_bwd.argtypes = [c_void_p] * 7 + [c_int, F, F, c_void_p]
         L.vqacl_attention_fwd.argtypes = [c_void_p] * 3 + [c_int] * 3 + [c_void_p, c_int, c_void_p] + [c_int] * 4 + [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]
         L.vqacl_attention_bwd.argtypes = ([c_void_p] * 3 + [c_int] * 3 + [c_void_p, c_int, c_void_p] + [c_void_p] * 3 + [c_int] * 3 + [c_int] * 4 +
-                                          [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p])
+                                          [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p])
         L.vqacl_proto_means.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]
         L.vqacl_proto_scatter_mean.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]
         L.vqacl_proto_update.argtypes = [c_void_p] * 8 + [c_int] * 5 + [F, F, c_void_p]
@@ -59,12 +59,12 @@ def attention_fwd(q, k, v, B, H, Sq, Sk, rel_table=None, rel_bucket=None, rel_mo
     return o, lse
 
 
-def attention_bwd(q, k, v, dO, lse, B, H, Sq, Sk, rel_table=None, rel_bucket=None, rel_mode=0, Lt=0, keymask=None, causal=0):
+def attention_bwd(q, k, v, dO, lse, B, H, Sq, Sk, rel_table=None, rel_bucket=None, rel_mode=0, Lt=0, keymask=None, causal=0, o_saved=None):
     dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
     dtab = torch.zeros_like(rel_table) if rel_table is not None else None
     check(_L().vqacl_attention_bwd(ptr(q), ptr(k), ptr(v), q.stride(0), k.stride(0), v.stride(0), ptr(dO), dO.stride(0), ptr(lse),
                                    ptr(dq), ptr(dk), ptr(dv), dq.stride(0), dk.stride(0), dv.stride(0), B, H, Sq, Sk, ptr(rel_table),
-                                   ptr(rel_bucket), rel_mode, Lt, ptr(keymask), causal, ptr(dtab), cur_stream()))
+                                   ptr(rel_bucket), rel_mode, Lt, ptr(keymask), causal, ptr(dtab), ptr(o_saved), cur_stream()))
     return dq, dk, dv, dtab
 
 

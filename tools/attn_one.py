@@ -16,7 +16,8 @@ elif mode == "dec":
     q, k, v = qkv[:, :768], qkv[:, 768:1536], qkv[:, 1536:]
 else:
     q = (torch.randn(B * Sq, 768, device="cuda") * 0.3).bfloat16()
-    kv = (torch.randn(B * Sk, 24 * 768, device="cuda") * 0.3).bfloat16()
+    kvw = int(os.environ.get("KVW", 24 * 768))
+    kv = (torch.randn(B * Sk, kvw, device="cuda") * 0.3).bfloat16()
     k, v = kv[:, :768], kv[:, 768:1536]
 table = torch.randn(32, H, device="cuda") * 0.5
 bucket = rel_bucket_table(mode == "enc")
@@ -25,7 +26,7 @@ kw = dict(rel_table=table, rel_bucket=bucket, rel_mode=1 if mode == "enc" else 2
 dO = torch.randn(B * Sq, 768, device="cuda").bfloat16()
 def fwd(): return cabi.attention_fwd(q, k, v, B, H, Sq, Sk, **kw)
 o, lse = fwd()
-def bwd(): return cabi.attention_bwd(q, k, v, dO, lse, B, H, Sq, Sk, **kw)
+def bwd(): return cabi.attention_bwd(q, k, v, dO, lse, B, H, Sq, Sk, o_saved=(o if mode == 'cross' else None), **kw)
 for fn, nm in ((fwd, "fwd"), (bwd, "bwd")):
     for _ in range(3): fn()
     torch.cuda.synchronize()

@@ -505,6 +505,307 @@ __global__ void __launch_bounds__(NW * 32 * HPC, NW == 4 ? 4 : 8 / HPC) attn_bwd
   }
 }
 
+// =====================================================================================================================
+// Key-split kernels for few queries against many keys (decoder cross-attention: Sq = T <= 16 queries, 58 keys).
+// One CTA per (batch, head), 4 warps, warp w owns keys [16w, 16w+16). With one 16-row query tile the generic kernel would
+// leave three warps idle; here every warp multiplies the query tile with its 16 keys (2 key tiles), the row maximum and
+// sum are exchanged through shared memory, and the partial P.V products (backward: partial dS.K) are summed with shared
+// fp32 atomics. Backward needs no cross-warp softmax statistic: P = exp(S - lse) from the saved log-sum-exp and
+// D = rowsum(dO * O) from the saved output (also valid with dropout: O was produced by the dropped probabilities).
+// =====================================================================================================================
+constexpr int KS_WARPS = 4;
+constexpr int KS_OP = 68;   // pitch (floats) of the fp32 [16][64] accumulator tile: conflict-light for the fragment layout
+struct KsSmemFwd {
+  __nv_bfloat16 q[16][AT_P], k[AT_S][AT_P], v[AT_S][AT_P];
+  float kmask[AT_S];
+  float pm[KS_WARPS][16], pl[KS_WARPS][16];
+  float o[16][KS_OP];
+};
+
+__global__ void __launch_bounds__(KS_WARPS * 32, 6) attn_ks_fwd_kernel(const AttnArgs p) {
+  vq_pdl_trigger();
+  vq_pdl_wait();
+  extern __shared__ __align__(16) uint8_t at_smem_base[];
+  KsSmemFwd& sm = *reinterpret_cast<KsSmemFwd*>(at_smem_base);
+  const int vblk = blockIdx.x, b = vblk / p.H, h = vblk % p.H;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  {
+    const AttnTile dst[3] = {sm.q, sm.k, sm.v};
+    const __nv_bfloat16* const src[3] = {p.q + (size_t)b * (p.q_bstride ? p.q_bstride : (long long)p.Sq * p.ldq) + h * AT_D,
+                                         p.k + (size_t)b * (p.k_bstride ? p.k_bstride : (long long)p.Sk * p.ldk) + h * AT_D,
+                                         p.v + (size_t)b * (p.v_bstride ? p.v_bstride : (long long)p.Sk * p.ldv) + h * AT_D};
+    const int ld[3] = {p.ldq, p.ldk, p.ldv};
+    const int rows[3] = {p.Sq, p.Sk, p.Sk};
+    const int fill[3] = {16, AT_S, AT_S};
+    if (tid < AT_S) sm.kmask[tid] = tid < p.Sk ? (p.keymask ? p.keymask[(size_t)b * p.Sk + tid] : 0.f) : -INFINITY;
+    for (int i = tid; i < 16 * KS_OP; i += KS_WARPS * 32) (&sm.o[0][0])[i] = 0.f;
+    load_heads<KS_WARPS, 3>(dst, src, ld, rows, fill, tid);
+  }
+  __syncthreads();
+  const int k0 = warp * 16;   // this warp's keys
+  float s[2][4];
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s[nt][i] = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    uint32_t a[4], bb[4];
+    frag_a(a, sm.q, 0, kk * 16, lane);
+    frag_b2(bb, sm.k, k0, kk * 16, lane);
+    mma2(s[0], s[1], a, bb);
+  }
+  float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt) {
+    const float2 ka = *reinterpret_cast<const float2*>(sm.kmask + k0 + nt * 8 + 2 * t);
+    s[nt][0] += ka.x; s[nt][1] += ka.y; s[nt][2] += ka.x; s[nt][3] += ka.y;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) mx[i >> 1] = fmaxf(mx[i >> 1], s[nt][i]);
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+    mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+  }
+  if (t == 0) { sm.pm[warp][g] = mx[0]; sm.pm[warp][g + 8] = mx[1]; }
+  __syncthreads();
+  float gm[2], sum[2] = {0.f, 0.f};
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    gm[r] = fmaxf(fmaxf(sm.pm[0][g + 8 * r], sm.pm[1][g + 8 * r]), fmaxf(sm.pm[2][g + 8 * r], sm.pm[3][g + 8 * r]));
+  }
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float e = __expf(s[nt][i] - gm[i >> 1]);   // keys beyond Sk: exp(-inf) = 0 (gm is finite: key 0 always exists)
+      s[nt][i] = e;
+      sum[i >> 1] += e;
+    }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 1);
+    sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 2);
+  }
+  if (t == 0) { sm.pl[warp][g] = sum[0]; sm.pl[warp][g + 8] = sum[1]; }
+  if (p.drop_thr) {
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        float d0, d1;
+        vq_dropout_pair(p.seed, attn_pair_idx(vblk, g + r * 8, k0 + nt * 8 + 2 * t), p.drop_thr, p.drop_inv_keep, d0, d1);
+        s[nt][2 * r] *= d0;
+        s[nt][2 * r + 1] *= d1;
+      }
+  }
+  // partial O = P_w V_w (un-normalised), summed over the warps with shared atomics
+  {
+    uint32_t a[4];
+    a[0] = pack_bf16(s[0][0], s[0][1]); a[1] = pack_bf16(s[0][2], s[0][3]);
+    a[2] = pack_bf16(s[1][0], s[1][1]); a[3] = pack_bf16(s[1][2], s[1][3]);
+    float o[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[nt][i] = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 8; nt += 2) {
+      uint32_t bb[4];
+      frag_b2_t(bb, sm.v, nt * 8, k0, lane);
+      mma2(o[nt], o[nt + 1], a, bb);
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int qi = g + r * 8;
+      if (qi < p.Sq) {
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          atomicAdd(&sm.o[qi][nt * 8 + 2 * t], o[nt][2 * r]);
+          atomicAdd(&sm.o[qi][nt * 8 + 2 * t + 1], o[nt][2 * r + 1]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // normalise and write: thread -> (row = tid / 8, 8 columns)
+  {
+    const int qi = tid >> 3, c0 = (tid & 7) * 8;
+    if (qi < p.Sq) {
+      const float l = sm.pl[0][qi] + sm.pl[1][qi] + sm.pl[2][qi] + sm.pl[3][qi];
+      const float inv = 1.f / l;
+      const float* so = &sm.o[qi][c0];
+      uint4 out;
+      out.x = pack_bf16(so[0] * inv, so[1] * inv); out.y = pack_bf16(so[2] * inv, so[3] * inv);
+      out.z = pack_bf16(so[4] * inv, so[5] * inv); out.w = pack_bf16(so[6] * inv, so[7] * inv);
+      __nv_bfloat16* dst = p.o + (size_t)b * (p.o_bstride ? p.o_bstride : (long long)p.Sq * p.ldo) + (size_t)qi * p.ldo + h * AT_D + c0;
+      *reinterpret_cast<uint4*>(dst) = out;
+      if (c0 == 0 && p.lse) {
+        const float m = fmaxf(fmaxf(sm.pm[0][qi], sm.pm[1][qi]), fmaxf(sm.pm[2][qi], sm.pm[3][qi]));
+        p.lse[((size_t)b * p.H + h) * p.Sq + qi] = m + __logf(l);
+      }
+    }
+  }
+}
+
+struct KsSmemBwd {
+  __nv_bfloat16 q[16][AT_P], dO[16][AT_P], k[AT_S][AT_P], v[AT_S][AT_P];
+  __nv_bfloat16 P[KS_WARPS][16][24], dS[KS_WARPS][16][24];   // per-warp [query][its 16 keys], 48-byte rows (ldmatrix-aligned)
+  float kmask[AT_S];
+  float D[16], lse[16];
+  float dq[16][KS_OP];
+};
+
+__global__ void __launch_bounds__(KS_WARPS * 32, 5) attn_ks_bwd_kernel(const AttnArgs p) {
+  vq_pdl_trigger();
+  vq_pdl_wait();
+  extern __shared__ __align__(16) uint8_t at_smem_base[];
+  KsSmemBwd& sm = *reinterpret_cast<KsSmemBwd*>(at_smem_base);
+  const int vblk = blockIdx.x, b = vblk / p.H, h = vblk % p.H;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  {
+    const AttnTile dst[4] = {sm.q, sm.dO, sm.k, sm.v};
+    const __nv_bfloat16* const src[4] = {p.q + (size_t)b * p.Sq * p.ldq + h * AT_D, p.dO + (size_t)b * p.Sq * p.ldo + h * AT_D,
+                                         p.k + (size_t)b * p.Sk * p.ldk + h * AT_D, p.v + (size_t)b * p.Sk * p.ldv + h * AT_D};
+    const int ld[4] = {p.ldq, p.ldo, p.ldk, p.ldv};
+    const int rows[4] = {p.Sq, p.Sq, p.Sk, p.Sk};
+    const int fill[4] = {16, 16, AT_S, AT_S};
+    if (tid < AT_S) sm.kmask[tid] = tid < p.Sk ? (p.keymask ? p.keymask[(size_t)b * p.Sk + tid] : 0.f) : -INFINITY;
+    for (int i = tid; i < 16 * KS_OP; i += KS_WARPS * 32) (&sm.dq[0][0])[i] = 0.f;
+    // D[q] = sum_d dO[q][d] * O[q][d]: 8 threads per query row, 8 columns each
+    {
+      const int qi = tid >> 3, c0 = (tid & 7) * 8;
+      float acc = 0.f;
+      if (qi < p.Sq) {
+        const uint4 a = *reinterpret_cast<const uint4*>(p.dO + ((size_t)b * p.Sq + qi) * p.ldo + h * AT_D + c0);
+        const uint4 o = *reinterpret_cast<const uint4*>(p.o_saved + ((size_t)b * p.Sq + qi) * p.ldo + h * AT_D + c0);
+        const uint32_t aa[4] = {a.x, a.y, a.z, a.w}, oo[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 x = unpack_bf16(aa[j]), y = unpack_bf16(oo[j]);
+          acc += x.x * y.x + x.y * y.y;
+        }
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      if ((tid & 7) == 0) {
+        sm.D[qi] = acc;
+        sm.lse[qi] = qi < p.Sq ? p.lse[((size_t)b * p.H + h) * p.Sq + qi] : INFINITY;   // rows >= Sq -> P = 0
+      }
+    }
+    load_heads<KS_WARPS, 4>(dst, src, ld, rows, fill, tid);
+  }
+  __syncthreads();
+  const int k0 = warp * 16;
+  float s[2][4], dp[2][4];
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s[nt][i] = dp[nt][i] = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    uint32_t a[4], a2[4], bk[4], bv[4];
+    frag_a(a, sm.q, 0, kk * 16, lane);
+    frag_a(a2, sm.dO, 0, kk * 16, lane);
+    frag_b2(bk, sm.k, k0, kk * 16, lane);
+    frag_b2(bv, sm.v, k0, kk * 16, lane);
+    mma2(s[0], s[1], a, bk);       // S = Q K_w^T
+    mma2(dp[0], dp[1], a2, bv);    // dPd = dO V_w^T
+  }
+  const float lse[2] = {sm.lse[g], sm.lse[g + 8]};
+  const float Dr[2] = {sm.D[g], sm.D[g + 8]};
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt) {
+    const float2 ka = *reinterpret_cast<const float2*>(sm.kmask + k0 + nt * 8 + 2 * t);
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      float sc0 = 1.f, sc1 = 1.f;
+      if (p.drop_thr) vq_dropout_pair(p.seed, attn_pair_idx(vblk, g + r * 8, k0 + nt * 8 + 2 * t), p.drop_thr, p.drop_inv_keep, sc0, sc1);
+      const float p0 = __expf(s[nt][2 * r] + ka.x - lse[r]), p1 = __expf(s[nt][2 * r + 1] + ka.y - lse[r]);
+      const float ds0 = p0 * (dp[nt][2 * r] * sc0 - Dr[r]), ds1 = p1 * (dp[nt][2 * r + 1] * sc1 - Dr[r]);
+      s[nt][2 * r] = ds0; s[nt][2 * r + 1] = ds1;
+      *reinterpret_cast<uint32_t*>(&sm.P[warp][g + r * 8][nt * 8 + 2 * t]) = pack_bf16(p0 * sc0, p1 * sc1);
+      *reinterpret_cast<uint32_t*>(&sm.dS[warp][g + r * 8][nt * 8 + 2 * t]) = pack_bf16(ds0, ds1);
+    }
+  }
+  // partial dQ = dS_w K_w, summed over warps with shared atomics
+  {
+    uint32_t a[4];
+    a[0] = pack_bf16(s[0][0], s[0][1]); a[1] = pack_bf16(s[0][2], s[0][3]);
+    a[2] = pack_bf16(s[1][0], s[1][1]); a[3] = pack_bf16(s[1][2], s[1][3]);
+    float dq[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) dq[nt][i] = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 8; nt += 2) {
+      uint32_t bb[4];
+      frag_b2_t(bb, sm.k, nt * 8, k0, lane);
+      mma2(dq[nt], dq[nt + 1], a, bb);
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int qi = g + r * 8;
+      if (qi < p.Sq) {
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          atomicAdd(&sm.dq[qi][nt * 8 + 2 * t], dq[nt][2 * r]);
+          atomicAdd(&sm.dq[qi][nt * 8 + 2 * t + 1], dq[nt][2 * r + 1]);
+        }
+      }
+    }
+  }
+  __syncwarp();
+  // dV_w = Pd_w^T dO, dK_w = dS_w^T Q  (A = transposed per-warp tile [16 keys x 16 queries]; one k-step over the 16 query slots)
+  if (k0 < p.Sk) {
+    uint32_t ap[4], as[4];
+    {
+      const int mi = lane >> 3, r = lane & 7;
+      ldsm_x4_t(ap, &sm.P[warp][(mi >> 1) * 8 + r][(mi & 1) * 8]);
+      ldsm_x4_t(as, &sm.dS[warp][(mi >> 1) * 8 + r][(mi & 1) * 8]);
+    }
+    float dv[8][4], dk[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) dv[nt][i] = dk[nt][i] = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 8; nt += 2) {
+      uint32_t b1[4], b2[4];
+      frag_b2_t(b1, sm.dO, nt * 8, 0, lane);
+      frag_b2_t(b2, sm.q, nt * 8, 0, lane);
+      mma2(dv[nt], dv[nt + 1], ap, b1);
+      mma2(dk[nt], dk[nt + 1], as, b2);
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int kj = k0 + g + r * 8;
+      if (kj < p.Sk) {
+        __nv_bfloat16* dstk = p.dk + ((size_t)b * p.Sk + kj) * p.lddk + h * AT_D + 2 * t;
+        __nv_bfloat16* dstv = p.dv + ((size_t)b * p.Sk + kj) * p.lddv + h * AT_D + 2 * t;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          *reinterpret_cast<uint32_t*>(dstk + nt * 8) = pack_bf16(dk[nt][2 * r], dk[nt][2 * r + 1]);
+          *reinterpret_cast<uint32_t*>(dstv + nt * 8) = pack_bf16(dv[nt][2 * r], dv[nt][2 * r + 1]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  {
+    const int qi = tid >> 3, c0 = (tid & 7) * 8;
+    if (qi < p.Sq) {
+      const float* so = &sm.dq[qi][c0];
+      uint4 out;
+      out.x = pack_bf16(so[0], so[1]); out.y = pack_bf16(so[2], so[3]); out.z = pack_bf16(so[4], so[5]); out.w = pack_bf16(so[6], so[7]);
+      *reinterpret_cast<uint4*>(p.dq + ((size_t)b * p.Sq + qi) * p.lddq + h * AT_D + c0) = out;
+    }
+  }
+}
+
 static int check_args(const AttnArgs& a) {
   VQ_CHECK(a.Sq >= 1 && a.Sq <= AT_S && a.Sk >= 1 && a.Sk <= AT_S, "attention: Sq=%d Sk=%d must be in [1,%d]", a.Sq, a.Sk, AT_S);
   VQ_CHECK(a.ldq % 8 == 0 && a.ldk % 8 == 0 && a.ldv % 8 == 0 && a.ldo % 8 == 0, "attention: pitches must be multiples of 8");
@@ -557,6 +858,16 @@ int attn_fwd(const AttnArgs& a, cudaStream_t stream) {
   AttnBuckets bk;
   if (make_buckets(a, &bk)) return 1;
   const int warps = (a.Sq + 15) / 16;   // one warp per 16 query rows
+  if (a.Sq <= 16 && a.Sk > 16 && a.rel_mode == 0 && !a.causal) {   // few queries, many keys (cross-attention): key-split kernel
+    static bool attr = false;
+    if (!attr) {
+      VQ_CUDA(cudaFuncSetAttribute(attn_ks_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KsSmemFwd)));
+      attr = true;
+    }
+    (void)vq_launch(attn_ks_fwd_kernel, dim3(a.B * a.H), dim3(KS_WARPS * 32), sizeof(KsSmemFwd), stream, a);
+    VQ_LAUNCH_CHECK();
+    return 0;
+  }
   if (warps == 1 && a.Sk <= 16) return launch_fwd<1, 2>(a, bk, stream);   // decoder self-attention / decode steps
   if (warps == 1) return launch_fwd<1, 8>(a, bk, stream);                  // cross-attention
   if (warps == 2) return launch_fwd<2, 8>(a, bk, stream);
@@ -570,6 +881,16 @@ int attn_bwd(const AttnArgs& a, cudaStream_t stream) {
   VQ_CHECK(a.lddq % 8 == 0 && a.lddk % 8 == 0 && a.lddv % 8 == 0, "attention bwd: pitches must be multiples of 8");
   AttnBuckets bk;
   if (make_buckets(a, &bk)) return 1;
+  if (a.o_saved && a.Sq <= 16 && a.Sk > 16 && a.rel_mode == 0 && !a.causal) {   // key-split backward (needs the forward output)
+    static bool attr = false;
+    if (!attr) {
+      VQ_CUDA(cudaFuncSetAttribute(attn_ks_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KsSmemBwd)));
+      attr = true;
+    }
+    (void)vq_launch(attn_ks_bwd_kernel, dim3(a.B * a.H), dim3(KS_WARPS * 32), sizeof(KsSmemBwd), stream, a);
+    VQ_LAUNCH_CHECK();
+    return 0;
+  }
   const int warps = (max(a.Sq, a.Sk) + 15) / 16;   // phase 1: 16 query rows per warp, phase 2: 16 key rows per warp
   if (warps == 1) return launch_bwd<1, 2>(a, bk, stream);
   if (warps == 2) return launch_bwd<2, 8>(a, bk, stream);

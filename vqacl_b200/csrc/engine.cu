@@ -542,6 +542,7 @@ static int backward(Engine& e, const float* w_rows, int accumulate, int stage_be
     x.ldo = d; x.lse = w.lse_c[l]; x.B = B; x.H = H; x.Sq = T; x.Sk = S2; x.rel_mode = 0; x.keymask = w.cross_mask; x.causal = 0;
     Dropout dp = e.drop(site_dec(l, 2));
     x.drop_thr = dp.thr; x.drop_inv_keep = dp.inv_keep; x.seed = dp.seed; x.site = dp.site;
+    x.o_saved = w.cao[l];
     x.dO = w.t_d768; x.dq = w.t_dcq[ri]; x.lddq = d; x.dk = w.dkv_all + (size_t)l * 2 * d; x.dv = x.dk + d; x.lddk = x.lddv = ldkv;
     VQ_TRY(attn_bwd(x, st));
     VQ_TRY(fork());
@@ -874,12 +875,13 @@ extern "C" int vqacl_attention_fwd(const void* q, const void* k, const void* v, 
 extern "C" int vqacl_attention_bwd(const void* q, const void* k, const void* v, int ldq, int ldk, int ldv, const void* dO, int ldo,
                                    const float* lse, void* dq, void* dk, void* dv, int lddq, int lddk, int lddv, int B, int H, int Sq,
                                    int Sk, const float* rel_table, const int32_t* rel_bucket, int rel_mode, int Lt,
-                                   const float* keymask, int causal, float* d_rel_table, void* stream) {
+                                   const float* keymask, int causal, float* d_rel_table, const void* o_saved, void* stream) {
   AttnArgs a = make_attn(q, k, v, ldq, ldk, ldv, ldo, const_cast<float*>(lse), B, H, Sq, Sk, rel_table, rel_bucket, rel_mode, Lt,
                          keymask, causal);
   a.dO = reinterpret_cast<const bf16*>(dO);
   a.dq = reinterpret_cast<bf16*>(dq); a.dk = reinterpret_cast<bf16*>(dk); a.dv = reinterpret_cast<bf16*>(dv);
   a.lddq = lddq; a.lddk = lddk; a.lddv = lddv; a.d_rel_table = d_rel_table;
+  a.o_saved = reinterpret_cast<const bf16*>(o_saved);
   return attn_bwd(a, ST(stream));
 }
 extern "C" int vqacl_proto_means(const float* h, int B, int S, int split, float* meanQ, float* meanV, void* stream) {

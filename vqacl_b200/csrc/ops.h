@@ -34,6 +34,7 @@ struct AttnArgs {
   uint32_t drop_thr; float drop_inv_keep; uint32_t seed, site;   // dropout on the probabilities
   // backward only
   const __nv_bfloat16* dO;
+  const __nv_bfloat16* o_saved; // forward output (pitch ldo); when given and Sq <= 16 < Sk the key-split backward is used
   __nv_bfloat16 *dq, *dk, *dv;
   int lddq, lddk, lddv;
   float* d_rel_table;       // [num_buckets, H] accumulated with atomics, or null
