@@ -111,12 +111,23 @@ int vqacl_generate(void* engine, const vqacl_batch* batch, const vqacl_proto_sta
 /* number of kernels this library has launched so far in this process (bench.py's gpu_launches) */
 long long vqacl_launch_count(void);
 
-/* ---- individual operators (unit-test / building-block surface); `rel_bucket` is a HOST int32[127] table ---- */
+/* ---- individual operators (unit-test / building-block surface); `rel_bucket` is a HOST int32[127] table ----
+ * Each entry replaces library calls the reference reaches through PyTorch / transformers 4.2.1:                              */
+
+/* nn.Linear forward / input-gradient / weight-gradient (every q,k,v,o,wi,wo, feat_embedding.0 and the tied lm_head:
+ * modeling_t5_our.py:39-48,659-671; HF T5Attention / T5DenseReluDense). C[M,N] = epilogue(A[M,K] * B[N,K]^T) on tcgen05;
+ * an operand flagged *_mn_major is stored transposed ([K,M] / [K,N]). epi: 0 bf16, 1 relu->bf16, 2 fp32 residual add (R),
+ * 3 fp32 atomic accumulate (split-K), 4 relu-backward mask (R = saved activations, bf16), 5 fp32.
+ * force_bn: 0 = cost model, 64/128/256 = single-CTA tile width, 512 = 256x256 CTA-pair tile (cta_group::2).                 */
 int vqacl_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major, void* C, int ldc,
                     const void* R, int ldr, int M, int N, int K, int epi, float alpha, int splits, int force_bn, void* stream);
+/* HF T5LayerNorm forward / backward (hf5.5 modeling_t5.py:46-68; used at modeling_t5_our.py:41,47,160 and in every block)  */
 int vqacl_rmsnorm_fwd(const float* x, const float* w, void* y_bf16, float* y_f32, int M, float eps, float scale, void* stream);
 int vqacl_rmsnorm_bwd(const void* dn_bf16, const float* x, const float* w, const float* g_in, float* g_out, void* gb_out,
                       float* dw, int M, float eps, float scale, void* stream);
+/* HF T5Attention core: softmax(Q K^T + relative bias + masks) V, no 1/sqrt(d) scale (hf5.5 modeling_t5.py:277-338), with the
+ * bias / mask construction of JointEncoder.forward (modeling_t5_our.py:225-273) and of the decoder stack folded in.
+ * rel_mode 0 none, 1 text x text corner (encoder, Lt = text length), 2 everywhere (decoder self). keymask: additive [B,Sk].   */
 int vqacl_attention_fwd(const void* q, const void* k, const void* v, int ldq, int ldk, int ldv, void* o, int ldo, float* lse,
                         int B, int H, int Sq, int Sk, const float* rel_table, const int32_t* rel_bucket, int rel_mode, int Lt,
                         const float* keymask, int causal, void* stream);
@@ -125,18 +136,25 @@ int vqacl_attention_bwd(const void* q, const void* k, const void* v, int ldq, in
                         const float* rel_table, const int32_t* rel_bucket, int rel_mode, int Lt, const float* keymask, int causal,
                         float* d_rel_table, const void* o_saved /* forward output (pitch ldo) or NULL: enables the key-split
                         backward for Sq <= 16 < Sk */, void* stream);
+/* SI prototype path (modeling_t5_our.py:583-615): token means of hidden[:, :split] / hidden[:, split:] (:585-588,601-605) */
 int vqacl_proto_means(const float* h, int B, int S, int split, float* meanQ, float* meanV, void* stream);
+/* VLT5.calculate_current_prototype (modeling_t5_our.py:500-511)                                                              */
 int vqacl_proto_scatter_mean(const float* mean, const float* labels, int B, int C, float* proto, float* cnt, void* stream);
+/* VLT5.update_prototype (modeling_t5_our.py:465-498) on explicit state buffers                                               */
 int vqacl_proto_update(const float* curQ, const float* curV, const float* cntQ, const float* cntV, float* Qproto, float* Vproto,
                        float* numQ, float* numV, int CQ, int CV, int task_id, int first_step_of_task, int has_mem, float alpha,
                        float beta, void* stream);
+/* VLT5.cosine_similarity_multi + the torch.cat of modeling_t5_our.py:434-462,615                                             */
 int vqacl_proto_retrieve(const float* P, int C, const float* x, int B, void* out_bf16, int out_pitch_rows, int out_row,
                          int64_t* idx, float* out_f32, float* scratch /* [C,768] fp32 */, void* stream);
+/* CrossEntropyLoss(ignore_index=-100, reduction='none') over the tied LM head (modeling_t5_our.py:675-686), fwd and grad     */
 int vqacl_ce_fwd(const void* logits_bf16, int ld, int M, int V, const int64_t* labels, float* lse, float* loss, void* stream);
 int vqacl_ce_bwd(void* logits_bf16, int ld, int M, int V, const int64_t* labels, const float* lse, const float* w, void* stream);
+/* VisualEmbedding.forward after the 2048->768 GEMM (modeling_t5_our.py:93-143)                                               */
 int vqacl_visual_embed_fwd(const float* featpre, const float* boxes, const float* bf, const float* wf, const float* Wp,
                            const float* bp, const float* wp, const float* img_emb, const float* shared, int V, int B, int N,
                            int S, int L, float eps, float* x, void* stream);
+/* transformers-4.2.1 AdamW.step + torch clip_grad_norm_ (trainer_base.py:130-198, vqacl.py:475-482) over a flat range         */
 int vqacl_adamw_hf(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, int64_t n_decay, float lr, float beta1,
                    float beta2, float eps, float weight_decay, int step, const float* sumsq, float max_norm, void* stream);
 int vqacl_grad_sumsq(const float* g, int64_t n, float* partials, float* out, void* stream);
