@@ -201,6 +201,8 @@ def run_native(args):
     model.encoder.visual_embedding.img_order_embedding.weight.data.normal_(0, 1)
     model = model.to(dev)
     model.train()
+    if os.environ.get("VQACL_COMM_SMS"):
+        model.comm_sms = int(os.environ["VQACL_COMM_SMS"])
     opt = V.FusedAdamW(model, lr=1e-4, eps=1e-6, weight_decay=0.01, overlap_with_next_forward=not args.no_overlap_optimizer)
     sched = V.get_constant_schedule_with_warmup(opt, 10)
 

@@ -108,6 +108,9 @@ int vqacl_param_sync(void* engine, void* stream);
 int64_t vqacl_generate_workspace_bytes(void* engine, int B, int L, int N, int max_len);
 int vqacl_generate(void* engine, const vqacl_batch* batch, const vqacl_proto_state* proto, int max_len, int64_t* out_tokens,
                    void* workspace, int64_t workspace_bytes, int* out_len, void* stream);
+/* SMs the persistent GEMM kernels may occupy (0 = all): lowered by the host while an NCCL all-reduce must make progress
+ * next to backward (the GEMM CTAs otherwise fill every SM's shared memory and starve the collective's CTAs) */
+int vqacl_set_gemm_sm_limit(int n_sms);
 /* number of kernels this library has launched so far in this process (bench.py's gpu_launches) */
 long long vqacl_launch_count(void);
 

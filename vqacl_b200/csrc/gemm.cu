@@ -103,7 +103,12 @@ void gemm_tmap_cache_clear() {
 }
 
 static int g_pair_enabled = 1;   // VQACL_GEMM_PAIR=0 disables the CTA-pair kernel (A/B measurements)
+// SMs the persistent GEMMs may occupy (0 = all). With N > 1 GPUs the host lowers it during backward so that the NCCL
+// all-reduce kernels, which need resident CTAs of their own, are not starved by 148 GEMM CTAs that each fill an SM's
+// shared memory (vqacl_set_gemm_sm_limit).
+static int g_sm_limit = 0;
 static int g_num_sms = 0;
+static int gemm_sms();
 int num_sms() {
   if (g_num_sms == 0) {
     int dev = 0;
@@ -116,6 +121,15 @@ int num_sms() {
   return g_num_sms;
 }
 
+static int gemm_sms() {
+  const int n = num_sms();
+  return (g_sm_limit > 0 && g_sm_limit < n) ? g_sm_limit : n;
+}
+extern "C" int vqacl_set_gemm_sm_limit(int n) {
+  g_sm_limit = n > 0 ? (n & ~1) : 0;   // even: the CTA-pair kernel launches clusters of two
+  return 0;
+}
+
 template <int BN, bool A_MN, bool B_MN>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
@@ -126,7 +140,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& 
     attr_set = true;
   }
   const int tiles = ((args.M + GEMM_BM - 1) / GEMM_BM) * ((args.N + BN - 1) / BN) * args.splits;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
+  const int grid = tiles < gemm_sms() ? tiles : gemm_sms();
   (void)vq_launch(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, ta, tb, args);
   VQ_LAUNCH_CHECK();
   return 0;
@@ -142,7 +156,7 @@ static int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmA
     attr_set = true;
   }
   const int work = ((args.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM)) * ((args.N + GEMM2_BN - 1) / GEMM2_BN) * args.splits;
-  const int max_pairs = num_sms() / 2;
+  const int max_pairs = gemm_sms() / 2;
   const int pairs = work < max_pairs ? work : max_pairs;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * pairs);
@@ -220,7 +234,8 @@ int gemm_bf16(const GemmOperand& A, const GemmOperand& B, GemmArgs args, int for
     //   tensor pipe — 128 x 256 runs at 2/3 of the MMA rate (measured), the narrow tiles re-read A even more often;
     //   256 x 256 CTA-pair tile (bn = 512): 4 MMAs at the full rate on two SMs.
     const int tiles_m = (args.M + GEMM_BM - 1) / GEMM_BM;
-    const int sms = num_sms();
+    (void)num_sms();
+    const int sms = gemm_sms();
     const int kb_split = (kblocks + args.splits - 1) / args.splits;
     const int cand[3] = {256, 128, 64};
     const int cyc[3] = {768, 400, 240};

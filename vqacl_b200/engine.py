@@ -78,6 +78,7 @@ def _declare(L):
                                  POINTER(c_int), c_void_p]
     L.vqacl_generate_workspace_bytes.argtypes = [c_void_p, c_int, c_int, c_int, c_int]
     L.vqacl_generate_workspace_bytes.restype = c_int64
+    L.vqacl_set_gemm_sm_limit.argtypes = [c_int]
     L.vqacl_launch_count.argtypes = []
     L.vqacl_launch_count.restype = c_int64
     _SIGS_DONE = True
@@ -257,6 +258,9 @@ class Engine:
         check(self.L.vqacl_generate(self.h, byref(cb), byref(ps), max_len, ptr(out), ptr(self.gen_ws), self.gen_ws.numel(),
                                     byref(n), cur_stream()))
         return out[:, :n.value]
+
+    def set_gemm_sm_limit(self, n):
+        check(self.L.vqacl_set_gemm_sm_limit(int(n)))
 
     def launch_count(self):
         return self.L.vqacl_launch_count()
