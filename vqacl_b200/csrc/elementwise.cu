@@ -335,18 +335,23 @@ int vis_embed_fwd(const VisArgs& a, cudaStream_t stream) {
   return 0;
 }
 
-// column-sum accumulators kept in shared memory per CTA, flushed once with global atomics
+// Column sums over all B*N rows for the 10 per-column gradients (d img_order, d wf, d bf, d wp, d bp, d Wp[:, 0..4]).
+// Each warp accumulates into its OWN shared-memory slice with plain read-modify-write (no atomics: a lane owns its
+// columns), the CTA folds its slices and writes one partial row to `part[cta][10*768]`; vis_embed_reduce_kernel then sums
+// the partials in a fixed order (deterministic) into the gradient arena.
 enum { VA_DIMG = 0, VA_DWF, VA_DBF, VA_DWP, VA_DBP, VA_DWP0, VA_COUNT = VA_DWP0 + 5 };
+constexpr int VB_WARPS = 4;
 
-__global__ void __launch_bounds__(ROW_WARPS * 32) vis_embed_bwd_kernel(const VisArgs a) {
+__global__ void __launch_bounds__(VB_WARPS * 32) vis_embed_bwd_kernel(const VisArgs a, float* __restrict__ part) {
   vq_pdl_trigger();
   vq_pdl_wait();
-  extern __shared__ float s_acc[];  // [VA_COUNT][DM]
+  extern __shared__ float s_acc[];  // [VB_WARPS][VA_COUNT][DM]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < VA_COUNT * DM; i += ROW_WARPS * 32) s_acc[i] = 0.f;
+  for (int i = threadIdx.x; i < VB_WARPS * VA_COUNT * DM; i += VB_WARPS * 32) s_acc[i] = 0.f;
   __syncthreads();
+  float* acc = s_acc + warp * (VA_COUNT * DM);
   const int rows = a.B * a.N;
-  for (int r = blockIdx.x * ROW_WARPS + warp; r < rows; r += gridDim.x * ROW_WARPS) {
+  for (int r = blockIdx.x * VB_WARPS + warp; r < rows; r += gridDim.x * VB_WARPS) {
     const int b = r / a.N, n = r % a.N;
     const size_t grow = (size_t)b * a.S + a.L + n;
     float g[RW_CHUNKS][4], u[RW_CHUNKS][4], t[RW_CHUNKS][4];
@@ -360,7 +365,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) vis_embed_bwd_kernel(const Vis
                    "f"(g[j][2]), "f"(g[j][3])
                    : "memory");
 #pragma unroll
-      for (int i = 0; i < 4; ++i) atomicAdd(&s_acc[VA_DIMG * DM + (lane + 32 * j) * 4 + i], g[j][i]);
+      for (int i = 0; i < 4; ++i) acc[VA_DIMG * DM + (lane + 32 * j) * 4 + i] += g[j][i];
     }
     // ---- feature branch
     load_row_f32(u, a.featpre + (size_t)r * DM, lane);
@@ -378,7 +383,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) vis_embed_bwd_kernel(const Vis
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         u[j][i] *= rstd;  // uhat
-        atomicAdd(&s_acc[VA_DWF * DM + (lane + 32 * j) * 4 + i], g[j][i] * u[j][i]);
+        acc[VA_DWF * DM + (lane + 32 * j) * 4 + i] += g[j][i] * u[j][i];
         dx[j][i] = g[j][i] * t[j][i];
         dot += dx[j][i] * u[j][i];
       }
@@ -388,7 +393,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) vis_embed_bwd_kernel(const Vis
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         dx[j][i] = rstd * (dx[j][i] - u[j][i] * dot);
-        atomicAdd(&s_acc[VA_DBF * DM + (lane + 32 * j) * 4 + i], dx[j][i]);
+        acc[VA_DBF * DM + (lane + 32 * j) * 4 + i] += dx[j][i];
       }
     store_row_bf16(a.dfeatpre + (size_t)r * DM, dx, lane);
     // ---- position branch
@@ -400,10 +405,10 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) vis_embed_bwd_kernel(const Vis
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float* wrow = a.Wp + (size_t)((lane + 32 * j) * 4 + i) * 5;
-        float acc = u[j][i];
+        float v = u[j][i];
 #pragma unroll
-        for (int k = 0; k < 5; ++k) acc += wrow[k] * p5[k];
-        u[j][i] = acc;
+        for (int k = 0; k < 5; ++k) v += wrow[k] * p5[k];
+        u[j][i] = v;
       }
     rstd = rsqrtf(row_sumsq(u) / DM + a.eps);
     load_row_f32(t, a.wp, lane);
@@ -413,7 +418,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) vis_embed_bwd_kernel(const Vis
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         u[j][i] *= rstd;
-        atomicAdd(&s_acc[VA_DWP * DM + (lane + 32 * j) * 4 + i], g[j][i] * u[j][i]);
+        acc[VA_DWP * DM + (lane + 32 * j) * 4 + i] += g[j][i] * u[j][i];
         dx[j][i] = g[j][i] * t[j][i];
         dot += dx[j][i] * u[j][i];
       }
@@ -424,35 +429,56 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) vis_embed_bwd_kernel(const Vis
       for (int i = 0; i < 4; ++i) {
         const float dv = rstd * (dx[j][i] - u[j][i] * dot);
         const int c = (lane + 32 * j) * 4 + i;
-        atomicAdd(&s_acc[VA_DBP * DM + c], dv);
+        acc[VA_DBP * DM + c] += dv;
 #pragma unroll
-        for (int k = 0; k < 5; ++k) atomicAdd(&s_acc[(VA_DWP0 + k) * DM + c], dv * p5[k]);
+        for (int k = 0; k < 5; ++k) acc[(VA_DWP0 + k) * DM + c] += dv * p5[k];
       }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < DM; c += ROW_WARPS * 32) {
-    atomicAdd(&a.dimg[c], s_acc[VA_DIMG * DM + c]);
-    atomicAdd(&a.dwf[c], s_acc[VA_DWF * DM + c]);
-    atomicAdd(&a.dbf[c], s_acc[VA_DBF * DM + c]);
-    atomicAdd(&a.dwp[c], s_acc[VA_DWP * DM + c]);
-    atomicAdd(&a.dbp[c], s_acc[VA_DBP * DM + c]);
+  float* out = part + (size_t)blockIdx.x * (VA_COUNT * DM);
+  for (int i = threadIdx.x; i < VA_COUNT * DM; i += VB_WARPS * 32) {
+    float v = 0.f;
 #pragma unroll
-    for (int k = 0; k < 5; ++k) atomicAdd(&a.dWp[(size_t)c * 5 + k], s_acc[(VA_DWP0 + k) * DM + c]);
+    for (int wv = 0; wv < VB_WARPS; ++wv) v += s_acc[wv * (VA_COUNT * DM) + i];
+    out[i] = v;
   }
 }
+
+__global__ void __launch_bounds__(256) vis_embed_reduce_kernel(const VisArgs a, const float* __restrict__ part, int nparts) {
+  vq_pdl_trigger();
+  vq_pdl_wait();
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= VA_COUNT * DM) return;
+  float v = 0.f;
+  for (int p = 0; p < nparts; ++p) v += part[(size_t)p * (VA_COUNT * DM) + i];
+  const int arr = i / DM, c = i % DM;
+  float* dst;
+  switch (arr) {
+    case VA_DIMG: dst = a.dimg + c; break;
+    case VA_DWF: dst = a.dwf + c; break;
+    case VA_DBF: dst = a.dbf + c; break;
+    case VA_DWP: dst = a.dwp + c; break;
+    case VA_DBP: dst = a.dbp + c; break;
+    default: dst = a.dWp + (size_t)c * 5 + (arr - VA_DWP0); break;
+  }
+  *dst += v;
+}
+
 int vis_embed_bwd(const VisArgs& a, cudaStream_t stream) {
   const int rows = a.B * a.N;
   if (rows <= 0) return 0;
-  const int smem = VA_COUNT * DM * (int)sizeof(float);
+  VQ_CHECK(a.partials, "vis_embed_bwd: partials scratch buffer missing");
+  const int smem = VB_WARPS * VA_COUNT * DM * (int)sizeof(float);
   static bool attr = false;
   if (!attr) {
     VQ_CUDA(cudaFuncSetAttribute(vis_embed_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr = true;
   }
-  int blocks = (rows + ROW_WARPS - 1) / ROW_WARPS;
-  const int cap = num_sms() * 2;
-  if (blocks > cap) blocks = cap;
-  (void)vq_launch(vis_embed_bwd_kernel, dim3(blocks), dim3(ROW_WARPS * 32), smem, stream, a);
+  int blocks = (rows + VB_WARPS - 1) / VB_WARPS;
+  if (blocks > num_sms()) blocks = num_sms();
+  (void)vq_launch(vis_embed_bwd_kernel, dim3(blocks), dim3(VB_WARPS * 32), smem, stream, a, a.partials);
+  VQ_LAUNCH_CHECK();
+  (void)vq_launch(vis_embed_reduce_kernel, dim3((VA_COUNT * DM + 255) / 256), dim3(256), 0, stream, a, (const float*)a.partials, blocks);
   VQ_LAUNCH_CHECK();
   return 0;
 }

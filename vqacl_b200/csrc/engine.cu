@@ -216,6 +216,7 @@ int64_t engine_carve(Engine& e, uint8_t* base, int B, int L, int N, int T) {
   w.dmem = bp.take<bf16>(M2 * d);
   w.dfeatpre = bp.take<bf16>((size_t)B * N * d);
   w.sumsq_partials = bp.take<float>(2048);
+  w.vis_partials = bp.take<float>((size_t)num_sms() * 10 * d);
   w.sumsq = bp.take<float>(4, "grad_sumsq");
   const int64_t total = (bp.off + 255) / 256 * 256;
   if (base) {
@@ -635,6 +636,7 @@ static int backward(Engine& e, const float* w_rows, int accumulate, int stage_be
     va.V = V; va.B = B; va.N = N; va.S = S; va.L = L; va.eps = c.eps; va.drop = e.drop(SITE_ENC_EMB);
     va.g = w.ge; va.dfeatpre = w.dfeatpre; va.dbf = e.G + e.o_bf; va.dwf = e.G + e.o_wf; va.dWp = e.G + e.o_Wp;
     va.dbp = e.G + e.o_bp; va.dwp = e.G + e.o_wp; va.dimg = e.G + e.o_img; va.dshared = e.G + e.o_shared;
+    va.partials = w.vis_partials;
     VQ_TRY(vis_embed_bwd(va, st));
     VQ_TRY(gemm_dw(w.dfeatpre, d, w.feats_bf16, c.feat_dim, e.G + e.o_Wf, d, c.feat_dim, B * N, st));
   }

@@ -56,6 +56,7 @@ struct Workspace {
   float* t_d768_f32;                                      // split-K target of the LM-head dX GEMM
   bf16* dkv_all; bf16* dmem; bf16* dfeatpre;
   float* sumsq_partials; float* sumsq;
+  float* vis_partials;            // [num_sms, 10*768] per-CTA column sums of the visual-embedding backward
 };
 
 struct Engine {

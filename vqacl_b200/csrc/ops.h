@@ -108,6 +108,7 @@ struct VisArgs {
   const float* g;             // [B, S, 768] gradient w.r.t. x
   __nv_bfloat16* dfeatpre;    // [B*N, 768] bf16 (A operand of the dWf GEMM)
   float *dbf, *dwf, *dWp, *dbp, *dwp, *dimg, *dshared;
+  float* partials;            // scratch [num_sms, 10*768] fp32 (per-CTA column sums, reduced in a fixed order)
 };
 int vis_embed_fwd(const VisArgs& a, cudaStream_t stream);
 int vis_embed_bwd(const VisArgs& a, cudaStream_t stream);
