@@ -1,5 +1,6 @@
-// Fused T5 attention for the VL-T5 shapes (S <= 64 keys/queries, d_kv = 64): one CTA per (batch, head) holds the whole
-// Q/K/V problem in shared memory. Scores are NOT scaled by 1/sqrt(d) (T5), the relative-position bias is read from the
+// Fused T5 attention for the VL-T5 shapes (S <= 64 keys/queries, d_kv = 64): the whole Q/K/V problem of one (batch, head)
+// lives in shared memory (encoder: one problem per 4-warp CTA; decoder self-attention: 4 single-warp problems per CTA;
+// cross-attention: key-split across the 4 warps of a CTA). Scores are NOT scaled by 1/sqrt(d) (T5), the relative-position bias is read from the
 // [num_buckets, H] embedding table through a host-precomputed rel->bucket map, and the additive masks of HF 4.2.1
 // (-10000 key padding / causal, -1e9 cross) are applied in-kernel, so the [B,H,S,S] bias tensor the reference
 // materialises (modeling_t5_our.py:258-273) never exists. Backward recomputes P from the saved log-sum-exp.
@@ -17,7 +18,6 @@ namespace vq {
 constexpr int AT_S = 64;      // max queries / keys per problem
 constexpr int AT_D = 64;      // head dim
 constexpr int AT_P = 72;      // smem pitch (elements): 144 B rows -> conflict-free ldmatrix
-constexpr int AT_THREADS = 128;
 
 VQ_DEVINL void ldsm_x4(uint32_t (&r)[4], const void* p) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"

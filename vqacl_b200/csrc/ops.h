@@ -10,10 +10,10 @@ int num_sms();  // gemm.cu
 constexpr int DM = 768;  // d_model of t5-base (the kernels are specialised for it; checked at engine creation)
 
 struct Dropout {
-  uint32_t thr = 0;       // p * 2^32, 0 disables
+  uint32_t thr = 0;       // 16-bit keep threshold round(p * 65536) (vq_dropout_pair), 0 disables
   float inv_keep = 1.f;   // 1 / (1 - p)
-  uint32_t seed = 0;
-  uint32_t site = 0;
+  uint32_t seed = 0;      // per-launch key = mix(step seed, site id), computed on the host (Engine::drop)
+  uint32_t site = 0;      // informational
 };
 
 // ---------------------------------------------------------------- attention (attention.cu)
