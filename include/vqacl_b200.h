@@ -90,7 +90,8 @@ int vqacl_forward_decoder(void* engine, const vqacl_batch* batch, const vqacl_pr
 /* backward of sum_r w[r] * loss_row[r] (loss.backward(), vqacl.py:461); fills the gradient arena (zeroed in stage 0 unless
  * accumulate != 0). Runs stages [stage_begin, stage_end) (stage_end < 0: to the end) so that the host can overlap the NCCL
  * all-reduce of a finished arena range (vqacl_backward_stage_range) with the remaining stages. */
-int vqacl_backward(void* engine, const float* w_rows, int accumulate, int stage_begin, int stage_end, void* stream);
+int vqacl_backward(void* engine, const float* w_rows, const float* gscale /* optional device scalar: upstream d(loss) */,
+                   int accumulate, int stage_begin, int stage_end, void* stream);
 int vqacl_backward_stages(void* engine);
 int vqacl_backward_stage_range(void* engine, int stage, int64_t* begin, int64_t* end);
 /* fused loss tail of VLT5VQA.train_step (vqa_model.py:46-54) */

@@ -249,7 +249,7 @@ int shift_right(const int64_t* labels, int64_t* dec_ids, int B, int T, int start
 }
 
 __global__ void keymask_kernel(const int64_t* __restrict__ ids, int B, int L, int S, int pad_id, float* __restrict__ enc,
-                               float* __restrict__ cross) {
+                               float* __restrict__ cross, float* __restrict__ mask01) {
   vq_pdl_trigger();
   vq_pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -257,12 +257,14 @@ __global__ void keymask_kernel(const int64_t* __restrict__ ids, int B, int L, in
   const int b = i / (S + 2), j = i % (S + 2);
   const bool pad = j < L && ids[b * L + j] == pad_id;
   if (cross) cross[i] = pad ? -1e9f : 0.f;
+  if (mask01) mask01[i] = pad ? 0.f : 1.f;
   if (enc && j < S) enc[b * S + j] = pad ? -10000.0f : 0.f;
 }
-int build_keymasks(const int64_t* ids, int B, int L, int S, int pad_id, float* enc_mask, float* cross_mask, cudaStream_t stream) {
+int build_keymasks(const int64_t* ids, int B, int L, int S, int pad_id, float* enc_mask, float* cross_mask, float* mask01,
+                   cudaStream_t stream) {
   const int n = B * (S + 2);
   if (n <= 0) return 0;
-  (void)vq_launch(keymask_kernel, dim3((n + 255) / 256), dim3(256), 0, stream, ids, B, L, S, pad_id, enc_mask, cross_mask);
+  (void)vq_launch(keymask_kernel, dim3((n + 255) / 256), dim3(256), 0, stream, ids, B, L, S, pad_id, enc_mask, cross_mask, mask01);
   VQ_LAUNCH_CHECK();
   return 0;
 }

@@ -162,6 +162,7 @@ int64_t engine_carve(Engine& e, uint8_t* base, int B, int L, int N, int T) {
   w.mem = bp.take<bf16>(M2 * d, "decoder_memory");
   w.enc_mask = bp.take<float>((size_t)B * S);
   w.cross_mask = bp.take<float>((size_t)B * S2, "cross_mask");
+  w.mask01 = bp.take<float>((size_t)B * S2, "encoder_attention_mask");
   w.meanQ = bp.take<float>((size_t)B * d, "meanQ");
   w.meanV = bp.take<float>((size_t)B * d, "meanV");
   w.curQ = bp.take<float>((size_t)c.n_ques * d, "curQ");
@@ -274,7 +275,7 @@ int encoder_forward(Engine& e, const vqacl_batch* b, cudaStream_t st) {
   const int B = b->B, L = b->L, N = b->N, S = L + N, S2 = S + 2;
   const int M = B * S;
   VQ_TRY(wait_params(e, 0, st));   // embeddings + visual projection + final norms
-  VQ_TRY(build_keymasks(b->input_ids, B, L, S, c.pad_id, w.enc_mask, w.cross_mask, st));
+  VQ_TRY(build_keymasks(b->input_ids, B, L, S, c.pad_id, w.enc_mask, w.cross_mask, w.mask01, st));
   // embeddings: text rows [0,L), visual rows [L,S)   (modeling_t5_our.py:196-214, :247)
   VQ_TRY(embed_fwd(b->input_ids, B, L, e.P + e.o_shared, w.x[0], S, 0, e.drop(SITE_ENC_EMB), st));
   VQ_TRY(cast_f32_to_bf16(b->vis_feats, w.feats_bf16, (size_t)B * N * c.feat_dim, st));
@@ -455,7 +456,7 @@ static int ensure_side_stream(Engine& e) {
 // launches (M = B*T rows: 78-117 CTAs), wave tails for the encoder's. Write-after-read safety: every dY buffer the side
 // stream reads comes from a ring 3 layers deep, and the main stream starts a layer only after the side stream has
 // finished the layer two above it (ev_layer).
-static int backward(Engine& e, const float* w_rows, int accumulate, int stage_begin, int stage_end, cudaStream_t st) {
+static int backward(Engine& e, const float* w_rows, const float* gscale, int accumulate, int stage_begin, int stage_end, cudaStream_t st) {
   VQ_CHECK(e.fwd_valid, "engine: backward called without a preceding training forward");
   VQ_CHECK(e.G, "engine: gradient arena not bound");
   if (ensure_side_stream(e)) return 1;
@@ -493,7 +494,7 @@ static int backward(Engine& e, const float* w_rows, int accumulate, int stage_be
     if (!accumulate) VQ_CUDA(cudaMemsetAsync(e.G, 0, e.n_train * sizeof(float), st));
     // ---- LM head + CE
     VQ_CHECK(w_rows, "backward: w_rows (dL/dloss_row) required");
-    VQ_TRY(ce_bwd(w.logits, e.ldv, Md, V, b.labels, w.lse_ce, w_rows, st));
+    VQ_TRY(ce_bwd(w.logits, e.ldv, Md, V, b.labels, w.lse_ce, w_rows, gscale, st));
     VQ_TRY(fork());
     VQ_TRY(gemm_dw(w.logits, e.ldv, w.yfin, d, e.G + e.o_shared, V, d, Md, sd));
     // dY_fin[Md, d] = dLogits[Md, V] * E[V, d]: few output tiles but a 32 200-deep contraction -> split-K into an fp32 buffer
@@ -774,8 +775,9 @@ extern "C" int vqacl_forward_decoder(void* engine, const vqacl_batch* batch, con
   e.fwd_valid = true;
   return 0;
 }
-extern "C" int vqacl_backward(void* engine, const float* w_rows, int accumulate, int stage_begin, int stage_end, void* stream) {
-  return backward(ENG(engine), w_rows, accumulate, stage_begin, stage_end, ST(stream));
+extern "C" int vqacl_backward(void* engine, const float* w_rows, const float* gscale, int accumulate, int stage_begin, int stage_end,
+                              void* stream) {
+  return backward(ENG(engine), w_rows, gscale, accumulate, stage_begin, stage_end, ST(stream));
 }
 extern "C" int vqacl_backward_stages(void* engine) { return n_backward_stages(ENG(engine)); }
 extern "C" int vqacl_backward_stage_range(void* engine, int stage, int64_t* begin, int64_t* end) {
@@ -908,7 +910,7 @@ extern "C" int vqacl_ce_fwd(const void* logits, int ld, int M, int V, const int6
   return ce_fwd(reinterpret_cast<const bf16*>(logits), ld, M, V, labels, lse, loss, ST(stream));
 }
 extern "C" int vqacl_ce_bwd(void* logits, int ld, int M, int V, const int64_t* labels, const float* lse, const float* w, void* stream) {
-  return ce_bwd(reinterpret_cast<bf16*>(logits), ld, M, V, labels, lse, w, ST(stream));
+  return ce_bwd(reinterpret_cast<bf16*>(logits), ld, M, V, labels, lse, w, nullptr, ST(stream));
 }
 extern "C" int vqacl_visual_embed_fwd(const float* featpre, const float* boxes, const float* bf, const float* wf, const float* Wp,
                                       const float* bp, const float* wp, const float* img_emb, const float* shared, int V, int B,

@@ -31,7 +31,7 @@ struct Workspace {
   std::vector<float*> lse_e;
   float* enc_hidden;              // [B,S,d] fp32 (post final norm/dropout) -> encoder_hidden_states
   bf16* mem;                      // [B,S+2,d] decoder memory
-  float *enc_mask, *cross_mask;
+  float *enc_mask, *cross_mask, *mask01;
   // SI path
   float *meanQ, *meanV, *curQ, *curV, *cntQ, *cntV, *pnorm;
   int64_t *idxQ, *idxV;

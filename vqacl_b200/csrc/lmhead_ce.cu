@@ -67,13 +67,13 @@ int ce_fwd(const __nv_bfloat16* logits, int ld, int M, int V, const int64_t* lab
 
 __global__ void __launch_bounds__(CE_THREADS)
 ce_bwd_kernel(__nv_bfloat16* __restrict__ logits, int ld, int V, const int64_t* __restrict__ labels, const float* __restrict__ lse,
-              const float* __restrict__ w) {
+              const float* __restrict__ w, const float* __restrict__ gscale) {
   vq_pdl_trigger();
   vq_pdl_wait();
   const int r = blockIdx.x;
   __nv_bfloat16* row = logits + (size_t)r * ld;
   const int64_t lab = labels[r];
-  const float wr = (lab >= 0 && lab < V) ? w[r] : 0.f;
+  const float wr = (lab >= 0 && lab < V) ? w[r] * (gscale ? *gscale : 1.f) : 0.f;   // gscale = upstream d(loss) (autograd)
   const float l = lse[r];
   const int nv = ld / 8;  // also clears the pitch padding beyond V
   for (int i = threadIdx.x; i < nv; i += CE_THREADS) {
@@ -93,10 +93,11 @@ ce_bwd_kernel(__nv_bfloat16* __restrict__ logits, int ld, int V, const int64_t* 
     reinterpret_cast<uint4*>(row)[i] = make_uint4(ww[0], ww[1], ww[2], ww[3]);
   }
 }
-int ce_bwd(__nv_bfloat16* logits, int ld, int M, int V, const int64_t* labels, const float* lse, const float* w, cudaStream_t stream) {
+int ce_bwd(__nv_bfloat16* logits, int ld, int M, int V, const int64_t* labels, const float* lse, const float* w, const float* gscale,
+           cudaStream_t stream) {
   if (M <= 0) return 0;
   VQ_CHECK(ld % 8 == 0, "ce_bwd: logits pitch %d must be a multiple of 8", ld);
-  (void)vq_launch(ce_bwd_kernel, dim3(M), dim3(CE_THREADS), 0, stream, logits, ld, V, labels, lse, w);
+  (void)vq_launch(ce_bwd_kernel, dim3(M), dim3(CE_THREADS), 0, stream, logits, ld, V, labels, lse, w, gscale);
   VQ_LAUNCH_CHECK();
   return 0;
 }

@@ -89,7 +89,8 @@ int embed_bwd(const int64_t* ids, int B, int L, const float* g, int S, int row0,
 // decoder_input_ids = shift_right(labels) (start 0, -100 -> pad 0)
 int shift_right(const int64_t* labels, int64_t* dec_ids, int B, int T, int start_id, int pad_id, cudaStream_t stream);
 // additive key masks from input_ids: enc [B,S] (-10000 on text pads), cross [B,S+2] (-1e9 on text pads)
-int build_keymasks(const int64_t* ids, int B, int L, int S, int pad_id, float* enc_mask, float* cross_mask, cudaStream_t stream);
+int build_keymasks(const int64_t* ids, int B, int L, int S, int pad_id, float* enc_mask, float* cross_mask, float* mask01,
+                   cudaStream_t stream);   // mask01 [B,S+2]: the 1/0 encoder_attention_mask the reference returns
 
 // VisualEmbedding (modeling_t5_our.py:93-143) after the 2048->768 GEMM: bias + RMSNorm, box/area projection + RMSNorm,
 // image-order and object-order embeddings, dropout; writes rows [L, L+N) of x [B,S,768].
@@ -142,7 +143,8 @@ int proto_retrieve(const float* P, int C, const float* x, int B, __nv_bfloat16* 
 // per-row log-sum-exp and CE loss over bf16 logits [M, V] (pitch ld); label -100 -> loss 0
 int ce_fwd(const __nv_bfloat16* logits, int ld, int M, int V, const int64_t* labels, float* lse, float* loss, cudaStream_t stream);
 // in place: logits <- (softmax - onehot) * w[row]   (w = dL/dloss_row; 0 for ignored rows)
-int ce_bwd(__nv_bfloat16* logits, int ld, int M, int V, const int64_t* labels, const float* lse, const float* w, cudaStream_t stream);
+int ce_bwd(__nv_bfloat16* logits, int ld, int M, int V, const int64_t* labels, const float* lse, const float* w, const float* gscale,
+           cudaStream_t stream);   // gscale: optional device scalar multiplied into every w[row]
 // fused loss tail of VLT5VQA.train_step (vqa_model.py:46-54): loss = mean_b(score_b * sum_t loss_bt / max(n_b,1));
 // also emits the per-row weights w[b,t] = score_b / (max(n_b,1) * B) for valid labels
 int loss_tail(const float* loss_rows, const int64_t* labels, const float* scores, int B, int T, float* loss_out, float* w_rows, cudaStream_t stream);

@@ -67,7 +67,7 @@ def _declare(L):
     L.vqacl_forward_encoder.argtypes = [c_void_p, POINTER(CBatch), POINTER(CProtoState), c_uint32, c_int, c_void_p]
     L.vqacl_forward_decoder.argtypes = [c_void_p, POINTER(CBatch), POINTER(CProtoState), c_int, c_void_p]
     L.vqacl_proto_sums.argtypes = [c_void_p, POINTER(CBatch), c_void_p]
-    L.vqacl_backward.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]
+    L.vqacl_backward.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]
     L.vqacl_backward_stages.argtypes = [c_void_p]
     L.vqacl_backward_stage_range.argtypes = [c_void_p, c_int, POINTER(c_int64), POINTER(c_int64)]
     L.vqacl_loss_tail.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]
@@ -231,8 +231,8 @@ class Engine:
         check(self.L.vqacl_backward_stage_range(self.h, stage, byref(a), byref(b)))
         return a.value, b.value
 
-    def backward(self, w_rows, accumulate=False, stage_begin=0, stage_end=-1):
-        check(self.L.vqacl_backward(self.h, ptr(w_rows), int(accumulate), stage_begin, stage_end, cur_stream()))
+    def backward(self, w_rows, accumulate=False, stage_begin=0, stage_end=-1, gscale=None):
+        check(self.L.vqacl_backward(self.h, ptr(w_rows), ptr(gscale), int(accumulate), stage_begin, stage_end, cur_stream()))
 
     def clip_adamw(self, m, v, lr, beta1, beta2, eps, wd, step, max_norm, norm_out=None, overlap=False):
         """norm_out (fp32[1], device) receives the SQUARED global gradient norm."""

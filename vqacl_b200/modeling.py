@@ -480,17 +480,17 @@ class VLT5(nn.Module):
         eng = self._engine
         accumulate = self._grad_views[0][0].grad is not None
         if gscale is not None:
-            w_rows = w_rows * gscale.to(w_rows.dtype)
+            gscale = gscale.detach().to(torch.float32).reshape(1).contiguous()     # device scalar, multiplied in ce_bwd
         world = self._world() if self.sync_grads else 1
         if world == 1:
-            eng.backward(w_rows, accumulate)
+            eng.backward(w_rows, accumulate, gscale=gscale)
         else:
-            self._backward_overlapped(w_rows, accumulate)
+            self._backward_overlapped(w_rows, accumulate, gscale)
         if not accumulate:
             for p, gv in self._grad_views:
                 p.grad = gv
 
-    def _backward_overlapped(self, w_rows, accumulate):
+    def _backward_overlapped(self, w_rows, accumulate, gscale=None):
         """Gradient all-reduce (avg) over NCCL, bucketed by backward stage and issued on a side stream so it overlaps the
         remaining stages (replaces the reference's DDP reducer, which never fires — H11)."""
         import torch.distributed as dist
@@ -508,7 +508,7 @@ class VLT5(nn.Module):
             eng.set_gemm_sm_limit(n_sms - self.comm_sms)     # keep a few SMs free so the collectives' CTAs become resident
 
         for s in range(n):
-            eng.backward(w_rows, False, s, s + 1)
+            eng.backward(w_rows, False, s, s + 1, gscale=gscale)
             for a, b in flush_after.get(s, ()):
                 ev = torch.cuda.Event()
                 ev.record(main)
@@ -567,8 +567,7 @@ class VLT5(nn.Module):
         out = VLSeq2SeqLMOutput()
         out.logits = eng.ws_tensor("logits", torch.bfloat16, (B, T, c.vocab_size), pitch=ldv)
         out.encoder_hidden_states = eng.ws_tensor("encoder_hidden_states", torch.float32, (B, S, c.d_model))
-        cm = eng.ws_tensor("cross_mask", torch.float32, (B, S + 2))
-        out.encoder_attention_mask = (cm == 0).to(torch.float32)
+        out.encoder_attention_mask = eng.ws_tensor("encoder_attention_mask", torch.float32, (B, S + 2))
         out.max_idx_Q = eng.ws_tensor("idxQ", torch.int64, (B,))
         out.max_idx_V = eng.ws_tensor("idxV", torch.int64, (B,))
         return out
