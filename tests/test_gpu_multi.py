@@ -35,7 +35,10 @@ def _worker(rank, world, port, q):
         m.grad_bucket_elems = 1 << 20          # several buckets even for the 2-layer model
         g = torch.Generator().manual_seed(5)
         m.Q_prototype = torch.randn(10, 768, generator=g)
-        r = m.train_step(shard, 2, 0.5, 0.3)
+        # the reference wraps the model in DDP and then calls model.module.train_step (vqacl.py:127-129,438): the wrapper's
+        # reducer never fires; gradient averaging happens inside loss.backward()
+        ddp = torch.nn.parallel.DistributedDataParallel(m, device_ids=[rank], find_unused_parameters=True)
+        r = ddp.module.train_step(shard, 2, 0.5, 0.3)
         r["loss"].backward()
         torch.cuda.synchronize()
         ok = True
