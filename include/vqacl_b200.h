@@ -92,6 +92,11 @@ int vqacl_forward_decoder(void* engine, const vqacl_batch* batch, const vqacl_pr
  * all-reduce of a finished arena range (vqacl_backward_stage_range) with the remaining stages. */
 int vqacl_backward(void* engine, const float* w_rows, const float* gscale /* optional device scalar: upstream d(loss) */,
                    int accumulate, int stage_begin, int stage_end, void* stream);
+/* whole backward in ONE call for N > 1 GPUs: after each stage the engine makes `comm_stream` wait for that stage on both of
+ * its streams and calls stage_cb(stage, user); the host enqueues the all-reduce of vqacl_backward_stage_range(stage) (or of
+ * a merged bucket) on comm_stream from inside the callback and joins comm_stream with `stream` afterwards. */
+int vqacl_backward_overlapped(void* engine, const float* w_rows, const float* gscale, int accumulate, void* comm_stream,
+                              void (*stage_cb)(int stage, void* user), void* user, void* stream);
 int vqacl_backward_stages(void* engine);
 int vqacl_backward_stage_range(void* engine, int stage, int64_t* begin, int64_t* end);
 /* fused loss tail of VLT5VQA.train_step (vqa_model.py:46-54) */

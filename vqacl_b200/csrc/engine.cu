@@ -456,7 +456,10 @@ static int ensure_side_stream(Engine& e) {
 // launches (M = B*T rows: 78-117 CTAs), wave tails for the encoder's. Write-after-read safety: every dY buffer the side
 // stream reads comes from a ring 3 layers deep, and the main stream starts a layer only after the side stream has
 // finished the layer two above it (ev_layer).
-static int backward(Engine& e, const float* w_rows, const float* gscale, int accumulate, int stage_begin, int stage_end, cudaStream_t st) {
+typedef void (*vq_stage_cb)(int stage, void* user);
+
+static int backward(Engine& e, const float* w_rows, const float* gscale, int accumulate, int stage_begin, int stage_end, cudaStream_t st,
+                    cudaStream_t comm = nullptr, vq_stage_cb cb = nullptr, void* cb_user = nullptr) {
   VQ_CHECK(e.fwd_valid, "engine: backward called without a preceding training forward");
   VQ_CHECK(e.G, "engine: gradient arena not bound");
   if (ensure_side_stream(e)) return 1;
@@ -477,6 +480,24 @@ static int backward(Engine& e, const float* w_rows, const float* gscale, int acc
   auto fork = [&]() -> int {
     VQ_CUDA(cudaEventRecord(e.ev_fork, st));
     VQ_CUDA(cudaStreamWaitEvent(sd, e.ev_fork, 0));
+    return 0;
+  };
+  // end of a stage: the gradient range it finalised (backward_stage_range) is complete once BOTH streams reach this point
+  auto stage_done = [&](int s) -> int {
+    if (!cb) return 0;
+    if ((int)e.ev_stage_main.size() < n_stages) {
+      e.ev_stage_main.resize(n_stages, nullptr);
+      e.ev_stage_side.resize(n_stages, nullptr);
+      for (int i = 0; i < n_stages; ++i) {
+        if (!e.ev_stage_main[i]) VQ_CUDA(cudaEventCreateWithFlags(&e.ev_stage_main[i], cudaEventDisableTiming));
+        if (!e.ev_stage_side[i]) VQ_CUDA(cudaEventCreateWithFlags(&e.ev_stage_side[i], cudaEventDisableTiming));
+      }
+    }
+    VQ_CUDA(cudaEventRecord(e.ev_stage_main[s], st));
+    VQ_CUDA(cudaEventRecord(e.ev_stage_side[s], sd));
+    VQ_CUDA(cudaStreamWaitEvent(comm, e.ev_stage_main[s], 0));
+    VQ_CUDA(cudaStreamWaitEvent(comm, e.ev_stage_side[s], 0));
+    cb(s, cb_user);   // the host enqueues the all-reduce(s) it planned for this stage on `comm`
     return 0;
   };
   int layer_no = 0;   // layers processed in this call (for the 2-layer lag)
@@ -513,6 +534,7 @@ static int backward(Engine& e, const float* w_rows, const float* gscale, int acc
     r.dw = e.G + e.o_dec_final; r.M = Md; r.eps = c.eps; r.scale = 1.f / sqrtf((float)d); r.own = e.drop(SITE_DEC_FINAL);
     r.consumer = e.drop(site_dec(Ld - 1, 5)); r.consumer_cols = d;
     VQ_TRY(rmsnorm_bwd(r, st));
+    VQ_TRY(stage_done(0));
   }
   for (int l = Ld - 1; l >= 0; --l) {
     if (!on(Ld - l)) continue;
@@ -572,6 +594,7 @@ static int backward(Engine& e, const float* w_rows, const float* gscale, int acc
     q.consumer = l > 0 ? e.drop(site_dec(l - 1, 5)) : Dropout();
     VQ_TRY(rmsnorm_bwd(q, st));
     VQ_TRY(layer_end());
+    VQ_TRY(stage_done(Ld - l));
   }
   if (on(Ld + 1)) {
     // decoder token embedding (tied `shared`)
@@ -587,6 +610,7 @@ static int backward(Engine& e, const float* w_rows, const float* gscale, int acc
     en.g_in = nullptr; en.g_out = w.ge; en.gb_out = w.geb_ring[e.geb_i]; en.dw = e.G + e.o_enc_final; en.M = M; en.eps = c.eps; en.scale = 1.f;
     en.own = e.drop(SITE_ENC_FINAL); en.consumer = e.drop(site_enc(Le - 1, 3)); en.consumer_cols = d;
     VQ_TRY(rmsnorm_bwd(en, st));
+    VQ_TRY(stage_done(Ld + 1));
   }
   for (int l = Le - 1; l >= 0; --l) {
     if (!on(Ld + 1 + Le - l)) continue;
@@ -627,6 +651,7 @@ static int backward(Engine& e, const float* w_rows, const float* gscale, int acc
     if (l == 0) q.gb_out = nullptr;
     VQ_TRY(rmsnorm_bwd(q, st));
     VQ_TRY(layer_end());
+    VQ_TRY(stage_done(Ld + 1 + Le - l));
   }
   if (on(Ld + Le + 2)) {
     // ---- embeddings: text tokens (tied shared) and the VisualEmbedding
@@ -640,6 +665,7 @@ static int backward(Engine& e, const float* w_rows, const float* gscale, int acc
     va.partials = w.vis_partials;
     VQ_TRY(vis_embed_bwd(va, st));
     VQ_TRY(gemm_dw(w.dfeatpre, d, w.feats_bf16, c.feat_dim, e.G + e.o_Wf, d, c.feat_dim, B * N, st));
+    VQ_TRY(stage_done(Ld + Le + 2));
   }
   // join: the caller's stream owns every gradient written by this call
   VQ_CUDA(cudaEventRecord(e.ev_join, sd));
@@ -675,6 +701,8 @@ extern "C" void vqacl_engine_destroy(void* engine) {
       cudaEventDestroy(e.ev_opt_fork);
       cudaStreamDestroy(e.opt_stream);
     }
+    for (auto& ev : e.ev_stage_main) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : e.ev_stage_side) if (ev) cudaEventDestroy(ev);
     if (e.side) {
       cudaStreamSynchronize(e.side);
       cudaEventDestroy(e.ev_fork);
@@ -778,6 +806,11 @@ extern "C" int vqacl_forward_decoder(void* engine, const vqacl_batch* batch, con
 extern "C" int vqacl_backward(void* engine, const float* w_rows, const float* gscale, int accumulate, int stage_begin, int stage_end,
                               void* stream) {
   return backward(ENG(engine), w_rows, gscale, accumulate, stage_begin, stage_end, ST(stream));
+}
+extern "C" int vqacl_backward_overlapped(void* engine, const float* w_rows, const float* gscale, int accumulate, void* comm_stream,
+                                         void (*stage_cb)(int, void*), void* user, void* stream) {
+  VQ_CHECK(comm_stream && stage_cb, "backward_overlapped: communication stream and stage callback required");
+  return backward(ENG(engine), w_rows, gscale, accumulate, 0, -1, ST(stream), ST(comm_stream), stage_cb, user);
 }
 extern "C" int vqacl_backward_stages(void* engine) { return n_backward_stages(ENG(engine)); }
 extern "C" int vqacl_backward_stage_range(void* engine, int stage, int64_t* begin, int64_t* end) {

@@ -82,6 +82,9 @@ struct Engine {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_layer[4] = {nullptr, nullptr, nullptr, nullptr};
   int gdb_i = 0, geb_i = 0;
+  // multi-GPU: per-stage completion events (main / side stream) that the host's communication stream waits on before the
+  // stage callback issues the all-reduce of the gradient range that stage finalised (no main<->side join per stage)
+  std::vector<cudaEvent_t> ev_stage_main, ev_stage_side;
   // optimizer overlapped with the next forward: chunks of the arena are updated on `opt_stream` in the order the forward
   // uses them (embeddings+visual | encoder layer 0..Le-1 | decoder+cross-KV); ev_opt[k] marks chunk k ready
   cudaStream_t opt_stream = nullptr;

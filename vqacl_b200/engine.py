@@ -42,6 +42,7 @@ class CProtoState(Structure):
 
 
 _SIGS_DONE = False
+STAGE_CB = ctypes.CFUNCTYPE(None, c_int, c_void_p)
 
 
 def _declare(L):
@@ -68,6 +69,7 @@ def _declare(L):
     L.vqacl_forward_decoder.argtypes = [c_void_p, POINTER(CBatch), POINTER(CProtoState), c_int, c_void_p]
     L.vqacl_proto_sums.argtypes = [c_void_p, POINTER(CBatch), c_void_p]
     L.vqacl_backward.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]
+    L.vqacl_backward_overlapped.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p, STAGE_CB, c_void_p, c_void_p]
     L.vqacl_backward_stages.argtypes = [c_void_p]
     L.vqacl_backward_stage_range.argtypes = [c_void_p, c_int, POINTER(c_int64), POINTER(c_int64)]
     L.vqacl_loss_tail.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]
@@ -233,6 +235,22 @@ class Engine:
 
     def backward(self, w_rows, accumulate=False, stage_begin=0, stage_end=-1, gscale=None):
         check(self.L.vqacl_backward(self.h, ptr(w_rows), ptr(gscale), int(accumulate), stage_begin, stage_end, cur_stream()))
+
+    def backward_overlapped(self, w_rows, accumulate, comm_stream, on_stage, gscale=None):
+        """One-call backward; `on_stage(stage)` runs on the host right after the engine ordered `comm_stream` behind that stage."""
+        errors = []
+
+        def _cb(stage, _user):
+            try:
+                on_stage(stage)
+            except BaseException as e:     # exceptions cannot cross the C frame: re-raised below
+                errors.append(e)
+        cb = STAGE_CB(_cb)
+        rc = self.L.vqacl_backward_overlapped(self.h, ptr(w_rows), ptr(gscale), int(accumulate), c_void_p(comm_stream.cuda_stream), cb, None,
+                                              cur_stream())
+        if errors:
+            raise errors[0]
+        check(rc)
 
     def clip_adamw(self, m, v, lr, beta1, beta2, eps, wd, step, max_norm, norm_out=None, overlap=False):
         """norm_out (fp32[1], device) receives the SQUARED global gradient norm."""

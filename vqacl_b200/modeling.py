@@ -498,7 +498,9 @@ class VLT5(nn.Module):
         if accumulate:
             raise VqaclError("gradient accumulation across backward calls is not supported with multi-GPU sync")
         if self._comm_stream is None:
-            self._comm_stream = torch.cuda.Stream(device=eng.device)
+            # high priority: the collectives' CTAs must become resident as soon as an SM frees up, otherwise the back-to-back
+            # persistent GEMMs (whose successor is already queued through PDL) starve them until backward is over
+            self._comm_stream = torch.cuda.Stream(device=eng.device, priority=-1)
         main = torch.cuda.current_stream()
         n = eng.n_backward_stages()
         ranges = [eng.backward_stage_range(s) for s in range(n)]
@@ -507,14 +509,13 @@ class VLT5(nn.Module):
         if self.comm_sms > 0:
             eng.set_gemm_sm_limit(n_sms - self.comm_sms)     # keep a few SMs free so the collectives' CTAs become resident
 
-        for s in range(n):
-            eng.backward(w_rows, False, s, s + 1, gscale=gscale)
+        def on_stage(s):
+            # the engine has already made the communication stream wait for stage s on both of its streams
             for a, b in flush_after.get(s, ()):
-                ev = torch.cuda.Event()
-                ev.record(main)
-                self._comm_stream.wait_event(ev)
                 with torch.cuda.stream(self._comm_stream):
                     dist.all_reduce(eng.G[a:b], op=dist.ReduceOp.AVG)
+
+        eng.backward_overlapped(w_rows, False, self._comm_stream, on_stage, gscale=gscale)
         eng.set_gemm_sm_limit(0)
         main.wait_stream(self._comm_stream)
 
