@@ -37,4 +37,7 @@ def rel_err(a, b):
 
 def cos(a, b):
     a, b = a.float().flatten(), b.float().flatten()
-    return (torch.dot(a, b) / (a.norm() * b.norm()).clamp(min=1e-30)).item()
+    na, nb = a.norm().item(), b.norm().item()
+    if na < 1e-20 and nb < 1e-20:
+        return 1.0            # both exactly zero (e.g. attention over a single key has no q/k gradient)
+    return (torch.dot(a, b) / max(na * nb, 1e-30)).item()

@@ -214,3 +214,21 @@ def test_task_loop_with_rehearsal_checkpoint_and_eval(tmp_path):
     m2.V_prototype = torch.load(os.path.join(out, "V_prototype.pt"))
     b = O.synthetic_batch(8, seed=3)
     assert torch.equal(model.test_step(b)["token_ids"], m2.test_step(b)["token_ids"])
+
+
+@pytest.mark.parametrize("B,L,T,N", [(1, 3, 1, 36), (3, 20, 10, 42), (2, 1, 2, 24), (5, 20, 5, 36)])
+def test_edge_shapes(B, L, T, N):
+    """Smallest / largest shapes the path accepts: single sample, one-token question, one-token target, the 62-token
+    encoder limit (20 + 42, + 2 prototype rows = 64 cross-attention keys), few boxes (the reference needs more than 20
+    encoder tokens: with fewer the V-side mean of modeling_t5_our.py:587 is taken over an empty slice and is NaN there too)."""
+    om, m = make_pair(layers=1)
+    om.train(); m.train()
+    b = O.synthetic_batch(B, seed=B * 7 + L, L=L, T=T, n_boxes=N, task_id=0)
+    _check_step(om, m, b, 0)
+
+
+def test_oversized_shapes_fail_loudly():
+    _, m = make_pair(layers=1)
+    b = O.synthetic_batch(2, seed=1, L=20, n_boxes=43)          # 63 encoder tokens (+2 prototype rows) > 64 keys
+    with pytest.raises(V.VqaclError):
+        m.train_step(b, 0, 0.5, 0.3)

@@ -262,7 +262,8 @@ int check_batch(const Engine& e, const vqacl_batch* b, bool need_labels) {
   VQ_CHECK(b->B == e.B && b->L == e.L && b->N == e.N && (!need_labels || b->T == e.T),
            "engine: batch shape (B=%d L=%d N=%d T=%d) does not match the bound workspace (B=%d L=%d N=%d T=%d)", b->B, b->L,
            b->N, b->T, e.B, e.L, e.N, e.T);
-  VQ_CHECK(b->L + b->N <= 64 && b->L >= 1 && b->N >= 1, "engine: encoder length L+N=%d must be in [2,64]", b->L + b->N);
+  // the decoder attends to the encoder output plus the two retrieved prototype rows: L + N + 2 keys in one 64-key tile
+  VQ_CHECK(b->L + b->N + 2 <= 64 && b->L >= 1 && b->N >= 1, "engine: encoder length L+N=%d must be in [2,62]", b->L + b->N);
   VQ_CHECK(!need_labels || (b->T >= 1 && b->T <= 64), "engine: target width T=%d must be in [1,64]", b->T);
   VQ_CHECK(b->vis_feats && b->boxes && b->input_ids, "engine: missing batch pointers");
   return 0;
