@@ -86,7 +86,10 @@ int vqacl_forward_encoder(void* engine, const vqacl_batch* batch, const vqacl_pr
  * this rank's batch into the workspace regions "curQ" [n_ques,d], "curV" [n_cate,d], "cntQ", "cntV"; the host all-reduces
  * (sum) them and passes sums_ready = 1 to forward_decoder, which then divides instead of recomputing. */
 int vqacl_proto_sums(void* engine, const vqacl_batch* batch, void* stream);
-int vqacl_forward_decoder(void* engine, const vqacl_batch* batch, const vqacl_proto_state* proto, int sums_ready, void* stream);
+/* prezero_grads != 0: the caller promises that the coming backward does NOT accumulate into existing gradients; the arena is
+ * then cleared on a side stream during the decoder forward instead of at the start of backward. */
+int vqacl_forward_decoder(void* engine, const vqacl_batch* batch, const vqacl_proto_state* proto, int sums_ready,
+                          int prezero_grads, void* stream);
 /* backward of sum_r w[r] * loss_row[r] (loss.backward(), vqacl.py:461); fills the gradient arena (zeroed in stage 0 unless
  * accumulate != 0). Runs stages [stage_begin, stage_end) (stage_end < 0: to the end) so that the host can overlap the NCCL
  * all-reduce of a finished arena range (vqacl_backward_stage_range) with the remaining stages. */

@@ -24,7 +24,7 @@ for it in range(8):
     marks = [("start", ev())]
     eng.forward_encoder(cb, it, True); marks.append(("enc fwd", ev()))
     ps = m._proto_state(True, 3, 0.5, 0.3)
-    eng.forward_decoder(cb, ps, False); marks.append(("SI + dec fwd + head + CE", ev()))
+    eng.forward_decoder(cb, ps, False, True); marks.append(("SI + dec fwd + head + CE", ev()))
     w_rows = torch.empty(B * 5, device="cuda")
     eng.loss_tail(keep[3], batch["scores"], B, 5, m._loss_buf, w_rows); marks.append(("loss tail", ev()))
     eng.backward(w_rows, False, 0, 1); marks.append(("bwd: CE + LM head", ev()))

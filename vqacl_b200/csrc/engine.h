@@ -82,6 +82,8 @@ struct Engine {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_layer[4] = {nullptr, nullptr, nullptr, nullptr};
   int gdb_i = 0, geb_i = 0;
+  // gradient arena zeroed ahead of backward on the side stream (during the decoder forward)
+  bool g_prezeroed = false; bool prezero_request = false; cudaEvent_t ev_gzero = nullptr;
   // multi-GPU: per-stage completion events (main / side stream) that the host's communication stream waits on before the
   // stage callback issues the all-reduce of the gradient range that stage finalised (no main<->side join per stage)
   std::vector<cudaEvent_t> ev_stage_main, ev_stage_side;

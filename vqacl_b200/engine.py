@@ -66,7 +66,7 @@ def _declare(L):
     L.vqacl_ws_offset.argtypes = [c_void_p, c_char_p]
     L.vqacl_ws_offset.restype = c_int64
     L.vqacl_forward_encoder.argtypes = [c_void_p, POINTER(CBatch), POINTER(CProtoState), c_uint32, c_int, c_void_p]
-    L.vqacl_forward_decoder.argtypes = [c_void_p, POINTER(CBatch), POINTER(CProtoState), c_int, c_void_p]
+    L.vqacl_forward_decoder.argtypes = [c_void_p, POINTER(CBatch), POINTER(CProtoState), c_int, c_int, c_void_p]
     L.vqacl_proto_sums.argtypes = [c_void_p, POINTER(CBatch), c_void_p]
     L.vqacl_backward.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]
     L.vqacl_backward_overlapped.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p, STAGE_CB, c_void_p, c_void_p]
@@ -218,8 +218,8 @@ class Engine:
     def proto_sums(self, cb):
         check(self.L.vqacl_proto_sums(self.h, byref(cb), cur_stream()))
 
-    def forward_decoder(self, cb, ps, sums_ready=False):
-        check(self.L.vqacl_forward_decoder(self.h, byref(cb), byref(ps), int(sums_ready), cur_stream()))
+    def forward_decoder(self, cb, ps, sums_ready=False, prezero_grads=False):
+        check(self.L.vqacl_forward_decoder(self.h, byref(cb), byref(ps), int(sums_ready), int(prezero_grads), cur_stream()))
 
     def loss_tail(self, labels, scores, B, T, loss_out, w_rows):
         lr = self.ws_tensor("loss_rows", torch.float32, (B * T,))

@@ -474,7 +474,10 @@ class VLT5(nn.Module):
             z = eng.L.vqacl_ws_offset(eng.h, b"cntV") + self.config.n_cate_classes * 4
             dist.all_reduce(eng.ws[a:z].view(torch.float32), op=dist.ReduceOp.SUM)
             sums_ready = True
-        eng.forward_decoder(cb, ps, sums_ready)
+        # gradients are None (the reference sets them to None after every step, vqacl.py:486-487) => the coming backward starts
+        # from zero and the arena can be cleared during the decoder forward
+        prezero = training and self._grad_views[0][0].grad is None
+        eng.forward_decoder(cb, ps, sums_ready, prezero_grads=prezero)
 
     def _native_backward(self, w_rows, gscale):
         eng = self._engine
