@@ -220,6 +220,16 @@ def test_clip_adamw_matches_hf_semantics():
         torch.testing.assert_close(pb16.cpu().float(), ref.bfloat16().float(), rtol=0, atol=0)
 
 
+def _pack_bits(bits):
+    """[M, N] bool -> [M, ceil(N/32)] int32, bit i of word w = column 32 w + i (the ReLU mask layout of the GEMM epilogues)."""
+    M, N = bits.shape
+    W = (N + 31) // 32
+    b = torch.zeros(M, W * 32, device=bits.device, dtype=torch.int64)
+    b[:, :N] = bits
+    v = (b.view(M, W, 32) << torch.arange(32, device=bits.device)).sum(-1)
+    return torch.where(v >= 2 ** 31, v - 2 ** 32, v).to(torch.int32)
+
+
 @pytest.mark.parametrize("epi", [0, 1, 2, 3, 4, 5])
 def test_gemm_epilogues_ragged(epi):
     torch.manual_seed(4 + epi)
@@ -232,16 +242,25 @@ def test_gemm_epilogues_ragged(epi):
     R = None
     if epi == 1:
         ref = ref.relu()
+        R = torch.zeros(M, (N + 31) // 32, device=DEV, dtype=torch.int32)       # sign bitmask output
     elif epi == 2:
         R = torch.randn(M, N, device=DEV)
         ref = ref + R
     elif epi == 3:
         ref = ref + 0.5
     elif epi == 4:
-        R = torch.randn(M, N, device=DEV).relu().bfloat16()
-        ref = ref * (R.float() > 0)
+        keep = torch.rand(M, N, device=DEV) > 0.5
+        R = _pack_bits(keep)
+        ref = ref * keep
     for bn in (64, 128, 256, 512):        # 512 = 256 x 256 tiles on CTA pairs (cta_group::2)
         C.fill_(0.5)
+        if epi == 1:
+            R.zero_()
         cabi.gemm(A, 0, Bm, 0, C, R, M, N, K, epi, bn=bn)
         torch.cuda.synchronize()
         assert rel_err(C, ref) < (3e-5 if f32 else 1e-2), (epi, bn)
+        if epi == 1:
+            # the mask marks exactly the stored non-zero activations (bits past column N are don't-care)
+            W = R.shape[1]
+            got = ((R.long().unsqueeze(-1) >> torch.arange(32, device=DEV)) & 1).view(M, W * 32)[:, :N].bool()
+            assert torch.equal(got, C.float() > 0), (epi, bn)

@@ -18,6 +18,15 @@ def gemm(A, a_mn, B, b_mn, C, R, M, N, K, epi, alpha=1.0, splits=1, bn=0):
                             splits, bn, cur_stream()))
 
 
+def pack_bits(bits):
+    M, N = bits.shape
+    W = (N + 31) // 32
+    b = torch.zeros(M, W * 32, device=bits.device, dtype=torch.int64)
+    b[:, :N] = bits
+    v = (b.view(M, W, 32) << torch.arange(32, device=bits.device)).sum(-1)
+    return torch.where(v >= 2 ** 31, v - 2 ** 32, v).to(torch.int32)
+
+
 def run_case(M, N, K, a_mn, b_mn, epi, bn, splits=1):
     g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K + bn)
     Al = torch.randn(M, K, device="cuda", generator=g).bfloat16()
@@ -38,8 +47,9 @@ def run_case(M, N, K, a_mn, b_mn, epi, bn, splits=1):
     elif epi == EPI_ATOMIC:
         ref = ref + 0.5
     elif epi == EPI_RELUBWD:
-        R = torch.randn(M, N, device="cuda", generator=g).relu().bfloat16()  # saved relu output: >= 0
-        ref = ref * (R.float() > 0)
+        keep = torch.rand(M, N, device="cuda", generator=g) > 0.5             # ReLU sign bitmask, bit i of word w = column 32w+i
+        R = pack_bits(keep)
+        ref = ref * keep
     gemm(A, a_mn, B, b_mn, C, R, M, N, K, epi, 1.0, splits, bn)
     torch.cuda.synchronize()
     err = (C.float() - ref).abs().max().item()
@@ -57,7 +67,7 @@ def bench(M, N, K, a_mn, b_mn, epi, bn, splits=1, iters=20):
     A = Al.t().contiguous() if a_mn else Al
     B = Bl.t().contiguous() if b_mn else Bl
     C = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16 if epi in (0, 1, 4) else torch.float32)
-    R = torch.zeros(M, N, device="cuda", dtype=torch.float32) if epi == EPI_RESID else (torch.ones(M, N, device="cuda", dtype=torch.bfloat16) if epi == EPI_RELUBWD else None)
+    R = torch.zeros(M, N, device="cuda", dtype=torch.float32) if epi == EPI_RESID else (torch.full((M, (N + 31) // 32), -1, device="cuda", dtype=torch.int32) if epi == EPI_RELUBWD else None)
     for _ in range(3):
         gemm(A, a_mn, B, b_mn, C, R, M, N, K, epi, 1.0, splits, bn)
     e0 = torch.cuda.Event(enable_timing=True)

@@ -10,7 +10,7 @@ A = torch.randn((K, M) if amn else (M, K), device="cuda").bfloat16()
 B = torch.randn((K, N) if bmn else (N, K), device="cuda").bfloat16()
 f32 = epi in (2, 3, 5)
 C = torch.zeros(M, N, device="cuda", dtype=torch.float32 if f32 else torch.bfloat16)
-R = torch.randn(M, N, device="cuda") if epi == 2 else (torch.randn(M, N, device="cuda").bfloat16() if epi == 4 else None)
+R = torch.randn(M, N, device="cuda") if epi == 2 else (torch.randint(-2**31, 2**31 - 1, (M, (N + 31) // 32), device="cuda", dtype=torch.int32) if epi == 4 else None)
 L = lib()
 def call():
     check(L.vqacl_gemm_bf16(ptr(A), A.stride(0), amn, ptr(B), B.stride(0), bmn, ptr(C), C.stride(0), ptr(R),

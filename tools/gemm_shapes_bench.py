@@ -29,7 +29,7 @@ for name, m, n, k, amn, bmn, epi, sp, cnt in S:
     f32 = epi in (2, 3, 5)
     ldc = (n + 255) // 256 * 256 if name == "lm head" else n
     C = torch.zeros(m, ldc, device="cuda", dtype=torch.float32 if f32 else torch.bfloat16)
-    R = torch.zeros(m, n, device="cuda") if epi == 2 else (torch.ones(m, n, device="cuda").bfloat16() if epi == 4 else None)
+    R = torch.zeros(m, n, device="cuda") if epi == 2 else (torch.full((m, (n + 31) // 32), -1, device="cuda", dtype=torch.int32) if epi in (1, 4) else None)
     if sp == 0: sp = splits_dw(m, n, k)
     def run(bn):
         def call():

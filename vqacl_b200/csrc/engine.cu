@@ -140,6 +140,7 @@ int64_t engine_carve(Engine& e, uint8_t* base, int B, int L, int N, int T) {
   const int d = c.d_model, f = c.d_ff, H = c.n_heads;
   const int S = L + N, S2 = S + 2;
   const size_t M = (size_t)B * S, Md = (size_t)B * T, M2 = (size_t)B * S2;
+  const size_t fw = (size_t)(f + 31) / 32;   // ReLU bitmask words per row
   const int Le = c.n_enc_layers, Ld = c.n_dec_layers;
   Workspace w;
   std::map<std::string, int64_t> names;
@@ -149,13 +150,14 @@ int64_t engine_carve(Engine& e, uint8_t* base, int B, int L, int N, int T) {
   w.featpre = bp.take<float>((size_t)B * N * d);
   w.x.resize(2 * Le + 1);
   for (auto& p : w.x) p = bp.take<float>(M * d);
-  w.n1.resize(Le); w.qkv.resize(Le); w.ao.resize(Le); w.n2.resize(Le); w.h.resize(Le); w.lse_e.resize(Le);
+  w.n1.resize(Le); w.qkv.resize(Le); w.ao.resize(Le); w.n2.resize(Le); w.h.resize(Le); w.hmask.resize(Le); w.lse_e.resize(Le);
   for (int l = 0; l < Le; ++l) {
     w.n1[l] = bp.take<bf16>(M * d);
     w.qkv[l] = bp.take<bf16>(M * 3 * d);
     w.ao[l] = bp.take<bf16>(M * d);
     w.n2[l] = bp.take<bf16>(M * d);
     w.h[l] = bp.take<bf16>(M * f);
+    w.hmask[l] = bp.take<uint32_t>(M * fw);
     w.lse_e[l] = bp.take<float>((size_t)B * H * S);
   }
   w.enc_hidden = bp.take<float>(M * d, "encoder_hidden_states");
@@ -176,7 +178,7 @@ int64_t engine_carve(Engine& e, uint8_t* base, int B, int L, int N, int T) {
   w.y.resize(3 * Ld + 1);
   for (auto& p : w.y) p = bp.take<float>(Md * d);
   w.dn1.resize(Ld); w.dqkv.resize(Ld); w.dao.resize(Ld); w.dn2.resize(Ld); w.cq.resize(Ld); w.cao.resize(Ld); w.dn3.resize(Ld);
-  w.dh.resize(Ld); w.lse_s.resize(Ld); w.lse_c.resize(Ld);
+  w.dh.resize(Ld); w.dhmask.resize(Ld); w.lse_s.resize(Ld); w.lse_c.resize(Ld);
   for (int l = 0; l < Ld; ++l) {
     w.dn1[l] = bp.take<bf16>(Md * d);
     w.dqkv[l] = bp.take<bf16>(Md * 3 * d);
@@ -186,6 +188,7 @@ int64_t engine_carve(Engine& e, uint8_t* base, int B, int L, int N, int T) {
     w.cao[l] = bp.take<bf16>(Md * d);
     w.dn3[l] = bp.take<bf16>(Md * d);
     w.dh[l] = bp.take<bf16>(Md * f);
+    w.dhmask[l] = bp.take<uint32_t>(Md * fw);
     w.lse_s[l] = bp.take<float>((size_t)B * H * T);
     w.lse_c[l] = bp.take<float>((size_t)B * H * T);
   }
@@ -303,7 +306,7 @@ int encoder_forward(Engine& e, const vqacl_batch* b, cudaStream_t st) {
     VQ_TRY(gemm_fwd(w.ao[l], d, e.W + P.o, d, w.x[2 * l + 1], d, M, d, EPI_RESID_F32, st, w.x[2 * l], d, e.drop(site_enc(l, 1))));
     r.x = w.x[2 * l + 1]; r.w = e.P + P.ln1; r.y_bf16 = w.n2[l];
     VQ_TRY(rmsnorm_fwd(r, st));
-    VQ_TRY(gemm_fwd(w.n2[l], d, e.W + P.wi, d, w.h[l], f, M, f, EPI_RELU_BF16, st, nullptr, 0, e.drop(site_enc(l, 2))));
+    VQ_TRY(gemm_fwd(w.n2[l], d, e.W + P.wi, d, w.h[l], f, M, f, EPI_RELU_BF16, st, w.hmask[l], (f + 31) / 32, e.drop(site_enc(l, 2))));
     VQ_TRY(gemm_fwd(w.h[l], f, e.W + P.wo, f, w.x[2 * l + 2], d, M, d, EPI_RESID_F32, st, w.x[2 * l + 1], d, e.drop(site_enc(l, 3))));
   }
   // final norm + dropout (:314-315): fp32 copy for the SI path / caller, bf16 straight into the [B,S+2,d] decoder memory
@@ -397,7 +400,7 @@ static int decoder_forward(Engine& e, const vqacl_batch* b, cudaStream_t st) {
     VQ_TRY(gemm_fwd(w.cao[l], d, e.W + P.co, d, w.y[3 * l + 2], d, Md, d, EPI_RESID_F32, st, w.y[3 * l + 1], d, e.drop(site_dec(l, 3))));
     r.x = w.y[3 * l + 2]; r.w = e.P + P.ln2; r.y_bf16 = w.dn3[l];
     VQ_TRY(rmsnorm_fwd(r, st));
-    VQ_TRY(gemm_fwd(w.dn3[l], d, e.W + P.wi, d, w.dh[l], f, Md, f, EPI_RELU_BF16, st, nullptr, 0, e.drop(site_dec(l, 4))));
+    VQ_TRY(gemm_fwd(w.dn3[l], d, e.W + P.wi, d, w.dh[l], f, Md, f, EPI_RELU_BF16, st, w.dhmask[l], (f + 31) / 32, e.drop(site_dec(l, 4))));
     VQ_TRY(gemm_fwd(w.dh[l], f, e.W + P.wo, f, w.y[3 * l + 3], d, Md, d, EPI_RESID_F32, st, w.y[3 * l + 2], d, e.drop(site_dec(l, 5))));
   }
   // final norm, dropout, x d^-1/2 (:666), tied LM head (:671), CE with reduction='none' (:683-686)
@@ -568,7 +571,7 @@ static int backward(Engine& e, const float* w_rows, const float* gscale, int acc
     // FFN
     VQ_TRY(fork());
     VQ_TRY(gemm_dw(gdb_in, d, w.dh[l], f, e.G + P.wo, d, f, Md, sd));
-    VQ_TRY(gemm_dx(gdb_in, d, e.W + P.wo, d, f, w.t_dh[ri], f, Md, EPI_RELUBWD_BF16, st, w.dh[l], f, e.drop(site_dec(l, 4)).inv_keep));
+    VQ_TRY(gemm_dx(gdb_in, d, e.W + P.wo, d, f, w.t_dh[ri], f, Md, EPI_RELUBWD_BF16, st, w.dhmask[l], (f + 31) / 32, e.drop(site_dec(l, 4)).inv_keep));
     VQ_TRY(fork());
     VQ_TRY(gemm_dw(w.t_dh[ri], f, w.dn3[l], d, e.G + P.wi, f, d, Md, sd));
     VQ_TRY(gemm_dx(w.t_dh[ri], f, e.W + P.wi, f, d, w.t_d768, d, Md, EPI_BF16, st));
@@ -642,7 +645,7 @@ static int backward(Engine& e, const float* w_rows, const float* gscale, int acc
     e.geb_i = (e.geb_i + 2) % (2 * RING);
     VQ_TRY(fork());
     VQ_TRY(gemm_dw(geb_in, d, w.h[l], f, e.G + P.wo, d, f, M, sd));
-    VQ_TRY(gemm_dx(geb_in, d, e.W + P.wo, d, f, w.t_eh[ri], f, M, EPI_RELUBWD_BF16, st, w.h[l], f, e.drop(site_enc(l, 2)).inv_keep));
+    VQ_TRY(gemm_dx(geb_in, d, e.W + P.wo, d, f, w.t_eh[ri], f, M, EPI_RELUBWD_BF16, st, w.hmask[l], (f + 31) / 32, e.drop(site_enc(l, 2)).inv_keep));
     VQ_TRY(fork());
     VQ_TRY(gemm_dw(w.t_eh[ri], f, w.n2[l], d, e.G + P.wi, f, d, M, sd));
     VQ_TRY(gemm_dx(w.t_eh[ri], f, e.W + P.wi, f, d, w.t_e768, d, M, EPI_BF16, st));

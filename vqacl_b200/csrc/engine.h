@@ -28,6 +28,7 @@ struct Workspace {
   bf16* feats_bf16; float* featpre;
   std::vector<float*> x;          // residual stream snapshots, 2*Le + 1
   std::vector<bf16*> n1, qkv, ao, n2, h;
+  std::vector<uint32_t*> hmask, dhmask;                    // ReLU sign bitmasks [rows, ceil(d_ff/32)] written by the wi epilogue
   std::vector<float*> lse_e;
   float* enc_hidden;              // [B,S,d] fp32 (post final norm/dropout) -> encoder_hidden_states
   bf16* mem;                      // [B,S+2,d] decoder memory

@@ -17,10 +17,12 @@ namespace vq {
 
 enum GemmEpi : int {
   EPI_BF16 = 0,          // C(bf16) = alpha * acc
-  EPI_RELU_BF16 = 1,     // C(bf16) = dropout(relu(alpha * acc))
+  EPI_RELU_BF16 = 1,     // C(bf16) = dropout(relu(alpha * acc)); if R != null also writes the sign bitmask (one u32 per row and
+                         // 32 columns, pitch ldr words) that EPI_RELUBWD_BF16 consumes
   EPI_RESID_F32 = 2,     // C(f32)  = R(f32) + dropout(alpha * acc)
   EPI_ATOMIC_F32 = 3,    // C(f32) += alpha * acc (red.global.add; split-K capable)
-  EPI_RELUBWD_BF16 = 4,  // C(bf16) = R(bf16) != 0 ? alpha * acc : 0      R = saved relu(+dropout) output (>= 0)
+  EPI_RELUBWD_BF16 = 4,  // C(bf16) = mask bit ? alpha * acc : 0      R = u32 bitmask written by EPI_RELU_BF16 (16x less traffic than
+                         // re-reading the saved activations)
   EPI_F32 = 5            // C(f32)  = alpha * acc
 };
 
@@ -82,7 +84,7 @@ VQ_DEVINL void gemm_epilogue_tile(const GemmArgs& p, uint32_t t_base, uint32_t s
   // extra-operand registers are double-buffered in time: the operand of chunk c+2 (this warp's next chunk) is requested right
   // after the accumulator of chunk c has been read, so its global-memory latency overlaps the math and stores of chunk c
   float4 rres[8];
-  uint4 rh[4];
+  uint32_t rmask = 0;   // ReLU-backward: bit i = activation (row = this lane's row, column col0 + i) was positive and kept
   auto prefetch = [&](int cc) {
     const int pcol0 = n_base + cc * 32;
     if (EPI == EPI_RESID_F32) {
@@ -96,14 +98,8 @@ VQ_DEVINL void gemm_epilogue_tile(const GemmArgs& p, uint32_t t_base, uint32_t s
       }
     }
     if (EPI == EPI_RELUBWD_BF16) {
-      const int gcol = pcol0 + (lane & 3) * 8;
-#pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        const int grow = row_base + it * 8 + (lane >> 2);
-        rh[it] = (cc < BN / 32 && grow < M && gcol < N)
-                     ? *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.R) + (size_t)grow * ldr + gcol)
-                     : make_uint4(0u, 0u, 0u, 0u);
-      }
+      const int grow = row_base + lane;   // row layout: this lane owns one accumulator row
+      rmask = (cc < BN / 32 && grow < M && pcol0 < N) ? reinterpret_cast<const uint32_t*>(p.R)[(size_t)grow * ldr + (pcol0 >> 5)] : 0u;
     }
   };
   prefetch(half);
@@ -112,15 +108,11 @@ VQ_DEVINL void gemm_epilogue_tile(const GemmArgs& p, uint32_t t_base, uint32_t s
     const int col0 = n_base + c * 32;
     if (col0 >= N) break;
     float4 cres[8];
-    uint4 ch[4];
     if (EPI == EPI_RESID_F32) {
 #pragma unroll
       for (int it = 0; it < 8; ++it) cres[it] = rres[it];
     }
-    if (EPI == EPI_RELUBWD_BF16) {
-#pragma unroll
-      for (int it = 0; it < 4; ++it) ch[it] = rh[it];
-    }
+    const uint32_t cmask = rmask;
     if (!waited) {
       mbar_wait(tfull, aphase);
       tc_fence_after();
@@ -147,6 +139,18 @@ VQ_DEVINL void gemm_epilogue_tile(const GemmArgs& p, uint32_t t_base, uint32_t s
         v[2 * j + 1] *= s1;
       }
     }
+    if (EPI == EPI_RELU_BF16 && p.R) {
+      // sign bitmask of the stored activations for the backward pass (dropped elements count as zero)
+      uint32_t m = 0;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) m |= (v[i] > 0.f ? 1u : 0u) << i;
+      const int grow = row_base + lane;
+      if (has_k && grow < M && col0 < N) reinterpret_cast<uint32_t*>(const_cast<void*>(p.R))[(size_t)grow * ldr + (col0 >> 5)] = m;
+    }
+    if (EPI == EPI_RELUBWD_BF16) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = ((cmask >> i) & 1u) ? v[i] : 0.f;
+    }
     if (OUT_BF16) {
       // stage 32 rows x 64 B; 16-byte piece j of row l lives at slot j ^ ((l >> 1) & 3)
       const uint32_t wrow = stg + lane * 64;
@@ -163,16 +167,6 @@ VQ_DEVINL void gemm_epilogue_tile(const GemmArgs& p, uint32_t t_base, uint32_t s
         const int rr = it * 8 + (lane >> 2);
         const int grow = row_base + rr;
         uint4 o = lds128(stg + rr * 64 + ((piece ^ ((rr >> 1) & 3)) << 4));
-        if (EPI == EPI_RELUBWD_BF16) {
-          const uint32_t hh[4] = {ch[it].x, ch[it].y, ch[it].z, ch[it].w};
-          uint32_t oo[4] = {o.x, o.y, o.z, o.w};
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint32_t m = ((hh[k] & 0x00007FFFu) ? 0x0000FFFFu : 0u) | ((hh[k] & 0x7FFF0000u) ? 0xFFFF0000u : 0u);
-            oo[k] &= m;
-          }
-          o = make_uint4(oo[0], oo[1], oo[2], oo[3]);
-        }
         if (has_k && grow < M && gcol < N) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)grow * ldc + gcol) = o;
       }
     } else {
