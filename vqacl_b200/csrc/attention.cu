@@ -76,6 +76,47 @@ VQ_DEVINL void load_heads(AttnTile const (&dst)[NM], const __nv_bfloat16* const 
   }
 }
 
+// ---- cp.async (LDGSTS) staging for the persistent, double-buffered encoder kernels: the tiles of problem i+1 stream into
+//      the other shared-memory stage while the warps work on problem i; rows past the end of a matrix are zero-filled
+//      by the copy itself (src-size 0).
+VQ_DEVINL void cp_async16(void* dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
+}
+VQ_DEVINL void cp_async4(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+VQ_DEVINL void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+VQ_DEVINL void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int NW, int NM>
+VQ_DEVINL void load_heads_async(AttnTile const (&dst)[NM], const __nv_bfloat16* const (&src)[NM], const int (&ld)[NM], const int (&rows)[NM],
+                                const int (&fill)[NM], int tid) {
+  constexpr int T = NW * 32;
+#pragma unroll
+  for (int m = 0; m < NM; ++m) {
+    const int total = fill[m] * (AT_D / 8);
+    for (int idx = tid; idx < total; idx += T) {
+      const int r = idx >> 3, c = (idx & 7) * 8;
+      const bool ok = r < rows[m];
+      cp_async16(&dst[m][r][c], ok ? src[m] + (size_t)r * ld[m] + c : src[m], ok ? 16 : 0);
+    }
+  }
+}
+// bias / key-mask header of a stage, asynchronously (gathers go through 4-byte cp.async, constants are plain stores: the
+// stage is not being read by anyone while it is filled)
+template <int NW>
+VQ_DEVINL void load_bias_mask_async(float* sbias, float* skmask, const AttnArgs& p, const AttnBuckets& bk, int b, int h, int tid) {
+  constexpr int T = NW * 32;
+  if (p.rel_mode) {
+    for (int r = tid; r < 2 * AT_S - 1; r += T) cp_async4(&sbias[r], &p.rel_table[(int)bk.b[r] * p.H + h]);
+  }
+  for (int j = tid; j < AT_S; j += T) {
+    if (j < p.Sk && p.keymask) cp_async4(&skmask[j], &p.keymask[(size_t)b * p.Sk + j]);
+    else skmask[j] = j < p.Sk ? 0.f : -INFINITY;
+  }
+}
+
 // A fragment (m16 x k16) of row-major X[m][k] at (m0, k0)
 VQ_DEVINL void frag_a(uint32_t (&a)[4], const __nv_bfloat16 (*X)[AT_P], int m0, int k0, int lane) {
   const int mi = lane >> 3, r = lane & 7;
@@ -95,6 +136,25 @@ VQ_DEVINL void frag_b(uint32_t (&b)[2], const __nv_bfloat16 (*X)[AT_P], int n0, 
 VQ_DEVINL void frag_b_t(uint32_t (&b)[2], const __nv_bfloat16 (*X)[AT_P], int n0, int k0, int lane) {
   const int l = lane & 15, mi = l >> 3, r = l & 7;
   ldsm_x2_t(b, &X[k0 + mi * 8 + r][n0]);
+}
+
+// Write a warp's [16 x 64] tile (m16n8 accumulator layout: rows m0 + g and m0 + g + 8, columns nt * 8 + 2t) to global memory
+// as full 128-byte rows: the tile is first packed into rows [m0, m0 + 16) of a shared tile that only this warp touches any
+// more, then each quarter-warp moves one row with 16-byte vectors (4-byte stores straight from the fragments cover only half
+// of every 32-byte sector per instruction and keep the LSU busy long after the math is done).
+VQ_DEVINL void store_tile16(AttnTile stg, int m0, const float (&acc)[8][4], __nv_bfloat16* gbase, int ld, int nrows, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) *reinterpret_cast<uint32_t*>(&stg[m0 + g + r * 8][nt * 8 + 2 * t]) = pack_bf16(acc[nt][2 * r], acc[nt][2 * r + 1]);
+  __syncwarp();
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int row = m0 + it * 4 + (lane >> 3), c = (lane & 7) * 8;
+    if (row < nrows) *reinterpret_cast<uint4*>(gbase + (size_t)row * ld + c) = *reinterpret_cast<const uint4*>(&stg[row][c]);
+  }
+  __syncwarp();
 }
 
 // dropout pair index of probabilities (q, k), (q, k+1) of problem `blk` (k even)
@@ -208,38 +268,20 @@ VQ_DEVINL void load_bias_mask(float* sbias, float* skmask, const AttnArgs& p, co
   }
 }
 
-// HPC > 1 (only with NW == 1): the CTA holds HPC independent single-warp problems (consecutive (batch, head) pairs), each
-// with its own smem slice — the decoder's 3840 tiny problems are otherwise bound by the CTA dispatch rate.
-template <int NW, int NKT, int HPC>
-__global__ void __launch_bounds__(NW * 32 * HPC, NW == 4 ? 6 : 16 / (NW * HPC)) attn_fwd_kernel(const AttnArgs p, const __grid_constant__ AttnBuckets bk) {
-  static_assert(HPC == 1 || NW == 1, "several problems per CTA only for single-warp problems");
-  vq_pdl_trigger();
-  vq_pdl_wait();
-  extern __shared__ __align__(16) uint8_t at_smem_base[];
-  const int vblk = HPC == 1 ? (int)blockIdx.x : (int)blockIdx.x * HPC + (int)(threadIdx.x >> 5);   // problem index = b * H + h
-  if (vblk >= p.B * p.H) return;
-  const int tid = HPC == 1 ? (int)threadIdx.x : (int)(threadIdx.x & 31);
-  uint8_t* at_smem_raw = at_smem_base + (HPC == 1 ? 0 : (threadIdx.x >> 5) * (AT_HDR_BYTES + (rows16(p.Sq) + 2 * NKT * 8) * AT_P * 2));
-  struct { float* bias; float* kmask; AttnTile q, k, v; } sm;
-  sm.bias = reinterpret_cast<float*>(at_smem_raw);
+struct AttnSmemF { float* bias; float* kmask; AttnTile q, k, v; };
+VQ_DEVINL AttnSmemF attn_carve_fwd(uint8_t* raw, int qrows, int krows) {
+  AttnSmemF sm;
+  sm.bias = reinterpret_cast<float*>(raw);
   sm.kmask = sm.bias + 2 * AT_S;
-  sm.q = reinterpret_cast<AttnTile>(at_smem_raw + AT_HDR_BYTES);
-  sm.k = sm.q + rows16(p.Sq);
-  sm.v = sm.k + NKT * 8;
-  const int b = vblk / p.H, h = vblk % p.H;
-  const int warp = tid >> 5, lane = tid & 31;
-  {
-    const AttnTile dst[3] = {sm.q, sm.k, sm.v};
-    const __nv_bfloat16* const src[3] = {p.q + (size_t)b * (p.q_bstride ? p.q_bstride : (long long)p.Sq * p.ldq) + h * AT_D,
-                                         p.k + (size_t)b * (p.k_bstride ? p.k_bstride : (long long)p.Sk * p.ldk) + h * AT_D,
-                                         p.v + (size_t)b * (p.v_bstride ? p.v_bstride : (long long)p.Sk * p.ldv) + h * AT_D};
-    const int ld[3] = {p.ldq, p.ldk, p.ldv};
-    const int rows[3] = {p.Sq, p.Sk, p.Sk};
-    const int fill[3] = {rows16(p.Sq), NKT * 8, NKT * 8};
-    load_bias_mask<NW>(sm.bias, sm.kmask, p, bk, b, h, tid);
-    load_heads<NW, 3>(dst, src, ld, rows, fill, tid);
-  }
-  if (NW == 1) __syncwarp(); else __syncthreads();
+  sm.q = reinterpret_cast<AttnTile>(raw + AT_HDR_BYTES);
+  sm.k = sm.q + qrows;
+  sm.v = sm.k + krows;
+  return sm;
+}
+
+// scores -> softmax (+ dropout) -> O = P V for the 16 query rows of one warp; the tiles of problem vblk = b * H + h are in sm
+template <int NW, int NKT>
+VQ_DEVINL void attn_fwd_compute(const AttnArgs& p, const AttnSmemF& sm, int vblk, int b, int h, int warp, int lane) {
   const int m0 = warp * 16;
   if (m0 >= p.Sq) return;
   float s[NKT][4];
@@ -311,53 +353,82 @@ __global__ void __launch_bounds__(NW * 32 * HPC, NW == 4 ? 6 : 16 / (NW * HPC)) 
       mma2(o[nt], o[nt + 1], a, bb);
     }
   }
-#pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    const int qi = m0 + g + r * 8;
-    if (qi < p.Sq) {
-      __nv_bfloat16* dst = p.o + (size_t)b * (p.o_bstride ? p.o_bstride : (long long)p.Sq * p.ldo) + (size_t)qi * p.ldo + h * AT_D + 2 * t;
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) *reinterpret_cast<uint32_t*>(dst + nt * 8) = pack_bf16(o[nt][2 * r], o[nt][2 * r + 1]);
-    }
-  }
+  // this warp's rows of the q tile are dead after the scores: stage O there
+  store_tile16(sm.q, m0, o, p.o + (size_t)b * (p.o_bstride ? p.o_bstride : (long long)p.Sq * p.ldo) + h * AT_D, p.ldo, p.Sq, lane);
 }
 
+// HPC > 1 (only with NW == 1): the CTA holds HPC independent single-warp problems (consecutive (batch, head) pairs), each
+// with its own smem slice — the decoder's 3840 tiny problems are otherwise bound by the CTA dispatch rate.
+// NW == 4 (encoder-sized problems): persistent CTAs, each walks over problems blockIdx.x, blockIdx.x + gridDim.x, ... with
+// two shared-memory stages; the cp.async copies of the next problem are in flight while the current one is computed, so
+// HBM stays busy during the math instead of only between CTA launches.
 template <int NW, int NKT, int HPC>
-__global__ void __launch_bounds__(NW * 32 * HPC, NW == 4 ? 4 : 8 / HPC) attn_bwd_kernel(const AttnArgs p, const __grid_constant__ AttnBuckets bk) {
+__global__ void __launch_bounds__(NW * 32 * HPC, NW == 4 ? 3 : 16 / (NW * HPC)) attn_fwd_kernel(const AttnArgs p, const __grid_constant__ AttnBuckets bk) {
   static_assert(HPC == 1 || NW == 1, "several problems per CTA only for single-warp problems");
   vq_pdl_trigger();
   vq_pdl_wait();
   extern __shared__ __align__(16) uint8_t at_smem_base[];
-  const int vblk = HPC == 1 ? (int)blockIdx.x : (int)blockIdx.x * HPC + (int)(threadIdx.x >> 5);   // problem index = b * H + h
-  if (vblk >= p.B * p.H) return;
-  const int tid = HPC == 1 ? (int)threadIdx.x : (int)(threadIdx.x & 31);
-  uint8_t* at_smem_raw = at_smem_base + (HPC == 1 ? 0 : (threadIdx.x >> 5) * (AT_HDR_BYTES + (4 * rows16(p.Sq) + 2 * NKT * 8) * AT_P * 2));
-  struct { float* bias; float* kmask; float* dbucket; AttnTile q, dO, P, dS, k, v; } sm;
-  sm.bias = reinterpret_cast<float*>(at_smem_raw);
-  sm.kmask = sm.bias + 2 * AT_S;
-  sm.dbucket = sm.kmask + AT_S;
-  sm.q = reinterpret_cast<AttnTile>(at_smem_raw + AT_HDR_BYTES);
-  sm.dO = sm.q + rows16(p.Sq);
-  sm.P = sm.dO + rows16(p.Sq);
-  sm.dS = sm.P + rows16(p.Sq);
-  sm.k = sm.dS + rows16(p.Sq);
-  sm.v = sm.k + NKT * 8;
-  const int b = vblk / p.H, h = vblk % p.H;
+  if constexpr (NW == 4) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nprob = p.B * p.H;
+    const int stage_bytes = AT_HDR_BYTES + (rows16(p.Sq) + 2 * NKT * 8) * AT_P * 2;
+    auto issue = [&](int vb, int stage) {
+      const AttnSmemF sm = attn_carve_fwd(at_smem_base + stage * stage_bytes, rows16(p.Sq), NKT * 8);
+      const int b = vb / p.H, h = vb % p.H;
+      const AttnTile dst[3] = {sm.q, sm.k, sm.v};
+      const __nv_bfloat16* const src[3] = {p.q + (size_t)b * (p.q_bstride ? p.q_bstride : (long long)p.Sq * p.ldq) + h * AT_D,
+                                           p.k + (size_t)b * (p.k_bstride ? p.k_bstride : (long long)p.Sk * p.ldk) + h * AT_D,
+                                           p.v + (size_t)b * (p.v_bstride ? p.v_bstride : (long long)p.Sk * p.ldv) + h * AT_D};
+      const int ld[3] = {p.ldq, p.ldk, p.ldv};
+      const int rows[3] = {p.Sq, p.Sk, p.Sk};
+      const int fill[3] = {rows16(p.Sq), NKT * 8, NKT * 8};
+      load_bias_mask_async<NW>(sm.bias, sm.kmask, p, bk, b, h, tid);
+      load_heads_async<NW, 3>(dst, src, ld, rows, fill, tid);
+    };
+    int vblk = blockIdx.x, stage = 0;
+    if (vblk < nprob) issue(vblk, 0);
+    cp_async_commit();
+    for (; vblk < nprob; vblk += gridDim.x) {
+      if (vblk + (int)gridDim.x < nprob) issue(vblk + gridDim.x, stage ^ 1);
+      cp_async_commit();
+      cp_async_wait<1>();        // everything but the copies just issued has landed: this problem's stage is complete
+      __syncthreads();
+      const AttnSmemF sm = attn_carve_fwd(at_smem_base + stage * stage_bytes, rows16(p.Sq), NKT * 8);
+      attn_fwd_compute<NW, NKT>(p, sm, vblk, vblk / p.H, vblk % p.H, warp, lane);
+      __syncthreads();           // all warps are done with this stage before the next-but-one problem is copied into it
+      stage ^= 1;
+    }
+  } else {
+    const int vblk = HPC == 1 ? (int)blockIdx.x : (int)blockIdx.x * HPC + (int)(threadIdx.x >> 5);   // problem index = b * H + h
+    if (vblk >= p.B * p.H) return;
+    const int tid = HPC == 1 ? (int)threadIdx.x : (int)(threadIdx.x & 31);
+    uint8_t* at_smem_raw = at_smem_base + (HPC == 1 ? 0 : (threadIdx.x >> 5) * (AT_HDR_BYTES + (rows16(p.Sq) + 2 * NKT * 8) * AT_P * 2));
+    const AttnSmemF sm = attn_carve_fwd(at_smem_raw, rows16(p.Sq), NKT * 8);
+    const int b = vblk / p.H, h = vblk % p.H;
+    const int warp = tid >> 5, lane = tid & 31;
+    {
+      const AttnTile dst[3] = {sm.q, sm.k, sm.v};
+      const __nv_bfloat16* const src[3] = {p.q + (size_t)b * (p.q_bstride ? p.q_bstride : (long long)p.Sq * p.ldq) + h * AT_D,
+                                           p.k + (size_t)b * (p.k_bstride ? p.k_bstride : (long long)p.Sk * p.ldk) + h * AT_D,
+                                           p.v + (size_t)b * (p.v_bstride ? p.v_bstride : (long long)p.Sk * p.ldv) + h * AT_D};
+      const int ld[3] = {p.ldq, p.ldk, p.ldv};
+      const int rows[3] = {p.Sq, p.Sk, p.Sk};
+      const int fill[3] = {rows16(p.Sq), NKT * 8, NKT * 8};
+      load_bias_mask<NW>(sm.bias, sm.kmask, p, bk, b, h, tid);
+      load_heads<NW, 3>(dst, src, ld, rows, fill, tid);
+    }
+    if (NW == 1) __syncwarp(); else __syncthreads();
+    attn_fwd_compute<NW, NKT>(p, sm, vblk, b, h, warp, lane);
+  }
+}
+
+struct AttnSmemB { float* bias; float* kmask; float* dbucket; AttnTile q, dO, P, dS, k, v; };
+
+// backward of one problem whose q / dO / k / v tiles (and bias header, zeroed dbucket) are in sm; P and dS are scratch tiles
+template <int NW, int NKT>
+VQ_DEVINL void attn_bwd_compute(const AttnArgs& p, const AttnBuckets& bk, const AttnSmemB& sm, int vblk, int b, int h, int tid) {
   const int warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
-  {
-    const AttnTile dst[4] = {sm.q, sm.k, sm.v, sm.dO};
-    const __nv_bfloat16* const src[4] = {p.q + (size_t)b * p.Sq * p.ldq + h * AT_D, p.k + (size_t)b * p.Sk * p.ldk + h * AT_D,
-                                         p.v + (size_t)b * p.Sk * p.ldv + h * AT_D, p.dO + (size_t)b * p.Sq * p.ldo + h * AT_D};
-    const int ld[4] = {p.ldq, p.ldk, p.ldv, p.ldo};
-    const int rows[4] = {p.Sq, p.Sk, p.Sk, p.Sq};
-    const int fill[4] = {rows16(p.Sq), NKT * 8, NKT * 8, rows16(p.Sq)};
-    load_bias_mask<NW>(sm.bias, sm.kmask, p, bk, b, h, tid);
-    load_heads<NW, 4>(dst, src, ld, rows, fill, tid);
-  }
-  for (int i = tid; i < 64; i += NW * 32) sm.dbucket[i] = 0.f;
-  if (NW == 1) __syncwarp(); else __syncthreads();
-
   const int nqk = (p.Sq + 15) >> 4;   // query blocks of 16
   // ---- phase 1: this warp owns 16 query rows (warps past the last query block only take part in phase 2) ----
   const int m0 = warp * 16;
@@ -452,11 +523,15 @@ __global__ void __launch_bounds__(NW * 32 * HPC, NW == 4 ? 4 : 8 / HPC) attn_bwd
     const int nq = p.rel_mode == 1 ? min(p.Sq, p.Lt) : p.Sq;
     const int nk = p.rel_mode == 1 ? min(p.Sk, p.Lt) : p.Sk;
     const int ndiag = nq + nk - 1;
-    for (int dgi = tid; dgi < ndiag; dgi += NW * 32) {
+    const int parts = min(4, max(1, (NW * 32) / ndiag));   // split every diagonal over up to 4 threads: the loop is latency-bound
+    for (int wi = tid; wi < ndiag * parts; wi += NW * 32) {
+      const int dgi = wi / parts, part = wi - dgi * parts;
       const int rel = dgi - (nq - 1);   // k - q
+      const int q_lo = max(0, -rel), len = min(nq, nk - rel) - q_lo;
+      const int qa = q_lo + len * part / parts, qb = q_lo + len * (part + 1) / parts;
       float acc = 0.f;
-      for (int qi = max(0, -rel); qi < nq && qi + rel < nk; ++qi) acc += __bfloat162float(sm.dS[qi][qi + rel]);
-      atomicAdd(&sm.dbucket[(int)bk.b[rel + (AT_S - 1)]], acc);
+      for (int qi = qa; qi < qb; ++qi) acc += __bfloat162float(sm.dS[qi][qi + rel]);
+      if (qb > qa) atomicAdd(&sm.dbucket[(int)bk.b[rel + (AT_S - 1)]], acc);
     }
   }
   // ---- phase 2: this warp owns 16 key rows: dV = Pd^T dO, dK = dS^T Q (contraction over the query blocks that exist) ----
@@ -482,19 +557,9 @@ __global__ void __launch_bounds__(NW * 32 * HPC, NW == 4 ? 4 : 8 / HPC) attn_bwd
         }
       }
     }
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const int kj = m0 + g + r * 8;
-      if (kj < p.Sk) {
-        __nv_bfloat16* dstk = p.dk + ((size_t)b * p.Sk + kj) * p.lddk + h * AT_D + 2 * t;
-        __nv_bfloat16* dstv = p.dv + ((size_t)b * p.Sk + kj) * p.lddv + h * AT_D + 2 * t;
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-          *reinterpret_cast<uint32_t*>(dstk + nt * 8) = pack_bf16(dk[nt][2 * r], dk[nt][2 * r + 1]);
-          *reinterpret_cast<uint32_t*>(dstv + nt * 8) = pack_bf16(dv[nt][2 * r], dv[nt][2 * r + 1]);
-        }
-      }
-    }
+    // the k / v tiles are dead since the end of phase 1: stage this warp's 16 rows of dK / dV in them
+    store_tile16(sm.k, m0, dk, p.dk + (size_t)b * p.Sk * p.lddk + h * AT_D, p.lddk, p.Sk, lane);
+    store_tile16(sm.v, m0, dv, p.dv + (size_t)b * p.Sk * p.lddv + h * AT_D, p.lddv, p.Sk, lane);
   }
   if (p.d_rel_table) {
     if (NW == 1) __syncwarp(); else __syncthreads();
@@ -502,6 +567,46 @@ __global__ void __launch_bounds__(NW * 32 * HPC, NW == 4 ? 4 : 8 / HPC) attn_bwd
       const float v = sm.dbucket[i];
       if (v != 0.f) atomicAdd(&p.d_rel_table[i * p.H + h], v);
     }
+  }
+}
+
+template <int NW, int NKT, int HPC>
+__global__ void __launch_bounds__(NW * 32 * HPC, NW == 4 ? 4 : 8 / HPC) attn_bwd_kernel(const AttnArgs p, const __grid_constant__ AttnBuckets bk) {
+  static_assert(HPC == 1 || NW == 1, "several problems per CTA only for single-warp problems");
+  vq_pdl_trigger();
+  vq_pdl_wait();
+  extern __shared__ __align__(16) uint8_t at_smem_base[];
+  // (a persistent double-buffered variant like the forward kernel's was measured slower here: its 93 KB of shared memory
+  //  allow 2 CTAs = 8 warps per SM, and the backward math needs more resident warps than that to hide its own latency)
+  {
+    const int vblk = HPC == 1 ? (int)blockIdx.x : (int)blockIdx.x * HPC + (int)(threadIdx.x >> 5);   // problem index = b * H + h
+    if (vblk >= p.B * p.H) return;
+    const int tid = HPC == 1 ? (int)threadIdx.x : (int)(threadIdx.x & 31);
+    uint8_t* at_smem_raw = at_smem_base + (HPC == 1 ? 0 : (threadIdx.x >> 5) * (AT_HDR_BYTES + (4 * rows16(p.Sq) + 2 * NKT * 8) * AT_P * 2));
+    AttnSmemB sm;
+    sm.bias = reinterpret_cast<float*>(at_smem_raw);
+    sm.kmask = sm.bias + 2 * AT_S;
+    sm.dbucket = sm.kmask + AT_S;
+    sm.q = reinterpret_cast<AttnTile>(at_smem_raw + AT_HDR_BYTES);
+    sm.dO = sm.q + rows16(p.Sq);
+    sm.P = sm.dO + rows16(p.Sq);
+    sm.dS = sm.P + rows16(p.Sq);
+    sm.k = sm.dS + rows16(p.Sq);
+    sm.v = sm.k + NKT * 8;
+    const int b = vblk / p.H, h = vblk % p.H;
+    {
+      const AttnTile dst[4] = {sm.q, sm.k, sm.v, sm.dO};
+      const __nv_bfloat16* const src[4] = {p.q + (size_t)b * p.Sq * p.ldq + h * AT_D, p.k + (size_t)b * p.Sk * p.ldk + h * AT_D,
+                                           p.v + (size_t)b * p.Sk * p.ldv + h * AT_D, p.dO + (size_t)b * p.Sq * p.ldo + h * AT_D};
+      const int ld[4] = {p.ldq, p.ldk, p.ldv, p.ldo};
+      const int rows[4] = {p.Sq, p.Sk, p.Sk, p.Sq};
+      const int fill[4] = {rows16(p.Sq), NKT * 8, NKT * 8, rows16(p.Sq)};
+      load_bias_mask<NW>(sm.bias, sm.kmask, p, bk, b, h, tid);
+      load_heads<NW, 4>(dst, src, ld, rows, fill, tid);
+    }
+    for (int i = tid; i < 64; i += NW * 32) sm.dbucket[i] = 0.f;
+    if (NW == 1) __syncwarp(); else __syncthreads();
+    attn_bwd_compute<NW, NKT>(p, bk, sm, vblk, b, h, tid);
   }
 }
 
@@ -827,14 +932,18 @@ constexpr int AT_HPC = 4;   // single-warp problems per CTA
 template <int NW, int NKT>
 static int launch_fwd(const AttnArgs& a, const AttnBuckets& bk, cudaStream_t stream) {
   constexpr int HPC = NW == 1 ? AT_HPC : 1;
+  constexpr int STAGES = NW == 4 ? 2 : 1;       // NW == 4: persistent CTAs with two cp.async stages, 3 CTAs per SM
   static bool attr = false;
   if (!attr) {
-    VQ_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<NW, NKT, HPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, HPC * attn_smem_fwd(NW * 16, NKT * 8)));
+    VQ_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<NW, NKT, HPC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 STAGES * HPC * attn_smem_fwd(NW * 16, NKT * 8)));
     VQ_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<NW, NKT, HPC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     attr = true;
   }
-  (void)vq_launch(attn_fwd_kernel<NW, NKT, HPC>, dim3((a.B * a.H + HPC - 1) / HPC), dim3(32 * NW * HPC),
-                  (size_t)HPC * attn_smem_fwd(a.Sq, NKT * 8), stream, a, bk);
+  int grid = (a.B * a.H + HPC - 1) / HPC;
+  if (NW == 4 && grid > 3 * num_sms()) grid = 3 * num_sms();
+  (void)vq_launch(attn_fwd_kernel<NW, NKT, HPC>, dim3(grid), dim3(32 * NW * HPC),
+                  (size_t)STAGES * HPC * attn_smem_fwd(a.Sq, NKT * 8), stream, a, bk);
   VQ_LAUNCH_CHECK();
   return 0;
 }

@@ -36,6 +36,7 @@ void vq_set_error(const char* fmt, ...);
 
 // every kernel launch of the library goes through this: counts launches (bench.py reports them) and surfaces errors
 extern long long g_vq_launches;
+extern int g_vq_pdl;   // gemm.cu: 1 unless VQACL_NO_PDL=1
 #define VQ_LAUNCH_CHECK()            \
   do {                               \
     ++g_vq_launches;                 \
@@ -63,7 +64,7 @@ static inline cudaError_t vq_launch(void (*kern)(KArgs...), dim3 grid, dim3 bloc
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  attr[0].val.programmaticStreamSerializationAllowed = g_vq_pdl;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kern, static_cast<Args&&>(args)...);

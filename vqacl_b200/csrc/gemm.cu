@@ -21,6 +21,9 @@ void vq_set_error(const char* fmt, ...) {
 }
 extern "C" const char* vqacl_last_error() { return g_err; }
 long long g_vq_launches = 0;
+// VQACL_NO_PDL=1: plain stream ordering for every launch (measurement only: with PDL a kernel's CUPTI duration includes
+// the time it waits for its predecessor, so per-kernel timelines are taken with this set)
+int g_vq_pdl = [] { const char* e = getenv("VQACL_NO_PDL"); return (e && e[0] == '1') ? 0 : 1; }();
 void vq_kernel_first_use(const void* kern) {
   static std::mutex mu;
   static std::unordered_map<const void*, bool> seen;
@@ -169,7 +172,7 @@ static int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmA
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  attr[1].val.programmaticStreamSerializationAllowed = g_vq_pdl;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
   VQ_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, args));
