@@ -624,9 +624,16 @@ struct KsSmemFwd {
   __nv_bfloat16 q[16][AT_P], k[AT_S][AT_P], v[AT_S][AT_P];
   float kmask[AT_S];
   float pm[KS_WARPS][16], pl[KS_WARPS][16];
-  float o[16][KS_OP];
 };
+// fp32 partial [16 queries x 64] tile of warp w, parked in shared memory the warp owns and no longer needs: query rows 0-7 in
+// its 16 rows of the k tile, rows 8-15 in its 16 rows of the v tile (8 x KS_OP floats = 2176 B <= 16 x 144 B)
+VQ_DEVINL float* ks_partial_row(__nv_bfloat16 (*k)[AT_P], __nv_bfloat16 (*v)[AT_P], int w, int qi) {
+  return reinterpret_cast<float*>(qi < 8 ? &k[16 * w][0] : &v[16 * w][0]) + (qi & 7) * KS_OP;
+}
 
+// Every warp runs a complete softmax over ITS 16 keys (own maximum m_w, own sum l_w, un-normalised partial O_w = P_w V_w) and
+// parks the partial in shared memory; the partials are merged flash-decoding style, O = sum_w e^(m_w - M) O_w / sum_w e^(m_w - M) l_w
+// with M = max_w m_w: one barrier after the loads and one before the merge, no shared atomics (fp32 shared atomicAdd is a CAS loop).
 __global__ void __launch_bounds__(KS_WARPS * 32, 6) attn_ks_fwd_kernel(const AttnArgs p) {
   vq_pdl_trigger();
   vq_pdl_wait();
@@ -643,7 +650,6 @@ __global__ void __launch_bounds__(KS_WARPS * 32, 6) attn_ks_fwd_kernel(const Att
     const int rows[3] = {p.Sq, p.Sk, p.Sk};
     const int fill[3] = {16, AT_S, AT_S};
     if (tid < AT_S) sm.kmask[tid] = tid < p.Sk ? (p.keymask ? p.keymask[(size_t)b * p.Sk + tid] : 0.f) : -INFINITY;
-    for (int i = tid; i < 16 * KS_OP; i += KS_WARPS * 32) (&sm.o[0][0])[i] = 0.f;
     load_heads<KS_WARPS, 3>(dst, src, ld, rows, fill, tid);
   }
   __syncthreads();
@@ -668,23 +674,18 @@ __global__ void __launch_bounds__(KS_WARPS * 32, 6) attn_ks_fwd_kernel(const Att
 #pragma unroll
     for (int i = 0; i < 4; ++i) mx[i >> 1] = fmaxf(mx[i >> 1], s[nt][i]);
   }
+  float sum[2] = {0.f, 0.f};
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
     mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
     mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
   }
-  if (t == 0) { sm.pm[warp][g] = mx[0]; sm.pm[warp][g + 8] = mx[1]; }
-  __syncthreads();
-  float gm[2], sum[2] = {0.f, 0.f};
-#pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    gm[r] = fmaxf(fmaxf(sm.pm[0][g + 8 * r], sm.pm[1][g + 8 * r]), fmaxf(sm.pm[2][g + 8 * r], sm.pm[3][g + 8 * r]));
-  }
 #pragma unroll
   for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float e = __expf(s[nt][i] - gm[i >> 1]);   // keys beyond Sk: exp(-inf) = 0 (gm is finite: key 0 always exists)
+      // a warp whose 16 keys all lie beyond Sk has m_w = -inf: its probabilities, sum and partial are exactly zero
+      const float e = mx[i >> 1] == -INFINITY ? 0.f : __expf(s[nt][i] - mx[i >> 1]);
       s[nt][i] = e;
       sum[i >> 1] += e;
     }
@@ -693,7 +694,10 @@ __global__ void __launch_bounds__(KS_WARPS * 32, 6) attn_ks_fwd_kernel(const Att
     sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 1);
     sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 2);
   }
-  if (t == 0) { sm.pl[warp][g] = sum[0]; sm.pl[warp][g + 8] = sum[1]; }
+  if (t == 0) {
+    sm.pm[warp][g] = mx[0]; sm.pm[warp][g + 8] = mx[1];
+    sm.pl[warp][g] = sum[0]; sm.pl[warp][g + 8] = sum[1];
+  }
   if (p.drop_thr) {
 #pragma unroll
     for (int nt = 0; nt < 2; ++nt)
@@ -705,7 +709,7 @@ __global__ void __launch_bounds__(KS_WARPS * 32, 6) attn_ks_fwd_kernel(const Att
         s[nt][2 * r + 1] *= d1;
       }
   }
-  // partial O = P_w V_w (un-normalised), summed over the warps with shared atomics
+  // partial O_w = P_w V_w (un-normalised, relative to m_w)
   {
     uint32_t a[4];
     a[0] = pack_bf16(s[0][0], s[0][1]); a[1] = pack_bf16(s[0][2], s[0][3]);
@@ -721,35 +725,42 @@ __global__ void __launch_bounds__(KS_WARPS * 32, 6) attn_ks_fwd_kernel(const Att
       frag_b2_t(bb, sm.v, nt * 8, k0, lane);
       mma2(o[nt], o[nt + 1], a, bb);
     }
+    __syncwarp();   // every lane has read its K / V fragments: the warp's rows of both tiles may now hold the partial
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       const int qi = g + r * 8;
       if (qi < p.Sq) {
+        float* dst = ks_partial_row(sm.k, sm.v, warp, qi) + 2 * t;
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-          atomicAdd(&sm.o[qi][nt * 8 + 2 * t], o[nt][2 * r]);
-          atomicAdd(&sm.o[qi][nt * 8 + 2 * t + 1], o[nt][2 * r + 1]);
-        }
+        for (int nt = 0; nt < 8; ++nt) *reinterpret_cast<float2*>(dst + nt * 8) = make_float2(o[nt][2 * r], o[nt][2 * r + 1]);
       }
     }
   }
   __syncthreads();
-  // normalise and write: thread -> (row = tid / 8, 8 columns)
+  // merge, normalise and write: thread -> (row = tid / 8, 8 columns)
   {
     const int qi = tid >> 3, c0 = (tid & 7) * 8;
     if (qi < p.Sq) {
-      const float l = sm.pl[0][qi] + sm.pl[1][qi] + sm.pl[2][qi] + sm.pl[3][qi];
+      const float m = fmaxf(fmaxf(sm.pm[0][qi], sm.pm[1][qi]), fmaxf(sm.pm[2][qi], sm.pm[3][qi]));   // finite: key 0 always exists
+      float l = 0.f, acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+      for (int w = 0; w < KS_WARPS; ++w) {
+        const float sc = __expf(sm.pm[w][qi] - m);   // exp(-inf) = 0 for a warp without keys
+        l += sc * sm.pl[w][qi];
+        const float* so = ks_partial_row(sm.k, sm.v, w, qi) + c0;
+        const float4 x = *reinterpret_cast<const float4*>(so), y = *reinterpret_cast<const float4*>(so + 4);
+        acc[0] += sc * x.x; acc[1] += sc * x.y; acc[2] += sc * x.z; acc[3] += sc * x.w;
+        acc[4] += sc * y.x; acc[5] += sc * y.y; acc[6] += sc * y.z; acc[7] += sc * y.w;
+      }
       const float inv = 1.f / l;
-      const float* so = &sm.o[qi][c0];
       uint4 out;
-      out.x = pack_bf16(so[0] * inv, so[1] * inv); out.y = pack_bf16(so[2] * inv, so[3] * inv);
-      out.z = pack_bf16(so[4] * inv, so[5] * inv); out.w = pack_bf16(so[6] * inv, so[7] * inv);
+      out.x = pack_bf16(acc[0] * inv, acc[1] * inv); out.y = pack_bf16(acc[2] * inv, acc[3] * inv);
+      out.z = pack_bf16(acc[4] * inv, acc[5] * inv); out.w = pack_bf16(acc[6] * inv, acc[7] * inv);
       __nv_bfloat16* dst = p.o + (size_t)b * (p.o_bstride ? p.o_bstride : (long long)p.Sq * p.ldo) + (size_t)qi * p.ldo + h * AT_D + c0;
       *reinterpret_cast<uint4*>(dst) = out;
-      if (c0 == 0 && p.lse) {
-        const float m = fmaxf(fmaxf(sm.pm[0][qi], sm.pm[1][qi]), fmaxf(sm.pm[2][qi], sm.pm[3][qi]));
-        p.lse[((size_t)b * p.H + h) * p.Sq + qi] = m + __logf(l);
-      }
+      if (c0 == 0 && p.lse) p.lse[((size_t)b * p.H + h) * p.Sq + qi] = m + __logf(l);
     }
   }
 }
@@ -759,14 +770,16 @@ struct KsSmemBwd {
   __nv_bfloat16 P[KS_WARPS][16][24], dS[KS_WARPS][16][24];   // per-warp [query][its 16 keys], 48-byte rows (ldmatrix-aligned)
   float kmask[AT_S];
   float D[16], lse[16];
-  float dq[16][KS_OP];
+  // followed by the per-warp fp32 dQ partials [KS_WARPS][Sq][KS_OP] (size depends on Sq, see ks_bwd_smem)
 };
+static inline int ks_bwd_smem(int Sq) { return (int)sizeof(KsSmemBwd) + KS_WARPS * Sq * KS_OP * 4; }
 
 __global__ void __launch_bounds__(KS_WARPS * 32, 5) attn_ks_bwd_kernel(const AttnArgs p) {
   vq_pdl_trigger();
   vq_pdl_wait();
   extern __shared__ __align__(16) uint8_t at_smem_base[];
   KsSmemBwd& sm = *reinterpret_cast<KsSmemBwd*>(at_smem_base);
+  float* dq_part = reinterpret_cast<float*>(at_smem_base + sizeof(KsSmemBwd));
   const int vblk = blockIdx.x, b = vblk / p.H, h = vblk % p.H;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   {
@@ -777,7 +790,6 @@ __global__ void __launch_bounds__(KS_WARPS * 32, 5) attn_ks_bwd_kernel(const Att
     const int rows[4] = {p.Sq, p.Sq, p.Sk, p.Sk};
     const int fill[4] = {16, 16, AT_S, AT_S};
     if (tid < AT_S) sm.kmask[tid] = tid < p.Sk ? (p.keymask ? p.keymask[(size_t)b * p.Sk + tid] : 0.f) : -INFINITY;
-    for (int i = tid; i < 16 * KS_OP; i += KS_WARPS * 32) (&sm.dq[0][0])[i] = 0.f;
     // D[q] = sum_d dO[q][d] * O[q][d]: 8 threads per query row, 8 columns each
     {
       const int qi = tid >> 3, c0 = (tid & 7) * 8;
@@ -851,15 +863,14 @@ __global__ void __launch_bounds__(KS_WARPS * 32, 5) attn_ks_bwd_kernel(const Att
       frag_b2_t(bb, sm.k, nt * 8, k0, lane);
       mma2(dq[nt], dq[nt + 1], a, bb);
     }
+    // parked per warp and summed after the barrier (fp32 shared atomicAdd would be a CAS loop per element)
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       const int qi = g + r * 8;
       if (qi < p.Sq) {
+        float* dst = dq_part + ((size_t)warp * p.Sq + qi) * KS_OP + 2 * t;
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-          atomicAdd(&sm.dq[qi][nt * 8 + 2 * t], dq[nt][2 * r]);
-          atomicAdd(&sm.dq[qi][nt * 8 + 2 * t + 1], dq[nt][2 * r + 1]);
-        }
+        for (int nt = 0; nt < 8; ++nt) *reinterpret_cast<float2*>(dst + nt * 8) = make_float2(dq[nt][2 * r], dq[nt][2 * r + 1]);
       }
     }
   }
@@ -885,27 +896,25 @@ __global__ void __launch_bounds__(KS_WARPS * 32, 5) attn_ks_bwd_kernel(const Att
       mma2(dv[nt], dv[nt + 1], ap, b1);
       mma2(dk[nt], dk[nt + 1], as, b2);
     }
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const int kj = k0 + g + r * 8;
-      if (kj < p.Sk) {
-        __nv_bfloat16* dstk = p.dk + ((size_t)b * p.Sk + kj) * p.lddk + h * AT_D + 2 * t;
-        __nv_bfloat16* dstv = p.dv + ((size_t)b * p.Sk + kj) * p.lddv + h * AT_D + 2 * t;
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-          *reinterpret_cast<uint32_t*>(dstk + nt * 8) = pack_bf16(dk[nt][2 * r], dk[nt][2 * r + 1]);
-          *reinterpret_cast<uint32_t*>(dstv + nt * 8) = pack_bf16(dv[nt][2 * r], dv[nt][2 * r + 1]);
-        }
-      }
-    }
+    // rows [k0, k0 + 16) of the k / v tiles are only ever read by this warp, and it is done with them: stage dK / dV there
+    store_tile16(sm.k, k0, dk, p.dk + (size_t)b * p.Sk * p.lddk + h * AT_D, p.lddk, p.Sk, lane);
+    store_tile16(sm.v, k0, dv, p.dv + (size_t)b * p.Sk * p.lddv + h * AT_D, p.lddv, p.Sk, lane);
   }
   __syncthreads();
   {
     const int qi = tid >> 3, c0 = (tid & 7) * 8;
     if (qi < p.Sq) {
-      const float* so = &sm.dq[qi][c0];
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+      for (int w = 0; w < KS_WARPS; ++w) {
+        const float* so = dq_part + ((size_t)w * p.Sq + qi) * KS_OP + c0;
+        const float4 x = *reinterpret_cast<const float4*>(so), y = *reinterpret_cast<const float4*>(so + 4);
+        acc[0] += x.x; acc[1] += x.y; acc[2] += x.z; acc[3] += x.w; acc[4] += y.x; acc[5] += y.y; acc[6] += y.z; acc[7] += y.w;
+      }
       uint4 out;
-      out.x = pack_bf16(so[0], so[1]); out.y = pack_bf16(so[2], so[3]); out.z = pack_bf16(so[4], so[5]); out.w = pack_bf16(so[6], so[7]);
+      out.x = pack_bf16(acc[0], acc[1]); out.y = pack_bf16(acc[2], acc[3]); out.z = pack_bf16(acc[4], acc[5]); out.w = pack_bf16(acc[6], acc[7]);
       *reinterpret_cast<uint4*>(p.dq + ((size_t)b * p.Sq + qi) * p.lddq + h * AT_D + c0) = out;
     }
   }
@@ -993,10 +1002,10 @@ int attn_bwd(const AttnArgs& a, cudaStream_t stream) {
   if (a.o_saved && a.Sq <= 16 && a.Sk > 16 && a.rel_mode == 0 && !a.causal) {   // key-split backward (needs the forward output)
     static bool attr = false;
     if (!attr) {
-      VQ_CUDA(cudaFuncSetAttribute(attn_ks_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KsSmemBwd)));
+      VQ_CUDA(cudaFuncSetAttribute(attn_ks_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ks_bwd_smem(16)));
       attr = true;
     }
-    (void)vq_launch(attn_ks_bwd_kernel, dim3(a.B * a.H), dim3(KS_WARPS * 32), sizeof(KsSmemBwd), stream, a);
+    (void)vq_launch(attn_ks_bwd_kernel, dim3(a.B * a.H), dim3(KS_WARPS * 32), (size_t)ks_bwd_smem(a.Sq), stream, a);
     VQ_LAUNCH_CHECK();
     return 0;
   }
