@@ -20,9 +20,15 @@ def main():
     rows = load(sys.argv[1])
     starts = [i for i, (n, _, _) in enumerate(rows) if "keymask" in n]
     k = int(sys.argv[2]) if len(sys.argv) > 2 else 0
-    if len(starts) < k + 2:
+    if len(starts) == 1:
+        # a window of ~one step's worth of consecutive launches taken mid-run (--launch-skip/--launch-count): rotate it so
+        # that it starts at the step boundary (the steady-state step is cyclic; at most a launch or two are missing)
+        step = rows[starts[0]:] + rows[:starts[0]]
+        print("(cyclic window: the capture holds one step boundary; rotated to start there)")
+    elif len(starts) < k + 2:
         print("need two step starts (keymask_kernel) in the capture; found", len(starts)); return
-    step = rows[starts[k]:starts[k + 1]]
+    else:
+        step = rows[starts[k]:starts[k + 1]]
     names = [short(n) for n, _, _ in step]
     tot = sum(t for _, t, _ in step)
     print(f"launches in step: {len(step)}   sum of kernel durations: {tot / 1e6:.3f} ms")
