@@ -42,19 +42,30 @@ struct GemmArgs {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_EPI_WARPS = 8;
+#ifndef GEMM_EPI_WARPS_N
+#define GEMM_EPI_WARPS_N 8
+#endif
+constexpr int GEMM_EPI_WARPS = GEMM_EPI_WARPS_N;            // 8 or 12: 2 or 3 warps per TMEM lane quarter, taking every 2nd / 3rd 32-column chunk.
+                                                             // Measured (profiles/r01_summary.md): 12 warps (512 threads, one smem stage less) make the
+                                                             // fp32-residual epilogue 6 % faster and every MMA-bound shape 3-5 % slower; 8 it is.
+constexpr int GEMM_EPI_GROUPS = GEMM_EPI_WARPS / 4;
 constexpr int GEMM_THREADS = 128 + GEMM_EPI_WARPS * 32;
 #ifndef GEMM_MAXREG
 #define GEMM_MAXREG 128   // 384 threads x 128 = 48 K registers: leaves room on the SM for a memory-bound kernel of another stream (168 measured no faster)
 #endif
 constexpr int EPI_TILE_BYTES = 4096;                         // one 32x32 fp32 (or 32x32 bf16 in half of it) tile per epilogue warp
+constexpr int GEMM_SMEM_MAX = 232448;                        // opt-in maximum per CTA on sm_100
+constexpr int gemm_stages(int stage_bytes, int max_stages) {  // as many pipeline stages as fit beside the epilogue staging tiles
+  const int fit = (GEMM_SMEM_MAX - 1024 - 256 - GEMM_EPI_WARPS * EPI_TILE_BYTES) / stage_bytes;
+  return fit < max_stages ? fit : max_stages;
+}
 
 template <int BN>
 struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int STAGES = gemm_stages(STAGE_BYTES, (BN == 256) ? 4 : (BN == 128 ? 6 : 8));
   static constexpr int TMEM_COLS = 2 * BN;  // two accumulator stages
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + GEMM_EPI_WARPS * EPI_TILE_BYTES;
 };
@@ -69,7 +80,7 @@ VQ_DEVINL uint4 lds128(uint32_t addr) {
 }
 
 // One 128 x BN accumulator tile: this warp owns TMEM lanes [32q, 32q+32) (= tile rows) and the 32-column chunks
-// c = half, half+2, ... tcgen05.ld 32x32b gives thread = row, registers = 32 consecutive columns; a global access from that
+// c = half, half + GEMM_EPI_GROUPS, ... (`half` = index of the warp among those sharing its lane quarter) tcgen05.ld 32x32b gives thread = row, registers = 32 consecutive columns; a global access from that
 // layout is 32 row-strided 16-byte requests per instruction. The fused math therefore runs in the row layout, the result is
 // transposed through a private XOR-swizzled smem tile (conflict-free 16-byte writes and reads, no padding), and global
 // memory is touched with 4 (bf16: 8) full rows of 128 (64) contiguous bytes per instruction. Extra operands (residual R,
@@ -81,7 +92,7 @@ VQ_DEVINL void gemm_epilogue_tile(const GemmArgs& p, uint32_t t_base, uint32_t s
   const int M = p.M, N = p.N, ldc = p.ldc, ldr = p.ldr;
   const float alpha = p.alpha;
   bool waited = false;
-  // extra-operand registers are double-buffered in time: the operand of chunk c+2 (this warp's next chunk) is requested right
+  // extra-operand registers are double-buffered in time: the operand of this warp's next chunk is requested right
   // after the accumulator of chunk c has been read, so its global-memory latency overlaps the math and stores of chunk c
   float4 rres[8];
   uint32_t rmask = 0;   // ReLU-backward: bit i = activation (row = this lane's row, column col0 + i) was positive and kept
@@ -104,7 +115,7 @@ VQ_DEVINL void gemm_epilogue_tile(const GemmArgs& p, uint32_t t_base, uint32_t s
   };
   prefetch(half);
 #pragma unroll 1
-  for (int c = half; c < BN / 32; c += 2) {
+  for (int c = half; c < BN / 32; c += GEMM_EPI_GROUPS) {
     const int col0 = n_base + c * 32;
     if (col0 >= N) break;
     float4 cres[8];
@@ -121,7 +132,7 @@ VQ_DEVINL void gemm_epilogue_tile(const GemmArgs& p, uint32_t t_base, uint32_t s
     uint32_t r[32];
     tmem_ld_32x32(t_base + c * 32, r);
     tmem_ld_wait();
-    prefetch(c + 2);
+    prefetch(c + GEMM_EPI_GROUPS);
     float v[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * alpha;
@@ -383,7 +394,7 @@ struct Gemm2Cfg {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;              // 128 rows of A
   static constexpr int B_BYTES = (GEMM2_BN / 2) * GEMM_BK * 2;       // this CTA's half of the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;              // 32 KB
-  static constexpr int STAGES = 6;
+  static constexpr int STAGES = gemm_stages(STAGE_BYTES, 6);
   static constexpr int TMEM_COLS = 2 * GEMM2_BN;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + GEMM_EPI_WARPS * EPI_TILE_BYTES;
 };
