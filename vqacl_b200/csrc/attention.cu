@@ -1,6 +1,8 @@
 // Fused T5 attention for the VL-T5 shapes (S <= 64 keys/queries, d_kv = 64): the whole Q/K/V problem of one (batch, head)
-// lives in shared memory (encoder: one problem per 4-warp CTA; decoder self-attention: 4 single-warp problems per CTA;
-// cross-attention: key-split across the 4 warps of a CTA). Scores are NOT scaled by 1/sqrt(d) (T5), the relative-position bias is read from the
+// lives in shared memory (encoder forward: persistent 4-warp CTAs that stream the next problem in with cp.async while they work
+// on the current one; encoder backward: one problem per 4-warp CTA; decoder self-attention: 4 single-warp problems per CTA;
+// cross-attention: key-split across the 4 warps of a CTA). Output tiles leave through shared memory as full 128-byte rows.
+// Scores are NOT scaled by 1/sqrt(d) (T5), the relative-position bias is read from the
 // [num_buckets, H] embedding table through a host-precomputed rel->bucket map, and the additive masks of HF 4.2.1
 // (-10000 key padding / causal, -1e9 cross) are applied in-kernel, so the [B,H,S,S] bias tensor the reference
 // materialises (modeling_t5_our.py:258-273) never exists. Backward recomputes P from the saved log-sum-exp.
@@ -613,9 +615,10 @@ __global__ void __launch_bounds__(NW * 32 * HPC, NW == 4 ? 4 : 8 / HPC) attn_bwd
 // =====================================================================================================================
 // Key-split kernels for few queries against many keys (decoder cross-attention: Sq = T <= 16 queries, 58 keys).
 // One CTA per (batch, head), 4 warps, warp w owns keys [16w, 16w+16). With one 16-row query tile the generic kernel would
-// leave three warps idle; here every warp multiplies the query tile with its 16 keys (2 key tiles), the row maximum and
-// sum are exchanged through shared memory, and the partial P.V products (backward: partial dS.K) are summed with shared
-// fp32 atomics. Backward needs no cross-warp softmax statistic: P = exp(S - lse) from the saved log-sum-exp and
+// leave three warps idle; here every warp runs a complete softmax over its 16 keys (2 key tiles) and the per-warp results
+// (row maximum, sum, partial P.V; backward: partial dS.K) are parked in shared memory and merged after one barrier
+// (profiles/r01_summary.md: the shared fp32 atomics this replaced were 28 % of the kernel's stall samples).
+// Backward needs no cross-warp softmax statistic: P = exp(S - lse) from the saved log-sum-exp and
 // D = rowsum(dO * O) from the saved output (also valid with dropout: O was produced by the dropped probabilities).
 // =====================================================================================================================
 constexpr int KS_WARPS = 4;
