@@ -51,3 +51,33 @@ def test_loss_tail_matches_reference():
     m = (labels != -100).float()
     loss = ((rows.view(B, T) * m).sum(1) / m.sum(1).clamp(min=1) * scores).mean()
     torch.testing.assert_close(loss, d["loss"], rtol=0, atol=0)
+
+
+def test_full_forward_glue_matches_reference():
+    """JointEncoder.forward + VLT5.forward executed from the reference's text (tools/gen_golden_forward.py): encoder bias /
+    mask construction (a3), SI path in place (a9-a13), shift-right, cross mask with the two prototype rows attendable,
+    decoder, x d^-1/2, tied LM head, CE(reduction='none') (a7, a8, a14), over four consecutive calls on one model."""
+    d = torch.load(os.path.join(G, "vlt5_forward.pt"))
+    cfg = O.VLT5Config(dropout_rate=0.0, **d["cfg"])
+    om = O.VLT5VQA(cfg).eval()
+    missing, unexpected = om.load_state_dict(d["state"], strict=False)
+    assert not unexpected, unexpected
+    assert all(k.startswith(("prototype_fc", "lm_head", "encoder.embed_tokens", "decoder.embed_tokens")) for k in missing), missing
+    for c in d["calls"]:
+        with torch.no_grad():
+            # the additive bias + mask tensor the reference hands to its first encoder block (modeling_t5_our.py:258-273)
+            L, S = c["input_ids"].size(1), c["input_ids"].size(1) + c["vis_feats"].size(1)
+            mask = torch.cat([c["input_ids"].ne(0).float(), torch.ones(c["input_ids"].size(0), S - L)], 1)
+            bias = torch.zeros(1, cfg.num_heads, S, S)
+            bias[:, :, :L, :L] = om.encoder.block[0].layer[0].SelfAttention.compute_bias(L, L)
+            torch.testing.assert_close(bias + (1.0 - mask[:, None, None, :]) * -10000.0, c["position_bias"], rtol=0, atol=0)
+            kw = dict(cate_labels=c["cate_labels"], ques_labels=c["ques_labels"], proto_update=True, task_id=c["task"],
+                      alpha=d["alpha"], beta=d["beta"]) if c["proto_update"] else {}
+            out = om(c["input_ids"], c["vis_feats"], c["boxes"], c["labels"], **kw)
+        torch.testing.assert_close(out["encoder_hidden_states"], c["encoder_hidden_states"], rtol=1e-5, atol=1e-5)
+        assert torch.equal(out["encoder_attention_mask"], c["encoder_attention_mask"])
+        torch.testing.assert_close(out["logits"], c["logits"], rtol=1e-4, atol=1e-4)
+        torch.testing.assert_close(out["loss"], c["loss"], rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(om.bank.Q_prototype, c["Q_prototype"], rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(om.bank.V_prototype, c["V_prototype"], rtol=1e-5, atol=1e-6)
+        assert torch.equal(om.bank.Q_prototype_num, c["Q_num"]) and torch.equal(om.bank.V_prototype_num, c["V_num"])
