@@ -88,3 +88,39 @@ def test_init_std_table():
     assert abs(m.shared.weight.std().item() - 1.0) < 2e-2
     assert m.lm_head.weight is m.shared.weight
     assert m.encoder.visual_embedding.obj_order_embedding.weight is m.shared.weight
+
+
+def test_greedy_loop_matches_hf_generate():
+    """The oracle's greedy loop (start token, argmax, pad after EOS, stop when every row is finished or at max_length;
+    SURVEY.md §8 a16) against transformers' own `generate` on the same decoder, memory and cross mask. A tiny vocabulary
+    makes rows hit EOS at different steps, so the finished-row bookkeeping is exercised."""
+    from transformers.modeling_outputs import BaseModelOutput
+    torch.manual_seed(2)
+    V = 8
+    cfg = T5Config(vocab_size=V, d_model=768, d_kv=64, d_ff=128, num_layers=2, num_decoder_layers=2, num_heads=12,
+                   relative_attention_num_buckets=32, relative_attention_max_distance=128, dropout_rate=0.0,
+                   feed_forward_proj="relu", tie_word_embeddings=True, decoder_start_token_id=0, pad_token_id=0, eos_token_id=1)
+    ref = hf.T5ForConditionalGeneration(cfg).eval()
+    with torch.no_grad():
+        ref.shared.weight.mul_(0.02)   # small tied embeddings: the next token is not simply the current one again
+    om = O.VLT5VQA(O.VLT5Config(vocab_size=V, d_ff=128, num_layers=2, num_decoder_layers=2, dropout_rate=0.0)).eval()
+    sd, mine = ref.state_dict(), om.state_dict()
+    for k in mine:
+        if k in sd and mine[k].shape == sd[k].shape:
+            mine[k].copy_(sd[k])
+    om.shared.weight.data.copy_(sd["shared.weight"])
+    B, L, S2 = 12, 9, 14
+    ids = torch.randint(2, V, (B, L))
+    ids[3, 6:] = 0                                     # padded text positions are masked in cross-attention
+    ids[7, 4:] = 0
+    mem = torch.randn(B, S2, 768)
+    mask = torch.cat([ids.ne(0).long(), torch.ones(B, S2 - L, dtype=torch.long)], 1)
+    mine_tok = om.greedy_decode(mem, ids, max_length=20)
+    with torch.no_grad():
+        theirs = ref.generate(encoder_outputs=BaseModelOutput(last_hidden_state=mem), attention_mask=mask, max_length=20,
+                              do_sample=False, num_beams=1)
+    n = min(mine_tok.size(1), theirs.size(1))
+    assert torch.equal(mine_tok[:, :n], theirs[:, :n])
+    assert (mine_tok[:, n:] == 0).all() and (theirs[:, n:] == 0).all()
+    finished_at = [(row == 1).nonzero()[0].item() if (row == 1).any() else -1 for row in mine_tok]
+    assert len({f for f in finished_at}) >= 3          # rows really stop at different steps (else the test is vacuous)
