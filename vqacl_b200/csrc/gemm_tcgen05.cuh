@@ -89,31 +89,52 @@ template <int EPI, int BN>
 VQ_DEVINL void gemm_epilogue_tile(const GemmArgs& p, uint32_t t_base, uint32_t stg, int row_base, int n_base, int half, int lane,
                                   bool has_k, uint64_t* tfull, uint32_t aphase) {
   constexpr bool OUT_BF16 = (EPI == EPI_BF16 || EPI == EPI_RELU_BF16 || EPI == EPI_RELUBWD_BF16);
-  const int M = p.M, N = p.N, ldc = p.ldc, ldr = p.ldr;
+  constexpr int ESZ = OUT_BF16 ? 2 : 4;          // bytes per output element
+  constexpr int RPI = OUT_BF16 ? 8 : 4;          // rows one store instruction covers (4 or 8 lanes x 16 B per row)
+  constexpr int NIT = 32 / RPI;                  // store instructions per 32-row chunk
+  constexpr int ROWB = 32 * ESZ;                 // bytes of one staged row (32 columns)
+  const int N = p.N;
   const float alpha = p.alpha;
-  bool waited = false;
+  // Everything that does not change from chunk to chunk is computed once per tile: the number of rows of this warp's 32-row
+  // slab that exist, this lane's byte pointers into C / R for its first row (later rows and chunks are reached by adding
+  // strides) and its shared-memory staging addresses. The staging tile is at least 128-byte aligned, so the XOR swizzle
+  // of a 16-byte piece index can be applied to the byte address.
+  const int rlim = has_k ? p.M - row_base : 0;                      // row r of the slab is written iff r < rlim
+  const int rr0 = OUT_BF16 ? (lane >> 2) : (lane >> 3);             // row inside a store instruction
+  const int piece = OUT_BF16 ? (lane & 3) : (lane & 7);             // 16-byte piece of that row
+  const int pcol = n_base + piece * (16 / ESZ);                     // + c * 32 = first column of this lane's piece
+  char* cbase = reinterpret_cast<char*>(p.C) + ((size_t)(row_base + rr0) * p.ldc + pcol) * ESZ;
+  const size_t cstep = (size_t)RPI * p.ldc * ESZ;
+  const uint32_t sts_base = stg + lane * ROWB + ((OUT_BF16 ? ((lane >> 1) & 3) : (lane & 7)) << 4);   // ^ (j << 4) per piece j
+  // fp32: rows it * 4 + rr0 have swizzle key (row & 7) = rr0 + 4 * (it & 1), i.e. odd `it` flip bit 2 of the piece index
+  const uint32_t lds_base = stg + rr0 * ROWB + ((OUT_BF16 ? (piece ^ ((rr0 >> 1) & 3)) : (piece ^ rr0)) << 4);
   // extra-operand registers are double-buffered in time: the operand of this warp's next chunk is requested right
   // after the accumulator of chunk c has been read, so its global-memory latency overlaps the math and stores of chunk c
   float4 rres[8];
   uint32_t rmask = 0;   // ReLU-backward: bit i = activation (row = this lane's row, column col0 + i) was positive and kept
+  const char* rbase = nullptr;
+  size_t rstep = 0;
+  if (EPI == EPI_RESID_F32) {
+    rbase = reinterpret_cast<const char*>(p.R) + ((size_t)(row_base + rr0) * p.ldr + pcol) * 4;
+    rstep = (size_t)4 * p.ldr * 4;
+  }
+  if (EPI == EPI_RELU_BF16 || EPI == EPI_RELUBWD_BF16)   // one mask word per (row = this lane's accumulator row, chunk)
+    rbase = reinterpret_cast<const char*>(p.R) + ((size_t)(row_base + lane) * p.ldr + (n_base >> 5)) * 4;
   auto prefetch = [&](int cc) {
-    const int pcol0 = n_base + cc * 32;
+    const bool ok = cc < BN / 32 && n_base + cc * 32 < N;
     if (EPI == EPI_RESID_F32) {
-      const int gcol = pcol0 + (lane & 7) * 4;
+      const bool colok = ok && pcol + cc * 32 < N;
+      const char* rp = rbase + cc * 128;
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
-        const int grow = row_base + it * 4 + (lane >> 3);
-        rres[it] = (cc < BN / 32 && grow < M && gcol < N)
-                       ? *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.R) + (size_t)grow * ldr + gcol)
-                       : make_float4(0.f, 0.f, 0.f, 0.f);
+        rres[it] = (colok && it * 4 + rr0 < rlim) ? *reinterpret_cast<const float4*>(rp) : make_float4(0.f, 0.f, 0.f, 0.f);
+        rp += rstep;
       }
     }
-    if (EPI == EPI_RELUBWD_BF16) {
-      const int grow = row_base + lane;   // row layout: this lane owns one accumulator row
-      rmask = (cc < BN / 32 && grow < M && pcol0 < N) ? reinterpret_cast<const uint32_t*>(p.R)[(size_t)grow * ldr + (pcol0 >> 5)] : 0u;
-    }
+    if (EPI == EPI_RELUBWD_BF16) rmask = (ok && lane < rlim) ? *reinterpret_cast<const uint32_t*>(rbase + cc * 4) : 0u;
   };
   prefetch(half);
+  bool waited = false;
 #pragma unroll 1
   for (int c = half; c < BN / 32; c += GEMM_EPI_GROUPS) {
     const int col0 = n_base + c * 32;
@@ -155,60 +176,44 @@ VQ_DEVINL void gemm_epilogue_tile(const GemmArgs& p, uint32_t t_base, uint32_t s
       uint32_t m = 0;
 #pragma unroll
       for (int i = 0; i < 32; ++i) m |= (v[i] > 0.f ? 1u : 0u) << i;
-      const int grow = row_base + lane;
-      if (has_k && grow < M && col0 < N) reinterpret_cast<uint32_t*>(const_cast<void*>(p.R))[(size_t)grow * ldr + (col0 >> 5)] = m;
+      if (lane < rlim) *reinterpret_cast<uint32_t*>(const_cast<char*>(rbase) + c * 4) = m;
     }
     if (EPI == EPI_RELUBWD_BF16) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = ((cmask >> i) & 1u) ? v[i] : 0.f;
     }
+    // stage the 32 x 32 chunk (thread = row) with its 16-byte pieces XOR-swizzled, read it back as full rows
     if (OUT_BF16) {
-      // stage 32 rows x 64 B; 16-byte piece j of row l lives at slot j ^ ((l >> 1) & 3)
-      const uint32_t wrow = stg + lane * 64;
-      const int sw = (lane >> 1) & 3;
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        sts128(wrow + ((j ^ sw) << 4), pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+        sts128(sts_base ^ (j << 4), pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
                pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-      __syncwarp();
-      const int piece = lane & 3;
-      const int gcol = col0 + piece * 8;
-#pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        const int rr = it * 8 + (lane >> 2);
-        const int grow = row_base + rr;
-        uint4 o = lds128(stg + rr * 64 + ((piece ^ ((rr >> 1) & 3)) << 4));
-        if (has_k && grow < M && gcol < N) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)grow * ldc + gcol) = o;
-      }
     } else {
-      // stage 32 rows x 128 B; 16-byte piece j of row l lives at slot j ^ (l & 7)
-      const uint32_t wrow = stg + lane * 128;
-      const int sw = lane & 7;
 #pragma unroll
       for (int j = 0; j < 8; ++j)
-        sts128(wrow + ((j ^ sw) << 4), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
+        sts128(sts_base ^ (j << 4), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
                __float_as_uint(v[4 * j + 3]));
-      __syncwarp();
-      const int piece = lane & 7;
-      const int gcol = col0 + piece * 4;
+    }
+    __syncwarp();
+    const bool colok = pcol + c * 32 < N;
+    char* cp = cbase + c * (32 * ESZ);
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int rr = it * 4 + (lane >> 3);
-        const int grow = row_base + rr;
-        const uint4 u = lds128(stg + rr * 128 + ((piece ^ (rr & 7)) << 4));
-        float4 o = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
-        if (has_k && grow < M && gcol < N) {
-          float* dst = reinterpret_cast<float*>(p.C) + (size_t)grow * ldc + gcol;
-          if (EPI == EPI_RESID_F32) {
-            o.x += cres[it].x; o.y += cres[it].y; o.z += cres[it].z; o.w += cres[it].w;
-            *reinterpret_cast<float4*>(dst) = o;
-          } else if (EPI == EPI_ATOMIC_F32) {
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
-          } else {
-            *reinterpret_cast<float4*>(dst) = o;
-          }
+    for (int it = 0; it < NIT; ++it) {
+      const uint4 u = lds128((OUT_BF16 || !(it & 1) ? lds_base : (lds_base ^ 64u)) + it * (RPI * ROWB));
+      if (colok && it * RPI + rr0 < rlim) {
+        if (EPI == EPI_RESID_F32) {
+          float4 o = make_float4(__uint_as_float(u.x) + cres[it].x, __uint_as_float(u.y) + cres[it].y, __uint_as_float(u.z) + cres[it].z,
+                                 __uint_as_float(u.w) + cres[it].w);
+          *reinterpret_cast<float4*>(cp) = o;
+        } else if (EPI == EPI_ATOMIC_F32) {
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cp), "f"(__uint_as_float(u.x)), "f"(__uint_as_float(u.y)),
+                       "f"(__uint_as_float(u.z)), "f"(__uint_as_float(u.w))
+                       : "memory");
+        } else {
+          *reinterpret_cast<uint4*>(cp) = u;
         }
       }
+      cp += cstep;
     }
     __syncwarp();
   }
