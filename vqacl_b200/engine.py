@@ -6,7 +6,7 @@ by libvqacl_b200.so; there is no eager/PyTorch fallback (a missing library or a 
 """
 import ctypes
 import math
-from ctypes import POINTER, Structure, byref, c_char_p, c_float, c_int, c_int32, c_int64, c_uint32, c_void_p
+from ctypes import POINTER, Structure, byref, c_char_p, c_float, c_int, c_int64, c_uint32, c_void_p
 
 import torch
 

@@ -14,8 +14,6 @@ kernel of forward, backward, optimizer and greedy decode is launched from C++ (v
 module is only a parameter container (init, load_state_dict, resize) — calling the hot path there raises: there is no
 CPU fallback.
 """
-import ctypes
-import math
 from collections import OrderedDict
 from dataclasses import dataclass
 from typing import Any, Optional
@@ -23,7 +21,7 @@ from typing import Any, Optional
 import torch
 import torch.nn as nn
 
-from ._lib import VqaclError, ptr
+from ._lib import VqaclError
 from .config import VLT5Config
 from .engine import CProtoState, Engine
 
