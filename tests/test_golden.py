@@ -56,7 +56,8 @@ def test_loss_tail_matches_reference():
 def test_full_forward_glue_matches_reference():
     """JointEncoder.forward + VLT5.forward executed from the reference's text (tools/gen_golden_forward.py): encoder bias /
     mask construction (a3), SI path in place (a9-a13), shift-right, cross mask with the two prototype rows attendable,
-    decoder, x d^-1/2, tied LM head, CE(reduction='none') (a7, a8, a14), over four consecutive calls on one model."""
+    decoder, x d^-1/2, tied LM head, CE(reduction='none') (a7, a8, a14), over four consecutive calls on one model, then one
+    step through the reference's VLT5VQA.train_step text (a1)."""
     d = torch.load(os.path.join(G, "vlt5_forward.pt"))
     cfg = O.VLT5Config(dropout_rate=0.0, **d["cfg"])
     om = O.VLT5VQA(cfg).eval()
@@ -81,3 +82,14 @@ def test_full_forward_glue_matches_reference():
         torch.testing.assert_close(om.bank.Q_prototype, c["Q_prototype"], rtol=1e-5, atol=1e-6)
         torch.testing.assert_close(om.bank.V_prototype, c["V_prototype"], rtol=1e-5, atol=1e-6)
         assert torch.equal(om.bank.Q_prototype_num, c["Q_num"]) and torch.equal(om.bank.V_prototype_num, c["V_num"])
+    # one more step through the reference's VLT5VQA.train_step text (vqa_model.py:18-65) on the same model state
+    t = d["train_call"]
+    with torch.no_grad():
+        res = om.train_step({k: t[k] for k in ("input_ids", "vis_feats", "boxes", "target_ids", "cate_labels", "ques_labels", "scores")},
+                            t["task"], d["alpha"], d["beta"], 3, 1000)
+    assert set(t["keys"]) <= set(res.keys()) and tuple(res["BL"]) == tuple(t["BL"])
+    torch.testing.assert_close(res["loss"], t["loss"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(res["encoder_hidden_states"], t["encoder_hidden_states"], rtol=1e-5, atol=1e-5)
+    assert torch.equal(res["encoder_attention_mask"], t["encoder_attention_mask"])
+    torch.testing.assert_close(om.bank.Q_prototype, t["Q_prototype"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(om.bank.V_prototype, t["V_prototype"], rtol=1e-5, atol=1e-6)

@@ -13,7 +13,8 @@ The two methods are lifted from the file with `ast` and run unmodified. What the
     the signature and the constant); `get_head_mask`: [None] * n. These two lines are restated, not executed.
 Weights are tiny (d_model must stay 768 — the reference hard-codes it at :503 — but 2 heads x 16, d_ff 64, 1 + 1 layers) and
 stored in the fixture under the reference's state_dict names; tests/test_golden.py loads them into the oracle and compares
-every output of three consecutive calls (first step of task 0, a later step of task 2, an eval call with frozen banks).
+every output of four consecutive forward calls (first step of task 0, two steps of task 2 incl. a rehearsal batch, an eval
+call with frozen banks) and of one more step through the reference's VLT5VQA.train_step text (vqa_model.py:18-65).
 
     python tools/gen_golden_forward.py [/root/reference]
 """
@@ -56,6 +57,11 @@ def main():
     assert "torch.device('cuda')" in vlt5_src
     exec(vlt5_src.replace("torch.device('cuda')", "torch.device('cpu')"), ns)
     VisualEmbedding, JointEncoder, VLT5 = ns["VisualEmbedding"], ns["JointEncoder"], ns["VLT5"]
+    # VLT5VQA.train_step (vqa_model.py:18-65) on top of that forward: `self(...)` and `self.parameters()` are all it needs
+    VLT5.__call__ = VLT5.forward
+    exec(lift(os.path.join(REF, "VL-T5", "src", "vqa_model.py"), "VLT5VQA", only=["train_step"]).replace(
+        "class VLT5VQA:", "class VLT5VQA(VLT5):"), ns)
+    VLT5VQA = ns["VLT5VQA"]
 
     cfg = T5Config(vocab_size=VOCAB, d_model=D, d_kv=DKV, d_ff=FF, num_layers=1, num_decoder_layers=1, num_heads=H,
                    relative_attention_num_buckets=32, relative_attention_max_distance=128, dropout_rate=0.0,
@@ -105,7 +111,8 @@ def main():
                          encoder_attention_mask=encoder_attention_mask, use_cache=False, return_dict=True)
 
     # ---- the VLT5 object the reference's VLT5.forward runs on (no __init__: exactly the attributes the method touches)
-    m = VLT5.__new__(VLT5)
+    m = VLT5VQA.__new__(VLT5VQA)
+    m.parameters = lambda: iter([shared.weight])
     m.config = cfg
     m.encoder = lambda **kw: JointEncoder.forward(enc, **kw)
     m.decoder = decoder
@@ -165,6 +172,16 @@ def main():
                               encoder_attention_mask=out.encoder_attention_mask.clone(),
                               position_bias=enc.block[0].seen_bias.clone(), Q_prototype=m.Q_prototype.clone(),
                               V_prototype=m.V_prototype.clone(), Q_num=m.Q_prototype_num.clone(), V_num=m.V_prototype_num.clone()))
+    # one more training call through the reference's VLT5VQA.train_step text (kwargs plumbing, loss tail, result dict)
+    with torch.no_grad():
+        b = batch(510, 2, False)
+        b["target_ids"] = b.pop("labels")
+        b["scores"] = torch.tensor([0.3, 0.6, 0.9, 1.0, 0.6])
+        res = m.train_step(b, 2, 0.5, 0.3, 3, 1000)
+    train_call = dict(task=2, **b, loss=res["loss"].clone(), BL=res["BL"], keys=sorted(res.keys()),
+                      encoder_hidden_states=res["encoder_hidden_states"].clone(),
+                      encoder_attention_mask=res["encoder_attention_mask"].clone(), Q_prototype=m.Q_prototype.clone(),
+                      V_prototype=m.V_prototype.clone())
     # state under the reference's names (modeling_t5_our.py state_dict layout)
     state = {"shared.weight": shared.weight.detach().clone()}
     for k, v in enc.visual_embedding.state_dict().items():
@@ -177,7 +194,7 @@ def main():
             state["decoder." + k] = v.clone()
     os.makedirs(OUT, exist_ok=True)
     path = os.path.join(OUT, "vlt5_forward.pt")
-    torch.save(dict(calls=calls, state=state, cfg=dict(vocab_size=VOCAB, d_model=D, d_kv=DKV, d_ff=FF, num_heads=H, feat_dim=FEAT,
+    torch.save(dict(calls=calls, train_call=train_call, state=state, cfg=dict(vocab_size=VOCAB, d_model=D, d_kv=DKV, d_ff=FF, num_heads=H, feat_dim=FEAT,
                                                        num_layers=1, num_decoder_layers=1), alpha=0.5, beta=0.3), path)
     print(path, os.path.getsize(path))
 
