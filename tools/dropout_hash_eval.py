@@ -1,9 +1,10 @@
 """Statistical screen for candidate counter-based dropout generators (CPU, numpy): the generator must give two 16-bit
 lanes per 32-bit output whose keep decisions are unbiased and uncorrelated across lanes, index lags (neighbours, rows,
 power-of-two strides) and keys. The shipped generator is `murmur` (vq_hash_pair, csrc/common.cuh: 9 integer instructions
-per pair); `mulxor2` (two 32x32->64 multiply + fold rounds, 5 instructions) passes the same screen and is the candidate
-for the attention / GEMM-epilogue dropout cost noted in DESIGN.md §9; a single round (`mulxor1`) or a two-round
-multiply-xorshift without the third mixing step (`lite`) fail it.
+per pair); `mulxor2` (two 32x32->64 multiply + fold rounds) passes the same screen, a single round (`mulxor1`) or a
+two-round multiply-xorshift without the third mixing step (`lite`) fail it. Compiled for sm_100a, `mulxor2` saved only 16 of
+the 1 872 static SASS instructions of the encoder attention forward (the IMAD.WIDE pairs bring register moves), so the
+murmur3 finaliser stays; a real saving needs fewer hashes per element, not a cheaper mix.
 
     python tools/dropout_hash_eval.py
 """
