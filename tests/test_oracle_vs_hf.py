@@ -124,3 +124,27 @@ def test_greedy_loop_matches_hf_generate():
     assert (mine_tok[:, n:] == 0).all() and (theirs[:, n:] == 0).all()
     finished_at = [(row == 1).nonzero()[0].item() if (row == 1).any() else -1 for row in mine_tok]
     assert len({f for f in finished_at}) >= 3          # rows really stop at different steps (else the test is vacuous)
+
+
+def test_adamw_core_matches_torch_when_eps_and_decay_vanish():
+    """transformers 4.2.1's AdamW is not installed anywhere (5.5 removed it), so its two distinguishing choices — eps added
+    to sqrt(v) BEFORE the bias correction, weight decay applied AFTER the Adam step with lr — stay "parity unpinned"
+    (DESIGN.md §6). Everything else (moment updates, both bias corrections, step size) coincides with torch.optim.AdamW
+    once eps -> 0 and weight_decay = 0, which is what this test pins."""
+    torch.manual_seed(9)
+    w0 = torch.randn(37, 5)
+    a = torch.nn.Parameter(w0.clone()); b = torch.nn.Parameter(w0.clone())
+    mine = O.HFAdamW([("w", a)], lr=1e-2, betas=(0.9, 0.999), eps=1e-30, weight_decay=0.0)
+    ref = torch.optim.AdamW([b], lr=1e-2, betas=(0.9, 0.999), eps=1e-30, weight_decay=0.0)
+    for _ in range(7):
+        g = torch.randn(37, 5)
+        a.grad = g.clone(); b.grad = g.clone()
+        mine.step(); ref.step()
+    torch.testing.assert_close(a.data, b.data, rtol=2e-6, atol=2e-7)
+    # and the decay it applies is p <- p - lr * wd * p on the already-stepped parameter
+    c = torch.nn.Parameter(w0.clone())
+    dec = O.HFAdamW([("w", c)], lr=1e-2, eps=1e-6, weight_decay=0.1)
+    nodec = O.HFAdamW([("w", a)], lr=1e-2, eps=1e-6, weight_decay=0.0)
+    a.data.copy_(w0); g = torch.randn(37, 5); a.grad = g.clone(); c.grad = g.clone()
+    nodec.step(); dec.step()
+    torch.testing.assert_close(c.data, a.data * (1 - 1e-2 * 0.1), rtol=1e-6, atol=1e-7)
