@@ -116,8 +116,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 5))
-    warm = max(1, min(args.warmup, 1))
+    steps, warm = max(1, args.steps), max(0, args.warmup)      # one step = one B = 8 train step (~0.4 s on 16 cores)
     cb, B = cpu_reference(steps, warm)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "samples/s", "n_gpus": args.gpus, "steps": steps,
             "warmup": warm, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -186,8 +185,8 @@ def run_native(args):
     pk = peaks()
 
     cpu_base = None
-    if rank == 0 and not args.no_cpu_baseline:
-        cpu_base, _ = cpu_reference(3, 1)
+    if world == 1 and not args.no_cpu_baseline:      # N = 1 only (contract): at N > 1 torchrun pins OMP to one thread and
+        cpu_base, _ = cpu_reference(24, 1)           # the other ranks would sit in a barrier; the driver times the CPU arm itself
         torch.set_num_threads(max(1, (os.cpu_count() or 8) // max(1, world)))
     if world > 1:
         dist.barrier()
@@ -270,8 +269,15 @@ def run_native(args):
     ms, launches = timed(devb, args.steps, warm, False)
     ck = clocks.stop() if rank == 0 else None
     ms_e2e, _ = timed(host, args.steps, 2, True, prefetch=True)
+    # the literal drop-in call: pinned CPU batch straight into train_step, whose own .to(device) copies it on the compute stream
+    ms_dropin, _ = timed(host, args.steps, 2, True, prefetch=False)
     value = world * B * args.steps / (ms / 1e3)
     e2e = world * B * args.steps / (ms_e2e / 1e3)
+    e2e_dropin = world * B * args.steps / (ms_dropin / 1e3)
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r02_step_dram_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("dram_bytes_per_step")
     if rank == 0:
         tf = value / world * FLOP_PER_SAMPLE_STEP / 1e12
         line = {
@@ -285,11 +291,15 @@ def run_native(args):
                        "global_batch": B * world, "parallelism": f"dp{world}",
                        "l2": "per-step working set (activations ~6 GB, weights+optimizer 3.6 GB) >> 126 MB L2; 4 distinct batches rotate"},
             "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                    "ms_per_step": ms_e2e / args.steps},
+                    "ms_per_step": ms_e2e / args.steps, "path": "pinned host batch -> vqacl_b200.BatchPrefetcher -> VLT5VQA.train_step",
+                    "dropin_value": e2e_dropin, "dropin_ms_per_step": ms_dropin / args.steps,
+                    "dropin_path": "pinned host batch -> VLT5VQA.train_step (the reference's call, vqa_model.py:20-27; H2D on the compute stream)"},
             "gpu_launches": int(launches),
             "clocks": ck,
             "roofline": {"bound": "tensor", "achieved": round(tf, 1), "peak": pk["sustained"], "unit": "TFLOP/s",
-                         "frac": round(tf / pk["sustained"], 4), "traffic": None,
+                         "frac": round(tf / pk["sustained"], 4), "traffic": traffic,
+                         "traffic_note": "DRAM bytes read + written by all kernels of one step (ncu dram__bytes_read/write.sum over a step window, "
+                                         "profiles/r02_step_dram_traffic.json); null until captured",
                          "kernel": "whole train step: algorithmic 37.79 GFLOP/sample (98.7% in gemm_bf16_tcgen05 launches) / step time, per GPU",
                          "peak_source": pk["source"] + " sustained bf16 (kernel timed inside a long step)"},
         }
@@ -317,6 +327,9 @@ def main():
                     help="run clip+AdamW on the main stream instead of overlapping it with the next step's forward")
     args = ap.parse_args()
     if args.impl == "reference":
+        # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host core (set before torch is imported)
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+        os.environ.pop("MKL_NUM_THREADS", None)
         run_reference(args)
         return
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -111,6 +111,17 @@ int vqacl_clip_adamw(void* engine, float* exp_avg, float* exp_avg_sq, float lr, 
  * vqacl_forward_encoder/decoder/generate wait chunk by chunk; any OTHER consumer of the parameters must call
  * vqacl_param_sync(engine, its_stream) first. */
 int vqacl_param_sync(void* engine, void* stream);
+/* Sharded step tail for N > 1 GPUs (what the reference's DDP + per-rank AdamW would do, vqacl.py:125-129,466-487, with the
+ * optimizer state partitioned): after a bucketed reduce-scatter each rank owns some slices of the gradient arena.
+ * vqacl_grad_sumsq_ranges: *out (device fp32) = sum of squares over the given arena ranges (host int64 arrays);
+ * vqacl_adamw_range: clip (by *sumsq, the all-reduced global value) + HF AdamW + bf16 refresh over arena elements
+ * [begin, end); m / v point at the moment buffers of element `begin`. */
+int vqacl_grad_sumsq_ranges(void* engine, const int64_t* begin, const int64_t* end, int n_ranges, float* out, void* stream);
+int vqacl_adamw_range(void* engine, float* m, float* v, int64_t begin, int64_t end, float lr, float beta1, float beta2, float eps,
+                      float weight_decay, int step, const float* sumsq, float max_grad_norm, void* stream);
+/* Errors kernels cannot raise synchronously (bit 0: a token id outside [0, vocab) reached an embedding gather — torch
+ * raises IndexError at modeling_t5_our.py:196). Synchronises `stream`, returns and clears the flags (HOST int). */
+int vqacl_device_errors(void* engine, int* flags_out, void* stream);
 /* greedy generation (vqa_model.py:112-116; HF 4.2.1 generate/greedy_search with max_length 20):
  * out_tokens [B, max_len] int64 (column 0 = start token, finished rows emit pad); *out_len = columns produced.
  * Synchronises the stream once per generated token (the all-rows-finished test, as HF does). */
@@ -129,10 +140,15 @@ long long vqacl_launch_count(void);
 /* nn.Linear forward / input-gradient / weight-gradient (every q,k,v,o,wi,wo, feat_embedding.0 and the tied lm_head:
  * modeling_t5_our.py:39-48,659-671; HF T5Attention / T5DenseReluDense). C[M,N] = epilogue(A[M,K] * B[N,K]^T) on tcgen05;
  * an operand flagged *_mn_major is stored transposed ([K,M] / [K,N]). epi: 0 bf16, 1 relu->bf16, 2 fp32 residual add (R),
- * 3 fp32 atomic accumulate (split-K), 4 relu-backward mask (R = saved activations, bf16), 5 fp32.
+ * 3 fp32 atomic accumulate (split-K), 4 relu-backward mask (R = the u32 sign bitmask [M, ceil(N/32)] that epi 1 wrote), 5 fp32.
  * force_bn: 0 = cost model, 64/128/256 = single-CTA tile width, 512 = 256x256 CTA-pair tile (cta_group::2).                 */
 int vqacl_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major, void* C, int ldc,
                     const void* R, int ldr, int M, int N, int K, int epi, float alpha, int splits, int force_bn, void* stream);
+/* same with the dropout that nn.Dropout applies after the activation / before the residual add (HF T5LayerFF / T5LayerSelfAttention)
+ * fused into epilogues 1 and 2: drop_thr16 = round(p * 65536), inv_keep = 1 / (1 - p), drop_key = per-launch 32-bit key.      */
+int vqacl_gemm_bf16_ex(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major, void* C, int ldc,
+                       const void* R, int ldr, int M, int N, int K, int epi, float alpha, int splits, int force_bn,
+                       uint32_t drop_thr16, float inv_keep, uint32_t drop_key, void* stream);
 /* HF T5LayerNorm forward / backward (hf5.5 modeling_t5.py:46-68; used at modeling_t5_our.py:41,47,160 and in every block)  */
 int vqacl_rmsnorm_fwd(const float* x, const float* w, void* y_bf16, float* y_f32, int M, float eps, float scale, void* stream);
 int vqacl_rmsnorm_bwd(const void* dn_bf16, const float* x, const float* w, const float* g_in, float* g_out, void* gb_out,

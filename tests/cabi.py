@@ -29,6 +29,8 @@ def _L():
         L.vqacl_grad_sumsq.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]
         L.vqacl_gemm_bf16.argtypes = [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,
                                       c_int, F, c_int, c_int, c_void_p]
+        L.vqacl_gemm_bf16_ex.argtypes = [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,
+                                         c_int, F, c_int, c_int, ctypes.c_uint32, F, ctypes.c_uint32, c_void_p]
         L._ops_declared = True
     return L
 
@@ -140,3 +142,22 @@ def grad_sumsq(g):
 def gemm(A, a_mn, B, b_mn, C, R, M, N, K, epi, alpha=1.0, splits=1, bn=0):
     check(_L().vqacl_gemm_bf16(ptr(A), A.stride(0), int(a_mn), ptr(B), B.stride(0), int(b_mn), ptr(C), C.stride(0), ptr(R),
                                R.stride(0) if R is not None else 0, M, N, K, epi, alpha, splits, bn, cur_stream()))
+
+
+def gemm_dropout(A, B, C, R, M, N, K, epi, thr16, inv_keep, key, bn=0):
+    check(_L().vqacl_gemm_bf16_ex(ptr(A), A.stride(0), 0, ptr(B), B.stride(0), 0, ptr(C), C.stride(0), ptr(R),
+                                  R.stride(0) if R is not None else 0, M, N, K, epi, 1.0, 1, bn, thr16, inv_keep, key, cur_stream()))
+
+
+def dropout_scale_host(M, N, thr16, inv_keep, key, device):
+    """Host restatement of vq_dropout_pair (csrc/common.cuh): scale (0 or inv_keep) of every element of an [M, N] matrix."""
+    idx = torch.arange(M * N, device=device, dtype=torch.int64).view(M, N)
+    m32 = 0xFFFFFFFF
+    x = ((idx >> 1) * 0x9E3779B1 + key) & m32
+    x = x ^ (x >> 16)
+    x = (x * 0x85EBCA6B) & m32
+    x = x ^ (x >> 13)
+    x = (x * 0xC2B2AE35) & m32
+    x = x ^ (x >> 16)
+    lane = torch.where((idx & 1) == 1, x >> 16, x & 0xFFFF)
+    return (lane >= thr16).float() * inv_keep

@@ -264,3 +264,62 @@ def test_gemm_epilogues_ragged(epi):
             W = R.shape[1]
             got = ((R.long().unsqueeze(-1) >> torch.arange(32, device=DEV)) & 1).view(M, W * 32)[:, :N].bool()
             assert torch.equal(got, C.float() > 0), (epi, bn)
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 1)])
+@pytest.mark.parametrize("splits", [1, 4])
+def test_gemm_operand_majors_and_split_k(a_mn, b_mn, splits):
+    """The three operand layouts of the step — forward X W^T (K-major / K-major), dX = dY W (B MN-major), dW = dY^T X (both
+    MN-major) — on ragged sizes, every tile shape incl. the CTA-pair kernel, plain and split-K with the atomic fp32 epilogue."""
+    torch.manual_seed(20 + a_mn * 2 + b_mn + splits)
+    M, N, K = 392, 520, 1000            # ragged in all three dimensions (K not a multiple of 64)
+    At = torch.randn(M, K, device=DEV).bfloat16()
+    Bt = torch.randn(N, K, device=DEV).bfloat16()
+    ref = At.float() @ Bt.float().t()
+    A = At.t().contiguous() if a_mn else At          # MN-major = stored transposed ([K, M])
+    Bm = Bt.t().contiguous() if b_mn else Bt
+    for bn in (64, 128, 256, 512):
+        C = torch.full((M, N), 0.25, device=DEV, dtype=torch.float32)
+        cabi.gemm(A, a_mn, Bm, b_mn, C, None, M, N, K, 3, splits=splits, bn=bn)      # C += A B^T
+        torch.cuda.synchronize()
+        assert rel_err(C, ref + 0.25) < 3e-5, (a_mn, b_mn, splits, bn)
+        if splits == 1:
+            Cb = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+            cabi.gemm(A, a_mn, Bm, b_mn, Cb, None, M, N, K, 0, bn=bn)
+            assert rel_err(Cb, ref) < 1e-2, (a_mn, b_mn, bn)
+
+
+@pytest.mark.parametrize("epi", [1, 2])
+def test_gemm_dropout_epilogues_match_host_hash(epi):
+    """The ReLU(+dropout) and residual(+dropout) epilogues against a host restatement of the counter-based mask
+    (cabi.dropout_scale_host == vq_dropout_pair): same kept set bit for bit, values to bf16 / fp32 round-off."""
+    torch.manual_seed(30 + epi)
+    M, N, K = 520, 776, 264
+    p = 0.1
+    thr = int(p * 65536 + 0.5)
+    inv = 65536.0 / (65536.0 - thr)
+    key = 0x1234ABCD
+    A = torch.randn(M, K, device=DEV).bfloat16()
+    Bm = torch.randn(N, K, device=DEV).bfloat16()
+    acc = A.float() @ Bm.float().t()
+    scale = cabi.dropout_scale_host(M, N, thr, inv, key, DEV)
+    assert abs((scale == 0).float().mean().item() - p) < 5e-3
+    for bn in (128, 256, 512):
+        if epi == 1:
+            C = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+            R = torch.zeros(M, (N + 31) // 32, device=DEV, dtype=torch.int32)
+            cabi.gemm_dropout(A, Bm, C, R, M, N, K, 1, thr, inv, key, bn=bn)
+            ref = acc.relu() * scale
+            assert rel_err(C, ref) < 1e-2, bn
+            W = R.shape[1]
+            got = ((R.long().unsqueeze(-1) >> torch.arange(32, device=DEV)) & 1).view(M, W * 32)[:, :N].bool()
+            assert torch.equal(got, C.float() > 0), bn
+            # dropped positions are exactly zero wherever the pre-dropout activation is clearly positive
+            clear = acc > 0.5
+            assert torch.equal((C.float() == 0) & clear, (scale == 0) & clear), bn
+        else:
+            R = torch.randn(M, N, device=DEV)
+            C = torch.empty(M, N, device=DEV)
+            cabi.gemm_dropout(A, Bm, C, R, M, N, K, 2, thr, inv, key, bn=bn)
+            ref = R + acc * scale
+            assert rel_err(C, ref) < 3e-5, bn

@@ -144,6 +144,99 @@ def test_greedy_generation_matches_oracle():
     assert len(res["pred_ans"]) == 48
 
 
+def test_train_step_configs1_full_depth_batch_320():
+    """configs[1] itself against the oracle: T5-base depth, B = 320, task 3 on a seeded bank so the EMA branch
+    (update_prototype t > 0, modeling_t5_our.py:476-493) runs on the second step; fp32 oracle on the same GPU."""
+    om, m = make_pair(layers=12)
+    om.train(); m.train()
+    g = torch.Generator().manual_seed(7)
+    Q0, V0 = torch.randn(10, 768, generator=g), torch.randn(80, 768, generator=g)
+    om.bank.Q_prototype, om.bank.V_prototype = Q0.clone().cuda(), V0.clone().cuda()
+    m.Q_prototype, m.V_prototype = Q0, V0
+    for i in range(2):
+        batch = O.synthetic_batch(320, seed=1234 + i, task_id=3, rehearsal=(i == 1))
+        _check_step(om, m, batch, 3, grads=(i == 1))
+        if i == 0:
+            for p in om.parameters():
+                p.grad = None
+    assert sorted(m.Q_task_mem_proto) == [3]
+
+
+def test_greedy_generation_at_spec_configs4():
+    """configs[4]: greedy answers at spec — 12 + 12 layers, vocab 32 200, B = 512 — at least 99 % of the rows identical to the
+    fp32 oracle's (north_star). tools/greedy_at_spec.py prints the margins behind any mismatch."""
+    om, m = make_pair(layers=12)
+    om.eval(); m.eval()
+    g = torch.Generator().manual_seed(9)
+    Q0, V0 = torch.randn(10, 768, generator=g), torch.randn(80, 768, generator=g)
+    om.bank.Q_prototype, om.bank.V_prototype = Q0.clone().cuda(), V0.clone().cuda()
+    m.Q_prototype, m.V_prototype = Q0, V0
+    b = O.synthetic_batch(512, seed=77)
+    ours = m.test_step(b)["token_ids"]
+    refs = []
+    for s in range(0, 512, 128):           # the fp32 full re-decode oracle in chunks (rows are independent at eval time)
+        refs.append(om.generate(b["input_ids"][s:s + 128], b["vis_feats"][s:s + 128], b["boxes"][s:s + 128], max_length=20))
+    ref = torch.cat([torch.nn.functional.pad(r, (0, 20 - r.shape[1])) for r in refs])
+    o = torch.nn.functional.pad(ours, (0, 20 - ours.shape[1]))
+    same = (o == ref).all(dim=1).float().mean().item()
+    assert same >= 0.99, same
+
+
+def test_state_dict_between_load_and_forward_keeps_bf16_fresh():
+    """to(cuda) -> load_state_dict -> state_dict() -> train_step must run on the LOADED weights (state_dict()
+    used to clear the stale flag of the bf16 GEMM copies without refreshing them)."""
+    import vqacl_b200 as V
+    om, _ = make_pair(layers=1)
+    cfg = V.VLT5Config(vocab_size=32200, num_layers=1, num_decoder_layers=1, dropout_rate=0.0)
+    m = V.VLT5VQA(cfg).cuda()                       # packed with its own random weights
+    m.load_state_dict(om.state_dict())
+    _ = m.state_dict()
+    om.train(); m.train()
+    _check_step(om, m, O.synthetic_batch(4, seed=3, task_id=0), 0, grads=False)
+
+
+def test_overlapped_optimizer_then_generate_and_load():
+    """with FusedAdamW(overlap_with_next_forward=True) generate() must wait for the LAST optimizer chunk (decoder +
+    cross-KV weights) and load_state_dict() must not race a pending update: both orders give the answers of the
+    non-overlapped run."""
+    toks = []
+    for overlap in (False, True):
+        _, m = make_pair(layers=2, vocab=2048)
+        m.train()
+        opt = V.FusedAdamW(m, lr=1e-2, overlap_with_next_forward=overlap)
+        b = O.synthetic_batch(16, seed=21, task_id=0, vocab=2000)
+        m.train_step(b, 0, 0.5, 0.3)["loss"].backward()
+        opt.step(max_grad_norm=5.0)
+        opt.zero_grad()
+        toks.append(m.test_step(O.synthetic_batch(16, seed=22, vocab=2000))["token_ids"].clone())
+        sd = {k: v.clone() for k, v in m.state_dict().items()}
+        m.train()
+        m.train_step(b, 0, 0.5, 0.3)["loss"].backward()
+        opt.step(max_grad_norm=5.0)                 # pending (overlapped) update ...
+        m.load_state_dict(sd)                       # ... must be ordered before the load, not after it
+        torch.cuda.synchronize()
+        assert torch.equal(m.state_dict()["shared.weight"], sd["shared.weight"])
+    assert torch.equal(toks[0], toks[1])
+
+
+def test_second_backward_and_bad_token_ids_fail_loudly():
+    _, m = make_pair(layers=1)
+    m.train()
+    b = O.synthetic_batch(4, seed=8, task_id=0)
+    r = m.train_step(b, 0, 0.5, 0.3)
+    r["loss"].backward(retain_graph=True)
+    with pytest.raises(V.VqaclError):
+        r["loss"].backward()                        # the forward state was consumed (ce_bwd rewrote the logits in place)
+    bad = {k: v.clone() for k, v in b.items()}
+    bad["input_ids"][0, 0] = 40000                  # >= vocab: torch raises IndexError in the reference (modeling_t5_our.py:196)
+    with pytest.raises(IndexError):
+        m.train_step(bad, 0, 0.5, 0.3)
+    bad_dev = {k: v.cuda() for k, v in bad.items()}  # device-resident batch: flagged by the kernel, raised at the next check
+    m.train_step(bad_dev, 0, 0.5, 0.3)
+    with pytest.raises(IndexError):
+        m.state_dict()
+
+
 def test_full_size_batch_properties():
     """configs[1] size (B = 320): batch-row independence (rows of a big batch equal the same rows run as a small batch),
     finite gradients, and the fused sum-of-squares equals the norm of the arena."""

@@ -8,7 +8,7 @@ hot path that do not depend on the 4.2.1 internals can be lifted out of the file
     (the only edit: the hard-coded torch.device('cuda') string at :504 is evaluated on CPU)
   * the loss tail of VLT5VQA.train_step         VL-T5/src/vqa_model.py:46-54
 The fixtures hold seeded inputs and the reference's outputs; tests/test_golden.py checks the oracle against them on CPU
-and tests/test_gpu_golden.py checks the CUDA path. Nothing is copied into the repo except these tensors. (tools/gen_golden_forward.py does the same for the glue of a whole
+and tests/test_gpu_ops.py checks the CUDA path. Nothing is copied into the repo except these tensors. (tools/gen_golden_forward.py does the same for the glue of a whole
 call: JointEncoder.forward + VLT5.forward.)
 
     python tools/gen_golden.py [/root/reference]

@@ -73,7 +73,7 @@ static int decode_step(Engine& e, const DecodeWs& dw, int B, int S2, int max_len
   const int d = c.d_model, f = c.d_ff, H = c.n_heads, Ld = c.n_dec_layers;
   const int ldkv = Ld * 2 * d;
   const long long cache_bs = (long long)max_len * 3 * d;
-  VQ_TRY(embed_fwd(dw.cur, B, 1, e.P + e.o_shared, w.y[0], 1, 0, Dropout(), st));
+  VQ_TRY(embed_fwd(dw.cur, B, 1, e.P + e.o_shared, w.y[0], 1, 0, Dropout(), c.vocab_size, nullptr, st));
   for (int l = 0; l < Ld; ++l) {
     const DecLayer& P = e.dec[l];
     bf16* cache = dw.cache + (size_t)l * B * cache_bs;
@@ -144,6 +144,9 @@ extern "C" int vqacl_generate(void* engine, const vqacl_batch* batch, const vqac
   vqacl_proto_state ps = *proto;
   ps.proto_update = 0;                                     // modeling_t5_our.py:607-612: frozen banks at test time
   VQ_TRY(si_path(e, batch, &ps, false, st));
+  // encoder_forward waited for optimizer chunks 0..Le only; the cross-KV projection and every decode step read the
+  // decoder weights, which a pending overlapped optimizer step writes last
+  VQ_TRY(wait_params(e, 1 + c.n_enc_layers, st));
   VQ_TRY(gemm_fwd(e.w.mem, d, e.W + e.o_ckv, d, e.w.kv_all, Ld * 2 * d, B * S2, Ld * 2 * d, EPI_BF16, st));
   (void)vq_launch(decode_init_kernel, dim3((B + 255) / 256), dim3(256), 0, st, out_tokens, max_len, dw.cur, dw.unfinished, B, c.start_id);
   VQ_LAUNCH_CHECK();

@@ -184,7 +184,7 @@ int rmsnorm_bwd(const RmsBwdArgs& a, cudaStream_t stream) {
 // ------------------------------------------------------------------------------------------------ embeddings
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 embed_fwd_kernel(const int64_t* __restrict__ ids, int B, int L, const float* __restrict__ table, float* __restrict__ x, int S,
-                 int row0, Dropout drop) {
+                 int row0, Dropout drop, int vocab, int* __restrict__ err) {
   vq_pdl_trigger();
   vq_pdl_wait();
   const int lane = threadIdx.x & 31;
@@ -192,26 +192,34 @@ embed_fwd_kernel(const int64_t* __restrict__ ids, int B, int L, const float* __r
   if (r >= B * L) return;
   const int b = r / L, i = r % L;
   float v[RW_CHUNKS][4];
-  load_row_f32(v, table + (size_t)ids[r] * DM, lane);
+  int64_t id = ids[r];
+  if (id < 0 || id >= vocab) {   // torch raises IndexError here; we read row 0 and raise on the host at the next error check
+    if (lane == 0 && err) atomicOr(err, 1);
+    id = 0;
+  }
+  load_row_f32(v, table + (size_t)id * DM, lane);
   const size_t orow = (size_t)b * S + row0 + i;
   apply_dropout(v, drop, orow * DM, lane);
   store_row_f32(x + orow * DM, v, lane);
 }
-int embed_fwd(const int64_t* ids, int B, int L, const float* table, float* x, int S, int row0, Dropout drop, cudaStream_t stream) {
+int embed_fwd(const int64_t* ids, int B, int L, const float* table, float* x, int S, int row0, Dropout drop, int vocab, int* err,
+              cudaStream_t stream) {
   if (B * L <= 0) return 0;
-  (void)vq_launch(embed_fwd_kernel, dim3((B * L + ROW_WARPS - 1) / ROW_WARPS), dim3(ROW_WARPS * 32), 0, stream, ids, B, L, table, x, S, row0, drop);
+  (void)vq_launch(embed_fwd_kernel, dim3((B * L + ROW_WARPS - 1) / ROW_WARPS), dim3(ROW_WARPS * 32), 0, stream, ids, B, L, table, x, S, row0, drop,
+                  vocab, err);
   VQ_LAUNCH_CHECK();
   return 0;
 }
 
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 embed_bwd_kernel(const int64_t* __restrict__ ids, int B, int L, const float* __restrict__ g, int S, int row0,
-                 float* __restrict__ dtable, Dropout drop) {
+                 float* __restrict__ dtable, Dropout drop, int vocab) {
   vq_pdl_trigger();
   vq_pdl_wait();
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   if (r >= B * L) return;
+  if (ids[r] < 0 || ids[r] >= vocab) return;   // flagged by embed_fwd; never write outside the table's gradient
   const int b = r / L, i = r % L;
   const size_t grow = (size_t)b * S + row0 + i;
   float v[RW_CHUNKS][4];
@@ -224,9 +232,11 @@ embed_bwd_kernel(const int64_t* __restrict__ ids, int B, int L, const float* __r
                  "f"(v[j][2]), "f"(v[j][3])
                  : "memory");
 }
-int embed_bwd(const int64_t* ids, int B, int L, const float* g, int S, int row0, float* dtable, Dropout drop, cudaStream_t stream) {
+int embed_bwd(const int64_t* ids, int B, int L, const float* g, int S, int row0, float* dtable, Dropout drop, int vocab,
+              cudaStream_t stream) {
   if (B * L <= 0) return 0;
-  (void)vq_launch(embed_bwd_kernel, dim3((B * L + ROW_WARPS - 1) / ROW_WARPS), dim3(ROW_WARPS * 32), 0, stream, ids, B, L, g, S, row0, dtable, drop);
+  (void)vq_launch(embed_bwd_kernel, dim3((B * L + ROW_WARPS - 1) / ROW_WARPS), dim3(ROW_WARPS * 32), 0, stream, ids, B, L, g, S, row0, dtable, drop,
+                  vocab);
   VQ_LAUNCH_CHECK();
   return 0;
 }

@@ -219,9 +219,7 @@ int64_t engine_carve(Engine& e, uint8_t* base, int B, int L, int N, int T) {
   w.dkv_all = bp.take<bf16>(M2 * (size_t)Ld * 2 * d);
   w.dmem = bp.take<bf16>(M2 * d);
   w.dfeatpre = bp.take<bf16>((size_t)B * N * d);
-  w.sumsq_partials = bp.take<float>(2048);
   w.vis_partials = bp.take<float>((size_t)num_sms() * 10 * d);
-  w.sumsq = bp.take<float>(4, "grad_sumsq");
   const int64_t total = (bp.off + 255) / 256 * 256;
   if (base) {
     e.w = w;
@@ -281,7 +279,7 @@ int encoder_forward(Engine& e, const vqacl_batch* b, cudaStream_t st) {
   VQ_TRY(wait_params(e, 0, st));   // embeddings + visual projection + final norms
   VQ_TRY(build_keymasks(b->input_ids, B, L, S, c.pad_id, w.enc_mask, w.cross_mask, w.mask01, st));
   // embeddings: text rows [0,L), visual rows [L,S)   (modeling_t5_our.py:196-214, :247)
-  VQ_TRY(embed_fwd(b->input_ids, B, L, e.P + e.o_shared, w.x[0], S, 0, e.drop(SITE_ENC_EMB), st));
+  VQ_TRY(embed_fwd(b->input_ids, B, L, e.P + e.o_shared, w.x[0], S, 0, e.drop(SITE_ENC_EMB), c.vocab_size, e.err_flags(), st));
   VQ_TRY(cast_f32_to_bf16(b->vis_feats, w.feats_bf16, (size_t)B * N * c.feat_dim, st));
   VQ_TRY(gemm_fwd(w.feats_bf16, c.feat_dim, e.W + e.o_Wf, c.feat_dim, w.featpre, d, B * N, d, EPI_F32, st));
   VisArgs va{};
@@ -369,7 +367,7 @@ static int decoder_forward(Engine& e, const vqacl_batch* b, cudaStream_t st) {
     e.g_prezeroed = true;
   }
   VQ_TRY(shift_right(b->labels, w.dec_ids, B, T, c.start_id, c.pad_id, st));                      // :620
-  VQ_TRY(embed_fwd(w.dec_ids, B, T, e.P + e.o_shared, w.y[0], T, 0, e.drop(SITE_DEC_EMB), st));
+  VQ_TRY(embed_fwd(w.dec_ids, B, T, e.P + e.o_shared, w.y[0], T, 0, e.drop(SITE_DEC_EMB), c.vocab_size, e.err_flags(), st));
   // cross-attention K/V of every decoder layer in one GEMM over the decoder memory
   VQ_TRY(gemm_fwd(w.mem, d, e.W + e.o_ckv, d, w.kv_all, ldkv, M2, ldkv, EPI_BF16, st));
   for (int l = 0; l < Ld; ++l) {
@@ -620,7 +618,7 @@ static int backward(Engine& e, const float* w_rows, const float* gscale, int acc
   }
   if (on(Ld + 1)) {
     // decoder token embedding (tied `shared`)
-    VQ_TRY(embed_bwd(w.dec_ids, B, T, w.gd, T, 0, e.G + e.o_shared, e.drop(SITE_DEC_EMB), st));
+    VQ_TRY(embed_bwd(w.dec_ids, B, T, w.gd, T, 0, e.G + e.o_shared, e.drop(SITE_DEC_EMB), V, st));
     // cross-attention K/V projection of all layers: dW and the gradient flowing into the decoder memory
     VQ_TRY(fork());
     VQ_TRY(gemm_dw(w.dkv_all, ldkv, w.mem, d, e.G + e.o_ckv, ldkv, d, M2, sd));
@@ -677,7 +675,7 @@ static int backward(Engine& e, const float* w_rows, const float* gscale, int acc
   }
   if (on(Ld + Le + 2)) {
     // ---- embeddings: text tokens (tied shared) and the VisualEmbedding
-    VQ_TRY(embed_bwd(b.input_ids, B, L, w.ge, S, 0, e.G + e.o_shared, e.drop(SITE_ENC_EMB), st));
+    VQ_TRY(embed_bwd(b.input_ids, B, L, w.ge, S, 0, e.G + e.o_shared, e.drop(SITE_ENC_EMB), V, st));
     VisArgs va{};
     va.featpre = w.featpre; va.boxes = b.boxes; va.bf = e.P + e.o_bf; va.wf = e.P + e.o_wf; va.Wp = e.P + e.o_Wp;
     va.bp = e.P + e.o_bp; va.wp = e.P + e.o_wp; va.img_emb = e.P + e.o_img; va.shared = e.P + e.o_shared;
@@ -692,6 +690,9 @@ static int backward(Engine& e, const float* w_rows, const float* gscale, int acc
   // join: the caller's stream owns every gradient written by this call
   VQ_CUDA(cudaEventRecord(e.ev_join, sd));
   VQ_CUDA(cudaStreamWaitEvent(st, e.ev_join, 0));
+  // the last stage consumed the forward state (ce_bwd overwrote the logits with dLogits, the dY rings are spent): a second
+  // backward on the same forward must fail loudly instead of accumulating garbage
+  if (stage_end == n_stages) e.fwd_valid = false;
   return 0;
 }
 
@@ -734,6 +735,7 @@ extern "C" void vqacl_engine_destroy(void* engine) {
       cudaStreamDestroy(e.side);
     }
   }
+  if (reinterpret_cast<Engine*>(engine)->opt_scratch) cudaFree(reinterpret_cast<Engine*>(engine)->opt_scratch);
   g_saved.erase(reinterpret_cast<Engine*>(engine));
   delete reinterpret_cast<Engine*>(engine);
 }
@@ -764,6 +766,10 @@ extern "C" int vqacl_bind_arena(void* engine, float* params, float* grads, void*
   VQ_CHECK(((uintptr_t)params & 255) == 0 && ((uintptr_t)params_bf16 & 255) == 0 && ((uintptr_t)grads & 255) == 0,
            "bind_arena: arenas must be 256-byte aligned");
   e.P = params; e.G = grads; e.W = reinterpret_cast<bf16*>(params_bf16);
+  if (!e.opt_scratch) {
+    VQ_CUDA(cudaMalloc(&e.opt_scratch, (64 + Engine::OPT_PARTIALS) * sizeof(float)));
+    VQ_CUDA(cudaMemset(e.opt_scratch, 0, (64 + Engine::OPT_PARTIALS) * sizeof(float)));
+  }
   gemm_tmap_cache_clear();
   return 0;
 }
@@ -853,7 +859,7 @@ static AdamArgs adam_range(const Engine& e, float* m, float* v, size_t b, size_t
   a.p = e.P + b; a.g = e.G + b; a.m = m + b; a.v = v + b; a.p_bf16 = e.W + b; a.n = en - b;
   a.n_decay = e.n_decay > b ? (e.n_decay - b < a.n ? e.n_decay - b : a.n) : 0;
   a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay; a.step = step;
-  a.sumsq = e.w.sumsq; a.max_norm = max_norm;
+  a.sumsq = e.sumsq(); a.max_norm = max_norm;
   return a;
 }
 
@@ -866,8 +872,8 @@ extern "C" int vqacl_clip_adamw(void* engine, float* exp_avg, float* exp_avg_sq,
     VQ_CUDA(cudaStreamWaitEvent(st, e.ev_opt.back(), 0));
     e.opt_pending = false;
   }
-  VQ_TRY(grad_sumsq(e.G, e.n_train, e.w.sumsq_partials, e.w.sumsq, st));
-  if (grad_norm_out) VQ_CUDA(cudaMemcpyAsync(grad_norm_out, e.w.sumsq, sizeof(float), cudaMemcpyDeviceToDevice, st));
+  VQ_TRY(grad_sumsq(e.G, e.n_train, e.sumsq_partials(), e.sumsq(), st));
+  if (grad_norm_out) VQ_CUDA(cudaMemcpyAsync(grad_norm_out, e.sumsq(), sizeof(float), cudaMemcpyDeviceToDevice, st));
   if (!overlap) {
     VQ_TRY(adamw_hf(adam_range(e, exp_avg, exp_avg_sq, 0, e.n_train, lr, beta1, beta2, eps, weight_decay, step, max_grad_norm), st));
     return 0;
@@ -894,6 +900,24 @@ extern "C" int vqacl_clip_adamw(void* engine, float* exp_avg, float* exp_avg_sq,
   e.opt_pending = true;
   return 0;
 }
+// ---- sharded optimizer (N > 1 GPUs): each rank owns the slices of the arena its bucketed reduce-scatter left it with
+extern "C" int vqacl_grad_sumsq_ranges(void* engine, const int64_t* begin, const int64_t* end, int n_ranges, float* out, void* stream) {
+  Engine& e = ENG(engine);
+  VQ_CHECK(e.G && e.opt_scratch && out, "grad_sumsq_ranges: arena not bound");
+  return grad_sumsq_ranges(e.G, begin, end, n_ranges, e.sumsq_partials(), Engine::OPT_PARTIALS, out, ST(stream));
+}
+// AdamW (+ clip by *sumsq, + bf16 refresh) over arena elements [begin, end); m / v point at the moments of element `begin`
+extern "C" int vqacl_adamw_range(void* engine, float* m, float* v, int64_t begin, int64_t end, float lr, float beta1, float beta2, float eps,
+                                 float weight_decay, int step, const float* sumsq, float max_grad_norm, void* stream) {
+  Engine& e = ENG(engine);
+  VQ_CHECK(e.P && e.G && e.W, "adamw_range: arena not bound");
+  VQ_CHECK(begin >= 0 && begin <= end && (size_t)end <= e.n_train, "adamw_range: bad range [%lld, %lld)", (long long)begin, (long long)end);
+  if (end == begin) return 0;
+  AdamArgs a = adam_range(e, m - begin, v - begin, (size_t)begin, (size_t)end, lr, beta1, beta2, eps, weight_decay, step, max_grad_norm);
+  a.sumsq = sumsq;
+  return adamw_hf(a, ST(stream));
+}
+
 // order everything a pending overlapped optimizer step wrote before `stream` (state_dict(), evaluation, user code)
 extern "C" int vqacl_param_sync(void* engine, void* stream) {
   Engine& e = ENG(engine);
@@ -901,6 +925,19 @@ extern "C" int vqacl_param_sync(void* engine, void* stream) {
     VQ_CUDA(cudaStreamWaitEvent(ST(stream), e.ev_opt.back(), 0));
     e.opt_pending = false;
   }
+  return 0;
+}
+
+// Device-side error flags raised by kernels that cannot fail synchronously (bit 0: token id outside [0, vocab) in an embedding
+// gather — torch raises IndexError there). Synchronises `stream`, returns the flags and clears them.
+extern "C" int vqacl_device_errors(void* engine, int* flags_out, void* stream) {
+  Engine& e = ENG(engine);
+  VQ_CHECK(flags_out, "device_errors: null output");
+  *flags_out = 0;
+  if (!e.opt_scratch) return 0;
+  VQ_CUDA(cudaMemcpyAsync(flags_out, e.err_flags(), sizeof(int), cudaMemcpyDeviceToHost, ST(stream)));
+  VQ_CUDA(cudaStreamSynchronize(ST(stream)));
+  if (*flags_out) VQ_CUDA(cudaMemsetAsync(e.err_flags(), 0, sizeof(int), ST(stream)));
   return 0;
 }
 

@@ -56,7 +56,6 @@ struct Workspace {
   bf16 *t_d768, *t_e768;                                  // main-stream-only temporaries
   float* t_d768_f32;                                      // split-K target of the LM-head dX GEMM
   bf16* dkv_all; bf16* dmem; bf16* dfeatpre;
-  float* sumsq_partials; float* sumsq;
   float* vis_partials;            // [num_sms, 10*768] per-CTA column sums of the visual-embedding backward
 };
 
@@ -94,6 +93,14 @@ struct Engine {
   std::vector<cudaEvent_t> ev_opt;
   cudaEvent_t ev_opt_fork = nullptr;
   bool opt_pending = false;
+  // engine-owned scratch that must survive workspace re-binds (an overlapped optimizer step reads the gradient norm after
+  // step() returned, possibly after the next train_step re-carved the workspace): [0,4) sumsq | [4,8) device error flags
+  // | [64, 64 + OPT_PARTIALS) sum-of-squares partials
+  static constexpr int OPT_PARTIALS = 16384;
+  float* opt_scratch = nullptr;
+  float* sumsq() const { return opt_scratch; }
+  int* err_flags() const { return reinterpret_cast<int*>(opt_scratch + 4); }
+  float* sumsq_partials() const { return opt_scratch + 64; }
   // decode workspace (separate carve, see decode.cu)
   Dropout drop(uint32_t site) const;
   int S() const { return L + N; }

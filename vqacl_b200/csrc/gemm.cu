@@ -284,3 +284,21 @@ extern "C" int vqacl_gemm_bf16(const void* A, int lda, int a_mn_major, const voi
   g.splits = splits;
   return vq::gemm_bf16(a, b, g, force_bn, reinterpret_cast<cudaStream_t>(stream));
 }
+
+// same with the epilogue dropout exposed (epi 1 and 2): drop_thr16 = round(p * 65536) (0 disables), drop_key = the per-launch
+// 32-bit key; element (row, col) is kept iff the 16-bit lane ((row * N + col) & 1 ? hi : lo) of
+// murmur3_fmix32(((row * N + col) >> 1) * 0x9E3779B1 + drop_key) is >= drop_thr16 and is then scaled by inv_keep
+extern "C" int vqacl_gemm_bf16_ex(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major, void* C,
+                                  int ldc, const void* R, int ldr, int M, int N, int K, int epi, float alpha, int splits,
+                                  int force_bn, uint32_t drop_thr16, float inv_keep, uint32_t drop_key, void* stream) {
+  vq::GemmOperand a{A, lda, a_mn_major != 0}, b{B, ldb, b_mn_major != 0};
+  vq::GemmArgs g{};
+  g.epi = epi;
+  g.M = M; g.N = N; g.K = K;
+  g.C = C; g.ldc = ldc;
+  g.R = R; g.ldr = ldr;
+  g.alpha = alpha;
+  g.splits = splits;
+  g.drop_thr = drop_thr16; g.drop_inv_keep = inv_keep; g.seed = drop_key;
+  return vq::gemm_bf16(a, b, g, force_bn, reinterpret_cast<cudaStream_t>(stream));
+}

@@ -83,9 +83,11 @@ struct RmsBwdArgs {
 int rmsnorm_bwd(const RmsBwdArgs& a, cudaStream_t stream);
 
 // token embedding gather (+ dropout) into rows [row0, row0+L) of each batch element of x [B, S, 768]
-int embed_fwd(const int64_t* ids, int B, int L, const float* table, float* x, int S, int row0, Dropout drop, cudaStream_t stream);
+// ids outside [0, vocab) read row 0 and set bit 0 of *err (device int, may be null); the host raises at its next error check
+int embed_fwd(const int64_t* ids, int B, int L, const float* table, float* x, int S, int row0, Dropout drop, int vocab, int* err,
+              cudaStream_t stream);
 // scatter-add of g rows into dtable (same mapping/dropout as embed_fwd)
-int embed_bwd(const int64_t* ids, int B, int L, const float* g, int S, int row0, float* dtable, Dropout drop, cudaStream_t stream);
+int embed_bwd(const int64_t* ids, int B, int L, const float* g, int S, int row0, float* dtable, Dropout drop, int vocab, cudaStream_t stream);
 // decoder_input_ids = shift_right(labels) (start 0, -100 -> pad 0)
 int shift_right(const int64_t* labels, int64_t* dec_ids, int B, int T, int start_id, int pad_id, cudaStream_t stream);
 // additive key masks from input_ids: enc [B,S] (-10000 on text pads), cross [B,S+2] (-1e9 on text pads)
@@ -154,6 +156,8 @@ int argmax_rows(const __nv_bfloat16* logits, int ld, int M, int V, int64_t* out,
 // ---------------------------------------------------------------- optim.cu
 // sum of squares of g[0:n) -> *out (fp32), two-stage deterministic
 int grad_sumsq(const float* g, size_t n, float* partials, float* out, cudaStream_t stream);
+int grad_sumsq_ranges(const float* g, const int64_t* begin, const int64_t* end, int n_ranges, float* partials, int partials_cap,
+                      float* out, cudaStream_t stream);
 // HF-4.2.1 AdamW over a flat arena: elements [0, n_decay) get weight decay, [n_decay, n) do not.
 // clip coefficient = min(1, max_norm / (sqrt(*sumsq) + 1e-6)) when sumsq != null and max_norm > 0.
 struct AdamArgs {

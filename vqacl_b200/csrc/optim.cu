@@ -57,6 +57,29 @@ int grad_sumsq(const float* g, size_t n, float* partials, float* out, cudaStream
   return 0;
 }
 
+// sum of squares over several disjoint ranges of one arena (the slices a rank owns after a bucketed reduce-scatter):
+// one partial launch per range into consecutive segments of `partials`, one final reduction over all of them
+int grad_sumsq_ranges(const float* g, const int64_t* begin, const int64_t* end, int n_ranges, float* partials, int partials_cap,
+                      float* out, cudaStream_t stream) {
+  int used = 0;
+  for (int i = 0; i < n_ranges; ++i) {
+    const int64_t n = end[i] - begin[i];
+    if (n <= 0) continue;
+    const float* gi = g + begin[i];
+    VQ_CHECK((reinterpret_cast<uintptr_t>(gi) & 15) == 0, "grad_sumsq_ranges: range %d is not 16-byte aligned", i);
+    const size_t n4 = (size_t)n / 4;
+    size_t want = (n4 + SQ_THREADS - 1) / SQ_THREADS;
+    int blocks = (int)(want < 1 ? 1 : (want > 296 ? 296 : want));
+    VQ_CHECK(used + blocks <= partials_cap, "grad_sumsq_ranges: %d ranges need more than %d partials", n_ranges, partials_cap);
+    (void)vq_launch(sumsq_partial_kernel, dim3(blocks), dim3(SQ_THREADS), 0, stream, gi, n4, (size_t)n, partials + used);
+    VQ_LAUNCH_CHECK();
+    used += blocks;
+  }
+  (void)vq_launch(sumsq_final_kernel, dim3(1), dim3(256), 0, stream, (const float*)partials, used, out);
+  VQ_LAUNCH_CHECK();
+  return 0;
+}
+
 __global__ void __launch_bounds__(256) adamw_kernel(const AdamArgs a, float step_size, float clip_max) {
   vq_pdl_trigger();
   vq_pdl_wait();

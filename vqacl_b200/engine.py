@@ -76,6 +76,10 @@ def _declare(L):
     L.vqacl_clip_adamw.argtypes = [c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_float, c_float, c_int,
                                    c_float, c_void_p, c_int, c_void_p]
     L.vqacl_param_sync.argtypes = [c_void_p, c_void_p]
+    L.vqacl_device_errors.argtypes = [c_void_p, POINTER(c_int), c_void_p]
+    L.vqacl_grad_sumsq_ranges.argtypes = [c_void_p, POINTER(c_int64), POINTER(c_int64), c_int, c_void_p, c_void_p]
+    L.vqacl_adamw_range.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_float, c_float, c_float, c_float, c_float,
+                                    c_int, c_void_p, c_float, c_void_p]
     L.vqacl_generate.argtypes = [c_void_p, POINTER(CBatch), POINTER(CProtoState), c_int, c_void_p, c_void_p, c_int64,
                                  POINTER(c_int), c_void_p]
     L.vqacl_generate_workspace_bytes.argtypes = [c_void_p, c_int, c_int, c_int, c_int]
@@ -261,7 +265,26 @@ class Engine:
         """Order a pending overlapped optimizer step before the current stream (needed before touching parameters outside
         the engine's own forward / generate calls)."""
         check(self.L.vqacl_param_sync(self.h, cur_stream()))
-        self.bf16_stale = False   # the optimizer kernel refreshes the bf16 copies itself
+        # bf16_stale is NOT touched here: the fused optimizer refreshes the bf16 copies itself and never marks them stale;
+        # the flag only records fp32 edits made outside the engine (load_state_dict / apply / _pack), which need a refresh
+
+    def check_device_errors(self):
+        """Raise for errors that kernels could only flag (synchronises the current stream)."""
+        f = c_int(0)
+        check(self.L.vqacl_device_errors(self.h, byref(f), cur_stream()))
+        if f.value & 1:
+            raise IndexError("token id outside [0, vocab_size) reached an embedding gather (input_ids / target_ids); "
+                             "was resize_token_embeddings() skipped?")
+
+    def grad_sumsq_ranges(self, ranges, out):
+        n = len(ranges)
+        b = (c_int64 * n)(*[r[0] for r in ranges])
+        e = (c_int64 * n)(*[r[1] for r in ranges])
+        check(self.L.vqacl_grad_sumsq_ranges(self.h, b, e, n, ptr(out), cur_stream()))
+
+    def adamw_range(self, m, v, begin, end, lr, beta1, beta2, eps, wd, step, sumsq, max_norm):
+        check(self.L.vqacl_adamw_range(self.h, ptr(m), ptr(v), begin, end, lr, beta1, beta2, eps, wd, step, ptr(sumsq), max_norm,
+                                       cur_stream()))
 
     def generate(self, cb, ps, max_len):
         B = cb.B
@@ -275,6 +298,7 @@ class Engine:
         n = c_int(0)
         check(self.L.vqacl_generate(self.h, byref(cb), byref(ps), max_len, ptr(out), ptr(self.gen_ws), self.gen_ws.numel(),
                                     byref(n), cur_stream()))
+        self.check_device_errors()       # generate has synchronised anyway
         return out[:, :n.value]
 
     def set_gemm_sm_limit(self, n):

@@ -352,6 +352,8 @@ class VLT5(nn.Module):
 
     def state_dict(self, *a, **kw):
         self.param_sync()
+        if getattr(self, "_engine", None) is not None:
+            self._engine.check_device_errors()      # checkpoint time at the latest (the step itself never synchronises)
         return super().state_dict(*a, **kw)
 
     def _mark_params_dirty(self):
@@ -361,6 +363,7 @@ class VLT5(nn.Module):
 
     def load_state_dict(self, state_dict, strict=True, **kw):
         sd = OrderedDict((k[7:] if k.startswith("module.") else k, v) for k, v in state_dict.items())
+        self.param_sync()       # a pending overlapped optimizer step must not overwrite the weights loaded below
         res = super().load_state_dict(sd, strict=strict, **kw)
         self.tie_weights()
         self._mark_params_dirty()
@@ -419,6 +422,14 @@ class VLT5(nn.Module):
                 return None
             return t.to(device=dev, dtype=dtype, non_blocking=True).contiguous()
 
+        # torch raises IndexError for ids outside the embedding table (modeling_t5_our.py:196); on host tensors (what the
+        # reference's collate_fn hands over) the check is free, device-resident batches are checked by the kernels (flag)
+        V = self.config.vocab_size
+        for nm, t, lo in (("input_ids", input_ids, 0), ("target_ids", labels, -100)):
+            if t is not None and not t.is_cuda and t.numel():
+                mn, mx = int(t.min()), int(t.max())
+                if mx >= V or mn < lo or (lo == -100 and mn < 0 and bool(((t < 0) & (t != -100)).any())):
+                    raise IndexError(f"{nm} holds ids outside [0, {V}) (min {mn}, max {mx})")
         ids = dv(input_ids, torch.int64)
         feats = dv(vis_feats, torch.float32)
         bx = dv(boxes, torch.float32)
