@@ -61,6 +61,9 @@ typedef struct vqacl_proto_state {
   int first_step_of_task;      /* current_task_id not in Q_task_cur_proto */
   int has_mem;                 /* current_task_id in Q_task_mem_proto */
   float alpha, beta;           /* --proto_alpha / --proto_beta */
+  int memory_loss;             /* kwargs['memory'] (modeling_t5_our.py:590-592): also compute the prototype pull losses of
+                                  nextqa/modeling_t5_nextqa.py:544-555 against the banks as they stand BEFORE this step's update;
+                                  results in the workspace region "loss_memory" (float[2]: Q, V) */
 } vqacl_proto_state;
 
 /* ---- engine lifecycle ---- */
@@ -100,6 +103,9 @@ int vqacl_backward(void* engine, const float* w_rows, const float* gscale /* opt
  * a merged bucket) on comm_stream from inside the callback and joins comm_stream with `stream` afterwards. */
 int vqacl_backward_overlapped(void* engine, const float* w_rows, const float* gscale, int accumulate, void* comm_stream,
                               void (*stage_cb)(int stage, void* user), void* user, void* stream);
+/* weights of the two memory losses in the objective for the next backward: device float[2] = d loss / d (loss_memory_Q,
+ * loss_memory_V), i.e. (lambda_Q, lambda_V) * upstream gradient (vqacl.py:448-450); NULL = not part of the objective */
+int vqacl_set_memory_loss_grads(void* engine, const float* g2);
 int vqacl_backward_stages(void* engine);
 int vqacl_backward_stage_range(void* engine, int stage, int64_t* begin, int64_t* end);
 /* fused loss tail of VLT5VQA.train_step (vqa_model.py:46-54) */
@@ -124,7 +130,8 @@ int vqacl_adamw_range(void* engine, float* m, float* v, int64_t begin, int64_t e
 int vqacl_device_errors(void* engine, int* flags_out, void* stream);
 /* greedy generation (vqa_model.py:112-116; HF 4.2.1 generate/greedy_search with max_length 20):
  * out_tokens [B, max_len] int64 (column 0 = start token, finished rows emit pad); *out_len = columns produced.
- * Synchronises the stream once per generated token (the all-rows-finished test, as HF does). */
+ * The LM head runs with the argmax fused into its epilogue (fp32 accumulators; no [B, V] logits); the all-rows-finished test
+ * HF does after every token synchronises the stream once per 4 tokens here (finished rows emit pad, the result is identical). */
 int64_t vqacl_generate_workspace_bytes(void* engine, int B, int L, int N, int max_len);
 int vqacl_generate(void* engine, const vqacl_batch* batch, const vqacl_proto_state* proto, int max_len, int64_t* out_tokens,
                    void* workspace, int64_t workspace_bytes, int* out_len, void* stream);
@@ -140,7 +147,9 @@ long long vqacl_launch_count(void);
 /* nn.Linear forward / input-gradient / weight-gradient (every q,k,v,o,wi,wo, feat_embedding.0 and the tied lm_head:
  * modeling_t5_our.py:39-48,659-671; HF T5Attention / T5DenseReluDense). C[M,N] = epilogue(A[M,K] * B[N,K]^T) on tcgen05;
  * an operand flagged *_mn_major is stored transposed ([K,M] / [K,N]). epi: 0 bf16, 1 relu->bf16, 2 fp32 residual add (R),
- * 3 fp32 atomic accumulate (split-K), 4 relu-backward mask (R = the u32 sign bitmask [M, ceil(N/32)] that epi 1 wrote), 5 fp32.
+ * 3 fp32 atomic accumulate (split-K), 4 relu-backward mask (R = the u32 sign bitmask [M, ceil(N/32)] that epi 1 wrote),  5 fp32,
+ * 6 fused row argmax (no C matrix: C = float [M, ldc] per-tile maxima, R = int32 [M, ldr] their columns, slot = 2 * (column / 256)
+ * + epilogue-warp group; first maximum = lowest index among equals; 256-wide tiles only).
  * force_bn: 0 = cost model, 64/128/256 = single-CTA tile width, 512 = 256x256 CTA-pair tile (cta_group::2).                 */
 int vqacl_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major, void* C, int ldc,
                     const void* R, int ldr, int M, int N, int K, int epi, float alpha, int splits, int force_bn, void* stream);

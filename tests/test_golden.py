@@ -93,3 +93,19 @@ def test_full_forward_glue_matches_reference():
     assert torch.equal(res["encoder_attention_mask"], t["encoder_attention_mask"])
     torch.testing.assert_close(om.bank.Q_prototype, t["Q_prototype"], rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(om.bank.V_prototype, t["V_prototype"], rtol=1e-5, atol=1e-6)
+
+
+def test_memory_loss_matches_reference_fixture():
+    """oracle.memory_loss against the fixture made by executing the reference's own text of
+    VL-T5/nextqa/modeling_t5_nextqa.py:544-555 (tools/gen_golden_memory_loss.py): both losses and the gradient of
+    lambda_Q * loss_Q + lambda_V * loss_V with respect to the encoder hidden states."""
+    d = torch.load(os.path.join(G, "memory_loss.pt"))
+    om = O.VLT5VQA(O.VLT5Config(num_layers=1, num_decoder_layers=1, vocab_size=64))
+    om.bank.Q_prototype, om.bank.V_prototype = d["Q_prototype"], d["V_prototype"]
+    h = d["hidden"].float().requires_grad_()
+    lq, lv = om.memory_loss(h[:, :20], h[:, 20:], d["ques_labels"], d["cate_labels"])
+    torch.testing.assert_close(lq.detach(), d["loss_Q"], rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(lv.detach(), d["loss_V"], rtol=1e-6, atol=1e-6)
+    (d["lambda_Q"] * lq + d["lambda_V"] * lv).backward()
+    torch.testing.assert_close(h.grad[:, 0], d["grad_hidden_q_row"], rtol=1e-6, atol=1e-8)
+    torch.testing.assert_close(h.grad[:, 25], d["grad_hidden_v_row"], rtol=1e-6, atol=1e-8)

@@ -323,3 +323,33 @@ def test_gemm_dropout_epilogues_match_host_hash(epi):
             cabi.gemm_dropout(A, Bm, C, R, M, N, K, 2, thr, inv, key, bn=bn)
             ref = R + acc * scale
             assert rel_err(C, ref) < 3e-5, bn
+
+
+@pytest.mark.parametrize("bn", [256, 512])
+def test_gemm_fused_argmax_epilogue_first_max(bn):
+    """EPI_ARGMAX: the greedy token choice straight from the fp32 accumulators (what replaces logits -> argmax in
+    generate, vqa_model.py:112-116): per-tile maxima merged = torch.argmax of the fp32 product, including exact ties
+    (duplicate vocabulary rows -> lowest index) and a ragged last tile."""
+    torch.manual_seed(40)
+    M, N, K = 200, 32200, 768
+    A = torch.randn(M, K, device=DEV).bfloat16()
+    Bm = torch.randn(N, K, device=DEV).bfloat16()
+    Bm[777] = Bm[31999]                              # exact tie between two columns for whatever row prefers them
+    A[5] = Bm[31999] * 0.5                           # row 5's maximum is that tied pair
+    ref = (A.float() @ Bm.float().t()) * 0.125
+    slots = ((N + 255) // 256) * 2
+    pitch = (slots + 7) // 8 * 8
+    pv = torch.full((M, pitch), float("nan"), device=DEV)
+    pi = torch.full((M, pitch), -1, device=DEV, dtype=torch.int32)
+    cabi.gemm(A, 0, Bm, 0, pv, pi, M, N, K, 6, alpha=0.125, bn=bn)
+    v, slot = pv[:, :slots].max(dim=1)
+    # lowest index among the slots holding the row maximum
+    cand = torch.where(pv[:, :slots] == v[:, None], pi[:, :slots].long(), torch.full_like(pi[:, :slots].long(), 1 << 40))
+    idx = cand.min(dim=1).values
+    want = ref.argmax(dim=1)
+    assert idx[5].item() == 777
+    agree = (idx == want)
+    # fp32 accumulation order differs from torch's: allow a mismatch only where torch's own top-2 are within round-off
+    top2 = ref.topk(2, dim=1).values
+    assert bool((agree | ((top2[:, 0] - top2[:, 1]) < 1e-4)).all())
+    torch.testing.assert_close(v, ref.max(dim=1).values, rtol=1e-4, atol=1e-4)

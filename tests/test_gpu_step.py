@@ -237,6 +237,55 @@ def test_second_backward_and_bad_token_ids_fail_loudly():
         m.state_dict()
 
 
+def test_memory_loss_step_matches_oracle():
+    """f4: train_step(memory=True) returns the prototype pull losses of nextqa/modeling_t5_nextqa.py:544-555 against the banks
+    of the PREVIOUS step, and backward of loss + lambda_Q * loss_Q + lambda_V * loss_V (vqacl.py:448-450, param.py:178-179)
+    reproduces the oracle's gradients (the oracle's memory_loss is pinned to the reference text in tests/test_golden.py)."""
+    om, m = make_pair(layers=2)
+    om.train(); m.train()
+    lam_q, lam_v = 0.01, 0.1
+    zero = V.FusedAdamW(m).zero_grad
+    for i, task in enumerate((0, 0, 2, 2)):
+        batch = O.synthetic_batch(8, seed=300 + i, task_id=task, rehearsal=(i == 3))
+        ro = om.train_step(batch, task, 0.5, 0.3, memory=True)
+        r = m.train_step(batch, task, 0.5, 0.3, memory=True)
+        for k in range(2):
+            a, b = r["loss_memory"][k].item(), float(ro["loss_memory"][k])
+            assert abs(a - b) <= 1e-2 * max(abs(b), 1e-6), (i, k, a, b)
+        assert torch.equal(r["max_idx_Q"], ro["max_idx_Q"]) and torch.equal(m.Q_prototype_num, om.bank.Q_prototype_num)
+        (r["loss"] + lam_q * r["loss_memory"][0] + lam_v * r["loss_memory"][1]).backward()
+        (ro["loss"] + lam_q * ro["loss_memory"][0] + lam_v * ro["loss_memory"][1]).backward()
+        on = dict(om.named_parameters())
+        cs = sorted((cos(p.grad, on[n].grad), n) for n, p in m.named_parameters() if on[n].grad is not None)
+        assert cs[0][0] > 0.99, cs[:3]
+        for p in om.parameters():
+            p.grad = None
+        zero()
+    # the pull loss really takes part in backward: same forward, objective with and without it
+    batch = O.synthetic_batch(8, seed=310, task_id=2)
+    w = m.encoder.block[1].layer[1].DenseReluDense.wo.weight
+    seen, mem = dict(m.Q_task_cur_proto), dict(m.Q_task_mem_proto)
+    banks = (m.Q_prototype.clone(), m.V_prototype.clone())
+    r = m.train_step(batch, 2, 0.5, 0.3, memory=True)
+    (r["loss"] + lam_q * r["loss_memory"][0] + lam_v * r["loss_memory"][1]).backward()
+    g_with = w.grad.clone()
+    zero()
+    m.Q_task_cur_proto, m.Q_task_mem_proto = seen, mem
+    m.Q_prototype, m.V_prototype = banks
+    r = m.train_step(batch, 2, 0.5, 0.3, memory=True)
+    r["loss"].backward()
+    assert cos(g_with, w.grad) < 0.999 and torch.isfinite(w.grad).all()
+    zero()
+    # forward() API: fields loss_memory_Q / loss_memory_V of the output (modeling_t5_our.py:711-712); 0 without memory (:594)
+    b = O.synthetic_batch(4, seed=5, task_id=2)
+    kw = dict(input_ids=b["input_ids"], vis_inputs=(b["vis_feats"], b["boxes"]), labels=b["target_ids"], cate_labels=b["cate_labels"],
+              ques_labels=b["ques_labels"], proto_update=True, current_task_id=2, proto_alpha=0.5, proto_beta=0.3)
+    out = m(memory=True, **kw)
+    assert out.loss_memory_Q.ndim == 0 and out.loss_memory_Q.requires_grad and float(out.loss_memory_V) > 0
+    out2 = m(**kw)
+    assert out2.loss_memory_Q == 0 and out2.loss_memory_V == 0
+
+
 def test_full_size_batch_properties():
     """configs[1] size (B = 320): batch-row independence (rows of a big batch equal the same rows run as a small batch),
     finite gradients, and the fused sum-of-squares equals the norm of the arena."""

@@ -11,16 +11,17 @@ namespace vq {
 
 struct DecodeWs {
   bf16* cache;        // [Ld][B, max_len, 3d]  q|k|v of every generated position
-  bf16* logits;       // [B, ldv]
-  int64_t* next;      // [B] argmax
+  float* pval;        // [B, slots] per-tile maxima of the LM-head GEMM (EPI_ARGMAX): the [B, 32200] logits are never materialised
+  int* pidx;          // [B, slots] their column indices
+  int slots;          // row pitch of pval / pidx (>= 2 * ceil(V / 256), multiple of 8)
   int64_t* cur;       // [B] current input token
   int* unfinished;    // [B]
-  int* n_unfinished;  // [1]
+  int* n_unfinished;  // [max_len] rows still unfinished after each generated column
 };
 
 static int64_t decode_carve(const Engine& e, uint8_t* base, int B, int max_len, DecodeWs* out) {
   const int d = e.cfg.d_model, Ld = e.cfg.n_dec_layers;
-  const int ldv = (e.cfg.vocab_size + 255) / 256 * 256;
+  const int slots = (((e.cfg.vocab_size + 255) / 256) * 2 + 7) & ~7;
   int64_t off = 0;
   auto take = [&](size_t bytes) {
     off = (off + 255) / 256 * 256;
@@ -30,11 +31,12 @@ static int64_t decode_carve(const Engine& e, uint8_t* base, int B, int max_len, 
   };
   DecodeWs w;
   w.cache = reinterpret_cast<bf16*>(take((size_t)Ld * B * max_len * 3 * d * sizeof(bf16)));
-  w.logits = reinterpret_cast<bf16*>(take((size_t)B * ldv * sizeof(bf16)));
-  w.next = reinterpret_cast<int64_t*>(take((size_t)B * sizeof(int64_t)));
+  w.pval = reinterpret_cast<float*>(take((size_t)B * slots * sizeof(float)));
+  w.pidx = reinterpret_cast<int*>(take((size_t)B * slots * sizeof(int)));
+  w.slots = slots;
   w.cur = reinterpret_cast<int64_t*>(take((size_t)B * sizeof(int64_t)));
   w.unfinished = reinterpret_cast<int*>(take((size_t)B * sizeof(int)));
-  w.n_unfinished = reinterpret_cast<int*>(take(256));
+  w.n_unfinished = reinterpret_cast<int*>(take((size_t)(max_len + 1) * sizeof(int)));
   if (out) *out = w;
   return (off + 255) / 256 * 256;
 }
@@ -50,21 +52,38 @@ __global__ void decode_init_kernel(int64_t* __restrict__ out, int max_len, int64
   unfinished[b] = 1;
 }
 
-// HF greedy_search bookkeeping: next = argmax * unfinished + pad * (1 - unfinished); unfinished &= (next != eos)
-__global__ void decode_advance_kernel(const int64_t* __restrict__ next, int64_t* __restrict__ out, int max_len, int col,
-                                      int64_t* __restrict__ cur, int* __restrict__ unfinished, int* __restrict__ n_unfinished, int B,
-                                      int pad_id, int eos_id) {
+// Finish the fused LM-head argmax (merge the per-tile maxima: largest value, lowest index among equals = torch.argmax's first
+// maximum) and do HF greedy_search's bookkeeping: next = argmax * unfinished + pad * (1 - unfinished);
+// unfinished &= (next != eos). One warp per row.
+__global__ void __launch_bounds__(256)
+decode_advance_kernel(const float* __restrict__ pval, const int* __restrict__ pidx, int slots, int nslots, int64_t* __restrict__ out,
+                      int max_len, int col, int64_t* __restrict__ cur, int* __restrict__ unfinished, int* __restrict__ n_unfinished,
+                      int B, int pad_id, int eos_id) {
   vq_pdl_trigger();
   vq_pdl_wait();
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (b >= B) return;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = lane; i < nslots; i += 32) {
+    const float v = pval[(size_t)b * slots + i];
+    const int id = pidx[(size_t)b * slots + i];
+    if (v > best || (v == best && id < bi)) { best = v; bi = id; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float v2 = __shfl_xor_sync(0xffffffffu, best, o);
+    const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (v2 > best || (v2 == best && i2 < bi)) { best = v2; bi = i2; }
+  }
+  if (lane != 0) return;
   const int u = unfinished[b];
-  const int64_t tok = u ? next[b] : (int64_t)pad_id;
+  const int64_t tok = u ? (int64_t)bi : (int64_t)pad_id;
   out[(size_t)b * max_len + col] = tok;
   cur[b] = tok;
   const int nu = u && tok != eos_id;
   unfinished[b] = nu;
-  if (nu) atomicAdd(n_unfinished, 1);
+  if (nu) atomicAdd(&n_unfinished[col], 1);
 }
 
 static int decode_step(Engine& e, const DecodeWs& dw, int B, int S2, int max_len, int t, cudaStream_t st) {
@@ -107,8 +126,8 @@ static int decode_step(Engine& e, const DecodeWs& dw, int B, int S2, int max_len
   r.x = w.y[3 * Ld]; r.w = e.P + e.o_dec_final; r.y_bf16 = w.yfin; r.ld_bf16 = d; r.M = B; r.eps = c.eps;
   r.scale = 1.f / sqrtf((float)d);
   VQ_TRY(rmsnorm_fwd(r, st));
-  VQ_TRY(gemm_fwd(w.yfin, d, e.W + e.o_shared, d, dw.logits, e.ldv, B, c.vocab_size, EPI_BF16, st));
-  VQ_TRY(argmax_rows(dw.logits, e.ldv, B, c.vocab_size, dw.next, st));
+  // tied LM head with the greedy argmax fused into the epilogue (fp32 accumulators -> per-tile maxima)
+  VQ_TRY(gemm_fwd(w.yfin, d, e.W + e.o_shared, d, dw.pval, dw.slots, B, c.vocab_size, EPI_ARGMAX, st, dw.pidx, dw.slots));
   return 0;
 }
 
@@ -150,19 +169,30 @@ extern "C" int vqacl_generate(void* engine, const vqacl_batch* batch, const vqac
   VQ_TRY(gemm_fwd(e.w.mem, d, e.W + e.o_ckv, d, e.w.kv_all, Ld * 2 * d, B * S2, Ld * 2 * d, EPI_BF16, st));
   (void)vq_launch(decode_init_kernel, dim3((B + 255) / 256), dim3(256), 0, st, out_tokens, max_len, dw.cur, dw.unfinished, B, c.start_id);
   VQ_LAUNCH_CHECK();
-  static int* h_flag = nullptr;
-  if (!h_flag) VQ_CUDA(cudaMallocHost(&h_flag, sizeof(int)));
-  int len = 1;
+  // rows-still-unfinished counter per generated column; the host looks at it every CHECK_EVERY tokens (one stream
+  // synchronisation each) instead of after every token: finished rows emit pad, so running a few columns past the point
+  // where HF's loop stops changes nothing in the columns that are returned
+  constexpr int CHECK_EVERY = 4;
+  static int* h_cnt = nullptr;
+  if (!h_cnt) VQ_CUDA(cudaMallocHost(&h_cnt, 65 * sizeof(int)));
+  VQ_CUDA(cudaMemsetAsync(dw.n_unfinished, 0, (size_t)(max_len + 1) * sizeof(int), st));
+  const int nslots = ((c.vocab_size + 255) / 256) * 2;
+  int len = 1, checked = 1;
   for (int t = 0; t + 1 < max_len; ++t) {
     VQ_TRY(decode_step(e, dw, B, S2, max_len, t, st));
-    VQ_CUDA(cudaMemsetAsync(dw.n_unfinished, 0, sizeof(int), st));
-    (void)vq_launch(decode_advance_kernel, dim3((B + 255) / 256), dim3(256), 0, st, dw.next, out_tokens, max_len, t + 1, dw.cur, dw.unfinished,
-                                                           dw.n_unfinished, B, c.pad_id, c.eos_id);
+    (void)vq_launch(decode_advance_kernel, dim3((B + 7) / 8), dim3(256), 0, st, (const float*)dw.pval, (const int*)dw.pidx, dw.slots, nslots,
+                    out_tokens, max_len, t + 1, dw.cur, dw.unfinished, dw.n_unfinished, B, c.pad_id, c.eos_id);
     VQ_LAUNCH_CHECK();
     len = t + 2;
-    VQ_CUDA(cudaMemcpyAsync(h_flag, dw.n_unfinished, sizeof(int), cudaMemcpyDeviceToHost, st));
-    VQ_CUDA(cudaStreamSynchronize(st));
-    if (*h_flag == 0) break;                               // every row has produced EOS
+    if ((t + 1) % CHECK_EVERY == 0 || t + 2 == max_len) {
+      VQ_CUDA(cudaMemcpyAsync(h_cnt, dw.n_unfinished, (size_t)(max_len + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
+      VQ_CUDA(cudaStreamSynchronize(st));
+      bool done = false;
+      for (int col = checked; col <= t + 1; ++col)
+        if (h_cnt[col] == 0) { len = col + 1; done = true; break; }   // every row had produced EOS after column `col`
+      checked = t + 2;
+      if (done) break;
+    }
   }
   *out_len = len;
   return 0;

@@ -129,6 +129,17 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) rmsnorm_bwd_kernel(const RmsBw
 #pragma unroll
         for (int i = 0; i < 4; ++i) dy[j][i] += d2[j][i];
     }
+    if (a.bc_q) {
+      const int bb = r / a.bc_S, tt = r - bb * a.bc_S;
+      const bool qs = tt < a.bc_split;
+      const float cf = qs ? a.bc_g[0] * a.bc_cq : a.bc_g[1] * a.bc_cv;
+      float bc[RW_CHUNKS][4];
+      load_row_f32(bc, (qs ? a.bc_q : a.bc_v) + (size_t)bb * DM, lane);
+#pragma unroll
+      for (int j = 0; j < RW_CHUNKS; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dy[j][i] += cf * bc[j][i];
+    }
     apply_dropout(dy, a.own, (uint64_t)r * DM, lane);
     const float rstd = rsqrtf(row_sumsq(x) / DM + a.eps);
     float dot = 0.f;

@@ -172,6 +172,10 @@ int64_t engine_carve(Engine& e, uint8_t* base, int B, int L, int N, int T) {
   w.cntQ = bp.take<float>(c.n_ques, "cntQ");
   w.cntV = bp.take<float>(c.n_cate, "cntV");
   w.pnorm = bp.take<float>((size_t)(c.n_ques > c.n_cate ? c.n_ques : c.n_cate) * d);
+  w.memdQ = bp.take<float>((size_t)B * d);
+  w.memdV = bp.take<float>((size_t)B * d);
+  w.mem_ssq = bp.take<float>((size_t)2 * B);
+  w.mem_loss = bp.take<float>(4, "loss_memory");
   w.idxQ = bp.take<int64_t>(B, "idxQ");
   w.idxV = bp.take<int64_t>(B, "idxV");
   w.dec_ids = bp.take<int64_t>(Md, "decoder_input_ids");
@@ -322,9 +326,16 @@ int si_path(Engine& e, const vqacl_batch* b, const vqacl_proto_state* ps, bool s
   Workspace& w = e.w;
   const int B = b->B, S2 = b->L + b->N + 2, S = b->L + b->N;
   VQ_CHECK(ps && ps->Q_prototype && ps->V_prototype, "engine: prototype banks missing (Q_prototype / V_prototype)");
+  e.mem_loss_valid = false;
   if (ps->proto_update) {
     VQ_CHECK(b->cate_labels && b->ques_labels, "engine: proto_update needs cate_labels and ques_labels");
     VQ_CHECK(ps->Q_num && ps->V_num, "engine: proto_update needs the count buffers");
+    if (ps->memory_loss) {
+      // modeling_t5_our.py:590-592: against the banks as the PREVIOUS step left them (the update follows at :597)
+      VQ_TRY(proto_memory_loss(w.meanQ, w.meanV, b->ques_labels, b->cate_labels, ps->Q_prototype, ps->V_prototype, c.n_ques, c.n_cate, B,
+                               w.memdQ, w.memdV, w.mem_ssq, w.mem_loss, st));
+      e.mem_loss_valid = true;
+    }
     if (!sums_ready) {
       VQ_TRY(proto_scatter_mean(w.meanQ, b->ques_labels, B, c.n_ques, w.curQ, w.cntQ, st));
       VQ_TRY(proto_scatter_mean(w.meanV, b->cate_labels, B, c.n_cate, w.curV, w.cntV, st));
@@ -629,6 +640,13 @@ static int backward(Engine& e, const float* w_rows, const float* gscale, int acc
     en.dn = w.dmem; en.ld_dn = d; en.in_rpb = S; en.out_rpb = S2; en.x = w.x[2 * Le]; en.w = e.P + e.o_enc_final;
     en.g_in = nullptr; en.g_out = w.ge; en.gb_out = w.geb_ring[e.geb_i]; en.dw = e.G + e.o_enc_final; en.M = M; en.eps = c.eps; en.scale = 1.f;
     en.own = e.drop(SITE_ENC_FINAL); en.consumer = e.drop(site_enc(Le - 1, 3)); en.consumer_cols = d;
+    if (e.mem_loss_valid && e.mem_loss_g) {
+      // d loss_Q / d hidden[b,t,:] = 2 (mean_Q[b] - P_Q[label_b]) / (B * n_Q) for the n_Q tokens of the Q side, same for V
+      const int nq = c.split_L < S ? c.split_L : S, nv = S - nq;
+      en.bc_q = w.memdQ; en.bc_v = w.memdV; en.bc_g = e.mem_loss_g; en.bc_S = S; en.bc_split = nq;
+      en.bc_cq = 2.f / ((float)B * (float)nq);
+      en.bc_cv = nv > 0 ? 2.f / ((float)B * (float)nv) : 0.f;
+    }
     VQ_TRY(rmsnorm_bwd(en, st));
     VQ_TRY(stage_done(Ld + 1));
   }
@@ -841,6 +859,12 @@ extern "C" int vqacl_backward_overlapped(void* engine, const float* w_rows, cons
                                          void (*stage_cb)(int, void*), void* user, void* stream) {
   VQ_CHECK(comm_stream && stage_cb, "backward_overlapped: communication stream and stage callback required");
   return backward(ENG(engine), w_rows, gscale, accumulate, 0, -1, ST(stream), ST(comm_stream), stage_cb, user);
+}
+// d(total loss) / d(loss_memory_Q, loss_memory_V) for the next backward (device float[2]; null = the memory losses do not
+// take part in the objective). Only meaningful after a forward with vqacl_proto_state.memory_loss set.
+extern "C" int vqacl_set_memory_loss_grads(void* engine, const float* g2) {
+  ENG(engine).mem_loss_g = g2;
+  return 0;
 }
 extern "C" int vqacl_backward_stages(void* engine) { return n_backward_stages(ENG(engine)); }
 extern "C" int vqacl_backward_stage_range(void* engine, int stage, int64_t* begin, int64_t* end) {

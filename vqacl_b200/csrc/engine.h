@@ -35,6 +35,7 @@ struct Workspace {
   float *enc_mask, *cross_mask, *mask01;
   // SI path
   float *meanQ, *meanV, *curQ, *curV, *cntQ, *cntV, *pnorm;
+  float *memdQ, *memdV, *mem_ssq, *mem_loss;   // memory_loss: mean - assigned prototype per sample, scratch, the two losses
   int64_t *idxQ, *idxV;
   // decoder (Md = B*T rows)
   int64_t* dec_ids;
@@ -78,6 +79,8 @@ struct Engine {
   int ldv = 0;  // logits pitch
   // step state
   uint32_t seed = 0; bool training = false; bool fwd_valid = false;
+  bool mem_loss_valid = false;          // this forward computed memory_loss (its diffs are in the workspace)
+  const float* mem_loss_g = nullptr;    // device float[2]: d(total loss) / d(loss_memory_Q, loss_memory_V) for the coming backward
   // side stream for the weight-gradient GEMMs (nobody consumes dW before the optimizer, so they run beside the dX chain)
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_layer[4] = {nullptr, nullptr, nullptr, nullptr};

@@ -223,6 +223,12 @@ int gemm_bf16(const GemmOperand& A, const GemmOperand& B, GemmArgs args, int for
   VQ_CHECK(args.ldc % 8 == 0, "gemm: ldc=%d must be a multiple of 8", args.ldc);
   if (args.splits < 1) args.splits = 1;
   VQ_CHECK(args.splits == 1 || args.epi == EPI_ATOMIC_F32, "gemm: split-K needs the atomic epilogue");
+  if (args.epi == EPI_ARGMAX) {
+    if (force_bn == 0) force_bn = args.M >= 192 ? 512 : 256;
+    VQ_CHECK(force_bn == 256 || force_bn == 512, "gemm: the argmax epilogue needs 256-wide tiles");
+    const int slots = (args.N + 255) / 256 * GEMM_EPI_GROUPS;
+    VQ_CHECK(args.C && args.R && args.ldc >= slots && args.ldr >= slots, "gemm: argmax partial buffers need %d slots per row", slots);
+  }
   const int kblocks = (args.K + GEMM_BK - 1) / GEMM_BK;
   if (args.splits > kblocks) args.splits = kblocks;
   // make sure no split is empty

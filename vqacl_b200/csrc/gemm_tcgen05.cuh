@@ -23,7 +23,12 @@ enum GemmEpi : int {
   EPI_ATOMIC_F32 = 3,    // C(f32) += alpha * acc (red.global.add; split-K capable)
   EPI_RELUBWD_BF16 = 4,  // C(bf16) = mask bit ? alpha * acc : 0      R = u32 bitmask written by EPI_RELU_BF16 (16x less traffic than
                          // re-reading the saved activations)
-  EPI_F32 = 5            // C(f32)  = alpha * acc
+  EPI_F32 = 5,           // C(f32)  = alpha * acc
+  EPI_ARGMAX = 6         // no C matrix: per row the first maximum of alpha * acc over this tile's columns, straight from the fp32
+                         // accumulators. C = float [M, ldc] values, R = int32 [M, ldr] column indices, slot = n_block * 2 + (index of
+                         // the epilogue warp among the two sharing a TMEM lane quarter); needs 256-wide tiles (force_bn 256 / 512).
+                         // Greedy decoding never materialises the [B, 32200] logits and the argmax is not taken on bf16-rounded
+                         // values (two fp32 logits 0.01 apart round to the same bf16 above 2.0).
 };
 
 struct GemmArgs {
@@ -88,6 +93,32 @@ VQ_DEVINL uint4 lds128(uint32_t addr) {
 template <int EPI, int BN>
 VQ_DEVINL void gemm_epilogue_tile(const GemmArgs& p, uint32_t t_base, uint32_t stg, int row_base, int n_base, int half, int lane,
                                   bool has_k, uint64_t* tfull, uint32_t aphase) {
+  if constexpr (EPI == EPI_ARGMAX) {
+    const int rlim = has_k ? p.M - row_base : 0;
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    mbar_wait(tfull, aphase);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = half; c < BN / 32; c += GEMM_EPI_GROUPS) {
+      const int col0 = n_base + c * 32;
+      if (col0 >= p.N) break;
+      uint32_t r[32];
+      tmem_ld_32x32(t_base + c * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float v = __uint_as_float(r[i]) * p.alpha;
+        if (col0 + i < p.N && v > best) { best = v; bi = col0 + i; }   // ascending columns + strict '>' = first maximum
+      }
+    }
+    if (lane < rlim) {
+      const int slot = (n_base / BN) * GEMM_EPI_GROUPS + half;
+      reinterpret_cast<float*>(p.C)[(size_t)(row_base + lane) * p.ldc + slot] = best;
+      reinterpret_cast<int*>(const_cast<void*>(p.R))[(size_t)(row_base + lane) * p.ldr + slot] = bi;
+    }
+    return;
+  }
   constexpr bool OUT_BF16 = (EPI == EPI_BF16 || EPI == EPI_RELU_BF16 || EPI == EPI_RELUBWD_BF16);
   constexpr int ESZ = OUT_BF16 ? 2 : 4;          // bytes per output element
   constexpr int RPI = OUT_BF16 ? 8 : 4;          // rows one store instruction covers (4 or 8 lanes x 16 B per row)
@@ -366,6 +397,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         case EPI_RESID_F32: gemm_epilogue_tile<EPI_RESID_F32, BN>(p, t_base, stg, row_base, n_blk * BN, half, lane, has_k, tf, aphase); break;
         case EPI_ATOMIC_F32: gemm_epilogue_tile<EPI_ATOMIC_F32, BN>(p, t_base, stg, row_base, n_blk * BN, half, lane, has_k, tf, aphase); break;
         case EPI_RELUBWD_BF16: gemm_epilogue_tile<EPI_RELUBWD_BF16, BN>(p, t_base, stg, row_base, n_blk * BN, half, lane, has_k, tf, aphase); break;
+        case EPI_ARGMAX: gemm_epilogue_tile<EPI_ARGMAX, BN>(p, t_base, stg, row_base, n_blk * BN, half, lane, has_k, tf, aphase); break;
         default: gemm_epilogue_tile<EPI_F32, BN>(p, t_base, stg, row_base, n_blk * BN, half, lane, has_k, tf, aphase); break;
       }
       tc_fence_before();
@@ -547,6 +579,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
         case EPI_RESID_F32: gemm_epilogue_tile<EPI_RESID_F32, BN>(p, t_base, stg, row_base, n_blk * BN, half, lane, has_k, tf, aphase); break;
         case EPI_ATOMIC_F32: gemm_epilogue_tile<EPI_ATOMIC_F32, BN>(p, t_base, stg, row_base, n_blk * BN, half, lane, has_k, tf, aphase); break;
         case EPI_RELUBWD_BF16: gemm_epilogue_tile<EPI_RELUBWD_BF16, BN>(p, t_base, stg, row_base, n_blk * BN, half, lane, has_k, tf, aphase); break;
+        case EPI_ARGMAX: gemm_epilogue_tile<EPI_ARGMAX, BN>(p, t_base, stg, row_base, n_blk * BN, half, lane, has_k, tf, aphase); break;
         default: gemm_epilogue_tile<EPI_F32, BN>(p, t_base, stg, row_base, n_blk * BN, half, lane, has_k, tf, aphase); break;
       }
       tc_fence_before();

@@ -76,6 +76,9 @@ struct RmsBwdArgs {
   __nv_bfloat16* gb_out;                // may be null
   float* dw;                            // [768], accumulated
   int M; float eps; float scale;
+  // optional per-sample gradient broadcast over the tokens of each side of the Q/V split (memory_loss backward): row r of
+  // batch element b = r / bc_S gets bc_g[0] * bc_cq * bc_q[b] when r % bc_S < bc_split, else bc_g[1] * bc_cv * bc_v[b]
+  const float* bc_q; const float* bc_v; const float* bc_g; float bc_cq, bc_cv; int bc_S, bc_split;
   Dropout own;                          // dropout that was applied to this norm's output (final norms)
   Dropout consumer;                     // dropout of the residual branch that consumes gb_out
   int consumer_cols;                    // element index = row * consumer_cols + col  (== 768)
@@ -140,6 +143,11 @@ int proto_update(const ProtoUpdateArgs& a, cudaStream_t stream);
 // scratch: [C,768] fp32 (normalised tanh of the bank)
 int proto_retrieve(const float* P, int C, const float* x, int B, __nv_bfloat16* out, int out_pitch_rows, int out_row,
                    int64_t* idx, float* out_f32, float* scratch, cudaStream_t stream);
+
+// memory_loss (nextqa/modeling_t5_nextqa.py:544-555): loss2[0] = mean_b |meanQ[b] - ques_labels[b] @ PQ|^2, loss2[1] the same for
+// the V side; diffQ / diffV [B,768] (fp32) are kept for the backward pass, ssq is scratch [2*B]
+int proto_memory_loss(const float* meanQ, const float* meanV, const float* ques_labels, const float* cate_labels, const float* PQ,
+                      const float* PV, int CQ, int CV, int B, float* diffQ, float* diffV, float* ssq, float* loss2, cudaStream_t stream);
 
 // ---------------------------------------------------------------- lmhead_ce.cu
 // per-row log-sum-exp and CE loss over bf16 logits [M, V] (pitch ld); label -100 -> loss 0

@@ -259,4 +259,56 @@ int proto_retrieve(const float* P, int C, const float* x, int B, __nv_bfloat16* 
   return 0;
 }
 
+// memory_loss (VL-T5/nextqa/modeling_t5_nextqa.py:544-555, called at VL-T5/src/modeling_t5_our.py:591 BEFORE the bank
+// update): the prototype pull loss  loss = mean_b sum_d (mean_t(h)[b,d] - (labels @ P.detach())[b,d])^2  for the Q side
+// (question-type bank) and the V side (object-category bank). One CTA per (sample, side): diff[b] = mean[b] - sum_c
+// labels[b,c] P[c] is kept (fp32) for the backward pass, its squared norm goes to ssq[side][b]; a second single-CTA kernel
+// averages the B values in a fixed order (deterministic) into loss[side].
+__global__ void __launch_bounds__(192) proto_memloss_kernel(const float* __restrict__ meanQ, const float* __restrict__ meanV,
+                                                            const float* __restrict__ lq, const float* __restrict__ lv,
+                                                            const float* __restrict__ PQ, const float* __restrict__ PV, int CQ, int CV,
+                                                            int B, float* __restrict__ diffQ, float* __restrict__ diffV,
+                                                            float* __restrict__ ssq) {
+  vq_pdl_trigger();
+  vq_pdl_wait();
+  __shared__ float s_w[6];
+  const int b = blockIdx.x, side = blockIdx.y, col = threadIdx.x * 4;
+  const float* mean = side ? meanV : meanQ;
+  const float* lab = (side ? lv : lq) + (size_t)b * (side ? CV : CQ);
+  const float* P = side ? PV : PQ;
+  const int C = side ? CV : CQ;
+  float4 acc = *reinterpret_cast<const float4*>(mean + (size_t)b * DM + col);
+  for (int c = 0; c < C; ++c) {
+    const float w = lab[c];
+    if (w != 0.f) {                       // one-hot labels: one row of the bank per sample
+      const float4 p = *reinterpret_cast<const float4*>(P + (size_t)c * DM + col);
+      acc.x -= w * p.x; acc.y -= w * p.y; acc.z -= w * p.z; acc.w -= w * p.w;
+    }
+  }
+  *reinterpret_cast<float4*>((side ? diffV : diffQ) + (size_t)b * DM + col) = acc;
+  float sq = warp_sum(acc.x * acc.x + acc.y * acc.y + acc.z * acc.z + acc.w * acc.w);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = sq;
+  __syncthreads();
+  if (threadIdx.x == 0) ssq[(size_t)side * B + b] = s_w[0] + s_w[1] + s_w[2] + s_w[3] + s_w[4] + s_w[5];
+}
+__global__ void __launch_bounds__(64) proto_memloss_final_kernel(const float* __restrict__ ssq, int B, float* __restrict__ loss2) {
+  vq_pdl_trigger();
+  vq_pdl_wait();
+  const int side = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float acc = 0.f;
+  for (int b = lane; b < B; b += 32) acc += ssq[(size_t)side * B + b];
+  acc = warp_sum(acc);
+  if (lane == 0) loss2[side] = acc / (float)B;
+}
+int proto_memory_loss(const float* meanQ, const float* meanV, const float* ques_labels, const float* cate_labels, const float* PQ,
+                      const float* PV, int CQ, int CV, int B, float* diffQ, float* diffV, float* ssq, float* loss2, cudaStream_t stream) {
+  if (B <= 0) return 0;
+  (void)vq_launch(proto_memloss_kernel, dim3(B, 2), dim3(192), 0, stream, meanQ, meanV, ques_labels, cate_labels, PQ, PV, CQ, CV, B, diffQ,
+                  diffV, ssq);
+  VQ_LAUNCH_CHECK();
+  (void)vq_launch(proto_memloss_final_kernel, dim3(1), dim3(64), 0, stream, (const float*)ssq, B, loss2);
+  VQ_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace vq

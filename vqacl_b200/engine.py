@@ -37,7 +37,7 @@ class CProtoState(Structure):
     _fields_ = [
         ("Q_prototype", c_void_p), ("V_prototype", c_void_p), ("Q_num", c_void_p), ("V_num", c_void_p),
         ("proto_update", c_int), ("task_id", c_int), ("first_step_of_task", c_int), ("has_mem", c_int),
-        ("alpha", c_float), ("beta", c_float),
+        ("alpha", c_float), ("beta", c_float), ("memory_loss", c_int),
     ]
 
 
@@ -70,6 +70,7 @@ def _declare(L):
     L.vqacl_proto_sums.argtypes = [c_void_p, POINTER(CBatch), c_void_p]
     L.vqacl_backward.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]
     L.vqacl_backward_overlapped.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p, STAGE_CB, c_void_p, c_void_p]
+    L.vqacl_set_memory_loss_grads.argtypes = [c_void_p, c_void_p]
     L.vqacl_backward_stages.argtypes = [c_void_p]
     L.vqacl_backward_stage_range.argtypes = [c_void_p, c_int, POINTER(c_int64), POINTER(c_int64)]
     L.vqacl_loss_tail.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]
@@ -228,6 +229,10 @@ class Engine:
     def loss_tail(self, labels, scores, B, T, loss_out, w_rows):
         lr = self.ws_tensor("loss_rows", torch.float32, (B * T,))
         check(self.L.vqacl_loss_tail(ptr(lr), ptr(labels), ptr(scores), B, T, ptr(loss_out), ptr(w_rows), cur_stream()))
+
+    def set_memory_loss_grads(self, g2):
+        """g2: device fp32[2] = d loss / d (loss_memory_Q, loss_memory_V) for the next backward, or None."""
+        check(self.L.vqacl_set_memory_loss_grads(self.h, ptr(g2)))
 
     def n_backward_stages(self):
         return self.L.vqacl_backward_stages(self.h)

@@ -156,6 +156,31 @@ class _StepLoss(torch.autograd.Function):
         return None, None, None, None
 
 
+class _StepLossMem(torch.autograd.Function):
+    """train_step / forward with memory=True: (main loss or loss rows, loss_memory_Q, loss_memory_V) from ONE node, so that the
+    single native backward sees all three upstream gradients at once (the caller combines them as
+    loss + lambda_Q * loss_memory_Q + lambda_V * loss_memory_V, vqacl.py:448-450)."""
+
+    @staticmethod
+    def forward(ctx, anchor, model, main, w_rows, mem2):
+        ctx.model, ctx.w_rows = model, w_rows
+        return main.clone() if w_rows is None else main.reshape(()).clone(), mem2[0].clone(), mem2[1].clone()
+
+    @staticmethod
+    def backward(ctx, g, gq, gv):
+        m = ctx.model
+        m._mem_g = torch.stack([gq.reshape(()), gv.reshape(())]).to(torch.float32).contiguous()
+        m._engine.set_memory_loss_grads(m._mem_g)
+        try:
+            if ctx.w_rows is None:
+                m._native_backward(g.contiguous().float(), None)       # row losses: g is dL/dloss_row
+            else:
+                m._native_backward(ctx.w_rows, g)
+        finally:
+            m._engine.set_memory_loss_grads(None)
+        return None, None, None, None, None
+
+
 class _RowLoss(torch.autograd.Function):
     """Per-row CE loss of VLT5.forward (reduction='none'); backward(g[B*T]) = native backward with w_rows = g."""
 
@@ -447,13 +472,14 @@ class VLT5(nn.Module):
         cb = Engine.make_batch(B, Lt, N, T, feats, bx, ids, lab, cate, ques)
         return cb, keep, (B, Lt, N, T)
 
-    def _proto_state(self, proto_update, task_id=0, alpha=0.0, beta=0.0):
+    def _proto_state(self, proto_update, task_id=0, alpha=0.0, beta=0.0, memory=False):
         first = task_id not in self.Q_task_cur_proto
         has_mem = task_id in self.Q_task_mem_proto
         ps = CProtoState(Q_prototype=self._Q_prototype.data_ptr(), V_prototype=self._V_prototype.data_ptr(),
                          Q_num=self._Q_prototype_num.data_ptr(), V_num=self._V_prototype_num.data_ptr(),
                          proto_update=int(proto_update), task_id=int(task_id), first_step_of_task=int(first),
-                         has_mem=int(has_mem), alpha=float(alpha or 0.0), beta=float(beta or 0.0))
+                         has_mem=int(has_mem), alpha=float(alpha or 0.0), beta=float(beta or 0.0),
+                         memory_loss=int(bool(memory) and bool(proto_update)))
         if proto_update:
             # host-side image of the reference's dict bookkeeping (modeling_t5_our.py:467,476-485)
             if first:
@@ -468,13 +494,13 @@ class VLT5(nn.Module):
             return dist.get_world_size()
         return 1
 
-    def _forward_native(self, cb, shape, proto_update, task_id, alpha, beta, training):
+    def _forward_native(self, cb, shape, proto_update, task_id, alpha, beta, training, memory=False):
         eng = self._engine
         B, Lt, N, T = shape
         eng.bind(B, Lt, N, T)
         self._step_seed += 1
         eng.forward_encoder(cb, self._base_seed * 2654435761 + self._step_seed, training)
-        ps = self._proto_state(proto_update, task_id, alpha, beta)
+        ps = self._proto_state(proto_update, task_id, alpha, beta, memory)
         sums_ready = False
         if proto_update and self.sync_prototypes and self._world() > 1:
             import torch.distributed as dist
@@ -555,18 +581,23 @@ class VLT5(nn.Module):
                       ("decoder_attention_mask", decoder_attention_mask)):
             if v is not None:
                 raise NotImplementedError(f"forward(): argument {nm} is not used by the VQACL train path and is not supported")
-        if kwargs.get("memory"):
-            raise NotImplementedError("memory=True calls an undefined memory_loss in the reference (SURVEY.md H7)")
         proto_update = bool(kwargs.get("proto_update", False))
+        # memory=True: the prototype pull losses. `memory_loss` is called at modeling_t5_our.py:591 but defined only in the
+        # NExT-QA twin (nextqa/modeling_t5_nextqa.py:544-555); that definition is what runs here.
+        memory = bool(kwargs.get("memory")) and proto_update
         cb, keep, shape = self._stage_batch(input_ids, vis_inputs[0], vis_inputs[1], labels,
                                             kwargs.get("cate_labels") if proto_update else None,
                                             kwargs.get("ques_labels") if proto_update else None)
         self._forward_native(cb, shape, proto_update, kwargs.get("current_task_id", 0), kwargs.get("proto_alpha"),
-                             kwargs.get("proto_beta"), self.training)
+                             kwargs.get("proto_beta"), self.training, memory)
         self._keep = keep
         out = self._collect_outputs(shape, keep[0])
         rows = self._engine.ws_tensor("loss_rows", torch.float32, (shape[0] * shape[3],))
-        loss = _RowLoss.apply(self._anchor, self, rows)
+        if memory:
+            mem2 = self._engine.ws_tensor("loss_memory", torch.float32, (2,))
+            loss, out.loss_memory_Q, out.loss_memory_V = _StepLossMem.apply(self._anchor, self, rows, None, mem2)
+        else:
+            loss = _RowLoss.apply(self._anchor, self, rows)
         if reduce_loss:
             loss = loss.sum() / (keep[3].view(-1) != -100).sum().clamp(min=1)
         out.loss = loss
@@ -609,22 +640,29 @@ class VLT5VQA(VLT5):
     def train_step(self, batch, current_task_id, proto_alpha, proto_beta, mem_num_Q=0, total_num_Q=1000, memory=False):
         """vqa_model.py:18-65: H2D of the batch, forward with proto_update=True, per-sample masked mean x soft score,
         batch mean. `mem_num_Q`, `total_num_Q` are accepted and ignored, as in the reference."""
-        if memory:
-            raise NotImplementedError("memory=True calls an undefined memory_loss in the reference (SURVEY.md H7)")
         eng = self._need_engine()
         cb, keep, shape = self._stage_batch(batch["input_ids"], batch["vis_feats"], batch["boxes"], batch["target_ids"],
                                             batch["cate_labels"], batch["ques_labels"])
         B, Lt, N, T = shape
         scores = batch["scores"].to(device=eng.device, dtype=torch.float32, non_blocking=True).contiguous()
-        self._forward_native(cb, shape, True, current_task_id, proto_alpha, proto_beta, self.training)
+        self._forward_native(cb, shape, True, current_task_id, proto_alpha, proto_beta, self.training, memory)
         w_rows = torch.empty(B * T, dtype=torch.float32, device=eng.device)
         eng.loss_tail(keep[3], scores, B, T, self._loss_buf, w_rows)
         self._keep = keep + (scores,)
         out = self._collect_outputs(shape, keep[0])
-        loss = _StepLoss.apply(self._anchor, self, self._loss_buf[:1], w_rows)
-        return {"loss": loss, "encoder_hidden_states": out.encoder_hidden_states, "BL": (B, T),
-                "encoder_attention_mask": out.encoder_attention_mask, "logits": out.logits,
-                "max_idx_Q": out.max_idx_Q, "max_idx_V": out.max_idx_V}
+        result = {"encoder_hidden_states": out.encoder_hidden_states, "BL": (B, T),
+                  "encoder_attention_mask": out.encoder_attention_mask, "logits": out.logits,
+                  "max_idx_Q": out.max_idx_Q, "max_idx_V": out.max_idx_V}
+        if memory:
+            # The reference's train_step looks for a key 'loss_memory' that its forward never sets (vqa_model.py:61-62; the
+            # comment there names the intended value); the tuple is provided so that Trainer.train_step's
+            # `loss + lambda_Q * loss_memory_Q + lambda_V * loss_memory_V` (vqacl.py:448-450) takes effect.
+            mem2 = eng.ws_tensor("loss_memory", torch.float32, (2,))
+            result["loss"], lq, lv = _StepLossMem.apply(self._anchor, self, self._loss_buf[:1], w_rows, mem2)
+            result["loss_memory"] = (lq, lv)
+        else:
+            result["loss"] = _StepLoss.apply(self._anchor, self, self._loss_buf[:1], w_rows)
+        return result
 
     @torch.no_grad()
     def test_step(self, batch, **kwargs):
