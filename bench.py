@@ -313,6 +313,95 @@ def run_native(args):
         dist.destroy_process_group()
 
 
+def run_decode(args):
+    """configs[4]: eval-only greedy answer generation (VLT5VQA.test_step, vqa_model.py:68-121), batch 512 per GPU, <= 20
+    tokens, frozen prototype banks; every rank decodes its own shard (no data-path collective)."""
+    import torch
+    import torch.distributed as dist
+    import vqacl_b200 as V
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import vlt5_oracle as O                       # synthetic_batch generator only
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    pk = peaks()
+    B = args.batch if args.batch != 320 else 512
+    cfg = V.VLT5Config(vocab_size=32200, dropout_rate=0.0)
+    torch.manual_seed(66666)
+    model = V.VLT5VQA(cfg)
+    for mod in (model.encoder.visual_embedding.feat_embedding[0], model.encoder.visual_embedding.absolute_vis_pos_embedding[0],
+                model.encoder.visual_embedding.img_order_embedding):
+        mod.weight.data.normal_(0, 1)
+    model = model.to(dev).eval()
+    g = torch.Generator().manual_seed(9)
+    model.Q_prototype, model.V_prototype = torch.randn(10, 768, generator=g), torch.randn(80, 768, generator=g)
+    pool = 3
+    host = [{k: v.pin_memory() for k, v in O.synthetic_batch(B, seed=77 + rank * 100 + i).items()} for i in range(pool)]
+    devb = [{k: v.to(dev) for k, v in b.items()} for b in host]
+    h2d = sum(host[0][k].numel() * host[0][k].element_size() for k in ("vis_feats", "boxes", "input_ids"))
+
+    def timed(batches, steps, warmup, to_host):
+        ntok = 0
+        for i in range(warmup):
+            model.test_step(batches[i % pool])
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = model._engine.launch_count()
+        e0.record()
+        for i in range(steps):
+            t = model.test_step(batches[i % pool])["token_ids"]
+            ntok += t.shape[1] - 1
+            if to_host:
+                t = t.cpu()                        # the answers leave the device (tokenizer.batch_decode runs on the host)
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            tt = torch.tensor([ms], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = tt.item()
+        return ms, model._engine.launch_count() - l0, ntok
+
+    warm = max(3, args.warmup)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ms, launches, ntok = timed(devb, args.steps, warm, False)
+    ck = clocks.stop() if rank == 0 else None
+    ms_e2e, _, _ = timed(host, args.steps, 2, True)
+    if rank == 0:
+        c = cfg
+        dec_w = c.num_decoder_layers * (6 * c.d_model * c.d_model + 2 * c.d_model * c.d_ff) * 2 + c.vocab_size * c.d_model * 2
+        kv = B * 58 * c.num_decoder_layers * 2 * c.d_model * 2
+        per_tok = dec_w + kv                                   # bf16 decoder + LM-head weights + the cross-attention K/V of 12 layers
+        gbs = per_tok * ntok / (ms / 1e3) / 1e9
+        line = {"metric": "VQACL eval greedy-decode samples/s (VL-T5 base, 36 RoIs, max_length 20)", "value": world * B * args.steps / (ms / 1e3),
+                "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": f"configs[4]: eval-only greedy answer generation, batch {B} per GPU, 12+12 layers, vocab 32200, random init "
+                                       f"(no EOS: all {ntok // max(1, args.steps)} decode steps run), frozen SI prototype banks",
+                           "global_batch": B * world, "parallelism": f"dp{world}", "l2": f"{pool} distinct batches rotate; K/V + weights per token step {per_tok / 1e6:.0f} MB > 126 MB L2"},
+                "e2e": {"value": world * B * args.steps / (ms_e2e / 1e3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": B * 20 * 8, "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": int(launches), "clocks": ck,
+                "roofline": {"bound": "hbm", "achieved": round(gbs, 1), "peak": pk["hbm"], "unit": "GB/s", "frac": round(gbs / pk["hbm"], 4),
+                             "traffic": None, "kernel": "decode token steps: bytes that must stream per step (bf16 decoder + tied LM-head weights "
+                             f"{dec_w / 1e6:.0f} MB + cross-attention K/V {kv / 1e6:.0f} MB) x steps / whole generate time (encoder included in the time)",
+                             "peak_source": pk["source"]}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -321,6 +410,8 @@ def main():
     ap.add_argument("--batch", type=int, default=320)
     ap.add_argument("--dropout", type=float, default=0.1)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--mode", default="train", choices=["train", "decode"],
+                    help="train: configs[1] train step (the BASELINE.json metric); decode: configs[4] greedy evaluation, batch 512")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-roofline", action="store_true")
     ap.add_argument("--no-overlap-optimizer", action="store_true",
@@ -338,7 +429,10 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr",
                "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
-    run_native(args)
+    if args.mode == "decode":
+        run_decode(args)
+    else:
+        run_native(args)
 
 
 if __name__ == "__main__":

@@ -122,6 +122,8 @@ int vqacl_param_sync(void* engine, void* stream);
  * vqacl_grad_sumsq_ranges: *out (device fp32) = sum of squares over the given arena ranges (host int64 arrays);
  * vqacl_adamw_range: clip (by *sumsq, the all-reduced global value) + HF AdamW + bf16 refresh over arena elements
  * [begin, end); m / v point at the moment buffers of element `begin`. */
+int64_t vqacl_arena_tail(void* engine);   /* arena layout: [0, tail) GEMM-only matrices (sharded), [tail, n_train) replicated */
+int vqacl_set_param_events(void* engine, void* const* events, int n);   /* cudaEvent_t per parameter chunk; see engine.cu */
 int vqacl_grad_sumsq_ranges(void* engine, const int64_t* begin, const int64_t* end, int n_ranges, float* out, void* stream);
 int vqacl_adamw_range(void* engine, float* m, float* v, int64_t begin, int64_t end, float lr, float beta1, float beta2, float eps,
                       float weight_decay, int step, const float* sumsq, float max_grad_norm, void* stream);

@@ -60,21 +60,19 @@ int engine_build_layout(Engine& e) {
   e.enc.resize(c.n_enc_layers);
   char b[256];
   // ---- weight-decay group -------------------------------------------------------------------------------
+  // (1) the GEMM-only matrices, in the order backward finishes their gradients: with N > 1 GPUs this region is reduce-
+  //     scattered bucket by bucket, every rank runs AdamW on its slices only and the refreshed bf16 copies are all-gathered
   for (int l = 0; l < c.n_dec_layers; ++l) {
     DecLayer& L = e.dec[l];
-    snprintf(b, sizeof b, "decoder.block.%d.layer.0.layer_norm.weight", l); L.ln0 = add(b, 1, d, 0);
     snprintf(b, sizeof b, "decoder.block.%d.layer.0.SelfAttention.q.weight", l); L.qkv = add(b, d, d, 0);
     snprintf(b, sizeof b, "decoder.block.%d.layer.0.SelfAttention.k.weight", l); add(b, d, d, 0);
     snprintf(b, sizeof b, "decoder.block.%d.layer.0.SelfAttention.v.weight", l); add(b, d, d, 0);
     snprintf(b, sizeof b, "decoder.block.%d.layer.0.SelfAttention.o.weight", l); L.o = add(b, d, d, 0);
-    snprintf(b, sizeof b, "decoder.block.%d.layer.1.layer_norm.weight", l); L.ln1 = add(b, 1, d, 0);
     snprintf(b, sizeof b, "decoder.block.%d.layer.1.EncDecAttention.q.weight", l); L.cq = add(b, d, d, 0);
     snprintf(b, sizeof b, "decoder.block.%d.layer.1.EncDecAttention.o.weight", l); L.co = add(b, d, d, 0);
-    snprintf(b, sizeof b, "decoder.block.%d.layer.2.layer_norm.weight", l); L.ln2 = add(b, 1, d, 0);
     snprintf(b, sizeof b, "decoder.block.%d.layer.2.DenseReluDense.wi.weight", l); L.wi = add(b, f, d, 0);
     snprintf(b, sizeof b, "decoder.block.%d.layer.2.DenseReluDense.wo.weight", l); L.wo = add(b, d, f, 0);
   }
-  e.o_dec_final = add("decoder.final_layer_norm.weight", 1, d, 0);
   for (int l = 0; l < c.n_dec_layers; ++l) {
     snprintf(b, sizeof b, "decoder.block.%d.layer.1.EncDecAttention.k.weight", l);
     const size_t o = add(b, d, d, 0);
@@ -83,22 +81,37 @@ int engine_build_layout(Engine& e) {
   }
   for (int l = 0; l < c.n_enc_layers; ++l) {
     EncLayer& L = e.enc[l];
-    snprintf(b, sizeof b, "encoder.block.%d.layer.0.layer_norm.weight", l); L.ln0 = add(b, 1, d, 0);
     snprintf(b, sizeof b, "encoder.block.%d.layer.0.SelfAttention.q.weight", l); L.qkv = add(b, d, d, 0);
     snprintf(b, sizeof b, "encoder.block.%d.layer.0.SelfAttention.k.weight", l); add(b, d, d, 0);
     snprintf(b, sizeof b, "encoder.block.%d.layer.0.SelfAttention.v.weight", l); add(b, d, d, 0);
     snprintf(b, sizeof b, "encoder.block.%d.layer.0.SelfAttention.o.weight", l); L.o = add(b, d, d, 0);
-    snprintf(b, sizeof b, "encoder.block.%d.layer.1.layer_norm.weight", l); L.ln1 = add(b, 1, d, 0);
     snprintf(b, sizeof b, "encoder.block.%d.layer.1.DenseReluDense.wi.weight", l); L.wi = add(b, f, d, 0);
     snprintf(b, sizeof b, "encoder.block.%d.layer.1.DenseReluDense.wo.weight", l); L.wo = add(b, d, f, 0);
   }
-  e.o_enc_final = add("encoder.final_layer_norm.weight", 1, d, 0);
   e.o_Wf = add("encoder.visual_embedding.feat_embedding.0.weight", d, c.feat_dim, 0);
+  // (2) the tail: everything a kernel reads in fp32 (embedding table, norm weights, the small visual parameters, biases,
+  //     relative-position tables). With N > 1 GPUs it is all-reduced and updated by every rank, so the fp32 masters of
+  //     this region are always current everywhere; only region (1) is ever sharded.
+  off = align_up(off, 64);
+  e.o_tail = off;
+  e.o_shared = add("shared.weight", c.vocab_size, d, 0);
+  for (int l = 0; l < c.n_dec_layers; ++l) {
+    DecLayer& L = e.dec[l];
+    snprintf(b, sizeof b, "decoder.block.%d.layer.0.layer_norm.weight", l); L.ln0 = add(b, 1, d, 0);
+    snprintf(b, sizeof b, "decoder.block.%d.layer.1.layer_norm.weight", l); L.ln1 = add(b, 1, d, 0);
+    snprintf(b, sizeof b, "decoder.block.%d.layer.2.layer_norm.weight", l); L.ln2 = add(b, 1, d, 0);
+  }
+  e.o_dec_final = add("decoder.final_layer_norm.weight", 1, d, 0);
+  for (int l = 0; l < c.n_enc_layers; ++l) {
+    EncLayer& L = e.enc[l];
+    snprintf(b, sizeof b, "encoder.block.%d.layer.0.layer_norm.weight", l); L.ln0 = add(b, 1, d, 0);
+    snprintf(b, sizeof b, "encoder.block.%d.layer.1.layer_norm.weight", l); L.ln1 = add(b, 1, d, 0);
+  }
+  e.o_enc_final = add("encoder.final_layer_norm.weight", 1, d, 0);
   e.o_wf = add("encoder.visual_embedding.feat_embedding.1.weight", 1, d, 0);
   e.o_Wp = add("encoder.visual_embedding.absolute_vis_pos_embedding.0.weight", d, 5, 0);
   e.o_wp = add("encoder.visual_embedding.absolute_vis_pos_embedding.1.weight", 1, d, 0);
   e.o_img = add("encoder.visual_embedding.img_order_embedding.weight", c.n_images, d, 0);
-  e.o_shared = add("shared.weight", c.vocab_size, d, 0);
   off = align_up(off, 64);
   e.n_decay = off;
   // ---- no-decay group: names containing "bias" (trainer_base.py:148-160) ----------------------------------
@@ -438,28 +451,35 @@ static std::map<Engine*, SavedBatch> g_saved;
 //   stage Ld+Le+2      : text / visual embeddings
 static int n_backward_stages(const Engine& e) { return e.cfg.n_dec_layers + e.cfg.n_enc_layers + 3; }
 
-// arena range [*a, *b) whose gradients are final once `stage` has run (possibly empty)
+// arena range [*a, *b) whose gradients are final once `stage` has run (possibly empty). The tail region (embedding table,
+// norm weights, small visual parameters, biases: [o_tail, n_train)) collects contributions from every stage and is final
+// only after the last one, where it is reported together with the visual projection.
 static void backward_stage_range(const Engine& e, int stage, int64_t* a, int64_t* b) {
   const int Ld = e.cfg.n_dec_layers, Le = e.cfg.n_enc_layers;
   *a = *b = 0;
   if (stage >= 1 && stage <= Ld) {
     const int l = Ld - stage;
-    *a = (int64_t)e.dec[l].ln0;
-    *b = (int64_t)(l + 1 < Ld ? e.dec[l + 1].ln0 : e.o_dec_final);
+    *a = (int64_t)e.dec[l].qkv;
+    *b = (int64_t)(l + 1 < Ld ? e.dec[l + 1].qkv : e.o_ckv);
   } else if (stage == Ld + 1) {
-    *a = (int64_t)e.o_dec_final;
-    *b = (int64_t)(Le > 0 ? e.enc[0].ln0 : e.o_enc_final);
+    *a = (int64_t)e.o_ckv;
+    *b = (int64_t)(Le > 0 ? e.enc[0].qkv : e.o_Wf);
   } else if (stage >= Ld + 2 && stage <= Ld + 1 + Le) {
     const int l = Le - (stage - Ld - 1);
-    *a = (int64_t)e.enc[l].ln0;
-    *b = (int64_t)(l + 1 < Le ? e.enc[l + 1].ln0 : e.o_enc_final);
+    *a = (int64_t)e.enc[l].qkv;
+    *b = (int64_t)(l + 1 < Le ? e.enc[l + 1].qkv : e.o_Wf);
   } else if (stage == Ld + Le + 2) {
-    *a = (int64_t)e.o_enc_final;
+    *a = (int64_t)e.o_Wf;
     *b = (int64_t)e.n_train;
   }
 }
 
 int wait_params(Engine& e, int chunk, cudaStream_t st) {
+  if (e.ext_pending) {   // sharded optimizer: the host all-gathers refreshed bf16 weights on its communication stream
+    VQ_CHECK(chunk >= 0 && chunk < (int)e.ext_ev.size(), "wait_params: chunk %d out of range", chunk);
+    if (e.ext_ev[chunk]) VQ_CUDA(cudaStreamWaitEvent(st, e.ext_ev[chunk], 0));
+    if (chunk + 1 == (int)e.ext_ev.size()) e.ext_pending = false;
+  }
   if (!e.opt_pending) return 0;
   VQ_CHECK(chunk >= 0 && chunk < (int)e.ev_opt.size(), "wait_params: chunk %d out of range", chunk);
   VQ_CUDA(cudaStreamWaitEvent(st, e.ev_opt[chunk], 0));
@@ -778,6 +798,9 @@ extern "C" int64_t vqacl_arena_elems(void* engine, int64_t* n_decay, int64_t* n_
   if (n_train) *n_train = (int64_t)e.n_train;
   return (int64_t)e.n_total;
 }
+// first element of the tail region (see engine_build_layout): [0, tail) = GEMM-only matrices (sharded optimizer state with
+// N > 1 GPUs), [tail, n_train) = parameters every rank keeps current in fp32
+extern "C" int64_t vqacl_arena_tail(void* engine) { return (int64_t)ENG(engine).o_tail; }
 extern "C" int vqacl_bind_arena(void* engine, float* params, float* grads, void* params_bf16) {
   Engine& e = ENG(engine);
   VQ_CHECK(params && params_bf16, "bind_arena: null arena");
@@ -918,9 +941,9 @@ extern "C" int vqacl_clip_adamw(void* engine, float* exp_avg, float* exp_avg_sq,
     VQ_CUDA(cudaEventRecord(e.ev_opt[k], e.opt_stream));
     return 0;
   };
-  VQ_TRY(chunk(0, e.o_enc_final, e.n_train));
-  for (int l = 0; l < Le; ++l) VQ_TRY(chunk(1 + l, e.enc[l].ln0, l + 1 < Le ? e.enc[l + 1].ln0 : e.o_enc_final));
-  VQ_TRY(chunk(1 + Le, 0, Le > 0 ? e.enc[0].ln0 : e.o_enc_final));
+  VQ_TRY(chunk(0, e.o_Wf, e.n_train));     // visual projection + tail (embeddings, every norm weight, biases): read first
+  for (int l = 0; l < Le; ++l) VQ_TRY(chunk(1 + l, e.enc[l].qkv, l + 1 < Le ? e.enc[l + 1].qkv : e.o_Wf));
+  VQ_TRY(chunk(1 + Le, 0, Le > 0 ? e.enc[0].qkv : e.o_Wf));
   e.opt_pending = true;
   return 0;
 }
@@ -943,8 +966,24 @@ extern "C" int vqacl_adamw_range(void* engine, float* m, float* v, int64_t begin
 }
 
 // order everything a pending overlapped optimizer step wrote before `stream` (state_dict(), evaluation, user code)
+// Sharded optimizer (N > 1): events of the HOST's communication stream after which parameter chunk k (0: visual projection +
+// tail, 1..Le: encoder layer k-1, Le+1: decoder + cross-KV) holds every rank's refreshed bf16 weights; the next
+// forward_encoder / forward_decoder / generate waits chunk by chunk. The events must stay alive until that forward was issued.
+extern "C" int vqacl_set_param_events(void* engine, void* const* events, int n) {
+  Engine& e = ENG(engine);
+  VQ_CHECK(n == 0 || n == e.cfg.n_enc_layers + 2, "set_param_events: %d events given, %d chunks", n, e.cfg.n_enc_layers + 2);
+  e.ext_ev.assign(n, nullptr);
+  for (int i = 0; i < n; ++i) e.ext_ev[i] = reinterpret_cast<cudaEvent_t>(events[i]);
+  e.ext_pending = n > 0;
+  return 0;
+}
 extern "C" int vqacl_param_sync(void* engine, void* stream) {
   Engine& e = ENG(engine);
+  if (e.ext_pending) {
+    for (cudaEvent_t ev : e.ext_ev)
+      if (ev) VQ_CUDA(cudaStreamWaitEvent(ST(stream), ev, 0));
+    e.ext_pending = false;
+  }
   if (e.opt_pending) {
     VQ_CUDA(cudaStreamWaitEvent(ST(stream), e.ev_opt.back(), 0));
     e.opt_pending = false;

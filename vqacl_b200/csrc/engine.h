@@ -67,7 +67,7 @@ struct Engine {
   std::vector<EncLayer> enc;
   std::vector<DecLayer> dec;
   size_t o_dec_final = 0, o_ckv = 0, o_enc_final = 0, o_Wf = 0, o_wf = 0, o_Wp = 0, o_wp = 0, o_img = 0, o_shared = 0;
-  size_t o_bf = 0, o_bp = 0, o_enc_rel = 0, o_dec_rel = 0;
+  size_t o_bf = 0, o_bp = 0, o_enc_rel = 0, o_dec_rel = 0, o_tail = 0;
   float* P = nullptr; float* G = nullptr; bf16* W = nullptr;
   int enc_bucket_h[128] = {0}, dec_bucket_h[128] = {0};   // host copies of the rel -> bucket maps (go into kernel params)
   const int* enc_bucket = nullptr; const int* dec_bucket = nullptr;
@@ -96,6 +96,8 @@ struct Engine {
   std::vector<cudaEvent_t> ev_opt;
   cudaEvent_t ev_opt_fork = nullptr;
   bool opt_pending = false;
+  std::vector<cudaEvent_t> ext_ev;   // host-owned "chunk k gathered" events of the sharded optimizer (vqacl_set_param_events)
+  bool ext_pending = false;
   // engine-owned scratch that must survive workspace re-binds (an overlapped optimizer step reads the gradient norm after
   // step() returned, possibly after the next train_step re-carved the workspace): [0,4) sumsq | [4,8) device error flags
   // | [64, 64 + OPT_PARTIALS) sum-of-squares partials

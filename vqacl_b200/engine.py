@@ -77,6 +77,9 @@ def _declare(L):
     L.vqacl_clip_adamw.argtypes = [c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_float, c_float, c_int,
                                    c_float, c_void_p, c_int, c_void_p]
     L.vqacl_param_sync.argtypes = [c_void_p, c_void_p]
+    L.vqacl_arena_tail.argtypes = [c_void_p]
+    L.vqacl_arena_tail.restype = c_int64
+    L.vqacl_set_param_events.argtypes = [c_void_p, POINTER(c_void_p), c_int]
     L.vqacl_device_errors.argtypes = [c_void_p, POINTER(c_int), c_void_p]
     L.vqacl_grad_sumsq_ranges.argtypes = [c_void_p, POINTER(c_int64), POINTER(c_int64), c_int, c_void_p, c_void_p]
     L.vqacl_adamw_range.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_float, c_float, c_float, c_float, c_float,
@@ -147,6 +150,7 @@ class Engine:
         nd, nt = c_int64(), c_int64()
         self.n_total = L.vqacl_arena_elems(h, byref(nd), byref(nt))
         self.n_decay, self.n_train = nd.value, nt.value
+        self.n_tail = L.vqacl_arena_tail(h)      # [0, n_tail): GEMM-only matrices; [n_tail, n_train): fp32-read parameters
         with torch.cuda.device(self.device):
             self.P = torch.zeros(self.n_total, dtype=torch.float32, device=self.device)
             self.G = torch.zeros(self.n_total, dtype=torch.float32, device=self.device)
@@ -229,6 +233,24 @@ class Engine:
     def loss_tail(self, labels, scores, B, T, loss_out, w_rows):
         lr = self.ws_tensor("loss_rows", torch.float32, (B * T,))
         check(self.L.vqacl_loss_tail(ptr(lr), ptr(labels), ptr(scores), B, T, ptr(loss_out), ptr(w_rows), cur_stream()))
+
+    def set_param_events(self, events):
+        """events: one torch.cuda.Event (or None) per parameter chunk, or [] to clear."""
+        n = len(events)
+        arr = (c_void_p * max(n, 1))(*[c_void_p(ev.cuda_event) if ev is not None else c_void_p(0) for ev in events])
+        check(self.L.vqacl_set_param_events(self.h, arr, n))
+
+    def param_chunks(self):
+        """Arena ranges of the parameter chunks the forward waits for, in forward order (engine.cu: vqacl_clip_adamw)."""
+        t = self.table
+        Le, Ld = self.cfg.num_layers, self.cfg.num_decoder_layers
+        oWf = t["encoder.visual_embedding.feat_embedding.0.weight"][0]
+        enc = [t[f"encoder.block.{l}.layer.0.SelfAttention.q.weight"][0] for l in range(Le)]
+        out = [(oWf, self.n_train)]
+        for l in range(Le):
+            out.append((enc[l], enc[l + 1] if l + 1 < Le else oWf))
+        out.append((0, enc[0] if Le else oWf))
+        return out
 
     def set_memory_loss_grads(self, g2):
         """g2: device fp32[2] = d loss / d (loss_memory_Q, loss_memory_V) for the next backward, or None."""
