@@ -55,7 +55,40 @@ def _worker(rank, world, port, q):
                 dist.all_reduce(arena[a:b])
                 arena[a:b] /= world
         ok2 = torch.allclose(arena[100:], whole[100:], rtol=0, atol=1e-7)
-        q.put((rank, ok1, ok2))
+        # sharded step tail == replicated step tail: reduce-scatter (emulated: gloo has none) + AdamW on the owned slices +
+        # all-gather, tail all-reduced and updated everywhere, global norm from owned slices (+ tail once)
+        from vqacl_b200.modeling import owned_slices, plan_shards
+        n_tail, n_train = 960, 1040
+        sranges = [(0, 0), (320, 480), (160, 320), (0, 160), (480, 640), (800, 960), (640, 800), (960, 1040)]
+        _, buckets, tail = plan_shards(sranges, n_tail, n_train, 200, world)
+        gen = torch.Generator().manual_seed(200 + rank)
+        g_local = torch.randn(n_train, generator=gen)
+        p0 = torch.randn(n_train, generator=torch.Generator().manual_seed(5))
+        g_avg = g_local.clone()
+        dist.all_reduce(g_avg)
+        g_avg /= world
+
+        def adam(p, g, coef):          # first HF-AdamW step (m = v = 0), lr 0.1
+            g = g * coef
+            m, v = 0.1 * g, 0.001 * g * g
+            return p - 0.1 * (0.001 ** 0.5 / 0.1) * m / (v.sqrt() + 1e-6)
+        coef_full = min(1.0, 5.0 / (g_avg.norm().item() + 1e-6))
+        want = adam(p0, g_avg, coef_full)
+        own = owned_slices(buckets, world, rank)
+        ss = sum(float((g_avg[a:b] ** 2).sum()) for a, b in own) + (float((g_avg[tail[0]:tail[1]] ** 2).sum()) if rank == 0 else 0.0)
+        t = torch.tensor([ss], dtype=torch.float64)
+        dist.all_reduce(t)
+        coef = min(1.0, 5.0 / (t.item() ** 0.5 + 1e-6))
+        p = p0.clone()
+        for a, b in own:
+            p[a:b] = adam(p0[a:b], g_avg[a:b], coef)
+        p[tail[0]:tail[1]] = adam(p0[tail[0]:tail[1]], g_avg[tail[0]:tail[1]], coef)
+        for (a, b), (oa, ob) in zip(buckets, own):
+            parts = [torch.empty(ob - oa) for _ in range(world)]
+            dist.all_gather(parts, p[oa:ob].clone())
+            p[a:b] = torch.cat(parts)
+        ok3 = abs(coef - coef_full) < 1e-6 and torch.allclose(p, want, rtol=1e-5, atol=1e-6)
+        q.put((rank, ok1, ok2 and ok3))
     finally:
         dist.destroy_process_group()
 

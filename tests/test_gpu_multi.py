@@ -84,3 +84,77 @@ def test_two_gpu_step_equals_global_batch():
         p.join(timeout=60)
     for rank, ok, msg in res:
         assert ok, f"rank {rank}: {msg}"
+
+
+def _worker_sharded(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from helpers import O, cos, make_pair
+        import vqacl_b200 as V
+        B, steps = 16, 3
+        _, m = make_pair(layers=2, device=f"cuda:{rank}")
+        m.train()
+        m.grad_bucket_elems = 1 << 20
+        before = {k: v.clone() for k, v in m.state_dict().items()}
+        opt = V.FusedAdamW(m, lr=1e-3, overlap_with_next_forward=True)        # shard_state=None -> sharded (2 ranks)
+        assert opt.shard and m.shard_optimizer and opt.exp_avg.numel() < 0.75 * m._engine.n_train
+        for i in range(steps):
+            full = O.synthetic_batch(B, seed=500 + i, task_id=1, rehearsal=(i == 2))
+            shard = {k: v[rank * B // world:(rank + 1) * B // world].clone() for k, v in full.items()}
+            m.train_step(shard, 1, 0.5, 0.3)["loss"].backward()
+            opt.step(max_grad_norm=5.0)
+            opt.zero_grad()
+        toks = m.test_step(O.synthetic_batch(8, seed=9))["token_ids"]       # generate right after an overlapped sharded step
+        after = m.state_dict()                                              # all-gathers the fp32 masters
+        ok, msg = True, ""
+        if rank == 0:
+            _, ref = make_pair(layers=2, device="cuda:0")
+            ref.train()
+            ref.sync_grads = ref.sync_prototypes = False
+            ropt = V.FusedAdamW(ref, lr=1e-3, shard_state=False)
+            for i in range(steps):
+                full = O.synthetic_batch(B, seed=500 + i, task_id=1, rehearsal=(i == 2))
+                ref.train_step(full, 1, 0.5, 0.3)["loss"].backward()
+                ropt.step(max_grad_norm=5.0)
+                ropt.zero_grad()
+            rafter = ref.state_dict()
+            worst = (1.0, "")
+            for k in after:
+                du, dr = (after[k] - before[k]).float(), (rafter[k] - before[k]).float()
+                if dr.abs().max() == 0:
+                    continue
+                c = cos(du, dr)
+                if c < worst[0]:
+                    worst = (c, k)
+            rtoks = ref.test_step(O.synthetic_batch(8, seed=9))["token_ids"]
+            gn = abs(opt.grad_sumsq.item() - ropt.grad_sumsq.item()) / ropt.grad_sumsq.item()
+            ok = worst[0] > 0.99 and gn < 1e-3 and torch.equal(toks.cpu(), rtoks.cpu())
+            msg = f"worst update cosine {worst[0]:.5f} ({worst[1]}), grad-norm^2 rel diff {gn:.2e}, same answers {torch.equal(toks.cpu(), rtoks.cpu())}"
+        mine = torch.stack([v.double().sum() for v in after.values()])
+        other = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(other, mine)
+        same = all(torch.equal(o, other[0]) for o in other)
+        q.put((rank, ok and same, msg + f" identical-weights-across-ranks {same}"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_sharded_optimizer_equals_single_process():
+    """Reduce-scattered gradients + AdamW on each rank's slices + all-gathered bf16 weights (overlapped with the next forward)
+    leave every rank with the weights ONE process reaches on the global batch with the replicated optimizer."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_sharded, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, ok, msg in res:
+        assert ok, f"rank {rank}: {msg}"
+    print("2-GPU sharded step:", [m for _, _, m in res])

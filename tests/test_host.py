@@ -132,3 +132,59 @@ def test_scheduler_and_bucket_table_helpers():
     assert t.shape == (127,) and t[63] == 0 and t[64] == 0 and t[62] == 1      # unidirectional: future keys -> bucket 0
     t = rel_bucket_table(True)
     assert t[63] == 0 and t[64] == 17 and t[62] == 1
+
+
+def _host_engine_layout(layers=12):
+    """Arena layout + backward stage ranges straight from the C library (pure host code: no GPU needed)."""
+    from ctypes import POINTER, byref, c_int64, c_void_p
+    from vqacl_b200._lib import check, lib
+    from vqacl_b200.engine import CConfig, _declare
+    L = lib()
+    _declare(L)
+    c = V.VLT5Config(vocab_size=32200, num_layers=layers, num_decoder_layers=layers)
+    cc = CConfig(vocab_size=c.vocab_size, d_model=c.d_model, d_kv=c.d_kv, n_heads=c.num_heads, d_ff=c.d_ff, n_enc_layers=layers,
+                 n_dec_layers=layers, n_buckets=32, feat_dim=2048, n_images=2, n_ques=10, n_cate=80, split_L=20, pad_id=0, eos_id=1,
+                 start_id=0, eps=1e-6, dropout=0.0)
+    h = c_void_p()
+    check(L.vqacl_engine_create(byref(cc), byref(h)))
+    nd, nt = c_int64(), c_int64()
+    total = L.vqacl_arena_elems(h, byref(nd), byref(nt))
+    tail = L.vqacl_arena_tail(h)
+    ranges = []
+    for s in range(L.vqacl_backward_stages(h)):
+        a, b = c_int64(), c_int64()
+        check(L.vqacl_backward_stage_range(h, s, byref(a), byref(b)))
+        ranges.append((a.value, b.value))
+    L.vqacl_engine_destroy(h)
+    return ranges, tail, nd.value, nt.value, total
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_shard_plan_tiles_the_sharded_region_of_the_real_arena(world):
+    """The reduce-scatter buckets of the sharded step tail tile [0, tail) of the engine's arena exactly once, every bucket
+    splits into `world` 32-byte aligned slices, stage order is respected, and the decay boundary lies in the tail."""
+    from vqacl_b200.modeling import owned_slices, plan_shards
+    ranges, tail, n_decay, n_train, total = _host_engine_layout()
+    assert 0 < tail < n_decay <= n_train <= total and n_train - tail < 0.15 * n_train      # the replicated tail is small
+    flush_after, buckets, (ta, tb) = plan_shards(ranges, tail, n_train, 8 << 20, world)
+    assert (ta, tb) == (tail, n_train)
+    cover = sorted(buckets)
+    assert cover[0][0] == 0 and cover[-1][1] == tail
+    for (a0, b0), (a1, b1) in zip(cover, cover[1:]):
+        assert b0 == a1
+    for s, lst in flush_after.items():
+        for a, b in lst:        # a bucket flushed after stage s only holds ranges of stages <= s
+            assert all(not (ra < b and min(rb, tail) > a) or st <= s for st, (ra, rb) in enumerate(ranges) if min(rb, tail) > ra)
+    owned = [owned_slices(buckets, world, r) for r in range(world)]
+    for i, (a, b) in enumerate(buckets):
+        parts = sorted(o[i] for o in owned)
+        assert parts[0][0] == a and parts[-1][1] == b and all(p[0] % 8 == 0 and (p[1] - p[0]) == (b - a) // world for p in parts)
+
+
+def test_chunk_events_map_forward_chunks_to_gathered_buckets():
+    from vqacl_b200.modeling import chunk_events
+    buckets_backward = [(0, 40), (40, 100), (100, 160), (160, 200)]       # decoder ... encoder, as backward finishes them
+    gather_order = buckets_backward[::-1]                                  # forward order: encoder side first
+    chunks = [(190, 260), (150, 190), (100, 150), (0, 100)]               # tail+visual, enc layer 0, enc layer 1, decoder
+    assert chunk_events(chunks, gather_order) == [0, 1, 1, 3]
+    assert chunk_events([(200, 260)], gather_order) == [None]              # nothing sharded in a pure-tail chunk

@@ -222,6 +222,39 @@ def plan_grad_buckets(stage_ranges, min_elems):
     return out
 
 
+def plan_shards(stage_ranges, n_tail, n_train, min_elems, world):
+    """Reduce-scatter plan of the sharded step tail (N > 1 GPUs).
+
+    The arena is [0, n_tail) GEMM-only matrices | [n_tail, n_train) parameters every rank reads in fp32 (engine layout).
+    The first region is reduce-scattered in buckets (the stage ranges clipped to it, merged like plan_grad_buckets): rank r
+    then owns elements [a + r * (b - a) / world, a + (r + 1) * (b - a) / world) of bucket (a, b), runs AdamW on them and
+    all-gathers the refreshed bf16 weights into the same bucket. The tail is all-reduced after the last stage and updated by
+    every rank. Returns (flush_after {stage: [(a, b), ...]}, buckets [(a, b), ...] in backward order, tail (a, b))."""
+    clipped = [(min(a, n_tail), min(b, n_tail)) for a, b in stage_ranges]
+    flush_after = plan_grad_buckets(clipped, min_elems)
+    buckets = [ab for s in sorted(flush_after) for ab in flush_after[s]]
+    for a, b in buckets:
+        if (b - a) % (8 * world) or a % 8:
+            raise VqaclError(f"bucket [{a}, {b}) cannot be split into {world} 32-byte aligned slices")
+    return flush_after, buckets, (n_tail, n_train)
+
+
+def owned_slices(buckets, world, rank):
+    return [(a + rank * ((b - a) // world), a + (rank + 1) * ((b - a) // world)) for a, b in buckets]
+
+
+def chunk_events(chunks, buckets_in_gather_order):
+    """For every parameter chunk (a, b) the index of the LAST gathered bucket that overlaps it (None: no sharded data in it)."""
+    out = []
+    for ca, cb in chunks:
+        last = None
+        for i, (a, b) in enumerate(buckets_in_gather_order):
+            if a < cb and ca < b:
+                last = i
+        out.append(last)
+    return out
+
+
 class VLT5(nn.Module):
     def __init__(self, config: VLT5Config):
         super().__init__()
@@ -257,6 +290,12 @@ class VLT5(nn.Module):
         self._comm_stream = None
         self.grad_bucket_elems = 8 << 20   # ~32 MB fp32 per NCCL all-reduce bucket
         self.comm_sms = 0                  # SMs to leave to NCCL during backward (0: none reserved — measured neutral at 8 GPUs)
+        # N > 1: reduce-scatter gradients instead of all-reducing them and let FusedAdamW update only this rank's slices
+        # (set by FusedAdamW(shard_state=...)); fp32 masters of the other ranks' slices are refreshed by gather_params()
+        self.shard_optimizer = False
+        self._shard_plan = None
+        self._masters_stale = False
+        self._param_events = None
 
     # -- construction helpers the reference calls --------------------------------------------------------------------
     @classmethod
@@ -375,8 +414,32 @@ class VLT5(nn.Module):
         if getattr(self, "_engine", None) is not None:
             self._engine.param_sync()
 
+    def grad_shard_plan(self):
+        """(flush_after, buckets, tail) of the sharded step tail for the current world size (cached)."""
+        world = self._world()
+        if self._shard_plan is None or self._shard_plan[0] != world:
+            eng = self._engine
+            ranges = [eng.backward_stage_range(s) for s in range(eng.n_backward_stages())]
+            self._shard_plan = (world,) + plan_shards(ranges, eng.n_tail, eng.n_train, self.grad_bucket_elems, world)
+        return self._shard_plan[1:]
+
+    def gather_params(self):
+        """Sharded optimizer: all-gather the fp32 master weights of the GEMM matrices (each rank only updates its own slices;
+        the forward runs on the all-gathered bf16 copies). Needed before reading parameters: state_dict() calls it."""
+        if not self._masters_stale:
+            return
+        import torch.distributed as dist
+        eng = self._engine
+        self.param_sync()
+        _, buckets, _ = self.grad_shard_plan()
+        world, rank = dist.get_world_size(), dist.get_rank()
+        for (a, b), (oa, ob) in zip(buckets, owned_slices(buckets, world, rank)):
+            dist.all_gather_into_tensor(eng.P[a:b], eng.P[oa:ob])
+        self._masters_stale = False
+
     def state_dict(self, *a, **kw):
         self.param_sync()
+        self.gather_params()
         if getattr(self, "_engine", None) is not None:
             self._engine.check_device_errors()      # checkpoint time at the latest (the step itself never synchronises)
         return super().state_dict(*a, **kw)
@@ -542,16 +605,27 @@ class VLT5(nn.Module):
         main = torch.cuda.current_stream()
         n = eng.n_backward_stages()
         ranges = [eng.backward_stage_range(s) for s in range(n)]
-        flush_after = plan_grad_buckets(ranges, self.grad_bucket_elems)
+        shard = self.shard_optimizer
+        if shard:
+            flush_after, buckets, tail = self.grad_shard_plan()
+            world, rank = dist.get_world_size(), dist.get_rank()
+        else:
+            flush_after = plan_grad_buckets(ranges, self.grad_bucket_elems)
         n_sms = torch.cuda.get_device_properties(eng.device).multi_processor_count
         if self.comm_sms > 0:
             eng.set_gemm_sm_limit(n_sms - self.comm_sms)     # keep a few SMs free so the collectives' CTAs become resident
 
         def on_stage(s):
             # the engine has already made the communication stream wait for stage s on both of its streams
-            for a, b in flush_after.get(s, ()):
-                with torch.cuda.stream(self._comm_stream):
-                    dist.all_reduce(eng.G[a:b], op=dist.ReduceOp.AVG)
+            with torch.cuda.stream(self._comm_stream):
+                for a, b in flush_after.get(s, ()):
+                    if shard:      # in place: this rank's slice of the bucket receives the average, the rest is scratch
+                        k = (b - a) // world
+                        dist.reduce_scatter_tensor(eng.G[a + rank * k:a + (rank + 1) * k], eng.G[a:b], op=dist.ReduceOp.AVG)
+                    else:
+                        dist.all_reduce(eng.G[a:b], op=dist.ReduceOp.AVG)
+                if shard and s == n - 1:
+                    dist.all_reduce(eng.G[tail[0]:tail[1]], op=dist.ReduceOp.AVG)
 
         eng.backward_overlapped(w_rows, False, self._comm_stream, on_stage, gscale=gscale)
         eng.set_gemm_sm_limit(0)
