@@ -33,6 +33,14 @@ FLOP_PER_SAMPLE_STEP = 37.79e9          # forward 12.634 GFLOP
 METRIC = "VQACL train samples/s (VL-T5 base, 36 RoIs)"
 
 
+def step_flops(N=36, L=20, T=5, d=768, f=3072, V=32200, F=2048, Le=12, Ld=12):
+    """Algorithmic tensor FLOPs of one train step per sample (SURVEY.md §8d formulas; 37.79e9 at the configs[1] shape)."""
+    S, S2 = L + N, L + N + 2
+    fwd = (N * 2 * (F + 5) * d + Le * (8 * S * d * d + 4 * S * S * d + 4 * S * d * f)
+           + Ld * (8 * T * d * d + 4 * T * T * d + 4 * T * d * d + 4 * S2 * d * d + 4 * T * S2 * d + 4 * T * d * f) + 2 * T * d * V)
+    return 3 * fwd - N * 2 * F * d
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -210,7 +218,7 @@ def run_native(args):
     pool = 4
     host, devb = [], []
     for i in range(pool):
-        b = O.synthetic_batch(B, seed=1234 + rank * 1000 + i, task_id=task, rehearsal=(i % 2 == 1))
+        b = O.synthetic_batch(B, seed=1234 + rank * 1000 + i, task_id=task, rehearsal=(i % 2 == 1), n_boxes=args.boxes)
         hb = {k: v.pin_memory() for k, v in b.items()}
         host.append(hb)
         devb.append({k: v.to(dev) for k, v in b.items()})
@@ -280,13 +288,14 @@ def run_native(args):
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get("dram_bytes_per_step")
     if rank == 0:
-        tf = value / world * FLOP_PER_SAMPLE_STEP / 1e12
+        flop = FLOP_PER_SAMPLE_STEP if args.boxes == 36 else step_flops(N=args.boxes)
+        tf = value / world * flop / 1e12
         line = {
             "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"configs[1]: VL-T5 base (T5-base geometry, random init, vocab 32200) VQACL train step, batch {B} per GPU, "
-                                   f"36 RoIs x 2048-d + boxes, 20 question tokens, 5 target tokens, SS encoder + SI prototype bank "
+                                   f"{args.boxes} RoIs x 2048-d + boxes, 20 question tokens, 5 target tokens, SS encoder + SI prototype bank "
                                    f"(10 question types + 80 object classes), dropout {args.dropout}, task id {task}, "
                                    "fwd + bwd + clip_grad_norm_(5) + HF AdamW",
                        "global_batch": B * world,
@@ -303,7 +312,7 @@ def run_native(args):
                          "frac": round(tf / pk["sustained"], 4), "traffic": traffic,
                          "traffic_note": "DRAM bytes read + written by all kernels of one step (ncu dram__bytes_read/write.sum over a step window, "
                                          "profiles/r02_step_dram_traffic.json); null until captured",
-                         "kernel": "whole train step: algorithmic 37.79 GFLOP/sample (98.7% in gemm_bf16_tcgen05 launches) / step time, per GPU",
+                         "kernel": f"whole train step: algorithmic {flop / 1e9:.2f} GFLOP/sample (98.7% in gemm_bf16_tcgen05 launches) / step time, per GPU",
                          "peak_source": pk["source"] + " sustained bf16 (kernel timed inside a long step)"},
         }
         if not args.no_kernel_roofline:
@@ -414,6 +423,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--batch", type=int, default=320)
     ap.add_argument("--dropout", type=float, default=0.1)
+    ap.add_argument("--boxes", type=int, default=36,
+                    help="visual tokens per sample (36 = configs[1]; 16 = NExT-QA; 64 / 128 = the configs[3] longer-visual-sequence sweep)")
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--mode", default="train", choices=["train", "decode"],
                     help="train: configs[1] train step (the BASELINE.json metric); decode: configs[4] greedy evaluation, batch 512")

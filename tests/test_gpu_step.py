@@ -371,6 +371,27 @@ def test_edge_shapes(B, L, T, N):
 
 def test_oversized_shapes_fail_loudly():
     _, m = make_pair(layers=1)
-    b = O.synthetic_batch(2, seed=1, L=20, n_boxes=43)          # 63 encoder tokens (+2 prototype rows) > 64 keys
+    b = O.synthetic_batch(2, seed=1, L=20, n_boxes=235)         # 255 encoder tokens (+2 prototype rows) > 256 keys
     with pytest.raises(V.VqaclError):
         m.train_step(b, 0, 0.5, 0.3)
+
+
+@pytest.mark.parametrize("N,L,B", [(43, 20, 3), (64, 20, 4), (128, 23, 3), (234, 20, 2)])
+def test_long_visual_sequence_multi_tile_attention(N, L, B):
+    """configs[3] "longer visual sequence": more than 62 encoder tokens (e.g. 8 frames x 16 clip features = 128 visual
+    tokens) run on the generic multi-tile attention kernels — encoder self-attention over L + N keys, decoder
+    cross-attention over L + N + 2 — with the same gates as every other shape, training and greedy decoding."""
+    om, m = make_pair(layers=2, vocab=2048)
+    om.train(); m.train()
+    for i, task in enumerate((0, 2)):
+        b = O.synthetic_batch(B, seed=60 + i + N, L=L, T=4, n_boxes=N, task_id=task, vocab=2000)
+        _check_step(om, m, b, task)
+        for p in om.parameters():
+            p.grad = None
+        V.FusedAdamW(m).zero_grad()
+    om.eval(); m.eval()
+    b = O.synthetic_batch(B, seed=99 + N, L=L, n_boxes=N, vocab=2000)
+    ours = m.test_step(b)["token_ids"].cpu()
+    ref = om.generate(b["input_ids"], b["vis_feats"], b["boxes"], max_length=12).cpu()
+    n = min(ours.shape[1], ref.shape[1])
+    assert torch.equal(ours[:, :n], ref[:, :n])

@@ -923,8 +923,394 @@ __global__ void __launch_bounds__(KS_WARPS * 32, 5) attn_ks_bwd_kernel(const Att
   }
 }
 
+
+// =====================================================================================================================
+// Generic multi-tile kernels: up to MT_MAX queries x MT_MAX keys per (batch, head) problem, in 64 x 64 tiles. They serve the
+// shapes the single-tile kernels above reject — a longer visual sequence (BASELINE.json configs[3]: NExT-QA-style clip
+// features, L + N up to 254 encoder tokens, and the decoder's cross-attention to those L + N + 2 memory rows). One 4-warp
+// CTA owns one problem and keeps Q, K, V (backward: + dO) of the whole problem in shared memory.
+//   forward : per 64-row query tile, flash-style online softmax over the key tiles (running max / sum / O in registers)
+//   backward: P is recomputed from the saved log-sum-exp, D = rowsum(dO * O) from the saved output.
+//             pass A — query tile outer, key tile inner: dQ accumulates in registers;
+//             pass B — key tile outer, query tile inner: P / dS of the tile pair go through two shared 64 x 64 tiles and
+//             dK / dV accumulate in registers (the tile math is done twice; QK^T / PV are ~1 % of the step's FLOPs).
+// The relative-position bias exists only between text tokens (Lt <= 64), i.e. inside tile pair (0, 0).
+// =====================================================================================================================
+constexpr int MT_MAX = 256;
+VQ_DEVINL uint32_t mt_pair_idx(uint32_t blk, int q, int k) { return ((blk * MT_MAX + (uint32_t)q) * MT_MAX + (uint32_t)k) >> 1; }
+VQ_DEVINL int rows64(int n) { return (n + 63) & ~63; }
+constexpr int MT_HDR_FLOATS = 2 * AT_S + MT_MAX + 64;   // bias[128] | kmask[256] | dbucket[64]
+static inline int mt_smem_fwd(int Sq, int Sk) { return MT_HDR_FLOATS * 4 + (((Sq + 15) & ~15) + 2 * ((Sk + 63) & ~63)) * AT_P * 2; }
+static inline int mt_smem_bwd(int Sq, int Sk) {
+  return MT_HDR_FLOATS * 4 + 2 * MT_MAX * 4 + (2 * ((Sq + 15) & ~15) + 2 * ((Sk + 63) & ~63) + 2 * AT_S) * AT_P * 2;
+}
+
+template <int NW>
+VQ_DEVINL void mt_load_header(float* sbias, float* skmask, const AttnArgs& p, const AttnBuckets& bk, int b, int h, int tid) {
+  if (p.rel_mode)
+    for (int r = tid; r < 2 * AT_S - 1; r += NW * 32) sbias[r] = p.rel_table[(int)bk.b[r] * p.H + h];
+  for (int j = tid; j < MT_MAX; j += NW * 32) skmask[j] = j < p.Sk ? (p.keymask ? p.keymask[(size_t)b * p.Sk + j] : 0.f) : -INFINITY;
+}
+
+__global__ void __launch_bounds__(128) attn_mt_fwd_kernel(const AttnArgs p, const __grid_constant__ AttnBuckets bk) {
+  vq_pdl_trigger();
+  vq_pdl_wait();
+  extern __shared__ __align__(16) uint8_t at_smem_base[];
+  const int vblk = blockIdx.x, b = vblk / p.H, h = vblk % p.H;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  float* sbias = reinterpret_cast<float*>(at_smem_base);
+  float* skmask = sbias + 2 * AT_S;
+  AttnTile sq = reinterpret_cast<AttnTile>(at_smem_base + MT_HDR_FLOATS * 4);
+  AttnTile sk = sq + rows16(p.Sq);
+  AttnTile sv = sk + rows64(p.Sk);
+  {
+    const AttnTile dst[3] = {sq, sk, sv};
+    const __nv_bfloat16* const src[3] = {p.q + (size_t)b * (p.q_bstride ? p.q_bstride : (long long)p.Sq * p.ldq) + h * AT_D,
+                                         p.k + (size_t)b * (p.k_bstride ? p.k_bstride : (long long)p.Sk * p.ldk) + h * AT_D,
+                                         p.v + (size_t)b * (p.v_bstride ? p.v_bstride : (long long)p.Sk * p.ldv) + h * AT_D};
+    const int ld[3] = {p.ldq, p.ldk, p.ldv};
+    const int rows[3] = {p.Sq, p.Sk, p.Sk};
+    const int fill[3] = {rows16(p.Sq), rows64(p.Sk), rows64(p.Sk)};
+    mt_load_header<4>(sbias, skmask, p, bk, b, h, tid);
+    load_heads<4, 3>(dst, src, ld, rows, fill, tid);
+  }
+  __syncthreads();
+  const int nqt = (p.Sq + 63) >> 6, nkt = (p.Sk + 63) >> 6;
+  for (int i = 0; i < nqt; ++i) {
+    const int m0 = warp * 16, qrow0 = i * 64 + m0;
+    if (qrow0 >= p.Sq) continue;                           // no barrier inside this loop: warps are independent
+    float mrun[2] = {-INFINITY, -INFINITY}, lrun[2] = {0.f, 0.f};
+    float o[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int x = 0; x < 4; ++x) o[nt][x] = 0.f;
+    for (int j = 0; j < nkt; ++j) {
+      AttnArgs pt = p;
+      pt.rel_mode = (i == 0 && j == 0) ? p.rel_mode : 0;   // bias only in the text x text corner
+      pt.causal = 0;
+      float s[8][4];
+      scores_tile<8>(s, sq + i * 64, sk + j * 64, sbias, skmask + j * 64, pt, m0, lane);
+      float mx[2] = {mrun[0], mrun[1]};
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int x = 0; x < 4; ++x) mx[x >> 1] = fmaxf(mx[x >> 1], s[nt][x]);
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+      }
+      float sc[2], sum[2] = {0.f, 0.f};
+#pragma unroll
+      for (int r = 0; r < 2; ++r) sc[r] = mrun[r] == -INFINITY ? 0.f : __expf(mrun[r] - mx[r]);   // key 0 exists: mx is finite
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+          const float e = __expf(s[nt][x] - mx[x >> 1]);
+          s[nt][x] = e;
+          sum[x >> 1] += e;
+        }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 1);
+        sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 2);
+        lrun[r] = lrun[r] * sc[r] + sum[r];
+        mrun[r] = mx[r];
+      }
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        o[nt][0] *= sc[0]; o[nt][1] *= sc[0]; o[nt][2] *= sc[1]; o[nt][3] *= sc[1];
+      }
+      if (p.drop_thr) {
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            float d0, d1;
+            vq_dropout_pair(p.seed, mt_pair_idx(vblk, qrow0 + g + r * 8, j * 64 + nt * 8 + 2 * t), p.drop_thr, p.drop_inv_keep, d0, d1);
+            s[nt][2 * r] *= d0;
+            s[nt][2 * r + 1] *= d1;
+          }
+      }
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        uint32_t a[4];
+        a[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
+        a[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
+        a[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+        a[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+        for (int nt = 0; nt < 8; nt += 2) {
+          uint32_t bb[4];
+          frag_b2_t(bb, sv + j * 64, nt * 8, kk * 16, lane);
+          mma2(o[nt], o[nt + 1], a, bb);
+        }
+      }
+    }
+    const float inv[2] = {1.f / lrun[0], 1.f / lrun[1]};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      o[nt][0] *= inv[0]; o[nt][1] *= inv[0]; o[nt][2] *= inv[1]; o[nt][3] *= inv[1];
+    }
+    if (t == 0 && p.lse) {
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int qi = qrow0 + g + r * 8;
+        if (qi < p.Sq) p.lse[((size_t)b * p.H + h) * p.Sq + qi] = mrun[r] + __logf(lrun[r]);
+      }
+    }
+    // this warp's 16 rows of the q tile are dead: stage O there and write full 128-byte rows
+    store_tile16(sq + i * 64, m0, o, p.o + (size_t)b * (p.o_bstride ? p.o_bstride : (long long)p.Sq * p.ldo) + (size_t)i * 64 * p.ldo + h * AT_D,
+                 p.ldo, p.Sq - i * 64, lane);
+  }
+}
+
+struct MtSmemB { float *bias, *kmask, *dbucket, *lse, *D; AttnTile q, dO, k, v, P, dS; };
+
+// P and dS of the tile pair (query tile i rows [16 warp, 16 warp + 16), key tile j) in the m16n8 accumulator layout of this
+// warp: ds[nt][x]; optionally also written (P with the dropout scale folded in, for dV) to the shared P / dS tiles
+template <bool STORE>
+VQ_DEVINL void mt_tile_p_ds(float (&ds)[8][4], const AttnArgs& p, const MtSmemB& sm, int vblk, int i, int j, int m0, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  AttnArgs pt = p;
+  pt.rel_mode = (i == 0 && j == 0) ? p.rel_mode : 0;
+  pt.causal = 0;
+  float s[8][4], dp[8][4];
+  scores_tile<8>(s, sm.q + i * 64, sm.k + j * 64, sm.bias, sm.kmask + j * 64, pt, m0, lane);
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+    for (int x = 0; x < 4; ++x) dp[nt][x] = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    uint32_t a[4];
+    frag_a(a, sm.dO + i * 64, m0, kk * 16, lane);
+#pragma unroll
+    for (int nt = 0; nt < 8; nt += 2) {
+      uint32_t bb[4];
+      frag_b2(bb, sm.v + j * 64, nt * 8, kk * 16, lane);
+      mma2(dp[nt], dp[nt + 1], a, bb);
+    }
+  }
+  float lse[2], Dr[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int qi = i * 64 + m0 + g + r * 8;
+    lse[r] = qi < p.Sq ? sm.lse[qi] : INFINITY;     // rows >= Sq: P = 0
+    Dr[r] = qi < p.Sq ? sm.D[qi] : 0.f;
+  }
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int qi = i * 64 + m0 + g + r * 8, kj = j * 64 + nt * 8 + 2 * t;
+      float sc0 = 1.f, sc1 = 1.f;
+      if (p.drop_thr) vq_dropout_pair(p.seed, mt_pair_idx(vblk, qi, kj), p.drop_thr, p.drop_inv_keep, sc0, sc1);
+      const float p0 = __expf(s[nt][2 * r] - lse[r]), p1 = __expf(s[nt][2 * r + 1] - lse[r]);
+      const float d0 = p0 * (dp[nt][2 * r] * sc0 - Dr[r]), d1 = p1 * (dp[nt][2 * r + 1] * sc1 - Dr[r]);
+      ds[nt][2 * r] = d0;
+      ds[nt][2 * r + 1] = d1;
+      if (STORE) {
+        *reinterpret_cast<uint32_t*>(&sm.P[m0 + g + r * 8][nt * 8 + 2 * t]) = pack_bf16(p0 * sc0, p1 * sc1);
+        *reinterpret_cast<uint32_t*>(&sm.dS[m0 + g + r * 8][nt * 8 + 2 * t]) = pack_bf16(d0, d1);
+      }
+    }
+}
+
+__global__ void __launch_bounds__(128) attn_mt_bwd_kernel(const AttnArgs p, const __grid_constant__ AttnBuckets bk) {
+  vq_pdl_trigger();
+  vq_pdl_wait();
+  extern __shared__ __align__(16) uint8_t at_smem_base[];
+  const int vblk = blockIdx.x, b = vblk / p.H, h = vblk % p.H;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  MtSmemB sm;
+  sm.bias = reinterpret_cast<float*>(at_smem_base);
+  sm.kmask = sm.bias + 2 * AT_S;
+  sm.dbucket = sm.kmask + MT_MAX;
+  sm.lse = sm.dbucket + 64;
+  sm.D = sm.lse + MT_MAX;
+  sm.q = reinterpret_cast<AttnTile>(at_smem_base + (MT_HDR_FLOATS + 2 * MT_MAX) * 4);
+  sm.dO = sm.q + rows16(p.Sq);
+  sm.k = sm.dO + rows16(p.Sq);
+  sm.v = sm.k + rows64(p.Sk);
+  sm.P = sm.v + rows64(p.Sk);
+  sm.dS = sm.P + AT_S;
+  {
+    const AttnTile dst[4] = {sm.q, sm.dO, sm.k, sm.v};
+    const __nv_bfloat16* const src[4] = {p.q + (size_t)b * p.Sq * p.ldq + h * AT_D, p.dO + (size_t)b * p.Sq * p.ldo + h * AT_D,
+                                         p.k + (size_t)b * p.Sk * p.ldk + h * AT_D, p.v + (size_t)b * p.Sk * p.ldv + h * AT_D};
+    const int ld[4] = {p.ldq, p.ldo, p.ldk, p.ldv};
+    const int rows[4] = {p.Sq, p.Sq, p.Sk, p.Sk};
+    const int fill[4] = {rows16(p.Sq), rows16(p.Sq), rows64(p.Sk), rows64(p.Sk)};
+    mt_load_header<4>(sm.bias, sm.kmask, p, bk, b, h, tid);
+    for (int x = tid; x < 64; x += 128) sm.dbucket[x] = 0.f;
+    // D[q] = sum_d dO[q][d] * O[q][d] (the saved forward output), lse[q]: 8 threads per row
+    for (int base = 0; base < p.Sq; base += 16) {
+      const int qi = base + (tid >> 3), c0 = (tid & 7) * 8;
+      float acc = 0.f;
+      if (qi < p.Sq) {
+        const uint4 a = *reinterpret_cast<const uint4*>(p.dO + ((size_t)b * p.Sq + qi) * p.ldo + h * AT_D + c0);
+        const uint4 o = *reinterpret_cast<const uint4*>(p.o_saved + ((size_t)b * p.Sq + qi) * p.ldo + h * AT_D + c0);
+        const uint32_t aa[4] = {a.x, a.y, a.z, a.w}, oo[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+          const float2 u = unpack_bf16(aa[x]), w = unpack_bf16(oo[x]);
+          acc += u.x * w.x + u.y * w.y;
+        }
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      if ((tid & 7) == 0 && qi < p.Sq) {
+        sm.D[qi] = acc;
+        sm.lse[qi] = p.lse[((size_t)b * p.H + h) * p.Sq + qi];
+      }
+    }
+    load_heads<4, 4>(dst, src, ld, rows, fill, tid);
+  }
+  __syncthreads();
+  const int nqt = (p.Sq + 63) >> 6, nkt = (p.Sk + 63) >> 6;
+  const int m0 = warp * 16;
+  // ---- pass A: dQ (and the bias-table gradient from tile pair (0, 0)) ----
+  for (int i = 0; i < nqt; ++i) {
+    const bool has_q = i * 64 + m0 < p.Sq;
+    float dq[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int x = 0; x < 4; ++x) dq[nt][x] = 0.f;
+    for (int j = 0; j < nkt; ++j) {
+      const bool bias_tile = p.d_rel_table && p.rel_mode && i == 0 && j == 0;
+      float ds[8][4];
+      if (has_q) {
+        if (bias_tile) mt_tile_p_ds<true>(ds, p, sm, vblk, i, j, m0, lane);
+        else mt_tile_p_ds<false>(ds, p, sm, vblk, i, j, m0, lane);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          uint32_t a[4];
+          a[0] = pack_bf16(ds[2 * kk][0], ds[2 * kk][1]);
+          a[1] = pack_bf16(ds[2 * kk][2], ds[2 * kk][3]);
+          a[2] = pack_bf16(ds[2 * kk + 1][0], ds[2 * kk + 1][1]);
+          a[3] = pack_bf16(ds[2 * kk + 1][2], ds[2 * kk + 1][3]);
+#pragma unroll
+          for (int nt = 0; nt < 8; nt += 2) {
+            uint32_t bb[4];
+            frag_b2_t(bb, sm.k + j * 64, nt * 8, kk * 16, lane);
+            mma2(dq[nt], dq[nt + 1], a, bb);
+          }
+        }
+      }
+      if (bias_tile) {      // block-uniform condition
+        __syncthreads();
+        const int nq = min(p.Sq, p.Lt), nk = min(p.Sk, p.Lt);
+        const int ndiag = nq + nk - 1;
+        for (int dgi = tid; dgi < ndiag; dgi += 128) {
+          const int rel = dgi - (nq - 1);
+          const int q_lo = max(0, -rel), q_hi = min(nq, nk - rel);
+          float acc = 0.f;
+          for (int qi = q_lo; qi < q_hi; ++qi) acc += __bfloat162float(sm.dS[qi][qi + rel]);
+          if (q_hi > q_lo) atomicAdd(&sm.dbucket[(int)bk.b[rel + (AT_S - 1)]], acc);
+        }
+        __syncthreads();
+        for (int x = tid; x < 64; x += 128) {
+          const float v = sm.dbucket[x];
+          if (v != 0.f) atomicAdd(&p.d_rel_table[x * p.H + h], v);
+        }
+      }
+    }
+    if (has_q) {
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int qi = i * 64 + m0 + g + r * 8;
+        if (qi < p.Sq) {
+          __nv_bfloat16* dst = p.dq + ((size_t)b * p.Sq + qi) * p.lddq + h * AT_D + 2 * t;
+#pragma unroll
+          for (int nt = 0; nt < 8; ++nt) *reinterpret_cast<uint32_t*>(dst + nt * 8) = pack_bf16(dq[nt][2 * r], dq[nt][2 * r + 1]);
+        }
+      }
+    }
+  }
+  // ---- pass B: dK, dV ----
+  for (int j = 0; j < nkt; ++j) {
+    const bool has_k = j * 64 + m0 < p.Sk;
+    float dv[8][4], dk[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int x = 0; x < 4; ++x) dv[nt][x] = dk[nt][x] = 0.f;
+    for (int i = 0; i < nqt; ++i) {
+      __syncthreads();                                   // the previous tile pair's P / dS have been consumed
+      if (i * 64 + m0 < p.Sq) {
+        float ds[8][4];
+        mt_tile_p_ds<true>(ds, p, sm, vblk, i, j, m0, lane);
+      } else {
+        // this warp has no query rows in tile i: its 16 rows of P / dS must read as zero in the contraction below
+        for (int x = lane; x < 16 * (AT_D / 8); x += 32) {
+          *reinterpret_cast<uint4*>(&sm.P[m0 + (x >> 3)][(x & 7) * 8]) = make_uint4(0, 0, 0, 0);
+          *reinterpret_cast<uint4*>(&sm.dS[m0 + (x >> 3)][(x & 7) * 8]) = make_uint4(0, 0, 0, 0);
+        }
+      }
+      __syncthreads();
+      if (has_k) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          if (i * 64 + kk * 16 < p.Sq) {
+            uint32_t ap[4], as[4];
+            frag_a_t(ap, sm.P, m0, kk * 16, lane);
+            frag_a_t(as, sm.dS, m0, kk * 16, lane);
+#pragma unroll
+            for (int nt = 0; nt < 8; nt += 2) {
+              uint32_t b1[4], b2[4];
+              frag_b2_t(b1, sm.dO + i * 64, nt * 8, kk * 16, lane);
+              frag_b2_t(b2, sm.q + i * 64, nt * 8, kk * 16, lane);
+              mma2(dv[nt], dv[nt + 1], ap, b1);
+              mma2(dk[nt], dk[nt + 1], as, b2);
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();      // every warp is done reading K_j / V_j (scores, dP) before their rows become staging space
+    if (has_k) {
+      store_tile16(sm.k + j * 64, m0, dk, p.dk + ((size_t)b * p.Sk + (size_t)j * 64) * p.lddk + h * AT_D, p.lddk, p.Sk - j * 64, lane);
+      store_tile16(sm.v + j * 64, m0, dv, p.dv + ((size_t)b * p.Sk + (size_t)j * 64) * p.lddv + h * AT_D, p.lddv, p.Sk - j * 64, lane);
+    }
+  }
+}
+
+static int launch_mt_fwd(const AttnArgs& a, const AttnBuckets& bk, cudaStream_t stream) {
+  const int smem = mt_smem_fwd(a.Sq, a.Sk);
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
+    VQ_CUDA(cudaFuncSetAttribute(attn_mt_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mt_smem_fwd(MT_MAX, MT_MAX)));
+    attr_smem = mt_smem_fwd(MT_MAX, MT_MAX);
+  }
+  (void)vq_launch(attn_mt_fwd_kernel, dim3(a.B * a.H), dim3(128), (size_t)smem, stream, a, bk);
+  VQ_LAUNCH_CHECK();
+  return 0;
+}
+static int launch_mt_bwd(const AttnArgs& a, const AttnBuckets& bk, cudaStream_t stream) {
+  VQ_CHECK(a.o_saved, "attention bwd: the multi-tile backward needs the saved forward output (o_saved)");
+  const int smem = mt_smem_bwd(a.Sq, a.Sk);
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
+    VQ_CUDA(cudaFuncSetAttribute(attn_mt_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mt_smem_bwd(MT_MAX, MT_MAX)));
+    attr_smem = mt_smem_bwd(MT_MAX, MT_MAX);
+  }
+  (void)vq_launch(attn_mt_bwd_kernel, dim3(a.B * a.H), dim3(128), (size_t)smem, stream, a, bk);
+  VQ_LAUNCH_CHECK();
+  return 0;
+}
+
 static int check_args(const AttnArgs& a) {
-  VQ_CHECK(a.Sq >= 1 && a.Sq <= AT_S && a.Sk >= 1 && a.Sk <= AT_S, "attention: Sq=%d Sk=%d must be in [1,%d]", a.Sq, a.Sk, AT_S);
+  VQ_CHECK(a.Sq >= 1 && a.Sq <= MT_MAX && a.Sk >= 1 && a.Sk <= MT_MAX, "attention: Sq=%d Sk=%d must be in [1,%d]", a.Sq, a.Sk, MT_MAX);
+  if (a.Sq > AT_S || a.Sk > AT_S) {
+    VQ_CHECK(!a.causal && a.rel_mode != 2, "attention: causal / everywhere-biased (decoder self-) attention is limited to %d positions", AT_S);
+    VQ_CHECK(a.rel_mode == 0 || a.Lt <= AT_S, "attention: the biased text x text corner must fit one tile (Lt=%d)", a.Lt);
+    VQ_CHECK(!a.q_off, "attention: multi-tile problems take no query offset");
+  }
   VQ_CHECK(a.ldq % 8 == 0 && a.ldk % 8 == 0 && a.ldv % 8 == 0 && a.ldo % 8 == 0, "attention: pitches must be multiples of 8");
   VQ_CHECK(a.rel_mode == 0 || (a.rel_table && a.rel_bucket), "attention: rel_mode needs rel_table and rel_bucket");
   return 0;
@@ -978,6 +1364,7 @@ int attn_fwd(const AttnArgs& a, cudaStream_t stream) {
   if (check_args(a)) return 1;
   AttnBuckets bk;
   if (make_buckets(a, &bk)) return 1;
+  if (a.Sq > AT_S || a.Sk > AT_S) return launch_mt_fwd(a, bk, stream);   // longer visual sequence: generic multi-tile kernel
   const int warps = (a.Sq + 15) / 16;   // one warp per 16 query rows
   if (a.Sq <= 16 && a.Sk > 16 && a.rel_mode == 0 && !a.causal) {   // few queries, many keys (cross-attention): key-split kernel
     static bool attr = false;
@@ -1002,6 +1389,7 @@ int attn_bwd(const AttnArgs& a, cudaStream_t stream) {
   VQ_CHECK(a.lddq % 8 == 0 && a.lddk % 8 == 0 && a.lddv % 8 == 0, "attention bwd: pitches must be multiples of 8");
   AttnBuckets bk;
   if (make_buckets(a, &bk)) return 1;
+  if (a.Sq > AT_S || a.Sk > AT_S) return launch_mt_bwd(a, bk, stream);
   if (a.o_saved && a.Sq <= 16 && a.Sk > 16 && a.rel_mode == 0 && !a.causal) {   // key-split backward (needs the forward output)
     static bool attr = false;
     if (!attr) {

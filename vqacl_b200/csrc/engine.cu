@@ -280,8 +280,10 @@ int check_batch(const Engine& e, const vqacl_batch* b, bool need_labels) {
   VQ_CHECK(b->B == e.B && b->L == e.L && b->N == e.N && (!need_labels || b->T == e.T),
            "engine: batch shape (B=%d L=%d N=%d T=%d) does not match the bound workspace (B=%d L=%d N=%d T=%d)", b->B, b->L,
            b->N, b->T, e.B, e.L, e.N, e.T);
-  // the decoder attends to the encoder output plus the two retrieved prototype rows: L + N + 2 keys in one 64-key tile
-  VQ_CHECK(b->L + b->N + 2 <= 64 && b->L >= 1 && b->N >= 1, "engine: encoder length L+N=%d must be in [2,62]", b->L + b->N);
+  // the decoder attends to the encoder output plus the two retrieved prototype rows: L + N + 2 keys. Up to 64 keys run on the
+  // single-tile attention kernels, longer visual sequences (configs[3]) on the generic multi-tile ones (<= 256 keys).
+  VQ_CHECK(b->L + b->N + 2 <= 256 && b->L >= 1 && b->N >= 1, "engine: encoder length L+N=%d must be in [2,254]", b->L + b->N);
+  VQ_CHECK(b->L <= 64, "engine: text width L=%d must be at most 64 (the relative-position bias corner must fit one attention tile)", b->L);
   VQ_CHECK(!need_labels || (b->T >= 1 && b->T <= 64), "engine: target width T=%d must be in [1,64]", b->T);
   VQ_CHECK(b->vis_feats && b->boxes && b->input_ids, "engine: missing batch pointers");
   return 0;
@@ -700,6 +702,7 @@ static int backward(Engine& e, const float* w_rows, const float* gscale, int acc
     a.drop_thr = dp.thr; a.drop_inv_keep = dp.inv_keep; a.seed = dp.seed; a.site = dp.site;
     a.dO = w.t_e768; a.dq = w.t_eqkv[ri]; a.dk = w.t_eqkv[ri] + d; a.dv = w.t_eqkv[ri] + 2 * d; a.lddq = a.lddk = a.lddv = 3 * d;
     a.d_rel_table = e.G + e.o_enc_rel;
+    a.o_saved = w.ao[l];      // used by the multi-tile backward (S > 64): D = rowsum(dO * O)
     VQ_TRY(attn_bwd(a, st));
     VQ_TRY(fork());
     VQ_TRY(gemm_dw(w.t_eqkv[ri], 3 * d, w.n1[l], d, e.G + P.qkv, 3 * d, d, M, sd));
