@@ -48,6 +48,9 @@ typedef struct vqacl_batch {
   const int64_t* labels;       /* [B,T], -100 = ignore (train only) */
   const float* cate_labels;    /* [B,n_cate] one-hot fp32 (train only) */
   const float* ques_labels;    /* [B,n_ques] one-hot fp32 (train only) */
+  const void* vis_feats_bf16;  /* optional [B,N,feat_dim] bf16: RoI features already in the GEMM operand format (packed feature
+                                  shards, vqacl_b200/pipeline.py). When set, vis_feats may be NULL and the fp32->bf16 cast is
+                                  skipped; results are bit-identical to passing the fp32 values they were rounded from. */
 } vqacl_batch;
 
 /* SI prototype bank state (the reference keeps these as Python attributes of VLT5, modeling_t5_our.py:391-396) */
@@ -193,6 +196,11 @@ int vqacl_ce_bwd(void* logits_bf16, int ld, int M, int V, const int64_t* labels,
 int vqacl_visual_embed_fwd(const float* featpre, const float* boxes, const float* bf, const float* wf, const float* Wp,
                            const float* bp, const float* wp, const float* img_emb, const float* shared, int V, int B, int N,
                            int S, int L, float eps, float* x, void* stream);
+/* Device-side tail of the reference's __getitem__ + collate_fn (vqa_data_memory.py:179-187, 386-393): boxes (x1,y1,x2,y2) in
+ * pixels -> divided by (img_w, img_h, img_w, img_h) and clamped to [0,1]; class ids -> one-hot fp32 rows
+ * (torch.zeros(B, C).scatter_(1, ids, 1)). boxes_px [B,N,4], img_wh [B,2], cate_ids / ques_ids int64 [B] (NULL: skipped). */
+int vqacl_collate_device(const float* boxes_px, const float* img_wh, int B, int N, float* boxes_out, const int64_t* cate_ids,
+                         int n_cate, float* cate_onehot, const int64_t* ques_ids, int n_ques, float* ques_onehot, void* stream);
 /* transformers-4.2.1 AdamW.step + torch clip_grad_norm_ (trainer_base.py:130-198, vqacl.py:475-482) over a flat range         */
 int vqacl_adamw_hf(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, int64_t n_decay, float lr, float beta1,
                    float beta2, float eps, float weight_decay, int step, const float* sumsq, float max_norm, void* stream);

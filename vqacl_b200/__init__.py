@@ -5,6 +5,7 @@ from .config import VLT5Config
 from .modeling import VLT5, VLT5VQA, VLSeq2SeqLMOutput
 from .optim import FusedAdamW, get_constant_schedule_with_warmup
 from .data import BatchPrefetcher
+from .pipeline import DeviceCollator, PackedFeatureReader, pack_features
 
 __all__ = ["VqaclError", "VLT5Config", "VLT5", "VLT5VQA", "VLSeq2SeqLMOutput", "FusedAdamW", "BatchPrefetcher",
-           "get_constant_schedule_with_warmup"]
+           "get_constant_schedule_with_warmup", "DeviceCollator", "PackedFeatureReader", "pack_features"]

@@ -4,6 +4,8 @@
 // wavefronts, warp-shuffle reductions, no shared memory on the forward paths.
 #include "ops.h"
 
+#include <stdlib.h>
+
 namespace vq {
 
 constexpr int RW_CHUNKS = DM / 4 / 32;  // 6 float4 chunks per lane
@@ -185,7 +187,8 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) rmsnorm_bwd_kernel(const RmsBw
 int rmsnorm_bwd(const RmsBwdArgs& a, cudaStream_t stream) {
   if (a.M <= 0) return 0;
   int blocks = (a.M + ROW_WARPS - 1) / ROW_WARPS;
-  const int cap = num_sms() * 2;
+  static const int per_sm = [] { const char* ev = getenv("VQACL_RMS_BWD_CTAS_PER_SM"); return ev && atoi(ev) > 0 ? atoi(ev) : 2; }();
+  const int cap = num_sms() * per_sm;
   if (blocks > cap) blocks = cap;
   (void)vq_launch(rmsnorm_bwd_kernel, dim3(blocks), dim3(ROW_WARPS * 32), 0, stream, a);
   VQ_LAUNCH_CHECK();
@@ -502,6 +505,40 @@ int vis_embed_bwd(const VisArgs& a, cudaStream_t stream) {
   (void)vq_launch(vis_embed_bwd_kernel, dim3(blocks), dim3(VB_WARPS * 32), smem, stream, a, a.partials);
   VQ_LAUNCH_CHECK();
   (void)vq_launch(vis_embed_reduce_kernel, dim3((VA_COUNT * DM + 255) / 256), dim3(256), 0, stream, a, (const float*)a.partials, blocks);
+  VQ_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ device collate
+// vqa_data_memory.py:179-187 (box normalisation + clamp) and :386-393 (one-hot labels), for batches assembled from packed
+// feature shards: one thread per box / per one-hot element.
+__global__ void collate_kernel(const float* __restrict__ boxes_px, const float* __restrict__ wh, int B, int N, float* __restrict__ boxes_out,
+                               const int64_t* __restrict__ cate_ids, int n_cate, float* __restrict__ cate_oh,
+                               const int64_t* __restrict__ ques_ids, int n_ques, float* __restrict__ ques_oh) {
+  vq_pdl_trigger();
+  vq_pdl_wait();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B * N) {
+    const int b = i / N;
+    const float w = wh[2 * b], h = wh[2 * b + 1];
+    float4 bx = *reinterpret_cast<const float4*>(boxes_px + (size_t)i * 4);
+    bx.x = fminf(fmaxf(bx.x / w, 0.f), 1.f);
+    bx.y = fminf(fmaxf(bx.y / h, 0.f), 1.f);
+    bx.z = fminf(fmaxf(bx.z / w, 0.f), 1.f);
+    bx.w = fminf(fmaxf(bx.w / h, 0.f), 1.f);
+    *reinterpret_cast<float4*>(boxes_out + (size_t)i * 4) = bx;
+  }
+  if (cate_ids && i < B * n_cate) cate_oh[i] = cate_ids[i / n_cate] == (int64_t)(i % n_cate) ? 1.f : 0.f;
+  if (ques_ids && i < B * n_ques) ques_oh[i] = ques_ids[i / n_ques] == (int64_t)(i % n_ques) ? 1.f : 0.f;
+}
+int collate_device(const float* boxes_px, const float* wh, int B, int N, float* boxes_out, const int64_t* cate_ids, int n_cate,
+                   float* cate_oh, const int64_t* ques_ids, int n_ques, float* ques_oh, cudaStream_t stream) {
+  int n = B * N;
+  if (cate_ids && B * n_cate > n) n = B * n_cate;
+  if (ques_ids && B * n_ques > n) n = B * n_ques;
+  if (n <= 0) return 0;
+  (void)vq_launch(collate_kernel, dim3((n + 255) / 256), dim3(256), 0, stream, boxes_px, wh, B, N, boxes_out, cate_ids, n_cate, cate_oh, ques_ids,
+                  n_ques, ques_oh);
   VQ_LAUNCH_CHECK();
   return 0;
 }

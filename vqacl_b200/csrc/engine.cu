@@ -13,6 +13,7 @@
 #include "engine.h"
 
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace vq {
@@ -285,7 +286,7 @@ int check_batch(const Engine& e, const vqacl_batch* b, bool need_labels) {
   VQ_CHECK(b->L + b->N + 2 <= 256 && b->L >= 1 && b->N >= 1, "engine: encoder length L+N=%d must be in [2,254]", b->L + b->N);
   VQ_CHECK(b->L <= 64, "engine: text width L=%d must be at most 64 (the relative-position bias corner must fit one attention tile)", b->L);
   VQ_CHECK(!need_labels || (b->T >= 1 && b->T <= 64), "engine: target width T=%d must be in [1,64]", b->T);
-  VQ_CHECK(b->vis_feats && b->boxes && b->input_ids, "engine: missing batch pointers");
+  VQ_CHECK((b->vis_feats || b->vis_feats_bf16) && b->boxes && b->input_ids, "engine: missing batch pointers");
   return 0;
 }
 
@@ -299,8 +300,13 @@ int encoder_forward(Engine& e, const vqacl_batch* b, cudaStream_t st) {
   VQ_TRY(build_keymasks(b->input_ids, B, L, S, c.pad_id, w.enc_mask, w.cross_mask, w.mask01, st));
   // embeddings: text rows [0,L), visual rows [L,S)   (modeling_t5_our.py:196-214, :247)
   VQ_TRY(embed_fwd(b->input_ids, B, L, e.P + e.o_shared, w.x[0], S, 0, e.drop(SITE_ENC_EMB), c.vocab_size, e.err_flags(), st));
-  VQ_TRY(cast_f32_to_bf16(b->vis_feats, w.feats_bf16, (size_t)B * N * c.feat_dim, st));
-  VQ_TRY(gemm_fwd(w.feats_bf16, c.feat_dim, e.W + e.o_Wf, c.feat_dim, w.featpre, d, B * N, d, EPI_F32, st));
+  // RoI features: fp32 from the reference's collate_fn (cast once) or already bf16 from a packed feature shard
+  const bf16* feats = reinterpret_cast<const bf16*>(b->vis_feats_bf16);
+  if (!feats) {
+    VQ_TRY(cast_f32_to_bf16(b->vis_feats, w.feats_bf16, (size_t)B * N * c.feat_dim, st));
+    feats = w.feats_bf16;
+  }
+  VQ_TRY(gemm_fwd(feats, c.feat_dim, e.W + e.o_Wf, c.feat_dim, w.featpre, d, B * N, d, EPI_F32, st));
   VisArgs va{};
   va.featpre = w.featpre; va.boxes = b->boxes; va.bf = e.P + e.o_bf; va.wf = e.P + e.o_wf; va.Wp = e.P + e.o_Wp;
   va.bp = e.P + e.o_bp; va.wp = e.P + e.o_wp; va.img_emb = e.P + e.o_img; va.shared = e.P + e.o_shared;
@@ -725,7 +731,8 @@ static int backward(Engine& e, const float* w_rows, const float* gscale, int acc
     va.dbp = e.G + e.o_bp; va.dwp = e.G + e.o_wp; va.dimg = e.G + e.o_img; va.dshared = e.G + e.o_shared;
     va.partials = w.vis_partials;
     VQ_TRY(vis_embed_bwd(va, st));
-    VQ_TRY(gemm_dw(w.dfeatpre, d, w.feats_bf16, c.feat_dim, e.G + e.o_Wf, d, c.feat_dim, B * N, st));
+    VQ_TRY(gemm_dw(w.dfeatpre, d, b.vis_feats_bf16 ? reinterpret_cast<const bf16*>(b.vis_feats_bf16) : w.feats_bf16, c.feat_dim,
+                   e.G + e.o_Wf, d, c.feat_dim, B * N, st));
     VQ_TRY(stage_done(Ld + Le + 2));
   }
   // join: the caller's stream owns every gradient written by this call
@@ -903,6 +910,7 @@ extern "C" int vqacl_loss_tail(const float* loss_rows, const int64_t* labels, co
                                float* w_rows, void* stream) {
   return loss_tail(loss_rows, labels, scores, B, T, loss_out, w_rows, ST(stream));
 }
+static int g_opt_blocks_per_sm = [] { const char* ev = getenv("VQACL_OPT_BLOCKS_PER_SM"); return ev ? atoi(ev) : 2; }();
 static AdamArgs adam_range(const Engine& e, float* m, float* v, size_t b, size_t en, float lr, float beta1, float beta2, float eps,
                            float weight_decay, int step, float max_norm) {
   AdamArgs a{};
@@ -939,8 +947,16 @@ extern "C" int vqacl_clip_adamw(void* engine, float* exp_avg, float* exp_avg_sq,
   }
   VQ_CUDA(cudaEventRecord(e.ev_opt_fork, st));
   VQ_CUDA(cudaStreamWaitEvent(e.opt_stream, e.ev_opt_fork, 0));
+  // 2 CTAs of 256 threads per SM: an AdamW grid that floods every SM's thread slots (8 CTAs = 2048 threads) keeps the forward's
+  // persistent GEMM CTAs (384 threads, all of the SM's shared memory) from becoming resident until it drains; two CTAs fit
+  // beside one and still hold ~64 KB of loads in flight per SM
+  const int opt_blocks = g_opt_blocks_per_sm * num_sms();
   auto chunk = [&](int k, size_t b, size_t en) -> int {
-    if (en > b) VQ_TRY(adamw_hf(adam_range(e, exp_avg, exp_avg_sq, b, en, lr, beta1, beta2, eps, weight_decay, step, max_grad_norm), e.opt_stream));
+    if (en > b) {
+      AdamArgs aa = adam_range(e, exp_avg, exp_avg_sq, b, en, lr, beta1, beta2, eps, weight_decay, step, max_grad_norm);
+      aa.max_blocks = opt_blocks;
+      VQ_TRY(adamw_hf(aa, e.opt_stream));
+    }
     VQ_CUDA(cudaEventRecord(e.ev_opt[k], e.opt_stream));
     return 0;
   };
@@ -1079,6 +1095,12 @@ extern "C" int vqacl_visual_embed_fwd(const float* featpre, const float* boxes, 
   va.featpre = featpre; va.boxes = boxes; va.bf = bf; va.wf = wf; va.Wp = Wp; va.bp = bp; va.wp = wp; va.img_emb = img_emb;
   va.shared = shared; va.V = V; va.B = B; va.N = N; va.S = S; va.L = L; va.eps = eps; va.x = x;
   return vis_embed_fwd(va, ST(stream));
+}
+extern "C" int vqacl_collate_device(const float* boxes_px, const float* img_wh, int B, int N, float* boxes_out, const int64_t* cate_ids,
+                                    int n_cate, float* cate_onehot, const int64_t* ques_ids, int n_ques, float* ques_onehot, void* stream) {
+  VQ_CHECK(boxes_px && img_wh && boxes_out, "collate_device: null box buffers");
+  VQ_CHECK((!cate_ids || cate_onehot) && (!ques_ids || ques_onehot), "collate_device: ids without an output buffer");
+  return collate_device(boxes_px, img_wh, B, N, boxes_out, cate_ids, n_cate, cate_onehot, ques_ids, n_ques, ques_onehot, ST(stream));
 }
 extern "C" int vqacl_adamw_hf(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, int64_t n_decay, float lr,
                               float beta1, float beta2, float eps, float weight_decay, int step, const float* sumsq, float max_norm,

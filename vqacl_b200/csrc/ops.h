@@ -97,6 +97,10 @@ int shift_right(const int64_t* labels, int64_t* dec_ids, int B, int T, int start
 int build_keymasks(const int64_t* ids, int B, int L, int S, int pad_id, float* enc_mask, float* cross_mask, float* mask01,
                    cudaStream_t stream);   // mask01 [B,S+2]: the 1/0 encoder_attention_mask the reference returns
 
+// box normalisation + clamp and one-hot labels on the device (vqa_data_memory.py:179-187, 386-393)
+int collate_device(const float* boxes_px, const float* wh, int B, int N, float* boxes_out, const int64_t* cate_ids, int n_cate,
+                   float* cate_oh, const int64_t* ques_ids, int n_ques, float* ques_oh, cudaStream_t stream);
+
 // VisualEmbedding (modeling_t5_our.py:93-143) after the 2048->768 GEMM: bias + RMSNorm, box/area projection + RMSNorm,
 // image-order and object-order embeddings, dropout; writes rows [L, L+N) of x [B,S,768].
 struct VisArgs {
@@ -174,6 +178,7 @@ struct AdamArgs {
   float lr, beta1, beta2, eps, weight_decay;
   int step;                 // 1-based
   const float* sumsq; float max_norm;
+  int max_blocks;           // 0 = fill the GPU; > 0 caps the grid (overlapped mode: leave the SMs' thread slots to the forward's GEMMs)
 };
 int adamw_hf(const AdamArgs& a, cudaStream_t stream);
 

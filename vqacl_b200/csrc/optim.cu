@@ -90,26 +90,40 @@ __global__ void __launch_bounds__(256) adamw_kernel(const AdamArgs a, float step
   }
   const float b1 = a.beta1, b2 = a.beta2;
   const size_t n4 = a.n / 4;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
-    float4 p = reinterpret_cast<float4*>(a.p)[i];
-    const float4 g4 = reinterpret_cast<const float4*>(a.g)[i];
-    float4 m = reinterpret_cast<float4*>(a.m)[i];
-    float4 v = reinterpret_cast<float4*>(a.v)[i];
-    const float wd = (i * 4 < a.n_decay) ? a.lr * a.weight_decay : 0.f;  // n_decay is a multiple of 4 (host-checked)
-    float* pp = &p.x; const float* gg = &g4.x; float* mm = &m.x; float* vv = &v.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  // two float4 groups per thread and iteration: all eight 16-byte loads are issued before the first use, so a small grid
+  // (the overlapped mode runs 2 CTAs per SM next to a persistent GEMM CTA) still keeps enough bytes in flight
+  for (size_t i0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i0 < n4; i0 += 2 * stride) {
+    const size_t idx[2] = {i0, i0 + stride};
+    float4 p[2], g4[2], m[2], v[2];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float g = gg[k] * coef;
-      mm[k] = b1 * mm[k] + (1.f - b1) * g;
-      vv[k] = b2 * vv[k] + (1.f - b2) * g * g;
-      float x = pp[k] - step_size * (mm[k] / (sqrtf(vv[k]) + a.eps));
-      x = x - wd * x;
-      pp[k] = x;
-    }
-    reinterpret_cast<float4*>(a.p)[i] = p;
-    reinterpret_cast<float4*>(a.m)[i] = m;
-    reinterpret_cast<float4*>(a.v)[i] = v;
-    if (a.p_bf16) reinterpret_cast<uint2*>(a.p_bf16)[i] = make_uint2(pack_bf16(p.x, p.y), pack_bf16(p.z, p.w));
+    for (int u = 0; u < 2; ++u)
+      if (idx[u] < n4) {
+        p[u] = reinterpret_cast<float4*>(a.p)[idx[u]];
+        g4[u] = reinterpret_cast<const float4*>(a.g)[idx[u]];
+        m[u] = reinterpret_cast<float4*>(a.m)[idx[u]];
+        v[u] = reinterpret_cast<float4*>(a.v)[idx[u]];
+      }
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+      if (idx[u] < n4) {
+        const size_t i = idx[u];
+        const float wd = (i * 4 < a.n_decay) ? a.lr * a.weight_decay : 0.f;  // n_decay is a multiple of 4 (host-checked)
+        float* pp = &p[u].x; const float* gg = &g4[u].x; float* mm = &m[u].x; float* vv = &v[u].x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float g = gg[k] * coef;
+          mm[k] = b1 * mm[k] + (1.f - b1) * g;
+          vv[k] = b2 * vv[k] + (1.f - b2) * g * g;
+          float x = pp[k] - step_size * (mm[k] / (sqrtf(vv[k]) + a.eps));
+          x = x - wd * x;
+          pp[k] = x;
+        }
+        reinterpret_cast<float4*>(a.p)[i] = p[u];
+        reinterpret_cast<float4*>(a.m)[i] = m[u];
+        reinterpret_cast<float4*>(a.v)[i] = v[u];
+        if (a.p_bf16) reinterpret_cast<uint2*>(a.p_bf16)[i] = make_uint2(pack_bf16(p[u].x, p[u].y), pack_bf16(p[u].z, p[u].w));
+      }
   }
 }
 int adamw_hf(const AdamArgs& a, cudaStream_t stream) {
@@ -121,8 +135,10 @@ int adamw_hf(const AdamArgs& a, cudaStream_t stream) {
   const float step_size = (float)((double)a.lr * sqrt(bc2) / bc1);
   const size_t n4 = a.n / 4;
   size_t want = (n4 + 255) / 256;
-  const size_t cap = (size_t)num_sms() * 16;
-  const int blocks = (int)(want > cap ? cap : want);
+  size_t cap = (size_t)num_sms() * 8;
+  if (a.max_blocks > 0 && (size_t)a.max_blocks < cap) cap = (size_t)a.max_blocks;
+  want = (want + 1) / 2;
+  const int blocks = (int)(want > cap ? cap : (want < 1 ? 1 : want));
   (void)vq_launch(adamw_kernel, dim3(blocks), dim3(256), 0, stream, a, step_size, a.max_norm);
   VQ_LAUNCH_CHECK();
   return 0;

@@ -28,7 +28,7 @@ class CBatch(Structure):
     _fields_ = [
         ("B", c_int), ("L", c_int), ("N", c_int), ("T", c_int),
         ("vis_feats", c_void_p), ("boxes", c_void_p), ("input_ids", c_void_p), ("labels", c_void_p),
-        ("cate_labels", c_void_p), ("ques_labels", c_void_p),
+        ("cate_labels", c_void_p), ("ques_labels", c_void_p), ("vis_feats_bf16", c_void_p),
     ]
 
 
@@ -80,6 +80,8 @@ def _declare(L):
     L.vqacl_arena_tail.argtypes = [c_void_p]
     L.vqacl_arena_tail.restype = c_int64
     L.vqacl_set_param_events.argtypes = [c_void_p, POINTER(c_void_p), c_int]
+    L.vqacl_collate_device.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p,
+                                       c_void_p]
     L.vqacl_device_errors.argtypes = [c_void_p, POINTER(c_int), c_void_p]
     L.vqacl_grad_sumsq_ranges.argtypes = [c_void_p, POINTER(c_int64), POINTER(c_int64), c_int, c_void_p, c_void_p]
     L.vqacl_adamw_range.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_float, c_float, c_float, c_float, c_float,
@@ -214,7 +216,9 @@ class Engine:
     # ---- step ----------------------------------------------------------------------------------------------------
     @staticmethod
     def make_batch(B, Lt, N, T, feats, boxes, ids, labels=None, cate=None, ques=None):
-        return CBatch(B=B, L=Lt, N=N, T=T, vis_feats=feats.data_ptr(), boxes=boxes.data_ptr(), input_ids=ids.data_ptr(),
+        bf = feats.dtype == torch.bfloat16      # packed feature shards hand the GEMM operand format over directly
+        return CBatch(B=B, L=Lt, N=N, T=T, vis_feats=None if bf else feats.data_ptr(), vis_feats_bf16=feats.data_ptr() if bf else None,
+                      boxes=boxes.data_ptr(), input_ids=ids.data_ptr(),
                       labels=labels.data_ptr() if labels is not None else None,
                       cate_labels=cate.data_ptr() if cate is not None else None,
                       ques_labels=ques.data_ptr() if ques is not None else None)

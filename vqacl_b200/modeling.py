@@ -519,7 +519,8 @@ class VLT5(nn.Module):
                 if mx >= V or mn < lo or (lo == -100 and mn < 0 and bool(((t < 0) & (t != -100)).any())):
                     raise IndexError(f"{nm} holds ids outside [0, {V}) (min {mn}, max {mx})")
         ids = dv(input_ids, torch.int64)
-        feats = dv(vis_feats, torch.float32)
+        # fp32 RoI features (the reference's collate_fn) or bf16 ones from a packed shard (pipeline.py): same results, half the bytes
+        feats = dv(vis_feats, torch.bfloat16 if vis_feats.dtype == torch.bfloat16 else torch.float32)
         bx = dv(boxes, torch.float32)
         lab = dv(labels, torch.int64)
         cate = dv(cate, torch.float32)
