@@ -24,6 +24,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import vqacl_b200 as V  # noqa: E402
+from vqacl_b200.continual import RehearsalMemory, load_training_state, save_training_state  # noqa: E402
 
 ALL_TASKS = ["q_recognition", "q_location", "q_judge", "q_commonsense", "q_count", "q_action", "q_color", "q_type",
              "q_subcategory", "q_causal"]                                    # Question_type.py:16
@@ -76,6 +77,15 @@ class SyntheticTaskData:
                        ques_labels=ques)
 
 
+def task_records(task_idx, n=200):
+    """Stand-in for datasets/vqa/Partition_Q/karpathy_train_<task>.json: training records of one task with an image id each."""
+    g = random.Random(4000 + task_idx)
+    return [{"img_id": f"img{g.randrange(500)}", "question_id": f"t{task_idx}-{k}", "seed": g.randrange(1 << 30)} for k in range(n)]
+
+
+IMG_CATE = {f"img{i}": (i * 7) % 90 + 1 for i in range(500)}                  # raw COCO ids 1..90 as in ImgId_cate_map.json (H10)
+
+
 def run(args, log=print):
     dev = torch.device("cuda", 0)
     torch.manual_seed(args.seed)
@@ -87,21 +97,35 @@ def run(args, log=print):
     splits = category_splits(args.groups)
     out_dir = args.output or tempfile.mkdtemp(prefix="vqacl_")
     history = []
+    memory = RehearsalMemory(splits, M=getattr(args, "m_size", 64))
+    first_task = 0
+    resume = getattr(args, "resume", None)
+    if resume:                                                               # true resume: weights + banks + bookkeeping + memory + RNG
+        last, _ = load_training_state(resume, model, memory)
+        first_task = last + 1
+        log(f"resumed after task {last}")
     for task_idx, task in enumerate(ALL_TASKS[:args.tasks]):
+        if task_idx < first_task:
+            continue
         log(f"======== task {task_idx} {task} ========")
+        if args.memory and task_idx > 0:                                     # vqacl.py:169-203
+            all_ex, each = memory.grow(task_idx, task_records(task_idx - 1), IMG_CATE)
+            log(f"  rehearsal memory: {len(all_ex)} exemplars ({each} per old task)")
         groups = list(splits)
         random.shuffle(groups)                                               # random_dic(Category_splits), vqacl.py:314
         for group in groups:
             train = SyntheticTaskData(task_idx, splits[group], args.iters, args.batch_size, seed=task_idx * 17 + int(group[1:]))
-            memory = (SyntheticTaskData(task_idx, splits[group], max(1, args.iters // 2), args.batch_size, seed=999 + task_idx,
-                                        old_tasks=list(range(task_idx))) if task_idx > 0 and args.memory else None)
-            total = (2 if memory else 1) * len(train) * args.batch_size
+            # rehearsal loader over the exemplar memory (here: synthetic batches seeded by the stored exemplar records)
+            mem_loader = (SyntheticTaskData(task_idx, splits[group], max(1, args.iters // 2), args.batch_size,
+                                            seed=999 + task_idx + sum(d["seed"] for d in all_ex) % 1000,
+                                            old_tasks=list(range(task_idx))) if task_idx > 0 and args.memory else None)
+            total = (2 if mem_loader else 1) * len(train) * args.batch_size
             t_total = int(total / args.batch_size) * args.epochs
             optim = V.FusedAdamW(model, lr=args.lr, eps=1e-6, weight_decay=0.01)     # new optimizer per group (vqacl.py:329)
             sched = V.get_constant_schedule_with_warmup(optim, int(t_total * 0.1))
             for epoch in range(args.epochs):
                 model.train()
-                loader = zip(train, itertools.cycle(memory)) if memory else ((b, None) for b in train)
+                loader = zip(train, itertools.cycle(mem_loader)) if mem_loader else ((b, None) for b in train)
                 for batch, mem_batch in loader:
                     for b in (batch, mem_batch):
                         if b is None:
@@ -114,6 +138,7 @@ def run(args, log=print):
                         history.append(res["loss"])
         ckpt = os.path.join(out_dir, f"{task}_LAST.pth")
         torch.save({"module." + k: v.cpu() for k, v in model.state_dict().items()}, ckpt)      # trainer_base.py:246-249
+        save_training_state(os.path.join(out_dir, f"{task}_STATE.pt"), model, task_idx, memory)  # what a resume needs on top
         # evaluate every task seen so far with greedy decoding (vqacl.py:416-417, 545-579)
         model.eval()
         for t in range(task_idx + 1):

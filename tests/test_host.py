@@ -188,3 +188,25 @@ def test_chunk_events_map_forward_chunks_to_gathered_buckets():
     chunks = [(190, 260), (150, 190), (100, 150), (0, 100)]               # tail+visual, enc layer 0, enc layer 1, decoder
     assert chunk_events(chunks, gather_order) == [0, 1, 1, 3]
     assert chunk_events([(200, 260)], gather_order) == [None]              # nothing sharded in a pure-tail chunk
+
+
+def test_rehearsal_memory_matches_reference_fixture():
+    """RehearsalMemory.grow against the fixture made by executing the reference's own block (vqacl.py:169-203,
+    tools/gen_golden_rehearsal.py): same exemplars, in the same order, for four consecutive tasks."""
+    import json
+    import random
+    from vqacl_b200.continual import RehearsalMemory
+    d = json.load(open(os.path.join(ROOT, "tests", "golden", "rehearsal_memory.json")))
+    mem = RehearsalMemory(d["splits"], M=d["M"])
+    for st in d["steps"]:
+        t = st["task_idx"]
+        random.seed(st["seed"])
+        items = [dict(x) for x in d["partitions"][d["tasks"][t - 1]]]
+        all_ex, each = mem.grow(t, items, d["img_cate"])
+        assert each == st["each_memory"]
+        assert [x["question_id"] for x in all_ex] == st["all_examplar"]
+        assert {g: [[x["question_id"] for x in ts] for ts in v] for g, v in mem.examplar_set.items()} == st["examplar_set"]
+    # state round trip
+    mem2 = RehearsalMemory({}, 0)
+    mem2.load_state_dict(json.loads(json.dumps(mem.state_dict())))
+    assert [x["question_id"] for x in mem2.all_examplars()] == d["steps"][-1]["all_examplar"]

@@ -406,8 +406,12 @@ class VLT5(nn.Module):
             if cur is not None:
                 buf.copy_(cur)
             setattr(self, attr, buf)
-        self._Q_prototype_num = torch.zeros(self.config.n_ques_classes, dtype=torch.float32, device=device)
-        self._V_prototype_num = torch.zeros(self.config.n_cate_classes, dtype=torch.float32, device=device)
+        for attr, n in (("_Q_prototype_num", self.config.n_ques_classes), ("_V_prototype_num", self.config.n_cate_classes)):
+            cur = getattr(self, attr)
+            buf = torch.zeros(n, dtype=torch.float32, device=device)
+            if cur is not None:
+                buf.copy_(cur)          # counts restored from a checkpoint before the model was moved to the GPU
+            setattr(self, attr, buf)
 
     def param_sync(self):
         """Make the current stream wait for a pending overlapped optimizer step (FusedAdamW(overlap_with_next_forward=True))."""
