@@ -43,7 +43,6 @@ VQ_DEVINL void mma16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&
 
 typedef __nv_bfloat16 (*AttnTile)[AT_P];
 
-struct AttnBuckets { int8_t b[2 * AT_S]; };   // rel -> bucket map, passed by value (constant bank)
 
 // Load NM [rows<=64, 64] bf16 head slices into smem with 16-byte vectors. All global loads of a batch (4 per matrix and
 // thread) are issued before the first shared store so that NM*4 requests per thread are in flight.
@@ -159,8 +158,6 @@ VQ_DEVINL void store_tile16(AttnTile stg, int m0, const float (&acc)[8][4], __nv
   __syncwarp();
 }
 
-// dropout pair index of probabilities (q, k), (q, k+1) of problem `blk` (k even)
-VQ_DEVINL uint32_t attn_pair_idx(uint32_t blk, int q, int k) { return ((blk * AT_S + (uint32_t)q) * AT_S + (uint32_t)k) >> 1; }
 
 // Shared memory is carved per launch for the rows that exist (rounded up to 16), and the CTA has one warp per 16 query
 // rows (backward: per 16 query or key rows), so the decoder's tiny problems (Sq = T <= 10) run as 1-warp CTAs with 7-21 KB
@@ -1365,6 +1362,7 @@ int attn_fwd(const AttnArgs& a, cudaStream_t stream) {
   AttnBuckets bk;
   if (make_buckets(a, &bk)) return 1;
   if (a.Sq > AT_S || a.Sk > AT_S) return launch_mt_fwd(a, bk, stream);   // longer visual sequence: generic multi-tile kernel
+  if (attn_tc_eligible(a)) return attn_enc_fwd_tc(a, bk, stream);         // encoder: tcgen05 + TMA kernel (attention_tc.cu)
   const int warps = (a.Sq + 15) / 16;   // one warp per 16 query rows
   if (a.Sq <= 16 && a.Sk > 16 && a.rel_mode == 0 && !a.causal) {   // few queries, many keys (cross-attention): key-split kernel
     static bool attr = false;

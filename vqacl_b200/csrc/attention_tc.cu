@@ -1,0 +1,300 @@
+// Encoder self-attention on the 5th-generation tensor cores: tcgen05.mma with the score / output accumulators in TMEM,
+// Q / K / V head slices staged by TMA (cp.async.bulk.tensor, 128-byte swizzle) straight from the packed [rows, 3d] QKV
+// activation, softmax done by threads that own ONE ROW each (tcgen05.ld 32x32b: thread = row), so the row maximum, the
+// sum, the mask / bias adds and the dropout decisions need no shuffles at all.
+//
+// Replaces, for the encoder shape (Sq = Sk = S <= 64, relative bias on the text x text corner, additive key-padding mask —
+// JointEncoder.forward, modeling_t5_our.py:225-301 + HF T5Attention, hf5.5 modeling_t5.py:277-338), the mma.sync kernel of
+// attention.cu, whose 1100 instructions per warp around 64 HMMA made it issue-bound at 2.4x the HBM time
+// (profiles/r01_step_kernel_metrics.md).
+//
+// One work item = one batch element x TWO adjacent heads, stacked into one M = 128 MMA:
+//   S2[128 x 128] = Q2[128 x 64] K2[128 x 64]^T   rows 0-63: head h queries, rows 64-127: head h+1; columns likewise for keys.
+//                                                 Only the two diagonal 64 x 64 blocks are meaningful; the MMA is ~1 % of the
+//                                                 step's FLOPs, so computing the off-diagonal blocks costs nothing.
+//   softmax rows -> P2[128 x 128] bf16 in shared memory, block diagonal (the off-diagonal halves are zeroed once and never
+//                                                 written), in the K-major 128-byte-swizzle operand layout
+//   O2[128 x 64]  = P2[128 x 128] V2[128 x 64]    V2 = the two heads' V slices stacked along the key axis (MN-major operand)
+// Roles: warps 0-3 softmax + epilogue (thread r = TMEM lane r = stacked query row r), warp 4 TMA producer (+ the per-item
+// bias / key-mask header), warp 5 MMA issuer and TMEM owner. Two shared-memory stages and two S accumulators let the loads
+// and the S MMA of item i+1 run under the softmax of item i; the O epilogue of item i-1 is folded into item i's softmax
+// phase so the softmax warps never wait for the O MMA.
+#include "gemm.h"
+#include "ops.h"
+
+#include <stdlib.h>
+
+namespace vq {
+
+constexpr int AT_S_TC = 64;                          // positions per head tile
+constexpr int TC_STAGE_BYTES = 3 * 16384;           // Q2 | K2 | V2, each 128 rows x 128 B
+constexpr int TC_P_BYTES = 2 * 16384;               // two K-atoms (keys of head h | keys of head h+1), each 128 rows x 128 B
+constexpr int TC_HDR_FLOATS = 64 + 2 * 128;         // kmask[64] | bias[2][128]
+constexpr int TC_SMEM_BYTES = 1024 + 2 * TC_STAGE_BYTES + TC_P_BYTES + 2 * TC_HDR_FLOATS * 4 + 256;
+constexpr int TC_THREADS = 192;
+constexpr int TC_TMEM_COLS = 512;                   // S0 [0,128) | S1 [128,256) | O [256,320)
+
+struct AttnTcArgs {
+  __nv_bfloat16* o; int ldo;
+  float* lse;
+  int B, H, S, Lt;
+  const float* rel_table;       // [buckets, H]
+  const float* keymask;         // [B, S] additive
+  uint32_t drop_thr; float drop_inv_keep; uint32_t seed;
+};
+
+VQ_DEVINL void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+attn_enc_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                       const __grid_constant__ CUtensorMap tmV, const AttnTcArgs p, const __grid_constant__ AttnBuckets bk) {
+  vq_pdl_trigger();
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t raw_u32 = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_u32 + 1023u) & ~1023u) - raw_u32);
+  uint8_t* sP = smem + 2 * TC_STAGE_BYTES;
+  float* hdr = reinterpret_cast<float*>(sP + TC_P_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(hdr) + 2 * TC_HDR_FLOATS * 4);
+  uint64_t* full_bar = bars;            // [2] TMA bytes of a stage landed (+ header written)
+  uint64_t* empty_bar = bars + 2;       // [2] both MMAs that read the stage are complete
+  uint64_t* sfull_bar = bars + 4;       // [2] S accumulator complete
+  uint64_t* sempty_bar = bars + 6;      // [2] S accumulator read by the 4 softmax warps
+  uint64_t* pfull_bar = bars + 8;       // P tile written (4 warps)
+  uint64_t* ofull_bar = bars + 9;       // O accumulator complete
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int hp = p.H >> 1;
+  const int nitems = p.B * hp;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+      mbar_init(&sfull_bar[i], 1);
+      mbar_init(&sempty_bar[i], 4);
+    }
+    mbar_init(pfull_bar, 4);
+    mbar_init(ofull_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 5) tmem_alloc(tmem_holder, TC_TMEM_COLS);
+  // the off-diagonal halves of the block-diagonal P tile stay zero for the whole kernel
+  for (int i = threadIdx.x; i < TC_P_BYTES / 16; i += TC_THREADS) reinterpret_cast<uint4*>(sP)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+  vq_pdl_wait();
+
+  if (warp == 4) {
+    // ------------------------------------------------ TMA producer + per-item header ------------------------------------------------
+    int n = 0;
+    for (int it = blockIdx.x; it < nitems; it += gridDim.x, ++n) {
+      const int stage = n & 1;
+      const uint32_t ph = (n >> 1) & 1;
+      const int b = it / hp, h = (it - b * hp) * 2;
+      mbar_wait(&empty_bar[stage], ph ^ 1);
+      float* hs = hdr + stage * TC_HDR_FLOATS;
+      for (int j = lane; j < 64; j += 32) hs[j] = j < p.S ? (p.keymask ? p.keymask[(size_t)b * p.S + j] : 0.f) : -INFINITY;
+      for (int r = lane; r < 2 * 128; r += 32) {
+        const int hd = r >> 7, rel = r & 127;
+        hs[64 + r] = rel < 127 ? p.rel_table[(int)bk.b[rel] * p.H + h + hd] : 0.f;
+      }
+      __syncwarp();
+      if (lane == 0) {
+        uint8_t* st = smem + stage * TC_STAGE_BYTES;
+        mbar_expect_tx(&full_bar[stage], TC_STAGE_BYTES);
+        const int row = b * p.S;
+        tma_load_2d(st, &tmQ, &full_bar[stage], h * 64, row);
+        tma_load_2d(st + 8192, &tmQ, &full_bar[stage], (h + 1) * 64, row);
+        tma_load_2d(st + 16384, &tmK, &full_bar[stage], h * 64, row);
+        tma_load_2d(st + 16384 + 8192, &tmK, &full_bar[stage], (h + 1) * 64, row);
+        tma_load_2d(st + 32768, &tmV, &full_bar[stage], h * 64, row);
+        tma_load_2d(st + 32768 + 8192, &tmV, &full_bar[stage], (h + 1) * 64, row);
+      }
+    }
+  } else if (warp == 5) {
+    // ------------------------------------------------ MMA issuer ------------------------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, false, true);
+      const uint32_t sP_u32 = smem_u32(sP);
+      auto issue_s = [&](int n) {
+        const int stage = n & 1;
+        const uint32_t ph = (n >> 1) & 1;
+        mbar_wait(&full_bar[stage], ph);
+        mbar_wait(&sempty_bar[stage], ph ^ 1);        // S buffer index == stage index (both alternate per item)
+        tc_fence_after();
+        const uint32_t sq = smem_u32(smem + stage * TC_STAGE_BYTES), sk = sq + 16384;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16(tmem_base + stage * 128, umma_smem_desc_sw128(sq + k * 32, 16, 1024), umma_smem_desc_sw128(sk + k * 32, 16, 1024),
+                   idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(&sfull_bar[stage]);
+      };
+      int n = 0;
+      if ((int)blockIdx.x < nitems) issue_s(0);
+      for (int it = blockIdx.x; it < nitems; it += gridDim.x, ++n) {
+        if (it + (int)gridDim.x < nitems) issue_s(n + 1);          // the next item's scores are computed under this item's softmax
+        const int stage = n & 1;
+        mbar_wait(pfull_bar, n & 1);
+        tc_fence_after();
+        const uint32_t sv = smem_u32(smem + stage * TC_STAGE_BYTES) + 32768;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          umma_f16(tmem_base + 256, umma_smem_desc_sw128(sP_u32 + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+                   umma_smem_desc_sw128(sv + kk * 2048, 8192, 1024), idesc_o, kk > 0 ? 1u : 0u);
+        umma_commit(ofull_bar);
+        umma_commit(&empty_bar[stage]);
+      }
+    }
+  } else {
+    // ------------------------------------------------ softmax + epilogue (thread = stacked row) ------------------------------------------------
+    const int r = threadIdx.x;                 // 0..127 = TMEM lane
+    const int hsel = r >> 6, q = r & 63;
+    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    const uint32_t sP_row = smem_u32(sP) + hsel * 16384 + r * 128;
+    const int sw = r & 7;
+    int n = 0, pb = 0, ph_ = 0;                // previous item's (batch, first head) for the deferred O epilogue
+    auto epilogue = [&](int nn, int b, int h) {
+      mbar_wait(ofull_bar, nn & 1);
+      tc_fence_after();
+      uint32_t o0[32], o1[32];
+      tmem_ld_32x32(tmem_base + 256 + lane_addr, o0);
+      tmem_ld_32x32(tmem_base + 256 + 32 + lane_addr, o1);
+      tmem_ld_wait();
+      if (q < p.S) {
+        uint4* dst = reinterpret_cast<uint4*>(p.o + ((size_t)b * p.S + q) * p.ldo + (h + hsel) * 64);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          dst[c] = make_uint4(pack_bf16(__uint_as_float(o0[8 * c]), __uint_as_float(o0[8 * c + 1])),
+                              pack_bf16(__uint_as_float(o0[8 * c + 2]), __uint_as_float(o0[8 * c + 3])),
+                              pack_bf16(__uint_as_float(o0[8 * c + 4]), __uint_as_float(o0[8 * c + 5])),
+                              pack_bf16(__uint_as_float(o0[8 * c + 6]), __uint_as_float(o0[8 * c + 7])));
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          dst[4 + c] = make_uint4(pack_bf16(__uint_as_float(o1[8 * c]), __uint_as_float(o1[8 * c + 1])),
+                                  pack_bf16(__uint_as_float(o1[8 * c + 2]), __uint_as_float(o1[8 * c + 3])),
+                                  pack_bf16(__uint_as_float(o1[8 * c + 4]), __uint_as_float(o1[8 * c + 5])),
+                                  pack_bf16(__uint_as_float(o1[8 * c + 6]), __uint_as_float(o1[8 * c + 7])));
+      }
+      tc_fence_before();
+    };
+    for (int it = blockIdx.x; it < nitems; it += gridDim.x, ++n) {
+      const int stage = n & 1;
+      const uint32_t ph = (n >> 1) & 1;
+      const int b = it / hp, h = (it - b * hp) * 2;
+      mbar_wait(&full_bar[stage], ph);         // header of this stage is visible
+      mbar_wait(&sfull_bar[stage], ph);
+      tc_fence_after();
+      float v[64];
+      {
+        uint32_t s0[32], s1[32];
+        const uint32_t ta = tmem_base + stage * 128 + hsel * 64 + lane_addr;
+        tmem_ld_32x32(ta, s0);
+        tmem_ld_32x32(ta + 32, s1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(s0[j]); v[32 + j] = __uint_as_float(s1[j]); }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sempty_bar[stage]);
+      const float* hs = hdr + stage * TC_HDR_FLOATS;
+      // additive key-side term (padding mask, -inf beyond S): the same for every row -> broadcast reads
+#pragma unroll
+      for (int j4 = 0; j4 < 16; ++j4) {
+        const float4 km = *reinterpret_cast<const float4*>(hs + 4 * j4);
+        v[4 * j4] += km.x; v[4 * j4 + 1] += km.y; v[4 * j4 + 2] += km.z; v[4 * j4 + 3] += km.w;
+      }
+      // relative-position bias on the text x text corner (rows and keys < Lt <= 32)
+      if (q < p.Lt) {
+        const float* bp = hs + 64 + hsel * 128 + (AT_S_TC - 1) - q;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < p.Lt) v[j] += bp[j];
+      }
+      float m = v[0];
+#pragma unroll
+      for (int j = 1; j < 64; ++j) m = fmaxf(m, v[j]);
+      float l = 0.f;
+#pragma unroll
+      for (int j = 0; j < 64; ++j) {
+        v[j] = __expf(v[j] - m);
+        l += v[j];
+      }
+      const float inv = 1.f / l;
+      if (q < p.S && p.lse) p.lse[((size_t)b * p.H + h + hsel) * p.S + q] = m + __logf(l);
+      uint32_t pk[32];
+      if (p.drop_thr) {
+        const uint32_t pi0 = attn_pair_idx((uint32_t)(b * p.H + h + hsel), q, 0);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float d0, d1;
+          vq_dropout_pair(p.seed, pi0 + j, p.drop_thr, p.drop_inv_keep, d0, d1);
+          pk[j] = pack_bf16(v[2 * j] * inv * d0, v[2 * j + 1] * inv * d1);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) pk[j] = pack_bf16(v[2 * j] * inv, v[2 * j + 1] * inv);
+      }
+      // the O epilogue of the previous item: its MMA finished long ago; doing it here also guarantees that the P tile of the
+      // previous item has been consumed before it is overwritten below
+      if (n > 0) epilogue(n - 1, pb, ph_);
+      pb = b; ph_ = h;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint32_t addr = sP_row + ((uint32_t)(c ^ sw) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * c]), "r"(pk[4 * c + 1]), "r"(pk[4 * c + 2]),
+                     "r"(pk[4 * c + 3]) : "memory");
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pfull_bar);
+    }
+    if (n > 0) epilogue(n - 1, pb, ph_);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TC_TMEM_COLS);
+  }
+}
+
+static int g_attn_tc = [] { const char* e = getenv("VQACL_ATTN_TC"); return (e && e[0] == '0') ? 0 : 1; }();
+
+// true when the tcgen05 kernel takes this problem (encoder form: square, 33..64 positions, text-corner bias, even head count)
+bool attn_tc_eligible(const AttnArgs& a) {
+  return g_attn_tc && a.rel_mode == 1 && a.Sq == a.Sk && a.Sq > 32 && a.Sq <= 64 && a.Lt <= 32 && (a.H & 1) == 0 && !a.causal && !a.q_off &&
+         !a.q_bstride && !a.k_bstride && !a.v_bstride && !a.o_bstride && a.ldq % 8 == 0 && a.ldk % 8 == 0 && a.ldv % 8 == 0 &&
+         (reinterpret_cast<uintptr_t>(a.q) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.k) & 15) == 0 &&
+         (reinterpret_cast<uintptr_t>(a.v) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.o) & 15) == 0 && a.ldo % 8 == 0;
+}
+
+int attn_enc_fwd_tc(const AttnArgs& a, const AttnBuckets& bk, cudaStream_t stream) {
+  CUtensorMap tq, tk, tv;
+  const uint64_t rows = (uint64_t)a.B * a.Sq, cols = (uint64_t)a.H * 64;
+  if (make_tmap_bf16_2d(&tq, a.q, cols, rows, a.ldq, 64, 64)) return 1;
+  if (make_tmap_bf16_2d(&tk, a.k, cols, rows, a.ldk, 64, 64)) return 1;
+  if (make_tmap_bf16_2d(&tv, a.v, cols, rows, a.ldv, 64, 64)) return 1;
+  static bool attr = false;
+  if (!attr) {
+    VQ_CUDA(cudaFuncSetAttribute(attn_enc_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    attr = true;
+  }
+  AttnTcArgs p{};
+  p.o = a.o; p.ldo = a.ldo; p.lse = a.lse; p.B = a.B; p.H = a.H; p.S = a.Sq; p.Lt = a.Lt; p.rel_table = a.rel_table; p.keymask = a.keymask;
+  p.drop_thr = a.drop_thr; p.drop_inv_keep = a.drop_inv_keep; p.seed = a.seed;
+  const int items = a.B * (a.H / 2);
+  const int grid = items < num_sms() ? items : num_sms();
+  (void)vq_launch(attn_enc_fwd_tc_kernel, dim3(grid), dim3(TC_THREADS), (size_t)TC_SMEM_BYTES, stream, tq, tk, tv, p, bk);
+  VQ_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace vq

@@ -100,6 +100,11 @@ static int make_tmap(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1
   return 0;
 }
 
+// shared with the tcgen05 attention kernels (attention_tc.cu)
+int make_tmap_bf16_2d(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t ld, uint32_t b0, uint32_t b1) {
+  return make_tmap(out, ptr, d0, d1, ld, b0, b1);
+}
+
 void gemm_tmap_cache_clear() {
   std::lock_guard<std::mutex> g(g_tm_mutex);
   g_tm_cache.clear();

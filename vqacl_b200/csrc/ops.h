@@ -45,6 +45,13 @@ struct AttnArgs {
 };
 int attn_fwd(const AttnArgs& a, cudaStream_t stream);
 int attn_bwd(const AttnArgs& a, cudaStream_t stream);
+// shared by attention.cu and attention_tc.cu
+struct AttnBuckets { int8_t b[128]; };   // rel -> bucket map (rel = key - query + 63), passed by value (constant bank)
+// dropout pair index of probabilities (q, k), (q, k+1) of problem `blk` = batch * H + head (k even), single-tile kernels
+VQ_DEVINL uint32_t attn_pair_idx(uint32_t blk, int q, int k) { return ((blk * 64u + (uint32_t)q) * 64u + (uint32_t)k) >> 1; }
+// attention_tc.cu: encoder self-attention on tcgen05 / TMEM / TMA
+bool attn_tc_eligible(const AttnArgs& a);
+int attn_enc_fwd_tc(const AttnArgs& a, const AttnBuckets& bk, cudaStream_t stream);
 
 // ---------------------------------------------------------------- elementwise.cu
 int cast_f32_to_bf16(const float* src, __nv_bfloat16* dst, size_t n, cudaStream_t stream);
