@@ -96,6 +96,7 @@ def run(args, log=print):
     model = model.to(dev)
     splits = category_splits(args.groups)
     out_dir = args.output or tempfile.mkdtemp(prefix="vqacl_")
+    os.makedirs(out_dir, exist_ok=True)
     history = []
     memory = RehearsalMemory(splits, M=getattr(args, "m_size", 64))
     first_task = 0

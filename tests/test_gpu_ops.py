@@ -44,11 +44,13 @@ def _attn_ref(q, k, v, B, H, Sq, Sk, bias):
     return (p @ vh).transpose(1, 2).reshape(B * Sq, H * 64)
 
 
-@pytest.mark.parametrize("mode", ["enc", "dec_self", "cross"])
+@pytest.mark.parametrize("mode", ["enc", "dec_self", "cross", "enc_many"])
 def test_attention_fwd_bwd_vs_torch(mode):
     from vqacl_b200.engine import rel_bucket_table
     torch.manual_seed(1)
     B, H = 5, 12
+    if mode == "enc_many":      # more (batch, head-pair) items than SMs: the persistent tcgen05 kernels pipeline several per CTA
+        B, mode = 110, "enc"
     if mode == "enc":
         Sq = Sk = 56; Lt = 20
     elif mode == "dec_self":

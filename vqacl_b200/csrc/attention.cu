@@ -1388,6 +1388,7 @@ int attn_bwd(const AttnArgs& a, cudaStream_t stream) {
   AttnBuckets bk;
   if (make_buckets(a, &bk)) return 1;
   if (a.Sq > AT_S || a.Sk > AT_S) return launch_mt_bwd(a, bk, stream);
+  if (attn_tc_bwd_eligible(a)) return attn_enc_bwd_tc(a, bk, stream);
   if (a.o_saved && a.Sq <= 16 && a.Sk > 16 && a.rel_mode == 0 && !a.causal) {   // key-split backward (needs the forward output)
     static bool attr = false;
     if (!attr) {

@@ -266,7 +266,309 @@ attn_enc_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   }
 }
 
-static int g_attn_tc = [] { const char* e = getenv("VQACL_ATTN_TC"); return (e && e[0] == '0') ? 0 : 1; }();
+
+// =====================================================================================================================
+// Backward of the same problem on the same machinery. Per item (batch element x two stacked heads):
+//   S2  = Q2 K2^T, dP2 = dO2 V2^T                       (two M = 128, N = 128 MMAs into TMEM)
+//   row threads: P = exp(S + mask + bias - lse), dP *= dropout, D = sum_j P dP (row-local: no shuffles),
+//                dS = P (dP - D); P (dropout folded in) and dS go to two block-diagonal bf16 tiles in shared memory
+//   dV2 = P2^T dO2, dK2 = dS2^T Q2   (the tiles read as MN-major A operands), dQ2 = dS2 K2   (read as K-major A operand)
+//   row threads: TMEM -> bf16 -> full 128-byte rows of dQ / dK / dV
+// The bias-table gradient (sums of dS along the diagonals of the text x text corner) is accumulated in a per-CTA shared
+// table across all items and flushed with one global atomic per (bucket, head) at the end of the kernel.
+// =====================================================================================================================
+constexpr int TCB_STAGE_BYTES = 4 * 16384;          // Q2 | K2 | V2 | dO2
+constexpr int TCB_HDR_FLOATS = 64 + 2 * 128 + 128;  // kmask[64] | bias[2][128] | lse[128] (stacked rows; +inf beyond S)
+constexpr int TCB_DTAB_FLOATS = 64 * 16;            // [bucket][head] accumulation table (H <= 16)
+constexpr int TCB_SMEM_BYTES = 1024 + 2 * TCB_STAGE_BYTES + 2 * TC_P_BYTES + 2 * TCB_HDR_FLOATS * 4 + TCB_DTAB_FLOATS * 4 + 256;
+
+struct AttnTcBwdArgs {
+  __nv_bfloat16 *dq, *dk, *dv; int lddq, lddk, lddv;
+  const float* lse;
+  int B, H, S, Lt;
+  const float* rel_table; const float* keymask;
+  float* d_rel_table;
+  uint32_t drop_thr; float drop_inv_keep; uint32_t seed;
+};
+
+VQ_DEVINL void store_row64(__nv_bfloat16* dst, const uint32_t (&a)[32], const uint32_t (&b)[32]) {
+  uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+    d4[c] = make_uint4(pack_bf16(__uint_as_float(a[8 * c]), __uint_as_float(a[8 * c + 1])), pack_bf16(__uint_as_float(a[8 * c + 2]), __uint_as_float(a[8 * c + 3])),
+                       pack_bf16(__uint_as_float(a[8 * c + 4]), __uint_as_float(a[8 * c + 5])), pack_bf16(__uint_as_float(a[8 * c + 6]), __uint_as_float(a[8 * c + 7])));
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+    d4[4 + c] = make_uint4(pack_bf16(__uint_as_float(b[8 * c]), __uint_as_float(b[8 * c + 1])), pack_bf16(__uint_as_float(b[8 * c + 2]), __uint_as_float(b[8 * c + 3])),
+                           pack_bf16(__uint_as_float(b[8 * c + 4]), __uint_as_float(b[8 * c + 5])), pack_bf16(__uint_as_float(b[8 * c + 6]), __uint_as_float(b[8 * c + 7])));
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+attn_enc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                       const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO, const AttnTcBwdArgs p,
+                       const __grid_constant__ AttnBuckets bk) {
+  vq_pdl_trigger();
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t raw_u32 = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_u32 + 1023u) & ~1023u) - raw_u32);
+  uint8_t* sP = smem + 2 * TCB_STAGE_BYTES;
+  uint8_t* sdS = sP + TC_P_BYTES;
+  float* hdr = reinterpret_cast<float*>(sdS + TC_P_BYTES);
+  float* dtab = hdr + 2 * TCB_HDR_FLOATS;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(dtab + TCB_DTAB_FLOATS);
+  uint64_t* full_bar = bars;            // [2]
+  uint64_t* empty_bar = bars + 2;       // [2]
+  uint64_t* sfull_bar = bars + 4;       // S and dP accumulators complete
+  uint64_t* sempty_bar = bars + 5;      // ... read by the 4 row warps
+  uint64_t* pfull_bar = bars + 6;       // P and dS tiles written
+  uint64_t* ofull_bar = bars + 7;       // dQ, dK, dV accumulators complete
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int hp = p.H >> 1;
+  const int nitems = p.B * hp;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(sfull_bar, 1);
+    mbar_init(sempty_bar, 4);
+    mbar_init(pfull_bar, 4);
+    mbar_init(ofull_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 5) tmem_alloc(tmem_holder, TC_TMEM_COLS);
+  for (int i = threadIdx.x; i < 2 * TC_P_BYTES / 16; i += TC_THREADS) reinterpret_cast<uint4*>(sP)[i] = make_uint4(0, 0, 0, 0);   // P and dS tiles
+  for (int i = threadIdx.x; i < TCB_DTAB_FLOATS; i += TC_THREADS) dtab[i] = 0.f;
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+  // TMEM columns: S [0,128) | dP [128,256) | dQ [256,320) | dK [320,384) | dV [384,448)
+  vq_pdl_wait();
+
+  if (warp == 4) {
+    int n = 0;
+    for (int it = blockIdx.x; it < nitems; it += gridDim.x, ++n) {
+      const int stage = n & 1;
+      const uint32_t ph = (n >> 1) & 1;
+      const int b = it / hp, h = (it - b * hp) * 2;
+      mbar_wait(&empty_bar[stage], ph ^ 1);
+      float* hs = hdr + stage * TCB_HDR_FLOATS;
+      for (int j = lane; j < 64; j += 32) hs[j] = j < p.S ? (p.keymask ? p.keymask[(size_t)b * p.S + j] : 0.f) : -INFINITY;
+      for (int r = lane; r < 2 * 128; r += 32) {
+        const int hd = r >> 7, rel = r & 127;
+        hs[64 + r] = rel < 127 ? p.rel_table[(int)bk.b[rel] * p.H + h + hd] : 0.f;
+      }
+      for (int r = lane; r < 128; r += 32) {
+        const int hd = r >> 6, q = r & 63;
+        hs[64 + 256 + r] = q < p.S ? p.lse[((size_t)b * p.H + h + hd) * p.S + q] : INFINITY;     // rows >= S: P = dS = 0
+      }
+      __syncwarp();
+      if (lane == 0) {
+        uint8_t* st = smem + stage * TCB_STAGE_BYTES;
+        mbar_expect_tx(&full_bar[stage], TCB_STAGE_BYTES);
+        const int row = b * p.S;
+        tma_load_2d(st, &tmQ, &full_bar[stage], h * 64, row);
+        tma_load_2d(st + 8192, &tmQ, &full_bar[stage], (h + 1) * 64, row);
+        tma_load_2d(st + 16384, &tmK, &full_bar[stage], h * 64, row);
+        tma_load_2d(st + 16384 + 8192, &tmK, &full_bar[stage], (h + 1) * 64, row);
+        tma_load_2d(st + 32768, &tmV, &full_bar[stage], h * 64, row);
+        tma_load_2d(st + 32768 + 8192, &tmV, &full_bar[stage], (h + 1) * 64, row);
+        tma_load_2d(st + 49152, &tmdO, &full_bar[stage], h * 64, row);
+        tma_load_2d(st + 49152 + 8192, &tmdO, &full_bar[stage], (h + 1) * 64, row);
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);     // S, dP: both operands K-major
+      constexpr uint32_t idesc_t = umma_idesc_bf16(128, 64, true, true);        // dV, dK: A = tile^T (MN-major), B MN-major
+      constexpr uint32_t idesc_q = umma_idesc_bf16(128, 64, false, true);       // dQ: A = dS tile K-major, B MN-major
+      const uint32_t sP_u32 = smem_u32(sP), sdS_u32 = smem_u32(sdS);
+      auto issue_sdp = [&](int n) {
+        const int stage = n & 1;
+        mbar_wait(&full_bar[stage], (n >> 1) & 1);
+        mbar_wait(sempty_bar, (n & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t sq = smem_u32(smem + stage * TCB_STAGE_BYTES), sk = sq + 16384, sv = sq + 32768, sdo = sq + 49152;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16(tmem_base, umma_smem_desc_sw128(sq + k * 32, 16, 1024), umma_smem_desc_sw128(sk + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16(tmem_base + 128, umma_smem_desc_sw128(sdo + k * 32, 16, 1024), umma_smem_desc_sw128(sv + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(sfull_bar);
+      };
+      int n = 0;
+      if ((int)blockIdx.x < nitems) issue_sdp(0);
+      for (int it = blockIdx.x; it < nitems; it += gridDim.x, ++n) {
+        const int stage = n & 1;
+        mbar_wait(pfull_bar, n & 1);
+        tc_fence_after();
+        const uint32_t sq = smem_u32(smem + stage * TCB_STAGE_BYTES), sk = sq + 16384, sdo = sq + 49152;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {      // contraction over the 128 stacked query rows, 16 per step
+          const uint64_t a_p = umma_smem_desc_sw128(sP_u32 + kk * 2048, 16384, 1024);
+          const uint64_t a_s = umma_smem_desc_sw128(sdS_u32 + kk * 2048, 16384, 1024);
+          umma_f16(tmem_base + 384, a_p, umma_smem_desc_sw128(sdo + kk * 2048, 8192, 1024), idesc_t, kk > 0 ? 1u : 0u);   // dV = P^T dO
+          umma_f16(tmem_base + 320, a_s, umma_smem_desc_sw128(sq + kk * 2048, 8192, 1024), idesc_t, kk > 0 ? 1u : 0u);    // dK = dS^T Q
+        }
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)         // contraction over the 128 stacked keys
+          umma_f16(tmem_base + 256, umma_smem_desc_sw128(sdS_u32 + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+                   umma_smem_desc_sw128(sk + kk * 2048, 8192, 1024), idesc_q, kk > 0 ? 1u : 0u);                          // dQ = dS K
+        umma_commit(ofull_bar);
+        umma_commit(&empty_bar[stage]);
+        // the next item's S / dP: its stage is loaded and the row threads have long read this item's S / dP
+        if (it + (int)gridDim.x < nitems) issue_sdp(n + 1);
+      }
+    }
+  } else {
+    const int r = threadIdx.x;
+    const int hsel = r >> 6, q = r & 63;
+    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    const uint32_t row_off = hsel * 16384 + r * 128;
+    const uint32_t sP_row = smem_u32(sP) + row_off, sdS_row = smem_u32(sdS) + row_off;
+    const int sw = r & 7;
+    int n = 0;
+    for (int it = blockIdx.x; it < nitems; it += gridDim.x, ++n) {
+      const int stage = n & 1;
+      const int b = it / hp, h = (it - b * hp) * 2;
+      mbar_wait(&full_bar[stage], (n >> 1) & 1);
+      mbar_wait(sfull_bar, n & 1);
+      tc_fence_after();
+      float s[64], dp[64];
+      {
+        uint32_t t0[32], t1[32];
+        const uint32_t ta = tmem_base + hsel * 64 + lane_addr;
+        tmem_ld_32x32(ta, t0);
+        tmem_ld_32x32(ta + 32, t1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { s[j] = __uint_as_float(t0[j]); s[32 + j] = __uint_as_float(t1[j]); }
+        tmem_ld_32x32(ta + 128, t0);
+        tmem_ld_32x32(ta + 128 + 32, t1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { dp[j] = __uint_as_float(t0[j]); dp[32 + j] = __uint_as_float(t1[j]); }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sempty_bar);
+      const float* hs = hdr + stage * TCB_HDR_FLOATS;
+      const float lse = hs[64 + 256 + r];
+#pragma unroll
+      for (int j4 = 0; j4 < 16; ++j4) {
+        const float4 km = *reinterpret_cast<const float4*>(hs + 4 * j4);
+        s[4 * j4] += km.x; s[4 * j4 + 1] += km.y; s[4 * j4 + 2] += km.z; s[4 * j4 + 3] += km.w;
+      }
+      if (q < p.Lt) {
+        const float* bp = hs + 64 + hsel * 128 + (AT_S_TC - 1) - q;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < p.Lt) s[j] += bp[j];
+      }
+      uint32_t keep_lo = 0xFFFFFFFFu, keep_hi = 0xFFFFFFFFu;     // bit j: probability j survived dropout
+      if (p.drop_thr) {
+        keep_lo = keep_hi = 0u;
+        const uint32_t pi0 = attn_pair_idx((uint32_t)(b * p.H + h + hsel), q, 0);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const uint32_t hsh = vq_hash_pair(p.seed, pi0 + j);
+          const uint32_t k0 = (hsh & 0xFFFFu) >= p.drop_thr ? 1u : 0u, k1 = (hsh >> 16) >= p.drop_thr ? 1u : 0u;
+          if (j < 16) keep_lo |= (k0 << (2 * j)) | (k1 << (2 * j + 1));
+          else keep_hi |= (k0 << (2 * j - 32)) | (k1 << (2 * j - 31));
+        }
+      }
+      const float ik = p.drop_thr ? p.drop_inv_keep : 1.f;
+      float dsum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 64; ++j) {
+        const bool kept = ((j < 32 ? keep_lo >> j : keep_hi >> (j - 32)) & 1u) != 0u;
+        s[j] = __expf(s[j] - lse);                 // exp(-inf) = 0: masked keys, rows beyond S (lse = +inf)
+        dp[j] = kept ? dp[j] * ik : 0.f;           // dP through the dropout
+        dsum += s[j] * dp[j];
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint32_t pw[4], dw[4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+          const int j = 8 * c + 2 * x;
+          const bool k0 = ((j < 32 ? keep_lo >> j : keep_hi >> (j - 32)) & 1u) != 0u;
+          const bool k1 = ((j + 1 < 32 ? keep_lo >> (j + 1) : keep_hi >> (j + 1 - 32)) & 1u) != 0u;
+          pw[x] = pack_bf16(k0 ? s[j] * ik : 0.f, k1 ? s[j + 1] * ik : 0.f);
+          dw[x] = pack_bf16(s[j] * (dp[j] - dsum), s[j + 1] * (dp[j + 1] - dsum));
+        }
+        const uint32_t off = (uint32_t)(c ^ sw) << 4;
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sP_row + off), "r"(pw[0]), "r"(pw[1]), "r"(pw[2]), "r"(pw[3]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sdS_row + off), "r"(dw[0]), "r"(dw[1]), "r"(dw[2]), "r"(dw[3]) : "memory");
+      }
+      fence_proxy_async();
+      if (p.d_rel_table) {
+        // bias-table gradient: thread (head hsel, diagonal q) sums dS along its diagonal of the text x text corner
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int ndiag = 2 * p.Lt - 1;
+        if (q < ndiag) {
+          const int rel = q - (p.Lt - 1);             // key - query
+          const int q_lo = max(0, -rel), q_hi = min(p.Lt, p.Lt - rel);
+          float acc = 0.f;
+          const uint8_t* tile = sdS + hsel * 16384;
+          for (int qi = q_lo; qi < q_hi; ++qi) {
+            const int row = hsel * 64 + qi, j = qi + rel;
+            acc += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(tile + row * 128 + (((j >> 3) ^ (row & 7)) << 4) + (j & 7) * 2));
+          }
+          atomicAdd(&dtab[(int)bk.b[rel + (AT_S_TC - 1)] * 16 + h + hsel], acc);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pfull_bar);
+      // ---- outputs of this item
+      mbar_wait(ofull_bar, n & 1);
+      tc_fence_after();
+      {
+        uint32_t o0[32], o1[32];
+        const bool ok = q < p.S;
+        const size_t grow = (size_t)b * p.S + q;
+        const int col = (h + hsel) * 64;
+        tmem_ld_32x32(tmem_base + 256 + lane_addr, o0);
+        tmem_ld_32x32(tmem_base + 256 + 32 + lane_addr, o1);
+        tmem_ld_wait();
+        if (ok) store_row64(p.dq + grow * p.lddq + col, o0, o1);
+        tmem_ld_32x32(tmem_base + 320 + lane_addr, o0);
+        tmem_ld_32x32(tmem_base + 320 + 32 + lane_addr, o1);
+        tmem_ld_wait();
+        if (ok) store_row64(p.dk + grow * p.lddk + col, o0, o1);
+        tmem_ld_32x32(tmem_base + 384 + lane_addr, o0);
+        tmem_ld_32x32(tmem_base + 384 + 32 + lane_addr, o1);
+        tmem_ld_wait();
+        if (ok) store_row64(p.dv + grow * p.lddv + col, o0, o1);
+      }
+      tc_fence_before();
+    }
+    if (p.d_rel_table) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int i = r; i < 64 * 16; i += 128) {
+        const float v = dtab[i];
+        const int bucket = i >> 4, head = i & 15;
+        if (v != 0.f && head < p.H) atomicAdd(&p.d_rel_table[bucket * p.H + head], v);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TC_TMEM_COLS);
+  }
+}
+
+static int g_attn_tc = [] { const char* e = getenv("VQACL_ATTN_TC"); return (e && e[0] == '1') ? 1 : 0; }();
 
 // true when the tcgen05 kernel takes this problem (encoder form: square, 33..64 positions, text-corner bias, even head count)
 bool attn_tc_eligible(const AttnArgs& a) {
@@ -293,6 +595,38 @@ int attn_enc_fwd_tc(const AttnArgs& a, const AttnBuckets& bk, cudaStream_t strea
   const int items = a.B * (a.H / 2);
   const int grid = items < num_sms() ? items : num_sms();
   (void)vq_launch(attn_enc_fwd_tc_kernel, dim3(grid), dim3(TC_THREADS), (size_t)TC_SMEM_BYTES, stream, tq, tk, tv, p, bk);
+  VQ_LAUNCH_CHECK();
+  return 0;
+}
+
+bool attn_tc_bwd_eligible(const AttnArgs& a) {
+  static const int on = [] { const char* e = getenv("VQACL_ATTN_TC_BWD"); return (e && e[0] == '1') ? 1 : 0; }();
+  return on && a.rel_mode == 1 && a.Sq == a.Sk && a.Sq > 32 && a.Sq <= 64 && a.Lt <= 32 && (a.H & 1) == 0 && !a.causal && a.ldq % 8 == 0 &&
+         a.ldk % 8 == 0 && a.ldv % 8 == 0 && a.ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(a.q) & 15) == 0 &&
+         (reinterpret_cast<uintptr_t>(a.k) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.v) & 15) == 0 && a.H <= 16 && a.lddq % 8 == 0 && a.lddk % 8 == 0 && a.lddv % 8 == 0 &&
+         (reinterpret_cast<uintptr_t>(a.dO) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.dq) & 15) == 0 &&
+         (reinterpret_cast<uintptr_t>(a.dk) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.dv) & 15) == 0;
+}
+
+int attn_enc_bwd_tc(const AttnArgs& a, const AttnBuckets& bk, cudaStream_t stream) {
+  CUtensorMap tq, tk, tv, tdo;
+  const uint64_t rows = (uint64_t)a.B * a.Sq, cols = (uint64_t)a.H * 64;
+  if (make_tmap_bf16_2d(&tq, a.q, cols, rows, a.ldq, 64, 64)) return 1;
+  if (make_tmap_bf16_2d(&tk, a.k, cols, rows, a.ldk, 64, 64)) return 1;
+  if (make_tmap_bf16_2d(&tv, a.v, cols, rows, a.ldv, 64, 64)) return 1;
+  if (make_tmap_bf16_2d(&tdo, a.dO, cols, rows, a.ldo, 64, 64)) return 1;
+  static bool attr = false;
+  if (!attr) {
+    VQ_CUDA(cudaFuncSetAttribute(attn_enc_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TCB_SMEM_BYTES));
+    attr = true;
+  }
+  AttnTcBwdArgs p{};
+  p.dq = a.dq; p.dk = a.dk; p.dv = a.dv; p.lddq = a.lddq; p.lddk = a.lddk; p.lddv = a.lddv; p.lse = a.lse;
+  p.B = a.B; p.H = a.H; p.S = a.Sq; p.Lt = a.Lt; p.rel_table = a.rel_table; p.keymask = a.keymask; p.d_rel_table = a.d_rel_table;
+  p.drop_thr = a.drop_thr; p.drop_inv_keep = a.drop_inv_keep; p.seed = a.seed;
+  const int items = a.B * (a.H / 2);
+  const int grid = items < num_sms() ? items : num_sms();
+  (void)vq_launch(attn_enc_bwd_tc_kernel, dim3(grid), dim3(TC_THREADS), (size_t)TCB_SMEM_BYTES, stream, tq, tk, tv, tdo, p, bk);
   VQ_LAUNCH_CHECK();
   return 0;
 }

@@ -52,6 +52,8 @@ VQ_DEVINL uint32_t attn_pair_idx(uint32_t blk, int q, int k) { return ((blk * 64
 // attention_tc.cu: encoder self-attention on tcgen05 / TMEM / TMA
 bool attn_tc_eligible(const AttnArgs& a);
 int attn_enc_fwd_tc(const AttnArgs& a, const AttnBuckets& bk, cudaStream_t stream);
+bool attn_tc_bwd_eligible(const AttnArgs& a);
+int attn_enc_bwd_tc(const AttnArgs& a, const AttnBuckets& bk, cudaStream_t stream);
 
 // ---------------------------------------------------------------- elementwise.cu
 int cast_f32_to_bf16(const float* src, __nv_bfloat16* dst, size_t n, cudaStream_t stream);
