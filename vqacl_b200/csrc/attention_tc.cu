@@ -27,12 +27,21 @@
 namespace vq {
 
 constexpr int AT_S_TC = 64;                          // positions per head tile
-constexpr int TC_STAGE_BYTES = 3 * 16384;           // Q2 | K2 | V2, each 128 rows x 128 B
 constexpr int TC_P_BYTES = 2 * 16384;               // two K-atoms (keys of head h | keys of head h+1), each 128 rows x 128 B
-constexpr int TC_HDR_FLOATS = 64 + 2 * 128;         // kmask[64] | bias[2][128]
-constexpr int TC_SMEM_BYTES = 1024 + 2 * TC_STAGE_BYTES + TC_P_BYTES + 2 * TC_HDR_FLOATS * 4 + 256;
-constexpr int TC_THREADS = 192;
-constexpr int TC_TMEM_COLS = 512;                   // S0 [0,128) | S1 [128,256) | O [256,320)
+constexpr int TC_THREADS = 192;                     // backward kernel: warps 0-3 rows, 4 producer, 5 MMA
+constexpr int TC_TMEM_COLS = 512;
+
+// ---- forward: small CTAs (48 KB of shared memory, 128 TMEM columns, <= 128 registers) so that THREE are resident per SM:
+//      inside a CTA the phases of one item run back to back (load -> S -> softmax -> O -> store) and the latency of each is
+//      covered by the other CTAs of the SM. (A first version with one pipelined CTA per SM — two smem stages, two S
+//      accumulators, deferred epilogue — was correct but slower than the mma.sync kernel: 58 vs 40 us; ncu showed 6 warps per
+//      SM, issue slots 16 % busy, 84 % of cycles without an eligible warp: profiles/r02_attention_tc.md.)
+constexpr int TCF_STAGE_BYTES = 3 * 16384;          // Q2 | K2 | V2; the P tile overwrites Q2 | K2 once the S MMA has completed
+constexpr int TCF_HDR_FLOATS = 64 + 2 * 128;        // kmask[64] | bias[2][128]
+constexpr int TCF_SMEM_BYTES = 1024 + TCF_STAGE_BYTES + 2 * TCF_HDR_FLOATS * 4 + 128;
+constexpr int TCF_THREADS = 160;                    // warps 0-3: one thread per stacked query row; warp 4: header, TMA, MMA issue, TMEM
+constexpr int TCF_TMEM_COLS = 128;                  // S2 [0,128); O2 reuses columns [0,64) after the rows have read S2
+constexpr int TCF_CTAS_PER_SM = 3;
 
 struct AttnTcArgs {
   __nv_bfloat16* o; int ldo;
@@ -44,45 +53,43 @@ struct AttnTcArgs {
 };
 
 VQ_DEVINL void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+VQ_DEVINL void sts128_u(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TCF_THREADS, TCF_CTAS_PER_SM)
 attn_enc_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, const AttnTcArgs p, const __grid_constant__ AttnBuckets bk) {
   vq_pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw_u32 = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_u32 + 1023u) & ~1023u) - raw_u32);
-  uint8_t* sP = smem + 2 * TC_STAGE_BYTES;
-  float* hdr = reinterpret_cast<float*>(sP + TC_P_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(hdr) + 2 * TC_HDR_FLOATS * 4);
-  uint64_t* full_bar = bars;            // [2] TMA bytes of a stage landed (+ header written)
-  uint64_t* empty_bar = bars + 2;       // [2] both MMAs that read the stage are complete
-  uint64_t* sfull_bar = bars + 4;       // [2] S accumulator complete
-  uint64_t* sempty_bar = bars + 6;      // [2] S accumulator read by the 4 softmax warps
-  uint64_t* pfull_bar = bars + 8;       // P tile written (4 warps)
-  uint64_t* ofull_bar = bars + 9;       // O accumulator complete
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 10);
+  float* hdr = reinterpret_cast<float*>(smem + TCF_STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(hdr + 2 * TCF_HDR_FLOATS);
+  uint64_t* full_bar = bars;        // TMA bytes landed (+ header written)
+  uint64_t* sfull_bar = bars + 1;   // S accumulator complete
+  uint64_t* pfull_bar = bars + 2;   // P tile written and S read by the 4 row warps
+  uint64_t* ofull_bar = bars + 3;   // O accumulator complete (=> the stage's shared memory is free)
+  uint64_t* oread_bar = bars + 4;   // O read by the 4 row warps (=> the TMEM columns are free)
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 5);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int hp = p.H >> 1;
   const int nitems = p.B * hp;
 
-  if (warp == 4 && lane == 0) {
-    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
-      mbar_init(&sfull_bar[i], 1);
-      mbar_init(&sempty_bar[i], 4);
+  if (warp == 4) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+      mbar_init(full_bar, 1);
+      mbar_init(sfull_bar, 1);
+      mbar_init(pfull_bar, 4);
+      mbar_init(ofull_bar, 1);
+      mbar_init(oread_bar, 4);
+      mbar_fence_init();
     }
-    mbar_init(pfull_bar, 4);
-    mbar_init(ofull_bar, 1);
-    mbar_fence_init();
+    __syncwarp();
+    tmem_alloc(tmem_holder, TCF_TMEM_COLS);
   }
-  if (warp == 5) tmem_alloc(tmem_holder, TC_TMEM_COLS);
-  // the off-diagonal halves of the block-diagonal P tile stay zero for the whole kernel
-  for (int i = threadIdx.x; i < TC_P_BYTES / 16; i += TC_THREADS) reinterpret_cast<uint4*>(sP)[i] = make_uint4(0, 0, 0, 0);
-  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -90,14 +97,14 @@ attn_enc_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   vq_pdl_wait();
 
   if (warp == 4) {
-    // ------------------------------------------------ TMA producer + per-item header ------------------------------------------------
+    // ------------------------------------------------ header + TMA + MMA issue ------------------------------------------------
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);
+    constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, false, true);
+    const uint32_t sq = smem_u32(smem), sk = sq + 16384, sv = sq + 32768;
     int n = 0;
     for (int it = blockIdx.x; it < nitems; it += gridDim.x, ++n) {
-      const int stage = n & 1;
-      const uint32_t ph = (n >> 1) & 1;
       const int b = it / hp, h = (it - b * hp) * 2;
-      mbar_wait(&empty_bar[stage], ph ^ 1);
-      float* hs = hdr + stage * TC_HDR_FLOATS;
+      float* hs = hdr + (n & 1) * TCF_HDR_FLOATS;       // the other copy may still be read by the rows working on item n-1
       for (int j = lane; j < 64; j += 32) hs[j] = j < p.S ? (p.keymask ? p.keymask[(size_t)b * p.S + j] : 0.f) : -INFINITY;
       for (int r = lane; r < 2 * 128; r += 32) {
         const int hd = r >> 7, rel = r & 127;
@@ -105,167 +112,154 @@ attn_enc_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       }
       __syncwarp();
       if (lane == 0) {
-        uint8_t* st = smem + stage * TC_STAGE_BYTES;
-        mbar_expect_tx(&full_bar[stage], TC_STAGE_BYTES);
+        const uint32_t par = n & 1, prev = (n - 1) & 1;
+        if (n > 0) mbar_wait(ofull_bar, prev);          // O MMA of the previous item done: Q2 | K2 (= P tile) and V2 may be overwritten
+        mbar_expect_tx(full_bar, TCF_STAGE_BYTES);
         const int row = b * p.S;
-        tma_load_2d(st, &tmQ, &full_bar[stage], h * 64, row);
-        tma_load_2d(st + 8192, &tmQ, &full_bar[stage], (h + 1) * 64, row);
-        tma_load_2d(st + 16384, &tmK, &full_bar[stage], h * 64, row);
-        tma_load_2d(st + 16384 + 8192, &tmK, &full_bar[stage], (h + 1) * 64, row);
-        tma_load_2d(st + 32768, &tmV, &full_bar[stage], h * 64, row);
-        tma_load_2d(st + 32768 + 8192, &tmV, &full_bar[stage], (h + 1) * 64, row);
-      }
-    }
-  } else if (warp == 5) {
-    // ------------------------------------------------ MMA issuer ------------------------------------------------
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);
-      constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, false, true);
-      const uint32_t sP_u32 = smem_u32(sP);
-      auto issue_s = [&](int n) {
-        const int stage = n & 1;
-        const uint32_t ph = (n >> 1) & 1;
-        mbar_wait(&full_bar[stage], ph);
-        mbar_wait(&sempty_bar[stage], ph ^ 1);        // S buffer index == stage index (both alternate per item)
+        tma_load_2d(smem, &tmQ, full_bar, h * 64, row);
+        tma_load_2d(smem + 8192, &tmQ, full_bar, (h + 1) * 64, row);
+        tma_load_2d(smem + 16384, &tmK, full_bar, h * 64, row);
+        tma_load_2d(smem + 16384 + 8192, &tmK, full_bar, (h + 1) * 64, row);
+        tma_load_2d(smem + 32768, &tmV, full_bar, h * 64, row);
+        tma_load_2d(smem + 32768 + 8192, &tmV, full_bar, (h + 1) * 64, row);
+        mbar_wait(full_bar, par);
+        if (n > 0) mbar_wait(oread_bar, prev);          // the rows have read O of the previous item: its TMEM columns are reused by S
         tc_fence_after();
-        const uint32_t sq = smem_u32(smem + stage * TC_STAGE_BYTES), sk = sq + 16384;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_f16(tmem_base + stage * 128, umma_smem_desc_sw128(sq + k * 32, 16, 1024), umma_smem_desc_sw128(sk + k * 32, 16, 1024),
-                   idesc_s, k > 0 ? 1u : 0u);
-        umma_commit(&sfull_bar[stage]);
-      };
-      int n = 0;
-      if ((int)blockIdx.x < nitems) issue_s(0);
-      for (int it = blockIdx.x; it < nitems; it += gridDim.x, ++n) {
-        if (it + (int)gridDim.x < nitems) issue_s(n + 1);          // the next item's scores are computed under this item's softmax
-        const int stage = n & 1;
-        mbar_wait(pfull_bar, n & 1);
+          umma_f16(tmem_base, umma_smem_desc_sw128(sq + k * 32, 16, 1024), umma_smem_desc_sw128(sk + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(sfull_bar);
+        mbar_wait(pfull_bar, par);
         tc_fence_after();
-        const uint32_t sv = smem_u32(smem + stage * TC_STAGE_BYTES) + 32768;
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
-          umma_f16(tmem_base + 256, umma_smem_desc_sw128(sP_u32 + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+          umma_f16(tmem_base, umma_smem_desc_sw128(sq + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
                    umma_smem_desc_sw128(sv + kk * 2048, 8192, 1024), idesc_o, kk > 0 ? 1u : 0u);
         umma_commit(ofull_bar);
-        umma_commit(&empty_bar[stage]);
       }
+      __syncwarp();      // the other lanes stay within one item of lane 0 (header double buffer)
     }
   } else {
     // ------------------------------------------------ softmax + epilogue (thread = stacked row) ------------------------------------------------
     const int r = threadIdx.x;                 // 0..127 = TMEM lane
     const int hsel = r >> 6, q = r & 63;
     const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
-    const uint32_t sP_row = smem_u32(sP) + hsel * 16384 + r * 128;
+    const uint32_t sP_row = smem_u32(smem) + hsel * 16384 + r * 128;          // this row's 128 B of the key atom of its own head
+    const uint32_t sZ_row = smem_u32(smem) + (hsel ^ 1) * 16384 + r * 128;    // ... and of the other head's atom (zeros: block diagonal)
     const int sw = r & 7;
-    int n = 0, pb = 0, ph_ = 0;                // previous item's (batch, first head) for the deferred O epilogue
-    auto epilogue = [&](int nn, int b, int h) {
-      mbar_wait(ofull_bar, nn & 1);
-      tc_fence_after();
-      uint32_t o0[32], o1[32];
-      tmem_ld_32x32(tmem_base + 256 + lane_addr, o0);
-      tmem_ld_32x32(tmem_base + 256 + 32 + lane_addr, o1);
-      tmem_ld_wait();
-      if (q < p.S) {
-        uint4* dst = reinterpret_cast<uint4*>(p.o + ((size_t)b * p.S + q) * p.ldo + (h + hsel) * 64);
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          dst[c] = make_uint4(pack_bf16(__uint_as_float(o0[8 * c]), __uint_as_float(o0[8 * c + 1])),
-                              pack_bf16(__uint_as_float(o0[8 * c + 2]), __uint_as_float(o0[8 * c + 3])),
-                              pack_bf16(__uint_as_float(o0[8 * c + 4]), __uint_as_float(o0[8 * c + 5])),
-                              pack_bf16(__uint_as_float(o0[8 * c + 6]), __uint_as_float(o0[8 * c + 7])));
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          dst[4 + c] = make_uint4(pack_bf16(__uint_as_float(o1[8 * c]), __uint_as_float(o1[8 * c + 1])),
-                                  pack_bf16(__uint_as_float(o1[8 * c + 2]), __uint_as_float(o1[8 * c + 3])),
-                                  pack_bf16(__uint_as_float(o1[8 * c + 4]), __uint_as_float(o1[8 * c + 5])),
-                                  pack_bf16(__uint_as_float(o1[8 * c + 6]), __uint_as_float(o1[8 * c + 7])));
-      }
-      tc_fence_before();
-    };
+    const uint32_t ts = tmem_base + hsel * 64 + lane_addr;                    // this row's 64 score columns
+    int n = 0;
     for (int it = blockIdx.x; it < nitems; it += gridDim.x, ++n) {
-      const int stage = n & 1;
-      const uint32_t ph = (n >> 1) & 1;
+      const uint32_t par = n & 1;
       const int b = it / hp, h = (it - b * hp) * 2;
-      mbar_wait(&full_bar[stage], ph);         // header of this stage is visible
-      mbar_wait(&sfull_bar[stage], ph);
+      const float* hs = hdr + (n & 1) * TCF_HDR_FLOATS;
+      const float* bp = hs + 64 + hsel * 128 + (AT_S_TC - 1) - q;
+      const bool biased = q < p.Lt;
+      mbar_wait(full_bar, par);                // header visible
+      mbar_wait(sfull_bar, par);
       tc_fence_after();
-      float v[64];
-      {
-        uint32_t s0[32], s1[32];
-        const uint32_t ta = tmem_base + stage * 128 + hsel * 64 + lane_addr;
-        tmem_ld_32x32(ta, s0);
-        tmem_ld_32x32(ta + 32, s1);
+      // pass 1: row maximum of S + key mask (+ bias); the scores stay in TMEM and are read again below, so only 32 are live
+      float m = -INFINITY;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t s0[32];
+        tmem_ld_32x32(ts + half * 32, s0);
         tmem_ld_wait();
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(s0[j]); v[32 + j] = __uint_as_float(s1[j]); }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sempty_bar[stage]);
-      const float* hs = hdr + stage * TC_HDR_FLOATS;
-      // additive key-side term (padding mask, -inf beyond S): the same for every row -> broadcast reads
-#pragma unroll
-      for (int j4 = 0; j4 < 16; ++j4) {
-        const float4 km = *reinterpret_cast<const float4*>(hs + 4 * j4);
-        v[4 * j4] += km.x; v[4 * j4 + 1] += km.y; v[4 * j4 + 2] += km.z; v[4 * j4 + 3] += km.w;
-      }
-      // relative-position bias on the text x text corner (rows and keys < Lt <= 32)
-      if (q < p.Lt) {
-        const float* bp = hs + 64 + hsel * 128 + (AT_S_TC - 1) - q;
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j < p.Lt) v[j] += bp[j];
-      }
-      float m = v[0];
-#pragma unroll
-      for (int j = 1; j < 64; ++j) m = fmaxf(m, v[j]);
-      float l = 0.f;
-#pragma unroll
-      for (int j = 0; j < 64; ++j) {
-        v[j] = __expf(v[j] - m);
-        l += v[j];
-      }
-      const float inv = 1.f / l;
-      if (q < p.S && p.lse) p.lse[((size_t)b * p.H + h + hsel) * p.S + q] = m + __logf(l);
-      uint32_t pk[32];
-      if (p.drop_thr) {
-        const uint32_t pi0 = attn_pair_idx((uint32_t)(b * p.H + h + hsel), q, 0);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float d0, d1;
-          vq_dropout_pair(p.seed, pi0 + j, p.drop_thr, p.drop_inv_keep, d0, d1);
-          pk[j] = pack_bf16(v[2 * j] * inv * d0, v[2 * j + 1] * inv * d1);
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 km = *reinterpret_cast<const float4*>(hs + half * 32 + 4 * j4);
+          float x0 = __uint_as_float(s0[4 * j4]) + km.x, x1 = __uint_as_float(s0[4 * j4 + 1]) + km.y;
+          float x2 = __uint_as_float(s0[4 * j4 + 2]) + km.z, x3 = __uint_as_float(s0[4 * j4 + 3]) + km.w;
+          if (half == 0 && biased) {
+            const int j = 4 * j4;
+            if (j < p.Lt) x0 += bp[j];
+            if (j + 1 < p.Lt) x1 += bp[j + 1];
+            if (j + 2 < p.Lt) x2 += bp[j + 2];
+            if (j + 3 < p.Lt) x3 += bp[j + 3];
+          }
+          mx[0] = fmaxf(mx[0], x0); mx[1] = fmaxf(mx[1], x1); mx[2] = fmaxf(mx[2], x2); mx[3] = fmaxf(mx[3], x3);
         }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) pk[j] = pack_bf16(v[2 * j] * inv, v[2 * j + 1] * inv);
+        m = fmaxf(m, fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])));
       }
-      // the O epilogue of the previous item: its MMA finished long ago; doing it here also guarantees that the P tile of the
-      // previous item has been consumed before it is overwritten below
-      if (n > 0) epilogue(n - 1, pb, ph_);
-      pb = b; ph_ = h;
+      // pass 2: e = exp(x - m) (un-normalised: the 1 / sum and the dropout scale are applied to the O row), P tile rows
+      float l4[4] = {0.f, 0.f, 0.f, 0.f};
+      const uint32_t pi0 = attn_pair_idx((uint32_t)(b * p.H + h + hsel), q, 0);
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const uint32_t addr = sP_row + ((uint32_t)(c ^ sw) << 4);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * c]), "r"(pk[4 * c + 1]), "r"(pk[4 * c + 2]),
-                     "r"(pk[4 * c + 3]) : "memory");
+      for (int half = 0; half < 2; ++half) {
+        uint32_t s0[32];
+        tmem_ld_32x32(ts + half * 32, s0);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 km = *reinterpret_cast<const float4*>(hs + half * 32 + 4 * j4);
+          float x0 = __uint_as_float(s0[4 * j4]) + km.x, x1 = __uint_as_float(s0[4 * j4 + 1]) + km.y;
+          float x2 = __uint_as_float(s0[4 * j4 + 2]) + km.z, x3 = __uint_as_float(s0[4 * j4 + 3]) + km.w;
+          if (half == 0 && biased) {
+            const int j = 4 * j4;
+            if (j < p.Lt) x0 += bp[j];
+            if (j + 1 < p.Lt) x1 += bp[j + 1];
+            if (j + 2 < p.Lt) x2 += bp[j + 2];
+            if (j + 3 < p.Lt) x3 += bp[j + 3];
+          }
+          float e0 = __expf(x0 - m), e1 = __expf(x1 - m), e2 = __expf(x2 - m), e3 = __expf(x3 - m);
+          l4[0] += e0; l4[1] += e1; l4[2] += e2; l4[3] += e3;
+          if (p.drop_thr) {
+            const uint32_t h0 = vq_hash_pair(p.seed, pi0 + half * 16 + 2 * j4), h1 = vq_hash_pair(p.seed, pi0 + half * 16 + 2 * j4 + 1);
+            e0 = (h0 & 0xFFFFu) >= p.drop_thr ? e0 : 0.f;
+            e1 = (h0 >> 16) >= p.drop_thr ? e1 : 0.f;
+            e2 = (h1 & 0xFFFFu) >= p.drop_thr ? e2 : 0.f;
+            e3 = (h1 >> 16) >= p.drop_thr ? e3 : 0.f;
+          }
+          pk[2 * j4] = pack_bf16(e0, e1);
+          pk[2 * j4 + 1] = pack_bf16(e2, e3);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t off = (uint32_t)((half * 4 + c) ^ sw) << 4;
+          sts128_u(sP_row + off, pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+          sts128_u(sZ_row + off, 0u, 0u, 0u, 0u);
+        }
       }
+      const float l = (l4[0] + l4[1]) + (l4[2] + l4[3]);
+      tc_fence_before();                         // S has been read: the O MMA may overwrite its columns
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(pfull_bar);
+      if (q < p.S && p.lse) p.lse[((size_t)b * p.H + h + hsel) * p.S + q] = m + __logf(l);
+      const float osc = (p.drop_thr ? p.drop_inv_keep : 1.f) / l;
+      mbar_wait(ofull_bar, par);
+      tc_fence_after();
+      __nv_bfloat16* orow = p.o + ((size_t)b * p.S + q) * p.ldo + (h + hsel) * 64;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t o0[32];
+        tmem_ld_32x32(tmem_base + lane_addr + half * 32, o0);
+        tmem_ld_wait();
+        if (q < p.S) {
+          uint4* dst = reinterpret_cast<uint4*>(orow + half * 32);
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            dst[c] = make_uint4(pack_bf16(__uint_as_float(o0[8 * c]) * osc, __uint_as_float(o0[8 * c + 1]) * osc),
+                                pack_bf16(__uint_as_float(o0[8 * c + 2]) * osc, __uint_as_float(o0[8 * c + 3]) * osc),
+                                pack_bf16(__uint_as_float(o0[8 * c + 4]) * osc, __uint_as_float(o0[8 * c + 5]) * osc),
+                                pack_bf16(__uint_as_float(o0[8 * c + 6]) * osc, __uint_as_float(o0[8 * c + 7]) * osc));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(oread_bar);
     }
-    if (n > 0) epilogue(n - 1, pb, ph_);
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 4) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TC_TMEM_COLS);
+    tmem_dealloc(tmem_base, TCF_TMEM_COLS);
   }
 }
-
 
 // =====================================================================================================================
 // Backward of the same problem on the same machinery. Per item (batch element x two stacked heads):
@@ -586,15 +580,16 @@ int attn_enc_fwd_tc(const AttnArgs& a, const AttnBuckets& bk, cudaStream_t strea
   if (make_tmap_bf16_2d(&tv, a.v, cols, rows, a.ldv, 64, 64)) return 1;
   static bool attr = false;
   if (!attr) {
-    VQ_CUDA(cudaFuncSetAttribute(attn_enc_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    VQ_CUDA(cudaFuncSetAttribute(attn_enc_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TCF_SMEM_BYTES));
     attr = true;
   }
   AttnTcArgs p{};
   p.o = a.o; p.ldo = a.ldo; p.lse = a.lse; p.B = a.B; p.H = a.H; p.S = a.Sq; p.Lt = a.Lt; p.rel_table = a.rel_table; p.keymask = a.keymask;
   p.drop_thr = a.drop_thr; p.drop_inv_keep = a.drop_inv_keep; p.seed = a.seed;
   const int items = a.B * (a.H / 2);
-  const int grid = items < num_sms() ? items : num_sms();
-  (void)vq_launch(attn_enc_fwd_tc_kernel, dim3(grid), dim3(TC_THREADS), (size_t)TC_SMEM_BYTES, stream, tq, tk, tv, p, bk);
+  const int cap = TCF_CTAS_PER_SM * num_sms();
+  const int grid = items < cap ? items : cap;
+  (void)vq_launch(attn_enc_fwd_tc_kernel, dim3(grid), dim3(TCF_THREADS), (size_t)TCF_SMEM_BYTES, stream, tq, tk, tv, p, bk);
   VQ_LAUNCH_CHECK();
   return 0;
 }
