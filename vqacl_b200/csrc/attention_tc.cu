@@ -31,17 +31,19 @@ constexpr int TC_P_BYTES = 2 * 16384;               // two K-atoms (keys of head
 constexpr int TC_THREADS = 192;                     // backward kernel: warps 0-3 rows, 4 producer, 5 MMA
 constexpr int TC_TMEM_COLS = 512;
 
-// ---- forward: small CTAs (48 KB of shared memory, 128 TMEM columns, <= 128 registers) so that THREE are resident per SM:
-//      inside a CTA the phases of one item run back to back (load -> S -> softmax -> O -> store) and the latency of each is
-//      covered by the other CTAs of the SM. (A first version with one pipelined CTA per SM — two smem stages, two S
-//      accumulators, deferred epilogue — was correct but slower than the mma.sync kernel: 58 vs 40 us; ncu showed 6 warps per
-//      SM, issue slots 16 % busy, 84 % of cycles without an eligible warp: profiles/r02_attention_tc.md.)
+// ---- forward: small CTAs (2 x 48 KB of shared memory, 128 TMEM columns, <= 128 registers) so that TWO are resident per SM;
+//      inside a CTA the compute phases of one item run back to back (S -> softmax -> O -> store) under the TMA loads of the
+//      next item, and the other CTA of the SM covers the hand-over latencies. History (profiles/r02_attention_tc.md):
+//      v1, one CTA per SM with two stages, two S accumulators and a deferred epilogue: correct, 58 us (mma.sync kernel: 40 us);
+//      ncu: 6 warps per SM, issue slots 16 % busy. v2, three single-stage CTAs per SM: 55 us; ncu: 37 % of the stall samples
+//      are the row warps waiting for the item's TMA loads (no prefetch), DRAM 22 %.
 constexpr int TCF_STAGE_BYTES = 3 * 16384;          // Q2 | K2 | V2; the P tile overwrites Q2 | K2 once the S MMA has completed
 constexpr int TCF_HDR_FLOATS = 64 + 2 * 128;        // kmask[64] | bias[2][128]
-constexpr int TCF_SMEM_BYTES = 1024 + TCF_STAGE_BYTES + 2 * TCF_HDR_FLOATS * 4 + 128;
+constexpr int TCF_STAGES = 2;                       // the TMA loads of item n+1 are in flight while item n is computed
+constexpr int TCF_SMEM_BYTES = 1024 + TCF_STAGES * TCF_STAGE_BYTES + 2 * TCF_HDR_FLOATS * 4 + 128;
 constexpr int TCF_THREADS = 160;                    // warps 0-3: one thread per stacked query row; warp 4: header, TMA, MMA issue, TMEM
 constexpr int TCF_TMEM_COLS = 128;                  // S2 [0,128); O2 reuses columns [0,64) after the rows have read S2
-constexpr int TCF_CTAS_PER_SM = 3;
+constexpr int TCF_CTAS_PER_SM = 2;
 
 struct AttnTcArgs {
   __nv_bfloat16* o; int ldo;
@@ -64,14 +66,14 @@ attn_enc_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw_u32 = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_u32 + 1023u) & ~1023u) - raw_u32);
-  float* hdr = reinterpret_cast<float*>(smem + TCF_STAGE_BYTES);
+  float* hdr = reinterpret_cast<float*>(smem + TCF_STAGES * TCF_STAGE_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(hdr + 2 * TCF_HDR_FLOATS);
-  uint64_t* full_bar = bars;        // TMA bytes landed (+ header written)
-  uint64_t* sfull_bar = bars + 1;   // S accumulator complete
-  uint64_t* pfull_bar = bars + 2;   // P tile written and S read by the 4 row warps
-  uint64_t* ofull_bar = bars + 3;   // O accumulator complete (=> the stage's shared memory is free)
-  uint64_t* oread_bar = bars + 4;   // O read by the 4 row warps (=> the TMEM columns are free)
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 5);
+  uint64_t* full_bar = bars;        // [2] TMA bytes of a stage landed (+ header written)
+  uint64_t* sfull_bar = bars + 2;   // S accumulator complete
+  uint64_t* pfull_bar = bars + 3;   // P tile written and S read by the 4 row warps
+  uint64_t* ofull_bar = bars + 4;   // O accumulator complete (=> the stage's shared memory is free)
+  uint64_t* oread_bar = bars + 5;   // O read by the 4 row warps (=> the TMEM columns are free)
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 6);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int hp = p.H >> 1;
@@ -80,7 +82,8 @@ attn_enc_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   if (warp == 4) {
     if (lane == 0) {
       tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
-      mbar_init(full_bar, 1);
+      mbar_init(&full_bar[0], 1);
+      mbar_init(&full_bar[1], 1);
       mbar_init(sfull_bar, 1);
       mbar_init(pfull_bar, 4);
       mbar_init(ofull_bar, 1);
@@ -100,11 +103,10 @@ attn_enc_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     // ------------------------------------------------ header + TMA + MMA issue ------------------------------------------------
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);
     constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, false, true);
-    const uint32_t sq = smem_u32(smem), sk = sq + 16384, sv = sq + 32768;
-    int n = 0;
-    for (int it = blockIdx.x; it < nitems; it += gridDim.x, ++n) {
+    // header (all lanes) + TMA loads (lane 0) of the item with running index m into stage m & 1
+    auto load_item = [&](int m, int it) {
       const int b = it / hp, h = (it - b * hp) * 2;
-      float* hs = hdr + (n & 1) * TCF_HDR_FLOATS;       // the other copy may still be read by the rows working on item n-1
+      float* hs = hdr + (m & 1) * TCF_HDR_FLOATS;
       for (int j = lane; j < 64; j += 32) hs[j] = j < p.S ? (p.keymask ? p.keymask[(size_t)b * p.S + j] : 0.f) : -INFINITY;
       for (int r = lane; r < 2 * 128; r += 32) {
         const int hd = r >> 7, rel = r & 127;
@@ -112,24 +114,37 @@ attn_enc_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       }
       __syncwarp();
       if (lane == 0) {
-        const uint32_t par = n & 1, prev = (n - 1) & 1;
-        if (n > 0) mbar_wait(ofull_bar, prev);          // O MMA of the previous item done: Q2 | K2 (= P tile) and V2 may be overwritten
-        mbar_expect_tx(full_bar, TCF_STAGE_BYTES);
+        uint8_t* st = smem + (m & 1) * TCF_STAGE_BYTES;
+        uint64_t* fb = &full_bar[m & 1];
+        mbar_expect_tx(fb, TCF_STAGE_BYTES);
         const int row = b * p.S;
-        tma_load_2d(smem, &tmQ, full_bar, h * 64, row);
-        tma_load_2d(smem + 8192, &tmQ, full_bar, (h + 1) * 64, row);
-        tma_load_2d(smem + 16384, &tmK, full_bar, h * 64, row);
-        tma_load_2d(smem + 16384 + 8192, &tmK, full_bar, (h + 1) * 64, row);
-        tma_load_2d(smem + 32768, &tmV, full_bar, h * 64, row);
-        tma_load_2d(smem + 32768 + 8192, &tmV, full_bar, (h + 1) * 64, row);
-        mbar_wait(full_bar, par);
+        tma_load_2d(st, &tmQ, fb, h * 64, row);
+        tma_load_2d(st + 8192, &tmQ, fb, (h + 1) * 64, row);
+        tma_load_2d(st + 16384, &tmK, fb, h * 64, row);
+        tma_load_2d(st + 16384 + 8192, &tmK, fb, (h + 1) * 64, row);
+        tma_load_2d(st + 32768, &tmV, fb, h * 64, row);
+        tma_load_2d(st + 32768 + 8192, &tmV, fb, (h + 1) * 64, row);
+      }
+    };
+    int n = 0;
+    if ((int)blockIdx.x < nitems) load_item(0, blockIdx.x);
+    for (int it = blockIdx.x; it < nitems; it += gridDim.x, ++n) {
+      const uint32_t prev = (n - 1) & 1;
+      // stage (n+1) & 1 and header copy (n+1) & 1 were last used by item n-1: free once its O MMA has completed (the rows
+      // finished with that header before they released the P tile)
+      if (n > 0 && lane == 0) mbar_wait(ofull_bar, prev);
+      __syncwarp();
+      if (it + (int)gridDim.x < nitems) load_item(n + 1, it + gridDim.x);
+      if (lane == 0) {
+        const uint32_t sq = smem_u32(smem + (n & 1) * TCF_STAGE_BYTES), sk = sq + 16384, sv = sq + 32768;
+        mbar_wait(&full_bar[n & 1], (n >> 1) & 1);
         if (n > 0) mbar_wait(oread_bar, prev);          // the rows have read O of the previous item: its TMEM columns are reused by S
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_f16(tmem_base, umma_smem_desc_sw128(sq + k * 32, 16, 1024), umma_smem_desc_sw128(sk + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
         umma_commit(sfull_bar);
-        mbar_wait(pfull_bar, par);
+        mbar_wait(pfull_bar, n & 1);
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
@@ -137,15 +152,15 @@ attn_enc_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                    umma_smem_desc_sw128(sv + kk * 2048, 8192, 1024), idesc_o, kk > 0 ? 1u : 0u);
         umma_commit(ofull_bar);
       }
-      __syncwarp();      // the other lanes stay within one item of lane 0 (header double buffer)
+      __syncwarp();
     }
   } else {
     // ------------------------------------------------ softmax + epilogue (thread = stacked row) ------------------------------------------------
     const int r = threadIdx.x;                 // 0..127 = TMEM lane
     const int hsel = r >> 6, q = r & 63;
     const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
-    const uint32_t sP_row = smem_u32(smem) + hsel * 16384 + r * 128;          // this row's 128 B of the key atom of its own head
-    const uint32_t sZ_row = smem_u32(smem) + (hsel ^ 1) * 16384 + r * 128;    // ... and of the other head's atom (zeros: block diagonal)
+    const uint32_t sP_row0 = smem_u32(smem) + hsel * 16384 + r * 128;         // this row's 128 B of the key atom of its own head
+    const uint32_t sZ_row0 = smem_u32(smem) + (hsel ^ 1) * 16384 + r * 128;   // ... and of the other head's atom (zeros: block diagonal)
     const int sw = r & 7;
     const uint32_t ts = tmem_base + hsel * 64 + lane_addr;                    // this row's 64 score columns
     int n = 0;
@@ -155,7 +170,8 @@ attn_enc_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       const float* hs = hdr + (n & 1) * TCF_HDR_FLOATS;
       const float* bp = hs + 64 + hsel * 128 + (AT_S_TC - 1) - q;
       const bool biased = q < p.Lt;
-      mbar_wait(full_bar, par);                // header visible
+      const uint32_t sP_row = sP_row0 + (n & 1) * TCF_STAGE_BYTES, sZ_row = sZ_row0 + (n & 1) * TCF_STAGE_BYTES;
+      mbar_wait(&full_bar[n & 1], (n >> 1) & 1);   // header visible
       mbar_wait(sfull_bar, par);
       tc_fence_after();
       // pass 1: row maximum of S + key mask (+ bias); the scores stay in TMEM and are read again below, so only 32 are live
