@@ -36,12 +36,18 @@ constexpr int TC_TMEM_COLS = 512;
 //      next item, and the other CTA of the SM covers the hand-over latencies. History (profiles/r02_attention_tc.md):
 //      v1, one CTA per SM with two stages, two S accumulators and a deferred epilogue: correct, 58 us (mma.sync kernel: 40 us);
 //      ncu: 6 warps per SM, issue slots 16 % busy. v2, three single-stage CTAs per SM: 55 us; ncu: 37 % of the stall samples
-//      are the row warps waiting for the item's TMA loads (no prefetch), DRAM 22 %.
+//      are the row warps waiting for the item's TMA loads (no prefetch), DRAM 22 %. v3, v2 + a second stage, two CTAs per
+//      SM: 58 us; the loads are hidden but 8 row warps per SM issue one instruction per 11 cycles each (thread = row keeps 64
+//      scores per thread and ~1200 dependent instructions per item). v4 (this one): two threads per row -> 16 row warps per
+//      SM, 32 scores per thread in registers, a single pass over TMEM; the halves of the row maximum / sum are exchanged
+//      through shared memory with a 64-thread named barrier per warp pair.
 constexpr int TCF_STAGE_BYTES = 3 * 16384;          // Q2 | K2 | V2; the P tile overwrites Q2 | K2 once the S MMA has completed
 constexpr int TCF_HDR_FLOATS = 64 + 2 * 128;        // kmask[64] | bias[2][128]
 constexpr int TCF_STAGES = 2;                       // the TMA loads of item n+1 are in flight while item n is computed
-constexpr int TCF_SMEM_BYTES = 1024 + TCF_STAGES * TCF_STAGE_BYTES + 2 * TCF_HDR_FLOATS * 4 + 128;
-constexpr int TCF_THREADS = 160;                    // warps 0-3: one thread per stacked query row; warp 4: header, TMA, MMA issue, TMEM
+constexpr int TCF_XCHG_FLOATS = 4 * 128;            // row maximum / row sum halves exchanged between the two threads of a row
+constexpr int TCF_SMEM_BYTES = 1024 + TCF_STAGES * TCF_STAGE_BYTES + 2 * TCF_HDR_FLOATS * 4 + TCF_XCHG_FLOATS * 4 + 128;
+constexpr int TCF_ROW_WARPS = 8;                    // warps 0-7: TWO threads per stacked query row (32 of its 64 score columns each)
+constexpr int TCF_THREADS = (TCF_ROW_WARPS + 1) * 32;   // + warp 8: header, TMA, MMA issue, TMEM
 constexpr int TCF_TMEM_COLS = 128;                  // S2 [0,128); O2 reuses columns [0,64) after the rows have read S2
 constexpr int TCF_CTAS_PER_SM = 2;
 
@@ -67,7 +73,8 @@ attn_enc_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   const uint32_t raw_u32 = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_u32 + 1023u) & ~1023u) - raw_u32);
   float* hdr = reinterpret_cast<float*>(smem + TCF_STAGES * TCF_STAGE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(hdr + 2 * TCF_HDR_FLOATS);
+  float* xchg = hdr + 2 * TCF_HDR_FLOATS;      // [2 halves][128 rows] maxima | [2][128] sums
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xchg + TCF_XCHG_FLOATS);
   uint64_t* full_bar = bars;        // [2] TMA bytes of a stage landed (+ header written)
   uint64_t* sfull_bar = bars + 2;   // S accumulator complete
   uint64_t* pfull_bar = bars + 3;   // P tile written and S read by the 4 row warps
@@ -79,15 +86,15 @@ attn_enc_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   const int hp = p.H >> 1;
   const int nitems = p.B * hp;
 
-  if (warp == 4) {
+  if (warp == TCF_ROW_WARPS) {
     if (lane == 0) {
       tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
       mbar_init(&full_bar[0], 1);
       mbar_init(&full_bar[1], 1);
       mbar_init(sfull_bar, 1);
-      mbar_init(pfull_bar, 4);
+      mbar_init(pfull_bar, TCF_ROW_WARPS);
       mbar_init(ofull_bar, 1);
-      mbar_init(oread_bar, 4);
+      mbar_init(oread_bar, TCF_ROW_WARPS);
       mbar_fence_init();
     }
     __syncwarp();
@@ -99,7 +106,7 @@ attn_enc_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   const uint32_t tmem_base = *tmem_holder;
   vq_pdl_wait();
 
-  if (warp == 4) {
+  if (warp == TCF_ROW_WARPS) {
     // ------------------------------------------------ header + TMA + MMA issue ------------------------------------------------
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);
     constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, false, true);
@@ -155,106 +162,92 @@ attn_enc_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       __syncwarp();
     }
   } else {
-    // ------------------------------------------------ softmax + epilogue (thread = stacked row) ------------------------------------------------
-    const int r = threadIdx.x;                 // 0..127 = TMEM lane
+    // ------------------------------------------------ softmax + epilogue (two threads per stacked row) ------------------------------------------------
+    const int rw = warp & 3, ch = warp >> 2;   // TMEM lane quarter (a warp may only touch lanes 32 * (warp % 4) ...) | column half
+    const int r = rw * 32 + lane;              // stacked query row = TMEM lane
     const int hsel = r >> 6, q = r & 63;
-    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    const uint32_t lane_addr = (uint32_t)(rw * 32) << 16;
     const uint32_t sP_row0 = smem_u32(smem) + hsel * 16384 + r * 128;         // this row's 128 B of the key atom of its own head
     const uint32_t sZ_row0 = smem_u32(smem) + (hsel ^ 1) * 16384 + r * 128;   // ... and of the other head's atom (zeros: block diagonal)
     const int sw = r & 7;
-    const uint32_t ts = tmem_base + hsel * 64 + lane_addr;                    // this row's 64 score columns
+    const uint32_t ts = tmem_base + hsel * 64 + ch * 32 + lane_addr;          // this thread's 32 score columns
+    float* xmax = xchg + r, *xsum = xchg + 256 + r;                            // [half][row]
+    const int bar_id = 1 + rw;                                                 // named barrier of the warp pair (rw, rw + 4)
     int n = 0;
     for (int it = blockIdx.x; it < nitems; it += gridDim.x, ++n) {
       const uint32_t par = n & 1;
       const int b = it / hp, h = (it - b * hp) * 2;
       const float* hs = hdr + (n & 1) * TCF_HDR_FLOATS;
       const float* bp = hs + 64 + hsel * 128 + (AT_S_TC - 1) - q;
-      const bool biased = q < p.Lt;
+      const bool biased = ch == 0 && q < p.Lt;       // the biased text x text corner lies in columns < Lt <= 32
       const uint32_t sP_row = sP_row0 + (n & 1) * TCF_STAGE_BYTES, sZ_row = sZ_row0 + (n & 1) * TCF_STAGE_BYTES;
       mbar_wait(&full_bar[n & 1], (n >> 1) & 1);   // header visible
       mbar_wait(sfull_bar, par);
       tc_fence_after();
-      // pass 1: row maximum of S + key mask (+ bias); the scores stay in TMEM and are read again below, so only 32 are live
-      float m = -INFINITY;
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
+      float x[32];
+      {
         uint32_t s0[32];
-        tmem_ld_32x32(ts + half * 32, s0);
+        tmem_ld_32x32(ts, s0);
         tmem_ld_wait();
-        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 km = *reinterpret_cast<const float4*>(hs + half * 32 + 4 * j4);
-          float x0 = __uint_as_float(s0[4 * j4]) + km.x, x1 = __uint_as_float(s0[4 * j4 + 1]) + km.y;
-          float x2 = __uint_as_float(s0[4 * j4 + 2]) + km.z, x3 = __uint_as_float(s0[4 * j4 + 3]) + km.w;
-          if (half == 0 && biased) {
-            const int j = 4 * j4;
-            if (j < p.Lt) x0 += bp[j];
-            if (j + 1 < p.Lt) x1 += bp[j + 1];
-            if (j + 2 < p.Lt) x2 += bp[j + 2];
-            if (j + 3 < p.Lt) x3 += bp[j + 3];
-          }
-          mx[0] = fmaxf(mx[0], x0); mx[1] = fmaxf(mx[1], x1); mx[2] = fmaxf(mx[2], x2); mx[3] = fmaxf(mx[3], x3);
+          const float4 km = *reinterpret_cast<const float4*>(hs + ch * 32 + 4 * j4);
+          x[4 * j4] = __uint_as_float(s0[4 * j4]) + km.x;
+          x[4 * j4 + 1] = __uint_as_float(s0[4 * j4 + 1]) + km.y;
+          x[4 * j4 + 2] = __uint_as_float(s0[4 * j4 + 2]) + km.z;
+          x[4 * j4 + 3] = __uint_as_float(s0[4 * j4 + 3]) + km.w;
         }
-        m = fmaxf(m, fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])));
       }
-      // pass 2: e = exp(x - m) (un-normalised: the 1 / sum and the dropout scale are applied to the O row), P tile rows
+      if (biased) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < p.Lt) x[j] += bp[j];
+      }
+      float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int j = 0; j < 32; ++j) mx[j & 3] = fmaxf(mx[j & 3], x[j]);
+      float m = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+      xmax[ch * 128] = m;
+      asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+      m = fmaxf(m, xmax[(ch ^ 1) * 128]);
+      // e = exp(x - m), un-normalised: 1 / sum and the dropout scale are applied to the O row
       float l4[4] = {0.f, 0.f, 0.f, 0.f};
-      const uint32_t pi0 = attn_pair_idx((uint32_t)(b * p.H + h + hsel), q, 0);
+      uint32_t pk[16];
+      const uint32_t pi0 = attn_pair_idx((uint32_t)(b * p.H + h + hsel), q, ch * 32);
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t s0[32];
-        tmem_ld_32x32(ts + half * 32, s0);
-        tmem_ld_wait();
-        uint32_t pk[16];
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 km = *reinterpret_cast<const float4*>(hs + half * 32 + 4 * j4);
-          float x0 = __uint_as_float(s0[4 * j4]) + km.x, x1 = __uint_as_float(s0[4 * j4 + 1]) + km.y;
-          float x2 = __uint_as_float(s0[4 * j4 + 2]) + km.z, x3 = __uint_as_float(s0[4 * j4 + 3]) + km.w;
-          if (half == 0 && biased) {
-            const int j = 4 * j4;
-            if (j < p.Lt) x0 += bp[j];
-            if (j + 1 < p.Lt) x1 += bp[j + 1];
-            if (j + 2 < p.Lt) x2 += bp[j + 2];
-            if (j + 3 < p.Lt) x3 += bp[j + 3];
-          }
-          float e0 = __expf(x0 - m), e1 = __expf(x1 - m), e2 = __expf(x2 - m), e3 = __expf(x3 - m);
-          l4[0] += e0; l4[1] += e1; l4[2] += e2; l4[3] += e3;
-          if (p.drop_thr) {
-            const uint32_t h0 = vq_hash_pair(p.seed, pi0 + half * 16 + 2 * j4), h1 = vq_hash_pair(p.seed, pi0 + half * 16 + 2 * j4 + 1);
-            e0 = (h0 & 0xFFFFu) >= p.drop_thr ? e0 : 0.f;
-            e1 = (h0 >> 16) >= p.drop_thr ? e1 : 0.f;
-            e2 = (h1 & 0xFFFFu) >= p.drop_thr ? e2 : 0.f;
-            e3 = (h1 >> 16) >= p.drop_thr ? e3 : 0.f;
-          }
-          pk[2 * j4] = pack_bf16(e0, e1);
-          pk[2 * j4 + 1] = pack_bf16(e2, e3);
+      for (int j2 = 0; j2 < 16; ++j2) {
+        float e0 = __expf(x[2 * j2] - m), e1 = __expf(x[2 * j2 + 1] - m);
+        l4[j2 & 3] += e0 + e1;
+        if (p.drop_thr) {
+          const uint32_t hh = vq_hash_pair(p.seed, pi0 + j2);
+          e0 = (hh & 0xFFFFu) >= p.drop_thr ? e0 : 0.f;
+          e1 = (hh >> 16) >= p.drop_thr ? e1 : 0.f;
         }
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const uint32_t off = (uint32_t)((half * 4 + c) ^ sw) << 4;
-          sts128_u(sP_row + off, pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-          sts128_u(sZ_row + off, 0u, 0u, 0u, 0u);
-        }
+        pk[j2] = pack_bf16(e0, e1);
       }
-      const float l = (l4[0] + l4[1]) + (l4[2] + l4[3]);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint32_t off = (uint32_t)((ch * 4 + c) ^ sw) << 4;
+        sts128_u(sP_row + off, pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        sts128_u(sZ_row + off, 0u, 0u, 0u, 0u);
+      }
+      xsum[ch * 128] = (l4[0] + l4[1]) + (l4[2] + l4[3]);
       tc_fence_before();                         // S has been read: the O MMA may overwrite its columns
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(pfull_bar);
-      if (q < p.S && p.lse) p.lse[((size_t)b * p.H + h + hsel) * p.S + q] = m + __logf(l);
-      const float osc = (p.drop_thr ? p.drop_inv_keep : 1.f) / l;
       mbar_wait(ofull_bar, par);
       tc_fence_after();
-      __nv_bfloat16* orow = p.o + ((size_t)b * p.S + q) * p.ldo + (h + hsel) * 64;
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
+      asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");     // the partner's half of the row sum is visible (long since)
+      const float l = xsum[0] + xsum[128];
+      if (ch == 0 && q < p.S && p.lse) p.lse[((size_t)b * p.H + h + hsel) * p.S + q] = m + __logf(l);
+      const float osc = (p.drop_thr ? p.drop_inv_keep : 1.f) / l;
+      {
         uint32_t o0[32];
-        tmem_ld_32x32(tmem_base + lane_addr + half * 32, o0);
+        tmem_ld_32x32(tmem_base + lane_addr + ch * 32, o0);
         tmem_ld_wait();
         if (q < p.S) {
-          uint4* dst = reinterpret_cast<uint4*>(orow + half * 32);
+          uint4* dst = reinterpret_cast<uint4*>(p.o + ((size_t)b * p.S + q) * p.ldo + (h + hsel) * 64 + ch * 32);
 #pragma unroll
           for (int c = 0; c < 4; ++c)
             dst[c] = make_uint4(pack_bf16(__uint_as_float(o0[8 * c]) * osc, __uint_as_float(o0[8 * c + 1]) * osc),
@@ -271,7 +264,7 @@ attn_enc_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == TCF_ROW_WARPS) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TCF_TMEM_COLS);
   }
