@@ -48,7 +48,8 @@ constexpr int TCF_XCHG_FLOATS = 4 * 128;            // row maximum / row sum hal
 constexpr int TCF_SMEM_BYTES = 1024 + TCF_STAGES * TCF_STAGE_BYTES + 2 * TCF_HDR_FLOATS * 4 + TCF_XCHG_FLOATS * 4 + 128;
 constexpr int TCF_ROW_WARPS = 8;                    // warps 0-7: TWO threads per stacked query row (32 of its 64 score columns each)
 constexpr int TCF_THREADS = (TCF_ROW_WARPS + 1) * 32;   // + warp 8: header, TMA, MMA issue, TMEM
-constexpr int TCF_TMEM_COLS = 128;                  // S2 [0,128); O2 reuses columns [0,64) after the rows have read S2
+constexpr int TCF_TMEM_COLS = 256;                  // two S2 accumulators [0,128) | [128,256); O2 of an item reuses the first 64 columns
+                                                    // of its own S2 once the rows have read it
 constexpr int TCF_CTAS_PER_SM = 2;
 
 struct AttnTcArgs {
@@ -76,11 +77,11 @@ attn_enc_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   float* xchg = hdr + 2 * TCF_HDR_FLOATS;      // [2 halves][128 rows] maxima | [2][128] sums
   uint64_t* bars = reinterpret_cast<uint64_t*>(xchg + TCF_XCHG_FLOATS);
   uint64_t* full_bar = bars;        // [2] TMA bytes of a stage landed (+ header written)
-  uint64_t* sfull_bar = bars + 2;   // S accumulator complete
-  uint64_t* pfull_bar = bars + 3;   // P tile written and S read by the 4 row warps
-  uint64_t* ofull_bar = bars + 4;   // O accumulator complete (=> the stage's shared memory is free)
-  uint64_t* oread_bar = bars + 5;   // O read by the 4 row warps (=> the TMEM columns are free)
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 6);
+  uint64_t* sfull_bar = bars + 2;   // [2] S accumulator complete
+  uint64_t* pfull_bar = bars + 4;   // P tile written and S read by the row warps
+  uint64_t* ofull_bar = bars + 5;   // O accumulator complete (=> the stage's shared memory is free)
+  uint64_t* oread_bar = bars + 6;   // O read by the row warps (=> the TMEM columns are free)
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 7);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int hp = p.H >> 1;
@@ -91,7 +92,8 @@ attn_enc_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
       mbar_init(&full_bar[0], 1);
       mbar_init(&full_bar[1], 1);
-      mbar_init(sfull_bar, 1);
+      mbar_init(&sfull_bar[0], 1);
+      mbar_init(&sfull_bar[1], 1);
       mbar_init(pfull_bar, TCF_ROW_WARPS);
       mbar_init(ofull_bar, 1);
       mbar_init(oread_bar, TCF_ROW_WARPS);
@@ -133,33 +135,41 @@ attn_enc_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         tma_load_2d(st + 32768 + 8192, &tmV, fb, (h + 1) * 64, row);
       }
     };
-    int n = 0;
-    if ((int)blockIdx.x < nitems) load_item(0, blockIdx.x);
-    for (int it = blockIdx.x; it < nitems; it += gridDim.x, ++n) {
-      const uint32_t prev = (n - 1) & 1;
-      // stage (n+1) & 1 and header copy (n+1) & 1 were last used by item n-1: free once its O MMA has completed (the rows
-      // finished with that header before they released the P tile)
-      if (n > 0 && lane == 0) mbar_wait(ofull_bar, prev);
-      __syncwarp();
-      if (it + (int)gridDim.x < nitems) load_item(n + 1, it + gridDim.x);
-      if (lane == 0) {
-        const uint32_t sq = smem_u32(smem + (n & 1) * TCF_STAGE_BYTES), sk = sq + 16384, sv = sq + 32768;
-        mbar_wait(&full_bar[n & 1], (n >> 1) & 1);
-        if (n > 0) mbar_wait(oread_bar, prev);          // the rows have read O of the previous item: its TMEM columns are reused by S
-        tc_fence_after();
+    // S2 = Q2 K2^T of item m (stage m & 1) into S accumulator m & 1
+    auto issue_s = [&](int m) {
+      const uint32_t sq = smem_u32(smem + (m & 1) * TCF_STAGE_BYTES), sk = sq + 16384;
+      mbar_wait(&full_bar[m & 1], (m >> 1) & 1);       // (the caller has made sure that O of item m-2, which lived in the first
+      tc_fence_after();                                //  columns of this accumulator, has been read)
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_f16(tmem_base, umma_smem_desc_sw128(sq + k * 32, 16, 1024), umma_smem_desc_sw128(sk + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
-        umma_commit(sfull_bar);
-        mbar_wait(pfull_bar, n & 1);
+      for (int k = 0; k < 4; ++k)
+        umma_f16(tmem_base + (m & 1) * 128, umma_smem_desc_sw128(sq + k * 32, 16, 1024), umma_smem_desc_sw128(sk + k * 32, 16, 1024),
+                 idesc_s, k > 0 ? 1u : 0u);
+      umma_commit(&sfull_bar[m & 1]);
+    };
+    const int it0 = blockIdx.x, gs = gridDim.x;
+    if (it0 < nitems) load_item(0, it0);
+    if (it0 + gs < nitems) load_item(1, it0 + gs);
+    if (it0 < nitems && lane == 0) issue_s(0);
+    __syncwarp();
+    int n = 0;
+    for (int it = it0; it < nitems; it += gs, ++n) {
+      if (lane == 0) {
+        const uint32_t sq = smem_u32(smem + (n & 1) * TCF_STAGE_BYTES), sv = sq + 32768;
+        mbar_wait(pfull_bar, n & 1);                    // P tile of item n written, its S read
+        // the rows released O of item n-1 before they started on item n, and cannot release O of item n before the MMA below
+        // exists: this wait returns at once and is exact (no phase can be skipped)
+        if (n >= 1) mbar_wait(oread_bar, (n - 1) & 1);
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
-          umma_f16(tmem_base, umma_smem_desc_sw128(sq + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+          umma_f16(tmem_base + (n & 1) * 128, umma_smem_desc_sw128(sq + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
                    umma_smem_desc_sw128(sv + kk * 2048, 8192, 1024), idesc_o, kk > 0 ? 1u : 0u);
         umma_commit(ofull_bar);
+        if (it + gs < nitems) issue_s(n + 1);           // the next item's scores are ready before the rows finish this item's epilogue
+        if (it + 2 * gs < nitems) mbar_wait(ofull_bar, n & 1);   // O MMA done: stage n & 1 (V2, P tile) and header copy n & 1 are free
       }
       __syncwarp();
+      if (it + 2 * gs < nitems) load_item(n + 2, it + 2 * gs);
     }
   } else {
     // ------------------------------------------------ softmax + epilogue (two threads per stacked row) ------------------------------------------------
@@ -182,12 +192,12 @@ attn_enc_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       const bool biased = ch == 0 && q < p.Lt;       // the biased text x text corner lies in columns < Lt <= 32
       const uint32_t sP_row = sP_row0 + (n & 1) * TCF_STAGE_BYTES, sZ_row = sZ_row0 + (n & 1) * TCF_STAGE_BYTES;
       mbar_wait(&full_bar[n & 1], (n >> 1) & 1);   // header visible
-      mbar_wait(sfull_bar, par);
+      mbar_wait(&sfull_bar[n & 1], (n >> 1) & 1);
       tc_fence_after();
       float x[32];
       {
         uint32_t s0[32];
-        tmem_ld_32x32(ts, s0);
+        tmem_ld_32x32(ts + (n & 1) * 128, s0);
         tmem_ld_wait();
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
@@ -244,7 +254,7 @@ attn_enc_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       const float osc = (p.drop_thr ? p.drop_inv_keep : 1.f) / l;
       {
         uint32_t o0[32];
-        tmem_ld_32x32(tmem_base + lane_addr + ch * 32, o0);
+        tmem_ld_32x32(tmem_base + (n & 1) * 128 + lane_addr + ch * 32, o0);
         tmem_ld_wait();
         if (q < p.S) {
           uint4* dst = reinterpret_cast<uint4*>(p.o + ((size_t)b * p.S + q) * p.ldo + (h + hsel) * 64 + ch * 32);
