@@ -44,12 +44,11 @@ constexpr int TC_TMEM_COLS = 512;
 constexpr int TCF_STAGE_BYTES = 3 * 16384;          // Q2 | K2 | V2; the P tile overwrites Q2 | K2 once the S MMA has completed
 constexpr int TCF_HDR_FLOATS = 64 + 2 * 128;        // kmask[64] | bias[2][128]
 constexpr int TCF_STAGES = 2;                       // the TMA loads of item n+1 are in flight while item n is computed
-constexpr int TCF_XCHG_FLOATS = 4 * 128;            // row maximum / row sum halves exchanged between the two threads of a row
+constexpr int TCF_XCHG_FLOATS = 256 + 2 * 512;      // row maximum halves [2][128] | row sum halves, one copy per item parity, [2][128] each at +512
 constexpr int TCF_SMEM_BYTES = 1024 + TCF_STAGES * TCF_STAGE_BYTES + 2 * TCF_HDR_FLOATS * 4 + TCF_XCHG_FLOATS * 4 + 128;
 constexpr int TCF_ROW_WARPS = 8;                    // warps 0-7: TWO threads per stacked query row (32 of its 64 score columns each)
 constexpr int TCF_THREADS = (TCF_ROW_WARPS + 1) * 32;   // + warp 8: header, TMA, MMA issue, TMEM
-constexpr int TCF_TMEM_COLS = 256;                  // two S2 accumulators [0,128) | [128,256); O2 of an item reuses the first 64 columns
-                                                    // of its own S2 once the rows have read it
+constexpr int TCF_TMEM_COLS = 256;                  // S2 [0,128) | O2 [128,192)
 constexpr int TCF_CTAS_PER_SM = 2;
 
 struct AttnTcArgs {
@@ -77,11 +76,11 @@ attn_enc_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   float* xchg = hdr + 2 * TCF_HDR_FLOATS;      // [2 halves][128 rows] maxima | [2][128] sums
   uint64_t* bars = reinterpret_cast<uint64_t*>(xchg + TCF_XCHG_FLOATS);
   uint64_t* full_bar = bars;        // [2] TMA bytes of a stage landed (+ header written)
-  uint64_t* sfull_bar = bars + 2;   // [2] S accumulator complete
-  uint64_t* pfull_bar = bars + 4;   // P tile written and S read by the row warps
+  uint64_t* sfull_bar = bars + 2;   // S accumulator complete
+  uint64_t* sread_bar = bars + 3;   // S read by the row warps (=> the next item's S MMA may overwrite it)
+  uint64_t* pfull_bar = bars + 4;   // P tile written (and the previous item's O read) by the row warps
   uint64_t* ofull_bar = bars + 5;   // O accumulator complete (=> the stage's shared memory is free)
-  uint64_t* oread_bar = bars + 6;   // O read by the row warps (=> the TMEM columns are free)
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 7);
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 6);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int hp = p.H >> 1;
@@ -92,11 +91,10 @@ attn_enc_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
       mbar_init(&full_bar[0], 1);
       mbar_init(&full_bar[1], 1);
-      mbar_init(&sfull_bar[0], 1);
-      mbar_init(&sfull_bar[1], 1);
+      mbar_init(sfull_bar, 1);
+      mbar_init(sread_bar, TCF_ROW_WARPS);
       mbar_init(pfull_bar, TCF_ROW_WARPS);
       mbar_init(ofull_bar, 1);
-      mbar_init(oread_bar, TCF_ROW_WARPS);
       mbar_fence_init();
     }
     __syncwarp();
@@ -135,16 +133,15 @@ attn_enc_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         tma_load_2d(st + 32768 + 8192, &tmV, fb, (h + 1) * 64, row);
       }
     };
-    // S2 = Q2 K2^T of item m (stage m & 1) into S accumulator m & 1
+    // S2 = Q2 K2^T of item m (stage m & 1); the caller has made sure the rows have read the previous S2
     auto issue_s = [&](int m) {
       const uint32_t sq = smem_u32(smem + (m & 1) * TCF_STAGE_BYTES), sk = sq + 16384;
-      mbar_wait(&full_bar[m & 1], (m >> 1) & 1);       // (the caller has made sure that O of item m-2, which lived in the first
-      tc_fence_after();                                //  columns of this accumulator, has been read)
+      mbar_wait(&full_bar[m & 1], (m >> 1) & 1);
+      tc_fence_after();
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        umma_f16(tmem_base + (m & 1) * 128, umma_smem_desc_sw128(sq + k * 32, 16, 1024), umma_smem_desc_sw128(sk + k * 32, 16, 1024),
-                 idesc_s, k > 0 ? 1u : 0u);
-      umma_commit(&sfull_bar[m & 1]);
+        umma_f16(tmem_base, umma_smem_desc_sw128(sq + k * 32, 16, 1024), umma_smem_desc_sw128(sk + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+      umma_commit(sfull_bar);
     };
     const int it0 = blockIdx.x, gs = gridDim.x;
     if (it0 < nitems) load_item(0, it0);
@@ -155,17 +152,17 @@ attn_enc_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     for (int it = it0; it < nitems; it += gs, ++n) {
       if (lane == 0) {
         const uint32_t sq = smem_u32(smem + (n & 1) * TCF_STAGE_BYTES), sv = sq + 32768;
-        mbar_wait(pfull_bar, n & 1);                    // P tile of item n written, its S read
-        // the rows released O of item n-1 before they started on item n, and cannot release O of item n before the MMA below
-        // exists: this wait returns at once and is exact (no phase can be skipped)
-        if (n >= 1) mbar_wait(oread_bar, (n - 1) & 1);
+        if (it + gs < nitems) {
+          mbar_wait(sread_bar, n & 1);                  // the rows hold S2 of item n in registers: the next S MMA runs under their softmax
+          issue_s(n + 1);
+        }
+        mbar_wait(pfull_bar, n & 1);                    // P tile of item n written; O2 of item n-1 read (the rows do that first)
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
-          umma_f16(tmem_base + (n & 1) * 128, umma_smem_desc_sw128(sq + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+          umma_f16(tmem_base + 128, umma_smem_desc_sw128(sq + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
                    umma_smem_desc_sw128(sv + kk * 2048, 8192, 1024), idesc_o, kk > 0 ? 1u : 0u);
         umma_commit(ofull_bar);
-        if (it + gs < nitems) issue_s(n + 1);           // the next item's scores are ready before the rows finish this item's epilogue
         if (it + 2 * gs < nitems) mbar_wait(ofull_bar, n & 1);   // O MMA done: stage n & 1 (V2, P tile) and header copy n & 1 are free
       }
       __syncwarp();
@@ -183,22 +180,47 @@ attn_enc_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const uint32_t ts = tmem_base + hsel * 64 + ch * 32 + lane_addr;          // this thread's 32 score columns
     float* xmax = xchg + r, *xsum = xchg + 256 + r;                            // [half][row]
     const int bar_id = 1 + rw;                                                 // named barrier of the warp pair (rw, rw + 4)
+    // O2 row of the item with running index m (its row sum halves are in xsum, parity m & 1): scale, convert, store
+    float m_prev = 0.f;
+    int b_prev = 0, h_prev = 0;
+    auto epilogue = [&](int m) {
+      mbar_wait(ofull_bar, m & 1);
+      tc_fence_after();
+      const float l = xsum[(m & 1) * 512] + xsum[(m & 1) * 512 + 128];
+      if (ch == 0 && q < p.S && p.lse) p.lse[((size_t)b_prev * p.H + h_prev + hsel) * p.S + q] = m_prev + __logf(l);
+      const float osc = (p.drop_thr ? p.drop_inv_keep : 1.f) / l;
+      uint32_t o0[32];
+      tmem_ld_32x32(tmem_base + 128 + lane_addr + ch * 32, o0);
+      tmem_ld_wait();
+      if (q < p.S) {
+        uint4* dst = reinterpret_cast<uint4*>(p.o + ((size_t)b_prev * p.S + q) * p.ldo + (h_prev + hsel) * 64 + ch * 32);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          dst[c] = make_uint4(pack_bf16(__uint_as_float(o0[8 * c]) * osc, __uint_as_float(o0[8 * c + 1]) * osc),
+                              pack_bf16(__uint_as_float(o0[8 * c + 2]) * osc, __uint_as_float(o0[8 * c + 3]) * osc),
+                              pack_bf16(__uint_as_float(o0[8 * c + 4]) * osc, __uint_as_float(o0[8 * c + 5]) * osc),
+                              pack_bf16(__uint_as_float(o0[8 * c + 6]) * osc, __uint_as_float(o0[8 * c + 7]) * osc));
+      }
+      tc_fence_before();
+    };
     int n = 0;
     for (int it = blockIdx.x; it < nitems; it += gridDim.x, ++n) {
-      const uint32_t par = n & 1;
       const int b = it / hp, h = (it - b * hp) * 2;
       const float* hs = hdr + (n & 1) * TCF_HDR_FLOATS;
       const float* bp = hs + 64 + hsel * 128 + (AT_S_TC - 1) - q;
       const bool biased = ch == 0 && q < p.Lt;       // the biased text x text corner lies in columns < Lt <= 32
       const uint32_t sP_row = sP_row0 + (n & 1) * TCF_STAGE_BYTES, sZ_row = sZ_row0 + (n & 1) * TCF_STAGE_BYTES;
       mbar_wait(&full_bar[n & 1], (n >> 1) & 1);   // header visible
-      mbar_wait(&sfull_bar[n & 1], (n >> 1) & 1);
+      mbar_wait(sfull_bar, n & 1);
       tc_fence_after();
       float x[32];
       {
         uint32_t s0[32];
-        tmem_ld_32x32(ts + (n & 1) * 128, s0);
+        tmem_ld_32x32(ts, s0);
         tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sread_bar);       // S2 is in registers: the next item's S MMA may start
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
           const float4 km = *reinterpret_cast<const float4*>(hs + ch * 32 + 4 * j4);
@@ -235,41 +257,22 @@ attn_enc_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         }
         pk[j2] = pack_bf16(e0, e1);
       }
+      // the previous item's O row: its MMA finished long ago (nobody waits here), and reading it now frees the O accumulator
+      // before this item's P tile is released to the MMA warp
+      if (n > 0) epilogue(n - 1);
+      xsum[(n & 1) * 512 + ch * 128] = (l4[0] + l4[1]) + (l4[2] + l4[3]);
+      m_prev = m; b_prev = b; h_prev = h;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const uint32_t off = (uint32_t)((ch * 4 + c) ^ sw) << 4;
         sts128_u(sP_row + off, pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
         sts128_u(sZ_row + off, 0u, 0u, 0u, 0u);
       }
-      xsum[ch * 128] = (l4[0] + l4[1]) + (l4[2] + l4[3]);
-      tc_fence_before();                         // S has been read: the O MMA may overwrite its columns
       fence_proxy_async();
-      __syncwarp();
+      asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");     // the partner's half of the row sum is visible to the next epilogue
       if (lane == 0) mbar_arrive(pfull_bar);
-      mbar_wait(ofull_bar, par);
-      tc_fence_after();
-      asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");     // the partner's half of the row sum is visible (long since)
-      const float l = xsum[0] + xsum[128];
-      if (ch == 0 && q < p.S && p.lse) p.lse[((size_t)b * p.H + h + hsel) * p.S + q] = m + __logf(l);
-      const float osc = (p.drop_thr ? p.drop_inv_keep : 1.f) / l;
-      {
-        uint32_t o0[32];
-        tmem_ld_32x32(tmem_base + (n & 1) * 128 + lane_addr + ch * 32, o0);
-        tmem_ld_wait();
-        if (q < p.S) {
-          uint4* dst = reinterpret_cast<uint4*>(p.o + ((size_t)b * p.S + q) * p.ldo + (h + hsel) * 64 + ch * 32);
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-            dst[c] = make_uint4(pack_bf16(__uint_as_float(o0[8 * c]) * osc, __uint_as_float(o0[8 * c + 1]) * osc),
-                                pack_bf16(__uint_as_float(o0[8 * c + 2]) * osc, __uint_as_float(o0[8 * c + 3]) * osc),
-                                pack_bf16(__uint_as_float(o0[8 * c + 4]) * osc, __uint_as_float(o0[8 * c + 5]) * osc),
-                                pack_bf16(__uint_as_float(o0[8 * c + 6]) * osc, __uint_as_float(o0[8 * c + 7]) * osc));
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(oread_bar);
     }
+    if (n > 0) epilogue(n - 1);
   }
 
   tc_fence_before();
