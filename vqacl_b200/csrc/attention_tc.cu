@@ -110,15 +110,30 @@ attn_enc_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     // ------------------------------------------------ header + TMA + MMA issue ------------------------------------------------
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);
     constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, false, true);
-    // header (all lanes) + TMA loads (lane 0) of the item with running index m into stage m & 1
+    // Per-item header (key mask of the batch element, relative-position bias of the two heads): the global loads are issued
+    // early into registers (hdr_fetch), the shared-memory copy is written — and the TMA loads of the item issued — only once
+    // the stage is free (load_item), so that no global-memory latency sits between "stage free" and "TMA in flight".
+    float hk[2], hb[8];
+    auto hdr_fetch = [&](int it) {
+      const int b = it / hp, h = (it - b * hp) * 2;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int j = lane + 32 * u;
+        hk[u] = j < p.S ? (p.keymask ? p.keymask[(size_t)b * p.S + j] : 0.f) : -INFINITY;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int r = lane + 32 * u, hd = r >> 7, rel = r & 127;
+        hb[u] = rel < 127 ? p.rel_table[(int)bk.b[rel] * p.H + h + hd] : 0.f;
+      }
+    };
     auto load_item = [&](int m, int it) {
       const int b = it / hp, h = (it - b * hp) * 2;
       float* hs = hdr + (m & 1) * TCF_HDR_FLOATS;
-      for (int j = lane; j < 64; j += 32) hs[j] = j < p.S ? (p.keymask ? p.keymask[(size_t)b * p.S + j] : 0.f) : -INFINITY;
-      for (int r = lane; r < 2 * 128; r += 32) {
-        const int hd = r >> 7, rel = r & 127;
-        hs[64 + r] = rel < 127 ? p.rel_table[(int)bk.b[rel] * p.H + h + hd] : 0.f;
-      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) hs[lane + 32 * u] = hk[u];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) hs[64 + lane + 32 * u] = hb[u];
       __syncwarp();
       if (lane == 0) {
         uint8_t* st = smem + (m & 1) * TCF_STAGE_BYTES;
@@ -144,12 +159,13 @@ attn_enc_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       umma_commit(sfull_bar);
     };
     const int it0 = blockIdx.x, gs = gridDim.x;
-    if (it0 < nitems) load_item(0, it0);
-    if (it0 + gs < nitems) load_item(1, it0 + gs);
+    if (it0 < nitems) { hdr_fetch(it0); load_item(0, it0); }
+    if (it0 + gs < nitems) { hdr_fetch(it0 + gs); load_item(1, it0 + gs); }
     if (it0 < nitems && lane == 0) issue_s(0);
     __syncwarp();
     int n = 0;
     for (int it = it0; it < nitems; it += gs, ++n) {
+      if (it + 2 * gs < nitems) hdr_fetch(it + 2 * gs);      // in flight while lane 0 waits below
       if (lane == 0) {
         const uint32_t sq = smem_u32(smem + (n & 1) * TCF_STAGE_BYTES), sv = sq + 32768;
         if (it + gs < nitems) {
