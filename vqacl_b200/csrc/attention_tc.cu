@@ -600,7 +600,8 @@ attn_enc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   }
 }
 
-static int g_attn_tc = [] { const char* e = getenv("VQACL_ATTN_TC"); return (e && e[0] == '1') ? 1 : 0; }();
+// VQACL_ATTN_TC=0 falls back to the mma.sync kernel of attention.cu (A/B measurements)
+static int g_attn_tc = [] { const char* e = getenv("VQACL_ATTN_TC"); return (e && e[0] == '0') ? 0 : 1; }();
 
 // true when the tcgen05 kernel takes this problem (encoder form: square, 33..64 positions, text-corner bias, even head count)
 bool attn_tc_eligible(const AttnArgs& a) {
