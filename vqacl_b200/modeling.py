@@ -459,6 +459,7 @@ class VLT5(nn.Module):
         res = super().load_state_dict(sd, strict=strict, **kw)
         self.tie_weights()
         self._mark_params_dirty()
+        self._masters_stale = False       # every fp32 master was just overwritten on every rank
         return res
 
     def apply(self, fn):

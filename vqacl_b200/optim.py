@@ -54,6 +54,8 @@ class FusedAdamW(torch.optim.Optimizer):
                 _, buckets, tail = model.grad_shard_plan()
             except VqaclError:
                 self.shard = False          # world size that does not divide the buckets into aligned slices: replicate
+        if not self.shard:
+            model.gather_params()       # a previous sharded optimizer left only this rank's fp32 master slices current
         model.shard_optimizer = self.shard
         if self.shard:
             self.owned = owned_slices(buckets, world, dist.get_rank())
