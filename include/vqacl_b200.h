@@ -143,6 +143,9 @@ int vqacl_generate(void* engine, const vqacl_batch* batch, const vqacl_proto_sta
 /* SMs the persistent GEMM kernels may occupy (0 = all): lowered by the host while an NCCL all-reduce must make progress
  * next to backward (the GEMM CTAs otherwise fill every SM's shared memory and starve the collective's CTAs) */
 int vqacl_set_gemm_sm_limit(int n_sms);
+/* dynamic (atomic-counter) tile schedule of the CTA-pair GEMM instead of the static round robin: a pair that becomes
+ * resident late (its SMs were held by a collective or by another stream's kernel) finds the work list drained */
+int vqacl_set_gemm_dynamic_schedule(int on);
 /* number of kernels this library has launched so far in this process (bench.py's gpu_launches) */
 long long vqacl_launch_count(void);
 

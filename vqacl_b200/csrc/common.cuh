@@ -247,6 +247,40 @@ VQ_DEVINL void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(rank));
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
 }
+// cluster-scope variants for data handed from one CTA of a pair to the other through distributed shared memory
+VQ_DEVINL bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+VQ_DEVINL void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (++spins > VQ_MBAR_SPIN_LIMIT) {
+      printf("vqacl_b200: cluster mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+// release.cluster arrive on the barrier at the same smem offset in CTA `rank` (orders this thread's earlier DSMEM stores)
+VQ_DEVINL void mbar_arrive_release_cluster(uint64_t* bar, uint32_t rank) {
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+VQ_DEVINL void st_shared_cluster_u32(const void* local_ptr, uint32_t rank, uint32_t v) {
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(local_ptr)), "r"(rank));
+  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(raddr), "r"(v) : "memory");
+}
 // TMA load issued by either CTA of the pair; the transaction bytes are counted on the LEADER's (even rank) mbarrier:
 // clearing bit 24 of the shared::cluster address selects the peer with rank bit 0 (cute: Sm100MmaPeerBitMask)
 VQ_DEVINL void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {

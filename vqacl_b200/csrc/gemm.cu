@@ -154,9 +154,29 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& 
   return 0;
 }
 
+// Dynamic tile schedule of the CTA-pair kernel: a ring of {next item, pairs finished} counter pairs in device memory, one per
+// launch in flight (the kernel's last pair resets its slot). VQACL_GEMM_DYN=0/1 overrides the default.
+constexpr int SCHED_SLOTS = 256;
+static uint32_t* g_sched = nullptr;
+static int g_sched_next = 0;
+static int g_dyn = [] { const char* e = getenv("VQACL_GEMM_DYN"); return e ? (e[0] == '1' ? 1 : 0) : 0; }();
+extern "C" int vqacl_set_gemm_dynamic_schedule(int on) {
+  g_dyn = on ? 1 : 0;
+  return 0;
+}
+
 // CTA-pair kernel: clusters of 2 CTAs, 256 x 256 tiles (see gemm_tcgen05.cuh)
 template <bool A_MN, bool B_MN>
-static int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, cudaStream_t stream) {
+static int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args_in, cudaStream_t stream) {
+  GemmArgs args = args_in;
+  args.sched = nullptr;
+  if (g_dyn) {
+    if (!g_sched) {
+      VQ_CUDA(cudaMalloc(&g_sched, SCHED_SLOTS * 2 * sizeof(uint32_t)));
+      VQ_CUDA(cudaMemset(g_sched, 0, SCHED_SLOTS * 2 * sizeof(uint32_t)));
+    }
+    args.sched = g_sched + 2 * (g_sched_next++ % SCHED_SLOTS);
+  }
   auto kern = gemm_bf16_tcgen05_2cta_kernel<A_MN, B_MN>;
   static bool attr_set = false;
   if (!attr_set) {

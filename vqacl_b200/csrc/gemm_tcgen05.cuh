@@ -43,6 +43,9 @@ struct GemmArgs {
   uint32_t drop_thr;  // 16-bit keep threshold (0 = no dropout), see vq_dropout_pair
   float drop_inv_keep;
   uint32_t seed, site;  // seed = per-launch dropout key (already mixed with the site id); site is informational
+  uint32_t* sched;      // CTA-pair kernel only: {next work item, pairs finished} counters of a DYNAMIC tile schedule (null = static
+                        // round robin). A pair that becomes resident late — its SMs were held by a collective's CTAs or by another
+                        // stream's kernel — then finds the work list drained instead of running its whole static share afterwards.
 };
 
 constexpr int GEMM_BM = 128;
@@ -451,6 +454,11 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  // dynamic schedule: ring of work-item indices, filled by the leader's producer lane in BOTH CTAs
+  constexpr int SCHED_DEPTH = 4;
+  uint64_t* sfull_bar = reinterpret_cast<uint64_t*>(tmem_holder + 2);   // [SCHED_DEPTH] per CTA: slot written
+  uint64_t* sempty_bar = sfull_bar + SCHED_DEPTH;                       // [SCHED_DEPTH] leader's: slot read by all 18 consumers
+  uint32_t* sched_w = reinterpret_cast<uint32_t*>(sempty_bar + SCHED_DEPTH);
   uint8_t* epi_stage = smem + STAGES * Cfg::STAGE_BYTES + 256;
 
   const int warp = threadIdx.x >> 5;
@@ -478,6 +486,10 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 2 * GEMM_EPI_WARPS);
     }
+    for (int i = 0; i < SCHED_DEPTH; ++i) {
+      mbar_init(&sfull_bar[i], 1);
+      mbar_init(&sempty_bar[i], 2 + 2 * GEMM_EPI_WARPS);   // leader MMA lane + peer producer lane + the epilogue warps of both CTAs
+    }
     mbar_fence_init();
   }
   if (warp == 2) tmem_alloc_2sm(tmem_holder, Cfg::TMEM_COLS);
@@ -486,13 +498,37 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
   vq_pdl_wait();
+  const bool dyn = p.sched != nullptr;
+  // next work item of a consumer role (anything but the leader's producer lane): read the ring slot, release it on the leader
+  auto next_work = [&](int& it) -> int {
+    const int slot = it % SCHED_DEPTH;
+    mbar_wait_cluster(&sfull_bar[slot], (it / SCHED_DEPTH) & 1);
+    const int w = (int)sched_w[slot];
+    mbar_arrive_cluster(&sempty_bar[slot], 0);
+    ++it;
+    return w;
+  };
 
   if (warp == 0) {
     // ------------------------------ TMA producer (both CTAs) ------------------------------
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int w = pair; w < total_work; w += npairs) {
+      int it = 0;
+      // leader: fetch the next item from the global counter and publish it to both CTAs; peer: take it from the ring
+      auto fetch = [&]() -> int {
+        if (rank != 0) return next_work(it);
+        const int slot = it % SCHED_DEPTH;
+        mbar_wait_cluster(&sempty_bar[slot], ((it / SCHED_DEPTH) & 1) ^ 1);
+        const int w = (int)atomicAdd(p.sched, 1u);
+        sched_w[slot] = (uint32_t)w;
+        st_shared_cluster_u32(&sched_w[slot], 1, (uint32_t)w);
+        mbar_arrive(&sfull_bar[slot]);
+        mbar_arrive_release_cluster(&sfull_bar[slot], 1);
+        ++it;
+        return w;
+      };
+      for (int w = dyn ? fetch() : pair; w < total_work; w = dyn ? fetch() : w + npairs) {
         const int split = w / tiles_mn;
         const int t = w - split * tiles_mn;
         const int m_blk = t / tiles_n, n_blk = t - m_blk * tiles_n;
@@ -531,7 +567,8 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
       uint32_t phase = 0;
       int astage = 0;
       uint32_t aphase = 0;
-      for (int w = pair; w < total_work; w += npairs) {
+      int it = 0;
+      for (int w = dyn ? next_work(it) : pair; w < total_work; w = dyn ? next_work(it) : w + npairs) {
         const int split = w / tiles_mn;
         const int kb0 = split * kb_per_split;
         const int kb1 = min(kblocks, kb0 + kb_per_split);
@@ -565,7 +602,14 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
     const uint32_t stg = smem_u32(epi_stage) + (warp - 4) * EPI_TILE_BYTES;
     int astage = 0;
     uint32_t aphase = 0;
-    for (int w = pair; w < total_work; w += npairs) {
+    int it = 0;
+    // the ring slot is read by lane 0 of each epilogue warp (one arrival per warp on the leader's barrier) and broadcast
+    auto warp_next = [&]() -> int {
+      int w = 0;
+      if (lane == 0) w = next_work(it);
+      return __shfl_sync(0xffffffffu, w, 0);
+    };
+    for (int w = dyn ? warp_next() : pair; w < total_work; w = dyn ? warp_next() : w + npairs) {
       const int split = w / tiles_mn;
       const int t = w - split * tiles_mn;
       const int m_blk = t / tiles_n, n_blk = t - m_blk * tiles_n;
@@ -594,6 +638,15 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
+  }
+  // dynamic schedule: the last pair to drain the work list resets the counters for the next launch that uses this slot
+  if (dyn && rank == 0 && threadIdx.x == 0) {
+    const uint32_t done = atomicAdd(p.sched + 1, 1u);
+    if (done == (uint32_t)npairs - 1) {
+      p.sched[0] = 0u;
+      p.sched[1] = 0u;
+      __threadfence();
+    }
   }
 }
 
