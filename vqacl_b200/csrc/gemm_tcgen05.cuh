@@ -515,17 +515,21 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      // leader: fetch the next item from the global counter and publish it to both CTAs; peer: take it from the ring
+      // leader: take the next item from the global counter and publish it to both CTAs; peer: take it from the ring. The
+      // atomic for item i+1 is issued BEFORE the TMA loop of item i (its ~1 us round trip to L2 would otherwise sit between
+      // two tiles of the producer); its result is first touched when item i+1 is published.
+      int w_ahead = (dyn && rank == 0) ? (int)atomicAdd(p.sched, 1u) : 0;
       auto fetch = [&]() -> int {
         if (rank != 0) return next_work(it);
         const int slot = it % SCHED_DEPTH;
         mbar_wait_cluster(&sempty_bar[slot], ((it / SCHED_DEPTH) & 1) ^ 1);
-        const int w = (int)atomicAdd(p.sched, 1u);
+        const int w = w_ahead;
         sched_w[slot] = (uint32_t)w;
         st_shared_cluster_u32(&sched_w[slot], 1, (uint32_t)w);
         mbar_arrive(&sfull_bar[slot]);
         mbar_arrive_release_cluster(&sfull_bar[slot], 1);
         ++it;
+        if (w < total_work) w_ahead = (int)atomicAdd(p.sched, 1u);
         return w;
       };
       for (int w = dyn ? fetch() : pair; w < total_work; w = dyn ? fetch() : w + npairs) {
