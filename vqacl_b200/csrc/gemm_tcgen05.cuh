@@ -518,7 +518,9 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
       // leader: take the next item from the global counter and publish it to both CTAs; peer: take it from the ring. The
       // atomic for item i+1 is issued BEFORE the TMA loop of item i (its ~1 us round trip to L2 would otherwise sit between
       // two tiles of the producer); its result is first touched when item i+1 is published.
-      int w_ahead = (dyn && rank == 0) ? (int)atomicAdd(p.sched, 1u) : 0;
+      // The first item of every pair is its static one (no atomic round trip before the kernel's first TMA load); the
+      // counter hands out items npairs, npairs + 1, ...
+      int w_ahead = pair;
       auto fetch = [&]() -> int {
         if (rank != 0) return next_work(it);
         const int slot = it % SCHED_DEPTH;
@@ -529,7 +531,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
         mbar_arrive(&sfull_bar[slot]);
         mbar_arrive_release_cluster(&sfull_bar[slot], 1);
         ++it;
-        if (w < total_work) w_ahead = (int)atomicAdd(p.sched, 1u);
+        if (w < total_work) w_ahead = npairs + (int)atomicAdd(p.sched, 1u);
         return w;
       };
       for (int w = dyn ? fetch() : pair; w < total_work; w = dyn ? fetch() : w + npairs) {
