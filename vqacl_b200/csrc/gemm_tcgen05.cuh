@@ -564,6 +564,16 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
+      // dynamic schedule: this pair has taken its terminal index; the last pair to get here resets the counters for the next
+      // launch that uses the slot (done here, under the last tile's MMAs and epilogue, not on the kernel's tail)
+      if (dyn && rank == 0) {
+        const uint32_t done = atomicAdd(p.sched + 1, 1u);
+        if (done == (uint32_t)npairs - 1) {
+          p.sched[0] = 0u;
+          p.sched[1] = 0u;
+          __threadfence();
+        }
+      }
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer (leader CTA only) --------------------------------
@@ -644,15 +654,6 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
-  }
-  // dynamic schedule: the last pair to drain the work list resets the counters for the next launch that uses this slot
-  if (dyn && rank == 0 && threadIdx.x == 0) {
-    const uint32_t done = atomicAdd(p.sched + 1, 1u);
-    if (done == (uint32_t)npairs - 1) {
-      p.sched[0] = 0u;
-      p.sched[1] = 0u;
-      __threadfence();
-    }
   }
 }
 
