@@ -166,6 +166,10 @@ int vqacl_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int l
 int vqacl_gemm_bf16_ex(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major, void* C, int ldc,
                        const void* R, int ldr, int M, int N, int K, int epi, float alpha, int splits, int force_bn,
                        uint32_t drop_thr16, float inv_keep, uint32_t drop_key, void* stream);
+/* nn.Linear + residual add + the T5LayerNorm that opens the NEXT sub-layer in one launch (HF T5LayerSelfAttention / T5LayerFF
+ * followed by the next layer_norm): C(f32)[M,768] = R + A[M,K] B[768,K]^T; n_out(bf16) = C * rsqrt(mean(C^2) + eps) * norm_w.       */
+int vqacl_gemm_resid_rmsnorm(const void* A, int lda, const void* B, int ldb, float* C, const float* R, int M, int K,
+                             const float* norm_w, float eps, void* n_out_bf16, void* stream);
 /* HF T5LayerNorm forward / backward (hf5.5 modeling_t5.py:46-68; used at modeling_t5_our.py:41,47,160 and in every block)  */
 int vqacl_rmsnorm_fwd(const float* x, const float* w, void* y_bf16, float* y_f32, int M, float eps, float scale, void* stream);
 int vqacl_rmsnorm_bwd(const void* dn_bf16, const float* x, const float* w, const float* g_in, float* g_out, void* gb_out,

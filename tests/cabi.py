@@ -31,6 +31,7 @@ def _L():
                                       c_int, F, c_int, c_int, c_void_p]
         L.vqacl_gemm_bf16_ex.argtypes = [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,
                                          c_int, F, c_int, c_int, ctypes.c_uint32, F, ctypes.c_uint32, c_void_p]
+        L.vqacl_gemm_resid_rmsnorm.argtypes = [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, F, c_void_p, c_void_p]
         L._ops_declared = True
     return L
 
@@ -161,3 +162,11 @@ def dropout_scale_host(M, N, thr16, inv_keep, key, device):
     x = x ^ (x >> 16)
     lane = torch.where((idx & 1) == 1, x >> 16, x & 0xFFFF)
     return (lane >= thr16).float() * inv_keep
+
+
+def gemm_resid_rmsnorm(A, B, R, norm_w, eps=1e-6):
+    M, K = A.shape
+    C = torch.empty(M, 768, device=A.device)
+    n = torch.empty(M, 768, device=A.device, dtype=torch.bfloat16)
+    check(_L().vqacl_gemm_resid_rmsnorm(ptr(A), A.stride(0), ptr(B), B.stride(0), ptr(C), ptr(R), M, K, ptr(norm_w), eps, ptr(n), cur_stream()))
+    return C, n

@@ -396,3 +396,25 @@ def test_attention_multi_tile_fwd_bwd_vs_torch(Sq, Sk, mode):
     if att is not None:
         tg = att.relative_attention_bias.weight.grad
         assert cos(dtab, tg) > 0.999 and rel_err(dtab, tg) < 2e-2
+
+
+@pytest.mark.parametrize("M,K", [(17920, 768), (1000, 3072), (300, 520)])
+def test_gemm_residual_with_rmsnorm_row_tail(M, K):
+    """The RMSNorm that opens a sub-layer folded into the residual GEMM that closes the previous one (CTA pairs own whole
+    256-row blocks and normalise them from L2): C equals the plain residual epilogue bit for bit, the bf16 norm output equals
+    the stand-alone rmsnorm kernel on that C bit for bit, and both match torch."""
+    torch.manual_seed(50 + K)
+    A = (torch.randn(M, K, device=DEV) * 0.5).bfloat16()
+    Bm = (torch.randn(768, K, device=DEV) * 0.05).bfloat16()
+    R = torch.randn(M, 768, device=DEV) * 3
+    w = torch.rand(768, device=DEV) + 0.5
+    C, n = cabi.gemm_resid_rmsnorm(A, Bm, R, w)
+    C2 = torch.empty(M, 768, device=DEV)
+    cabi.gemm(A, 0, Bm, 0, C2, R, M, 768, K, 2, bn=512)
+    assert torch.equal(C, C2)
+    nb, _ = cabi.rmsnorm_fwd(C, w)
+    assert torch.equal(n, nb)
+    ref = R + A.float() @ Bm.float().t()
+    assert rel_err(C, ref) < 3e-5
+    refn = ref * torch.rsqrt(ref.pow(2).mean(-1, keepdim=True) + 1e-6) * w
+    assert rel_err(n, refn) < 1e-2

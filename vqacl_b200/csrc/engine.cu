@@ -312,12 +312,23 @@ int encoder_forward(Engine& e, const vqacl_batch* b, cudaStream_t st) {
   va.bp = e.P + e.o_bp; va.wp = e.P + e.o_wp; va.img_emb = e.P + e.o_img; va.shared = e.P + e.o_shared;
   va.V = c.vocab_size; va.B = B; va.N = N; va.S = S; va.L = L; va.eps = c.eps; va.x = w.x[0]; va.drop = e.drop(SITE_ENC_EMB);
   VQ_TRY(vis_embed_fwd(va, st));
+  // The RMSNorm that opens a sub-layer is folded into the residual GEMM that closes the previous one (row tail of the CTA-pair
+  // kernel: the pair that wrote a 256-row block normalises it while it is still in L2) whenever the blocks fill the machine
+  // as well as the tiles would; otherwise (and for the first layer, which follows the embeddings) it is its own kernel.
+  const bool fold = gemm_row_tail_ok(M);
+  auto gemm_resid_norm = [&](const bf16* A, int lda, const bf16* Wt, int K, float* C, const float* R, Dropout dr, const float* nw, bf16* nout) -> int {
+    GemmArgs g{};
+    g.epi = EPI_RESID_F32; g.M = M; g.N = d; g.K = K; g.C = C; g.ldc = d; g.R = R; g.ldr = d; g.alpha = 1.f; g.splits = 1;
+    g.drop_thr = dr.thr; g.drop_inv_keep = dr.inv_keep; g.seed = dr.seed; g.site = dr.site;
+    g.tail = 1; g.tail_w = nw; g.tail_out = nout; g.tail_ld = d; g.tail_eps = c.eps;
+    return gemm_bf16(GemmOperand{A, lda, false}, GemmOperand{Wt, K, false}, g, 0, st);
+  };
   for (int l = 0; l < c.n_enc_layers; ++l) {
     const EncLayer& P = e.enc[l];
     VQ_TRY(wait_params(e, 1 + l, st));
     RmsFwdArgs r{};
     r.x = w.x[2 * l]; r.w = e.P + P.ln0; r.y_bf16 = w.n1[l]; r.ld_bf16 = d; r.M = M; r.eps = c.eps; r.scale = 1.f;
-    VQ_TRY(rmsnorm_fwd(r, st));
+    if (!fold || l == 0) VQ_TRY(rmsnorm_fwd(r, st));
     VQ_TRY(gemm_fwd(w.n1[l], d, e.W + P.qkv, d, w.qkv[l], 3 * d, M, 3 * d, EPI_BF16, st));
     AttnArgs a{};
     a.q = w.qkv[l]; a.k = w.qkv[l] + d; a.v = w.qkv[l] + 2 * d; a.ldq = a.ldk = a.ldv = 3 * d;
@@ -326,11 +337,19 @@ int encoder_forward(Engine& e, const vqacl_batch* b, cudaStream_t st) {
     const Dropout dp = e.drop(site_enc(l, 0));
     a.drop_thr = dp.thr; a.drop_inv_keep = dp.inv_keep; a.seed = dp.seed; a.site = dp.site;
     VQ_TRY(attn_fwd(a, st));
-    VQ_TRY(gemm_fwd(w.ao[l], d, e.W + P.o, d, w.x[2 * l + 1], d, M, d, EPI_RESID_F32, st, w.x[2 * l], d, e.drop(site_enc(l, 1))));
-    r.x = w.x[2 * l + 1]; r.w = e.P + P.ln1; r.y_bf16 = w.n2[l];
-    VQ_TRY(rmsnorm_fwd(r, st));
+    if (fold) {
+      VQ_TRY(gemm_resid_norm(w.ao[l], d, e.W + P.o, d, w.x[2 * l + 1], w.x[2 * l], e.drop(site_enc(l, 1)), e.P + P.ln1, w.n2[l]));
+    } else {
+      VQ_TRY(gemm_fwd(w.ao[l], d, e.W + P.o, d, w.x[2 * l + 1], d, M, d, EPI_RESID_F32, st, w.x[2 * l], d, e.drop(site_enc(l, 1))));
+      r.x = w.x[2 * l + 1]; r.w = e.P + P.ln1; r.y_bf16 = w.n2[l];
+      VQ_TRY(rmsnorm_fwd(r, st));
+    }
     VQ_TRY(gemm_fwd(w.n2[l], d, e.W + P.wi, d, w.h[l], f, M, f, EPI_RELU_BF16, st, w.hmask[l], (f + 31) / 32, e.drop(site_enc(l, 2))));
-    VQ_TRY(gemm_fwd(w.h[l], f, e.W + P.wo, f, w.x[2 * l + 2], d, M, d, EPI_RESID_F32, st, w.x[2 * l + 1], d, e.drop(site_enc(l, 3))));
+    if (fold && l + 1 < c.n_enc_layers) {     // + the first norm of the next layer
+      VQ_TRY(gemm_resid_norm(w.h[l], f, e.W + P.wo, f, w.x[2 * l + 2], w.x[2 * l + 1], e.drop(site_enc(l, 3)), e.P + e.enc[l + 1].ln0, w.n1[l + 1]));
+    } else {
+      VQ_TRY(gemm_fwd(w.h[l], f, e.W + P.wo, f, w.x[2 * l + 2], d, M, d, EPI_RESID_F32, st, w.x[2 * l + 1], d, e.drop(site_enc(l, 3))));
+    }
   }
   // final norm + dropout (:314-315): fp32 copy for the SI path / caller, bf16 straight into the [B,S+2,d] decoder memory
   RmsFwdArgs r{};

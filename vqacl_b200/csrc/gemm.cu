@@ -111,6 +111,7 @@ void gemm_tmap_cache_clear() {
 }
 
 static int g_pair_enabled = 1;   // VQACL_GEMM_PAIR=0 disables the CTA-pair kernel (A/B measurements)
+static int g_row_tail_off = [] { const char* e = getenv("VQACL_GEMM_ROW_TAIL"); return (e && e[0] == '0') ? 1 : 0; }();
 // SMs the persistent GEMMs may occupy (0 = all). With N > 1 GPUs the host lowers it during backward so that the NCCL
 // all-reduce kernels, which need resident CTAs of their own, are not starved by 148 GEMM CTAs that each fill an SM's
 // shared memory (vqacl_set_gemm_sm_limit).
@@ -133,6 +134,19 @@ static int gemm_sms() {
   const int n = num_sms();
   return (g_sm_limit > 0 && g_sm_limit < n) ? g_sm_limit : n;
 }
+// Is folding a row tail into an M-row GEMM with 768 output columns a good deal? In the tail mode a CTA pair owns whole 256-row
+// blocks, so the kernel's parallelism is ceil(M / 256) pairs instead of 3x as many tiles: only when the blocks fill the pairs
+// about as well as the tiles would (B = 320: 70 blocks on 74 pairs either way).
+bool gemm_row_tail_ok(int M) {
+  (void)num_sms();
+  if (!g_pair_enabled || g_row_tail_off) return false;
+  const int pairs = gemm_sms() / 2;
+  const int blocks = (M + 255) / 256, tiles = blocks * 3;
+  const double eff_own = (double)blocks / ((double)((blocks + pairs - 1) / pairs) * pairs);
+  const double eff_tiles = (double)tiles / ((double)((tiles + pairs - 1) / pairs) * pairs);
+  return eff_own >= eff_tiles - 0.02;
+}
+
 extern "C" int vqacl_set_gemm_sm_limit(int n) {
   g_sm_limit = n > 0 ? (n & ~1) : 0;   // even: the CTA-pair kernel launches clusters of two
   return 0;
@@ -170,7 +184,7 @@ template <bool A_MN, bool B_MN>
 static int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args_in, cudaStream_t stream) {
   GemmArgs args = args_in;
   args.sched = nullptr;
-  if (g_dyn) {
+  if (g_dyn && !args.tail) {
     if (!g_sched) {
       VQ_CUDA(cudaMalloc(&g_sched, SCHED_SLOTS * 2 * sizeof(uint32_t)));
       VQ_CUDA(cudaMemset(g_sched, 0, SCHED_SLOTS * 2 * sizeof(uint32_t)));
@@ -248,6 +262,12 @@ int gemm_bf16(const GemmOperand& A, const GemmOperand& B, GemmArgs args, int for
   VQ_CHECK(args.ldc % 8 == 0, "gemm: ldc=%d must be a multiple of 8", args.ldc);
   if (args.splits < 1) args.splits = 1;
   VQ_CHECK(args.splits == 1 || args.epi == EPI_ATOMIC_F32, "gemm: split-K needs the atomic epilogue");
+  if (args.tail) {
+    VQ_CHECK(args.tail == 1 && args.N == 768 && args.splits == 1 && (args.epi == EPI_RESID_F32 || args.epi == EPI_F32) && args.tail_w &&
+                 args.tail_out && args.tail_ld % 4 == 0 && !A.mn_major && g_pair_enabled,
+             "gemm: the RMSNorm row tail needs an fp32 768-wide output, no split-K and the CTA-pair kernel");
+    force_bn = 512;
+  }
   if (args.epi == EPI_ARGMAX) {
     if (force_bn == 0) force_bn = args.M >= 192 ? 512 : 256;
     VQ_CHECK(force_bn == 256 || force_bn == 512, "gemm: the argmax epilogue needs 256-wide tiles");
@@ -332,4 +352,16 @@ extern "C" int vqacl_gemm_bf16_ex(const void* A, int lda, int a_mn_major, const 
   g.splits = splits;
   g.drop_thr = drop_thr16; g.drop_inv_keep = inv_keep; g.seed = drop_key;
   return vq::gemm_bf16(a, b, g, force_bn, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// nn.Linear + residual add + the T5LayerNorm that opens the next sub-layer, in one launch (HF T5LayerSelfAttention / T5LayerFF:
+// hidden = hidden + dropout(layer(norm(hidden))) followed by the next layer_norm; hf5.5 modeling_t5.py:135-150, 347-377):
+//   C(f32)[M,768] = R + A[M,K] * B[768,K]^T;   N_out(bf16)[M,768] = C * rsqrt(mean(C^2) + eps) * norm_w
+// The norm runs as a row tail of the CTA-pair GEMM (see GemmArgs::tail).
+extern "C" int vqacl_gemm_resid_rmsnorm(const void* A, int lda, const void* B, int ldb, float* C, const float* R, int M, int K,
+                                        const float* norm_w, float eps, void* n_out_bf16, void* stream) {
+  vq::GemmArgs g{};
+  g.epi = vq::EPI_RESID_F32; g.M = M; g.N = 768; g.K = K; g.C = C; g.ldc = 768; g.R = R; g.ldr = 768; g.alpha = 1.f; g.splits = 1;
+  g.tail = 1; g.tail_w = norm_w; g.tail_out = n_out_bf16; g.tail_ld = 768; g.tail_eps = eps;
+  return vq::gemm_bf16(vq::GemmOperand{A, lda, false}, vq::GemmOperand{B, ldb, false}, g, 0, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -12,6 +12,7 @@ struct GemmOperand {
 
 // C[M,N] (+)= A[M,K] * B[N,K]^T with the epilogue in args.epi. force_bn = 0 picks the N tile by occupancy.
 int gemm_bf16(const GemmOperand& A, const GemmOperand& B, GemmArgs args, int force_bn, cudaStream_t stream);
+bool gemm_row_tail_ok(int M);   // fold a row-wise follow-up (RMSNorm) into a GEMM with 768 output columns? (see gemm.cu)
 void gemm_tmap_cache_clear();
 // cached 2-D bf16 tensor map, 128-byte swizzle: inner extent d0 (contiguous), outer extent d1, outer pitch ld elements, box b0 x b1
 int make_tmap_bf16_2d(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t ld, uint32_t b0, uint32_t b1);

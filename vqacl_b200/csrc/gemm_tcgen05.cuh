@@ -43,6 +43,15 @@ struct GemmArgs {
   uint32_t drop_thr;  // 16-bit keep threshold (0 = no dropout), see vq_dropout_pair
   float drop_inv_keep;
   uint32_t seed, site;  // seed = per-launch dropout key (already mixed with the site id); site is informational
+  // CTA-pair kernel only — row tail: every pair OWNS whole 256-row blocks (it computes all N tiles of a block back to back), so
+  // once the block's last tile has been written its epilogue warps can run a row-wise follow-up on the finished rows while they
+  // are still in L2, instead of a separate kernel launch:  tail = 1: T5 RMSNorm of the fp32 rows just written (N must be 768):
+  // tail_out(bf16)[r, :] = C[r, :] * rsqrt(mean(C[r, :]^2) + tail_eps) * tail_w   — the norm that feeds the NEXT sub-layer's GEMM.
+  int tail;
+  const float* tail_w;
+  void* tail_out;
+  int tail_ld;          // elements
+  float tail_eps;
   uint32_t* sched;      // CTA-pair kernel only: {next work item, pairs finished} counters of a DYNAMIC tile schedule (null = static
                         // round robin). A pair that becomes resident late — its SMs were held by a collective's CTAs or by another
                         // stream's kernel — then finds the work list drained instead of running its whole static share afterwards.
@@ -429,6 +438,31 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 //   tfull[a]  (one per CTA)     : tcgen05.commit multicast when a 256 x 256 accumulator is complete
 //   tempty[a] (leader's)        : 16 arrivals = 8 epilogue warps of each CTA (the peer arrives remotely)
 // ---------------------------------------------------------------------------------------------------------------------
+// Row tail of the CTA-pair kernel (GemmArgs::tail == 1): T5 RMSNorm (hf5.5 modeling_t5.py:46-68) of the CTA's 128 freshly written
+// fp32 rows [row0, row0 + 128) of C (768 wide), one warp per row, lane l holds the float4 chunks {l, l + 32, ..., l + 160}.
+VQ_DEVINL void gemm_tail_rmsnorm(const GemmArgs& p, int row0, int ew, int lane) {
+  constexpr int CH = 768 / 4 / 32;
+  float4 wv[CH];
+#pragma unroll
+  for (int j = 0; j < CH; ++j) wv[j] = *reinterpret_cast<const float4*>(p.tail_w + (lane + 32 * j) * 4);
+  const float* C = reinterpret_cast<const float*>(p.C);
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.tail_out);
+  for (int r = row0 + ew; r < row0 + GEMM_BM && r < p.M; r += GEMM_EPI_WARPS) {
+    float4 v[CH];
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      v[j] = __ldcg(reinterpret_cast<const float4*>(C + (size_t)r * p.ldc + (lane + 32 * j) * 4));   // L2: written by other warps of this CTA
+      ss += v[j].x * v[j].x; ss += v[j].y * v[j].y; ss += v[j].z * v[j].z; ss += v[j].w * v[j].w;   // same order as rmsnorm_fwd_kernel
+    }
+    const float rstd = rsqrtf(warp_sum(ss) / 768.f + p.tail_eps);
+#pragma unroll
+    for (int j = 0; j < CH; ++j)
+      *reinterpret_cast<uint2*>(out + (size_t)r * p.tail_ld + (lane + 32 * j) * 4) =
+          make_uint2(pack_bf16(v[j].x * rstd * wv[j].x, v[j].y * rstd * wv[j].y), pack_bf16(v[j].z * rstd * wv[j].z, v[j].w * rstd * wv[j].w));
+  }
+}
+
 constexpr int GEMM2_BN = 256;
 struct Gemm2Cfg {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;              // 128 rows of A
@@ -471,7 +505,9 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
   const int kblocks = (p.K + GEMM_BK - 1) / GEMM_BK;
   const int kb_per_split = (kblocks + p.splits - 1) / p.splits;
   const int tiles_mn = tiles_m * tiles_n;
-  const int total_work = tiles_mn * p.splits;
+  // work items: one (split, m, n) tile each — or, with a row tail, one 256-row block each = `run` consecutive tiles (n fastest)
+  const int run = p.tail ? tiles_n : 1;
+  const int total_work = p.tail ? tiles_m : tiles_mn * p.splits;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -534,7 +570,8 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
         if (w < total_work) w_ahead = npairs + (int)atomicAdd(p.sched, 1u);
         return w;
       };
-      for (int w = dyn ? fetch() : pair; w < total_work; w = dyn ? fetch() : w + npairs) {
+      for (int wi = dyn ? fetch() : pair; wi < total_work; wi = dyn ? fetch() : wi + npairs)
+      for (int w = wi * run; w < wi * run + run; ++w) {
         const int split = w / tiles_mn;
         const int t = w - split * tiles_mn;
         const int m_blk = t / tiles_n, n_blk = t - m_blk * tiles_n;
@@ -584,7 +621,8 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
       int astage = 0;
       uint32_t aphase = 0;
       int it = 0;
-      for (int w = dyn ? next_work(it) : pair; w < total_work; w = dyn ? next_work(it) : w + npairs) {
+      for (int wi = dyn ? next_work(it) : pair; wi < total_work; wi = dyn ? next_work(it) : wi + npairs)
+      for (int w = wi * run; w < wi * run + run; ++w) {
         const int split = w / tiles_mn;
         const int kb0 = split * kb_per_split;
         const int kb1 = min(kblocks, kb0 + kb_per_split);
@@ -625,7 +663,8 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
       if (lane == 0) w = next_work(it);
       return __shfl_sync(0xffffffffu, w, 0);
     };
-    for (int w = dyn ? warp_next() : pair; w < total_work; w = dyn ? warp_next() : w + npairs) {
+    for (int wi = dyn ? warp_next() : pair; wi < total_work; wi = dyn ? warp_next() : wi + npairs) {
+    for (int w = wi * run; w < wi * run + run; ++w) {
       const int split = w / tiles_mn;
       const int t = w - split * tiles_mn;
       const int m_blk = t / tiles_n, n_blk = t - m_blk * tiles_n;
@@ -646,6 +685,13 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&tempty_bar[astage], 0);   // the leader's MMA lane owns accumulator reuse
       if (++astage == 2) { astage = 0; aphase ^= 1; }
+    }
+    if (p.tail) {
+      // ---- row tail: this CTA's 128 rows of block wi are complete in C (written by these 8 warps) and still in L2
+      asm volatile("bar.sync 1, %0;" ::"n"(GEMM_EPI_WARPS * 32) : "memory");
+      const int row0 = wi * 2 * GEMM_BM + (int)rank * GEMM_BM;
+      gemm_tail_rmsnorm(p, row0, warp - 4, lane);
+    }
     }
   }
 
