@@ -111,7 +111,10 @@ void gemm_tmap_cache_clear() {
 }
 
 static int g_pair_enabled = 1;   // VQACL_GEMM_PAIR=0 disables the CTA-pair kernel (A/B measurements)
-static int g_row_tail_off = [] { const char* e = getenv("VQACL_GEMM_ROW_TAIL"); return (e && e[0] == '0') ? 1 : 0; }();
+// the engine folds the encoder's sub-layer-opening RMSNorms into the preceding residual GEMMs only on request
+// (VQACL_GEMM_ROW_TAIL=1): measured neutral at B = 320 (profiles/r02_summary.md) — 8 tail warps per SM pay the L2 latency of
+// 16 rows each, about what the stand-alone kernel costs
+static int g_row_tail_off = [] { const char* e = getenv("VQACL_GEMM_ROW_TAIL"); return (e && e[0] == '1') ? 0 : 1; }();
 // SMs the persistent GEMMs may occupy (0 = all). With N > 1 GPUs the host lowers it during backward so that the NCCL
 // all-reduce kernels, which need resident CTAs of their own, are not starved by 148 GEMM CTAs that each fill an SM's
 // shared memory (vqacl_set_gemm_sm_limit).
