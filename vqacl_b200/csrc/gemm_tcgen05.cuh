@@ -447,24 +447,12 @@ VQ_DEVINL void gemm_tail_rmsnorm(const GemmArgs& p, int row0, int ew, int lane) 
   for (int j = 0; j < CH; ++j) wv[j] = *reinterpret_cast<const float4*>(p.tail_w + (lane + 32 * j) * 4);
   const float* C = reinterpret_cast<const float*>(p.C);
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.tail_out);
-  const int rend = min(row0 + GEMM_BM, p.M);
-  // two rows in flight per warp: the loads of row r + 8 are issued before row r is reduced (only 8 warps per SM run this tail,
-  // so the L2 latency of one row would otherwise be fully exposed 16 times per CTA)
-  float4 v[CH], nx[CH];
-  int r = row0 + ew;
-  if (r < rend) {
-#pragma unroll
-    for (int j = 0; j < CH; ++j) v[j] = __ldcg(reinterpret_cast<const float4*>(C + (size_t)r * p.ldc + (lane + 32 * j) * 4));
-  }
-  for (; r < rend; r += GEMM_EPI_WARPS) {
-    const int rn = r + GEMM_EPI_WARPS;
-    if (rn < rend) {
-#pragma unroll
-      for (int j = 0; j < CH; ++j) nx[j] = __ldcg(reinterpret_cast<const float4*>(C + (size_t)rn * p.ldc + (lane + 32 * j) * 4));
-    }
+  for (int r = row0 + ew; r < row0 + GEMM_BM && r < p.M; r += GEMM_EPI_WARPS) {
+    float4 v[CH];
     float ss = 0.f;
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
+      v[j] = __ldcg(reinterpret_cast<const float4*>(C + (size_t)r * p.ldc + (lane + 32 * j) * 4));   // L2: written by other warps of this CTA
       ss += v[j].x * v[j].x; ss += v[j].y * v[j].y; ss += v[j].z * v[j].z; ss += v[j].w * v[j].w;   // same order as rmsnorm_fwd_kernel
     }
     const float rstd = rsqrtf(warp_sum(ss) / 768.f + p.tail_eps);
@@ -472,8 +460,6 @@ VQ_DEVINL void gemm_tail_rmsnorm(const GemmArgs& p, int row0, int ew, int lane) 
     for (int j = 0; j < CH; ++j)
       *reinterpret_cast<uint2*>(out + (size_t)r * p.tail_ld + (lane + 32 * j) * 4) =
           make_uint2(pack_bf16(v[j].x * rstd * wv[j].x, v[j].y * rstd * wv[j].y), pack_bf16(v[j].z * rstd * wv[j].z, v[j].w * rstd * wv[j].w));
-#pragma unroll
-    for (int j = 0; j < CH; ++j) v[j] = nx[j];
   }
 }
 
