@@ -208,6 +208,11 @@ int vqacl_visual_embed_fwd(const float* featpre, const float* boxes, const float
  * (torch.zeros(B, C).scatter_(1, ids, 1)). boxes_px [B,N,4], img_wh [B,2], cate_ids / ques_ids int64 [B] (NULL: skipped). */
 int vqacl_collate_device(const float* boxes_px, const float* img_wh, int B, int N, float* boxes_out, const int64_t* cate_ids,
                          int n_cate, float* cate_onehot, const int64_t* ques_ids, int n_ques, float* ques_onehot, void* stream);
+/* VisualEmbedding.forward in ONE launch (north_star: "the 2048->768 feature projection and the 4-d box projection, fused with
+ * LayerNorm in one TMA-staged GEMM epilogue"): tcgen05 GEMM of the bf16 RoI features with the rest of the module as a row tail. */
+int vqacl_visual_embed_fused(const void* feats_bf16, const void* Wf_bf16, int F, const float* boxes, const float* bf,
+                             const float* wf, const float* Wp, const float* bp, const float* wp, const float* img_emb,
+                             const float* shared, int V, int B, int N, int S, int L, float eps, float* featpre, float* x, void* stream);
 /* transformers-4.2.1 AdamW.step + torch clip_grad_norm_ (trainer_base.py:130-198, vqacl.py:475-482) over a flat range         */
 int vqacl_adamw_hf(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, int64_t n_decay, float lr, float beta1,
                    float beta2, float eps, float weight_decay, int step, const float* sumsq, float max_norm, void* stream);

@@ -32,6 +32,7 @@ def _L():
         L.vqacl_gemm_bf16_ex.argtypes = [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,
                                          c_int, F, c_int, c_int, ctypes.c_uint32, F, ctypes.c_uint32, c_void_p]
         L.vqacl_gemm_resid_rmsnorm.argtypes = [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, F, c_void_p, c_void_p]
+        L.vqacl_visual_embed_fused.argtypes = [c_void_p, c_void_p, c_int] + [c_void_p] * 8 + [c_int] * 5 + [F, c_void_p, c_void_p, c_void_p]
         L._ops_declared = True
     return L
 
@@ -170,3 +171,12 @@ def gemm_resid_rmsnorm(A, B, R, norm_w, eps=1e-6):
     n = torch.empty(M, 768, device=A.device, dtype=torch.bfloat16)
     check(_L().vqacl_gemm_resid_rmsnorm(ptr(A), A.stride(0), ptr(B), B.stride(0), ptr(C), ptr(R), M, K, ptr(norm_w), eps, ptr(n), cur_stream()))
     return C, n
+
+
+def visual_embed_fused(feats_bf16, Wf_bf16, boxes, bf, wf, Wp, bp, wp, img, shared, B, N, eps=1e-6):
+    Fd = feats_bf16.shape[-1]
+    featpre = torch.empty(B * N, 768, device=boxes.device)
+    x = torch.zeros(B, N, 768, device=boxes.device)
+    check(_L().vqacl_visual_embed_fused(ptr(feats_bf16), ptr(Wf_bf16), Fd, ptr(boxes), ptr(bf), ptr(wf), ptr(Wp), ptr(bp), ptr(wp), ptr(img),
+                                        ptr(shared), shared.shape[0], B, N, N, 0, eps, ptr(featpre), ptr(x), cur_stream()))
+    return x, featpre

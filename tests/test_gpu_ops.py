@@ -171,6 +171,35 @@ def test_visual_embedding_matches_reference_fixture():
     torch.testing.assert_close(x.cpu(), d["out"], rtol=1e-4, atol=1e-4)
 
 
+def test_visual_embedding_fused_single_launch():
+    """The whole VisualEmbedding as one launch (tcgen05 GEMM + row tail) against the fixture made by executing the reference
+    class, and bit-identical to GEMM + vis_embed_fwd_kernel on the same bf16 operands; also on a multi-block shape."""
+    d = torch.load(os.path.join(G, "visual_embedding.pt"))
+    s = {k: v.to(DEV) for k, v in d["state"].items()}
+    feats, boxes = d["feats"].to(DEV), d["boxes"].to(DEV).contiguous()
+    B, N, _ = feats.shape
+    args = (s["feat_embedding.0.bias"], s["feat_embedding.1.weight"], s["absolute_vis_pos_embedding.0.weight"].contiguous(),
+            s["absolute_vis_pos_embedding.0.bias"], s["absolute_vis_pos_embedding.1.weight"], s["img_order_embedding.weight"].contiguous(),
+            s["obj_order_embedding.weight"].contiguous())
+    fb = feats.view(B * N, -1).bfloat16().contiguous()
+    Wb = s["feat_embedding.0.weight"].bfloat16().contiguous()
+    x, featpre = cabi.visual_embed_fused(fb, Wb, boxes, *args, B, N)
+    torch.testing.assert_close(x.cpu(), d["out"], rtol=2e-2, atol=2e-2)          # bf16 operands vs the fp32 reference
+    ref_pre = (fb.float() @ Wb.float().t()).contiguous()
+    torch.testing.assert_close(featpre, ref_pre, rtol=1e-5, atol=1e-5)
+    x2 = cabi.visual_embed_fwd(featpre, boxes, *args, B, N)                       # the stand-alone tail kernel on the same projection
+    assert torch.equal(x, x2)
+    # 3 row blocks of 256 (two CTA pairs busy + a ragged one), real feature width
+    torch.manual_seed(9)
+    B2, N2 = 17, 36
+    f2 = torch.relu(torch.randn(B2 * N2, 2048, device=DEV)).bfloat16()
+    W2 = (torch.randn(768, 2048, device=DEV) * 0.02).bfloat16()
+    bx = torch.rand(B2, N2, 4, device=DEV)
+    xa, pa = cabi.visual_embed_fused(f2, W2, bx, *args, B2, N2)
+    xb = cabi.visual_embed_fwd(pa, bx, *args, B2, N2)
+    assert torch.equal(xa, xb) and rel_err(pa, f2.float() @ W2.float().t()) < 3e-5
+
+
 def test_ce_and_loss_tail():
     torch.manual_seed(2)
     M, V, ld = 40, 32200, 32256

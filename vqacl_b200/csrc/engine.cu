@@ -306,12 +306,28 @@ int encoder_forward(Engine& e, const vqacl_batch* b, cudaStream_t st) {
     VQ_TRY(cast_f32_to_bf16(b->vis_feats, w.feats_bf16, (size_t)B * N * c.feat_dim, st));
     feats = w.feats_bf16;
   }
-  VQ_TRY(gemm_fwd(feats, c.feat_dim, e.W + e.o_Wf, c.feat_dim, w.featpre, d, B * N, d, EPI_F32, st));
-  VisArgs va{};
-  va.featpre = w.featpre; va.boxes = b->boxes; va.bf = e.P + e.o_bf; va.wf = e.P + e.o_wf; va.Wp = e.P + e.o_Wp;
-  va.bp = e.P + e.o_bp; va.wp = e.P + e.o_wp; va.img_emb = e.P + e.o_img; va.shared = e.P + e.o_shared;
-  va.V = c.vocab_size; va.B = B; va.N = N; va.S = S; va.L = L; va.eps = c.eps; va.x = w.x[0]; va.drop = e.drop(SITE_ENC_EMB);
-  VQ_TRY(vis_embed_fwd(va, st));
+  if (gemm_vis_tail_on() && B * N >= 192) {
+    // VisualEmbedding.forward (modeling_t5_our.py:93-143) in ONE launch: the 2048 -> 768 projection on tcgen05 (TMA-staged), and —
+    // as the row tail of the CTA pair that owns a 256-row block — bias + RMSNorm, the 5 -> 768 box projection + RMSNorm, the
+    // image / object order embeddings and the embedding dropout, written straight into rows [L, S) of the residual stream.
+    // featpre (fp32) is still written: the backward re-reads it.
+    const Dropout dr = e.drop(SITE_ENC_EMB);
+    GemmArgs g{};
+    g.epi = EPI_F32; g.M = B * N; g.N = d; g.K = c.feat_dim; g.C = w.featpre; g.ldc = d; g.alpha = 1.f; g.splits = 1;
+    g.tail = 2; g.tail_eps = c.eps;
+    g.vt.boxes = b->boxes; g.vt.bf = e.P + e.o_bf; g.vt.wf = e.P + e.o_wf; g.vt.Wp = e.P + e.o_Wp; g.vt.bp = e.P + e.o_bp;
+    g.vt.wp = e.P + e.o_wp; g.vt.img_emb = e.P + e.o_img; g.vt.shared = e.P + e.o_shared; g.vt.x = w.x[0];
+    g.vt.V = c.vocab_size; g.vt.N = N; g.vt.S = S; g.vt.L = L;
+    g.vt.drop_thr = dr.thr; g.vt.drop_inv_keep = dr.inv_keep; g.vt.drop_seed = dr.seed;
+    VQ_TRY(gemm_bf16(GemmOperand{feats, c.feat_dim, false}, GemmOperand{e.W + e.o_Wf, c.feat_dim, false}, g, 0, st));
+  } else {
+    VQ_TRY(gemm_fwd(feats, c.feat_dim, e.W + e.o_Wf, c.feat_dim, w.featpre, d, B * N, d, EPI_F32, st));
+    VisArgs va{};
+    va.featpre = w.featpre; va.boxes = b->boxes; va.bf = e.P + e.o_bf; va.wf = e.P + e.o_wf; va.Wp = e.P + e.o_Wp;
+    va.bp = e.P + e.o_bp; va.wp = e.P + e.o_wp; va.img_emb = e.P + e.o_img; va.shared = e.P + e.o_shared;
+    va.V = c.vocab_size; va.B = B; va.N = N; va.S = S; va.L = L; va.eps = c.eps; va.x = w.x[0]; va.drop = e.drop(SITE_ENC_EMB);
+    VQ_TRY(vis_embed_fwd(va, st));
+  }
   // The RMSNorm that opens a sub-layer is folded into the residual GEMM that closes the previous one (row tail of the CTA-pair
   // kernel: the pair that wrote a 256-row block normalises it while it is still in L2) whenever the blocks fill the machine
   // as well as the tiles would; otherwise (and for the first layer, which follows the embeddings) it is its own kernel.

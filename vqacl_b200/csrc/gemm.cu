@@ -140,6 +140,11 @@ static int gemm_sms() {
 // Is folding a row tail into an M-row GEMM with 768 output columns a good deal? In the tail mode a CTA pair owns whole 256-row
 // blocks, so the kernel's parallelism is ceil(M / 256) pairs instead of 3x as many tiles: only when the blocks fill the pairs
 // about as well as the tiles would (B = 320: 70 blocks on 74 pairs either way).
+bool gemm_vis_tail_on() {
+  static const int on = [] { const char* e = getenv("VQACL_VIS_FUSED"); return (e && e[0] == '0') ? 0 : 1; }();
+  (void)num_sms();
+  return on && g_pair_enabled;
+}
 bool gemm_row_tail_ok(int M) {
   (void)num_sms();
   if (!g_pair_enabled || g_row_tail_off) return false;
@@ -266,9 +271,11 @@ int gemm_bf16(const GemmOperand& A, const GemmOperand& B, GemmArgs args, int for
   if (args.splits < 1) args.splits = 1;
   VQ_CHECK(args.splits == 1 || args.epi == EPI_ATOMIC_F32, "gemm: split-K needs the atomic epilogue");
   if (args.tail) {
-    VQ_CHECK(args.tail == 1 && args.N == 768 && args.splits == 1 && (args.epi == EPI_RESID_F32 || args.epi == EPI_F32) && args.tail_w &&
-                 args.tail_out && args.tail_ld % 4 == 0 && !A.mn_major && g_pair_enabled,
-             "gemm: the RMSNorm row tail needs an fp32 768-wide output, no split-K and the CTA-pair kernel");
+    VQ_CHECK((args.tail == 1 || args.tail == 2) && args.N == 768 && args.splits == 1 && (args.epi == EPI_RESID_F32 || args.epi == EPI_F32) &&
+                 !A.mn_major && g_pair_enabled,
+             "gemm: a row tail needs an fp32 768-wide output, no split-K and the CTA-pair kernel");
+    VQ_CHECK(args.tail != 1 || (args.tail_w && args.tail_out && args.tail_ld % 4 == 0), "gemm: RMSNorm row tail: missing operands");
+    VQ_CHECK(args.tail != 2 || (args.vt.boxes && args.vt.x && args.vt.N > 0), "gemm: VisualEmbedding row tail: missing operands");
     force_bn = 512;
   }
   if (args.epi == EPI_ARGMAX) {
@@ -367,4 +374,19 @@ extern "C" int vqacl_gemm_resid_rmsnorm(const void* A, int lda, const void* B, i
   g.epi = vq::EPI_RESID_F32; g.M = M; g.N = 768; g.K = K; g.C = C; g.ldc = 768; g.R = R; g.ldr = 768; g.alpha = 1.f; g.splits = 1;
   g.tail = 1; g.tail_w = norm_w; g.tail_out = n_out_bf16; g.tail_ld = 768; g.tail_eps = eps;
   return vq::gemm_bf16(vq::GemmOperand{A, lda, false}, vq::GemmOperand{B, ldb, false}, g, 0, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// VisualEmbedding.forward (modeling_t5_our.py:93-143) in one launch: feats(bf16)[B*N, F] @ Wf(bf16)[768, F]^T on tcgen05 with
+// the rest of the module as the row tail (bias + RMSNorm, box projection + RMSNorm, order embeddings); featpre (fp32
+// [B*N, 768]) receives the raw projection (the backward pass re-reads it); x [B, S, 768] rows [L, L + N) are written.
+extern "C" int vqacl_visual_embed_fused(const void* feats_bf16, const void* Wf_bf16, int F, const float* boxes, const float* bf,
+                                        const float* wf, const float* Wp, const float* bp, const float* wp, const float* img_emb,
+                                        const float* shared, int V, int B, int N, int S, int L, float eps, float* featpre, float* x,
+                                        void* stream) {
+  vq::GemmArgs g{};
+  g.epi = vq::EPI_F32; g.M = B * N; g.N = 768; g.K = F; g.C = featpre; g.ldc = 768; g.alpha = 1.f; g.splits = 1;
+  g.tail = 2; g.tail_eps = eps;
+  g.vt.boxes = boxes; g.vt.bf = bf; g.vt.wf = wf; g.vt.Wp = Wp; g.vt.bp = bp; g.vt.wp = wp; g.vt.img_emb = img_emb; g.vt.shared = shared;
+  g.vt.x = x; g.vt.V = V; g.vt.N = N; g.vt.S = S; g.vt.L = L;
+  return vq::gemm_bf16(vq::GemmOperand{feats_bf16, F, false}, vq::GemmOperand{Wf_bf16, F, false}, g, 0, reinterpret_cast<cudaStream_t>(stream));
 }

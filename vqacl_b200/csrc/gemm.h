@@ -12,6 +12,7 @@ struct GemmOperand {
 
 // C[M,N] (+)= A[M,K] * B[N,K]^T with the epilogue in args.epi. force_bn = 0 picks the N tile by occupancy.
 int gemm_bf16(const GemmOperand& A, const GemmOperand& B, GemmArgs args, int force_bn, cudaStream_t stream);
+bool gemm_vis_tail_on();        // VisualEmbedding as ONE launch (GEMM + row tail 2); VQACL_VIS_FUSED=0 keeps GEMM + vis_embed_fwd_kernel
 bool gemm_row_tail_ok(int M);   // fold a row-wise follow-up (RMSNorm) into a GEMM with 768 output columns? (see gemm.cu)
 void gemm_tmap_cache_clear();
 // cached 2-D bf16 tensor map, 128-byte swizzle: inner extent d0 (contiguous), outer extent d1, outer pitch ld elements, box b0 x b1

@@ -31,6 +31,14 @@ enum GemmEpi : int {
                          // values (two fp32 logits 0.01 apart round to the same bf16 above 2.0).
 };
 
+// row tail 2: the rest of VisualEmbedding.forward (modeling_t5_our.py:93-143) on the rows of feats @ Wf^T just written to C
+struct VisTail {
+  const float *boxes, *bf, *wf, *Wp, *bp, *wp, *img_emb, *shared;
+  float* x;                      // [B, S, 768]: rows [L, L + N) of every batch element are written
+  int V, N, S, L;
+  uint32_t drop_thr; float drop_inv_keep; uint32_t drop_seed;
+};
+
 struct GemmArgs {
   int epi;            // GemmEpi
   int M, N, K;        // C is MxN, contraction length K
@@ -47,7 +55,10 @@ struct GemmArgs {
   // once the block's last tile has been written its epilogue warps can run a row-wise follow-up on the finished rows while they
   // are still in L2, instead of a separate kernel launch:  tail = 1: T5 RMSNorm of the fp32 rows just written (N must be 768):
   // tail_out(bf16)[r, :] = C[r, :] * rsqrt(mean(C[r, :]^2) + tail_eps) * tail_w   — the norm that feeds the NEXT sub-layer's GEMM.
+  // tail = 2: VisualEmbedding tail (C = feats @ Wf^T, 768 wide): x[b, L + n] = RMSNorm(C + bf) wf + RMSNorm([box, area] Wp^T + bp) wp
+  // + img_order_embedding[0] + shared[V - 1 - n], with the embedding dropout (VisTail vt) — the whole VisualEmbedding in one launch.
   int tail;
+  VisTail vt;
   const float* tail_w;
   void* tail_out;
   int tail_ld;          // elements
@@ -463,6 +474,84 @@ VQ_DEVINL void gemm_tail_rmsnorm(const GemmArgs& p, int row0, int ew, int lane) 
   }
 }
 
+// Row tail 2 (see GemmArgs): one warp per row, the same arithmetic in the same order as vis_embed_fwd_kernel (elementwise.cu),
+// but in three passes over the row's six float4 chunks (two for the statistics, one that recomputes and writes) so that only a
+// handful of values are live at a time: this code shares the GEMM kernel's 128-register budget.
+VQ_DEVINL void gemm_tail_visual(const GemmArgs& p, int row0, int ew, int lane) {
+  constexpr int CH = 768 / 4 / 32;
+  const VisTail& a = p.vt;
+  const float* C = reinterpret_cast<const float*>(p.C);
+  const int rend = min(row0 + GEMM_BM, p.M);
+  for (int r = row0 + ew; r < rend; r += GEMM_EPI_WARPS) {
+    const int b = r / a.N, n = r - b * a.N;
+    const float* crow = C + (size_t)r * p.ldc;
+    const float4 bx = *reinterpret_cast<const float4*>(a.boxes + (size_t)r * 4);
+    const float p5[5] = {bx.x, bx.y, bx.z, bx.w, (bx.w - bx.z) * (bx.y - bx.x)};   // area as the reference writes it (:78-90)
+    auto feat4 = [&](int j, float (&u)[4]) {        // feats Wf^T + bf
+      const int c0 = (lane + 32 * j) * 4;
+      const float4 c = __ldcg(reinterpret_cast<const float4*>(crow + c0));
+      const float4 t = *reinterpret_cast<const float4*>(a.bf + c0);
+      u[0] = c.x + t.x; u[1] = c.y + t.y; u[2] = c.z + t.z; u[3] = c.w + t.w;
+    };
+    auto pos4 = [&](int j, float (&u)[4]) {         // [box, area] Wp^T + bp
+      const int c0 = (lane + 32 * j) * 4;
+      const float4 t = *reinterpret_cast<const float4*>(a.bp + c0);
+      const float tb[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float* wrow = a.Wp + (size_t)(c0 + i) * 5;
+        float acc = tb[i];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) acc += wrow[k] * p5[k];
+        u[i] = acc;
+      }
+    };
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+    for (int j = 0; j < CH; ++j) {
+      float u[4];
+      feat4(j, u);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) s1 += u[i] * u[i];
+    }
+#pragma unroll 1
+    for (int j = 0; j < CH; ++j) {
+      float u[4];
+      pos4(j, u);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) s2 += u[i] * u[i];
+    }
+    const float rstd1 = rsqrtf(warp_sum(s1) / 768.f + p.tail_eps), rstd2 = rsqrtf(warp_sum(s2) / 768.f + p.tail_eps);
+    const size_t orow = (size_t)b * a.S + a.L + n;
+#pragma unroll 1
+    for (int j = 0; j < CH; ++j) {
+      const int c0 = (lane + 32 * j) * 4;
+      float u[4], v[4], out[4];
+      feat4(j, u);
+      pos4(j, v);
+      const float4 wf = *reinterpret_cast<const float4*>(a.wf + c0), wp = *reinterpret_cast<const float4*>(a.wp + c0);
+      const float4 im = *reinterpret_cast<const float4*>(a.img_emb + c0);
+      const float4 sh = *reinterpret_cast<const float4*>(a.shared + (size_t)(a.V - 1 - n) * 768 + c0);
+      const float wfv[4] = {wf.x, wf.y, wf.z, wf.w}, wpv[4] = {wp.x, wp.y, wp.z, wp.w};
+      const float imv[4] = {im.x, im.y, im.z, im.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        out[i] = u[i] * rstd1 * wfv[i];
+        out[i] += v[i] * rstd2 * wpv[i];
+        out[i] += imv[i] + shv[i];
+      }
+      if (a.drop_thr) {
+        const uint32_t pi = (uint32_t)((orow * 768) >> 1) + (uint32_t)(lane + 32 * j) * 2u;
+        float d0, d1, d2, d3;
+        vq_dropout_pair(a.drop_seed, pi, a.drop_thr, a.drop_inv_keep, d0, d1);
+        vq_dropout_pair(a.drop_seed, pi + 1, a.drop_thr, a.drop_inv_keep, d2, d3);
+        out[0] *= d0; out[1] *= d1; out[2] *= d2; out[3] *= d3;
+      }
+      *reinterpret_cast<float4*>(a.x + orow * 768 + c0) = make_float4(out[0], out[1], out[2], out[3]);
+    }
+  }
+}
+
 constexpr int GEMM2_BN = 256;
 struct Gemm2Cfg {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;              // 128 rows of A
@@ -690,7 +779,8 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
       // ---- row tail: this CTA's 128 rows of block wi are complete in C (written by these 8 warps) and still in L2
       asm volatile("bar.sync 1, %0;" ::"n"(GEMM_EPI_WARPS * 32) : "memory");
       const int row0 = wi * 2 * GEMM_BM + (int)rank * GEMM_BM;
-      gemm_tail_rmsnorm(p, row0, warp - 4, lane);
+      if (p.tail == 1) gemm_tail_rmsnorm(p, row0, warp - 4, lane);
+      else gemm_tail_visual(p, row0, warp - 4, lane);
     }
     }
   }
