@@ -48,6 +48,9 @@ typedef struct vqacl_batch {
   const int64_t* labels;       /* [B,T], -100 = ignore (train only) */
   const float* cate_labels;    /* [B,n_cate] one-hot fp32 (train only) */
   const float* ques_labels;    /* [B,n_ques] one-hot fp32 (train only) */
+  const int64_t* decoder_input_ids; /* optional [B,T]: explicit decoder inputs (VLT5.forward(decoder_input_ids=...),
+                                  modeling_t5_our.py:617-629) instead of shift_right(labels); labels may then be NULL: the call
+                                  produces logits only (no loss, no backward) */
   const void* vis_feats_bf16;  /* optional [B,N,feat_dim] bf16: RoI features already in the GEMM operand format (packed feature
                                   shards, vqacl_b200/pipeline.py). When set, vis_feats may be NULL and the fp32->bf16 cast is
                                   skipped; results are bit-identical to passing the fp32 values they were rounded from. */

@@ -109,6 +109,39 @@ def test_forward_api_row_losses_and_backward():
     assert m.shared.weight.grad is not None and cos(m.shared.weight.grad, om.shared.weight.grad) > 0.995
 
 
+def test_forward_with_decoder_input_ids_returns_prefix_logits():
+    """VLT5.forward(decoder_input_ids=..., labels=None) — the call shape HF-style decoding loops use
+    (modeling_t5_our.py:617-629, 659-671): logits of a given decoder prefix on the frozen banks, no loss; and with labels AND
+    explicit decoder inputs the loss rows use those inputs instead of shift_right(labels)."""
+    om, m = make_pair(layers=2, vocab=2048)
+    om.eval(); m.eval()
+    g = torch.Generator().manual_seed(9)
+    Q0, V0 = torch.randn(10, 768, generator=g), torch.randn(80, 768, generator=g)
+    om.bank.Q_prototype, om.bank.V_prototype = Q0.clone().cuda(), V0.clone().cuda()
+    m.Q_prototype, m.V_prototype = Q0, V0
+    b = O.synthetic_batch(6, seed=31, vocab=2000)
+    dec = torch.randint(2, 2000, (6, 7), generator=g)
+    dec[:, 0] = 0
+    out = m(input_ids=b["input_ids"], vis_inputs=(b["vis_feats"], b["boxes"]), decoder_input_ids=dec)
+    assert out.loss is None and out.logits.shape == (6, 7, 2048)
+    with torch.no_grad():
+        ids = b["input_ids"].cuda()
+        hidden = om.encode(ids, b["vis_feats"].cuda(), b["boxes"].cuda())
+        mem, iq, iv = om.si_path(hidden, proto_update=False)
+        ref, _ = om.decode_logits(dec.cuda(), mem, ids)
+    assert rel_err(out.logits, ref) < 1e-2
+    assert torch.equal(out.max_idx_Q, iq) and torch.equal(out.max_idx_V, iv)
+    with pytest.raises(NotImplementedError):
+        m(input_ids=b["input_ids"], vis_inputs=(b["vis_feats"], b["boxes"]))
+    # labels + explicit decoder inputs equal to shift_right(labels): the same row losses as the labels-only call
+    lab = b["target_ids"]
+    sr = om.shift_right(lab)
+    a1 = m(input_ids=b["input_ids"], vis_inputs=(b["vis_feats"], b["boxes"]), labels=lab)
+    l1 = a1.loss.detach().clone()
+    a2 = m(input_ids=b["input_ids"], vis_inputs=(b["vis_feats"], b["boxes"]), labels=lab, decoder_input_ids=sr)
+    assert torch.equal(l1, a2.loss.detach())
+
+
 def test_dropout_is_consistent_between_forward_and_backward():
     """With dropout on, backward must regenerate exactly the forward masks: finite-difference check of the loss along the
     gradient direction of one weight (same seed => same masks)."""

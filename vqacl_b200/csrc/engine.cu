@@ -433,7 +433,11 @@ static int decoder_forward(Engine& e, const vqacl_batch* b, cudaStream_t st) {
     VQ_CUDA(cudaEventRecord(e.ev_gzero, e.side));
     e.g_prezeroed = true;
   }
-  VQ_TRY(shift_right(b->labels, w.dec_ids, B, T, c.start_id, c.pad_id, st));                      // :620
+  if (b->decoder_input_ids) {                                                                      // :617-629 (given explicitly)
+    VQ_CUDA(cudaMemcpyAsync(w.dec_ids, b->decoder_input_ids, (size_t)Md * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+  } else {
+    VQ_TRY(shift_right(b->labels, w.dec_ids, B, T, c.start_id, c.pad_id, st));                    // :620
+  }
   VQ_TRY(embed_fwd(w.dec_ids, B, T, e.P + e.o_shared, w.y[0], T, 0, e.drop(SITE_DEC_EMB), c.vocab_size, e.err_flags(), st));
   // cross-attention K/V of every decoder layer in one GEMM over the decoder memory
   VQ_TRY(gemm_fwd(w.mem, d, e.W + e.o_ckv, d, w.kv_all, ldkv, M2, ldkv, EPI_BF16, st));
@@ -474,7 +478,7 @@ static int decoder_forward(Engine& e, const vqacl_batch* b, cudaStream_t st) {
   r.scale = 1.f / sqrtf((float)d); r.drop = e.drop(SITE_DEC_FINAL);
   VQ_TRY(rmsnorm_fwd(r, st));
   VQ_TRY(gemm_fwd(w.yfin, d, e.W + e.o_shared, d, w.logits, e.ldv, Md, c.vocab_size, EPI_BF16, st));
-  VQ_TRY(ce_fwd(w.logits, e.ldv, Md, c.vocab_size, b->labels, w.lse_ce, w.loss_rows, st));
+  if (b->labels) VQ_TRY(ce_fwd(w.logits, e.ldv, Md, c.vocab_size, b->labels, w.lse_ce, w.loss_rows, st));
   return 0;
 }
 
@@ -911,12 +915,12 @@ extern "C" int vqacl_forward_decoder(void* engine, const vqacl_batch* batch, con
                                      int prezero_grads, void* stream) {
   Engine& e = ENG(engine);
   if (check_batch(e, batch, true)) return 1;
-  VQ_CHECK(batch->labels, "forward_decoder: labels required");
-  e.prezero_request = prezero_grads != 0;
+  VQ_CHECK(batch->labels || batch->decoder_input_ids, "forward_decoder: labels or decoder_input_ids required");
+  e.prezero_request = prezero_grads != 0 && batch->labels;
   if (si_path(e, batch, proto, sums_ready != 0, ST(stream))) return 1;
   if (decoder_forward(e, batch, ST(stream))) return 1;
   g_saved[&e].b = *batch;
-  e.fwd_valid = true;
+  e.fwd_valid = batch->labels != nullptr;      // logits-only calls (decoder_input_ids without labels) have no backward
   return 0;
 }
 extern "C" int vqacl_backward(void* engine, const float* w_rows, const float* gscale, int accumulate, int stage_begin, int stage_end,

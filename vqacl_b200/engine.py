@@ -28,7 +28,7 @@ class CBatch(Structure):
     _fields_ = [
         ("B", c_int), ("L", c_int), ("N", c_int), ("T", c_int),
         ("vis_feats", c_void_p), ("boxes", c_void_p), ("input_ids", c_void_p), ("labels", c_void_p),
-        ("cate_labels", c_void_p), ("ques_labels", c_void_p), ("vis_feats_bf16", c_void_p),
+        ("cate_labels", c_void_p), ("ques_labels", c_void_p), ("decoder_input_ids", c_void_p), ("vis_feats_bf16", c_void_p),
     ]
 
 
@@ -215,13 +215,14 @@ class Engine:
 
     # ---- step ----------------------------------------------------------------------------------------------------
     @staticmethod
-    def make_batch(B, Lt, N, T, feats, boxes, ids, labels=None, cate=None, ques=None):
+    def make_batch(B, Lt, N, T, feats, boxes, ids, labels=None, cate=None, ques=None, dec_ids=None):
         bf = feats.dtype == torch.bfloat16      # packed feature shards hand the GEMM operand format over directly
         return CBatch(B=B, L=Lt, N=N, T=T, vis_feats=None if bf else feats.data_ptr(), vis_feats_bf16=feats.data_ptr() if bf else None,
                       boxes=boxes.data_ptr(), input_ids=ids.data_ptr(),
                       labels=labels.data_ptr() if labels is not None else None,
                       cate_labels=cate.data_ptr() if cate is not None else None,
-                      ques_labels=ques.data_ptr() if ques is not None else None)
+                      ques_labels=ques.data_ptr() if ques is not None else None,
+                      decoder_input_ids=dec_ids.data_ptr() if dec_ids is not None else None)
 
     def forward_encoder(self, cb, seed, training):
         if self.bf16_stale:

@@ -506,7 +506,7 @@ class VLT5(nn.Module):
             setattr(self, attr, t.detach().float().clone())
 
     # -- hot path ------------------------------------------------------------------------------------------------------
-    def _stage_batch(self, input_ids, vis_feats, boxes, labels=None, cate=None, ques=None):
+    def _stage_batch(self, input_ids, vis_feats, boxes, labels=None, cate=None, ques=None, dec_ids=None):
         eng = self._need_engine()
         dev = eng.device
 
@@ -530,15 +530,18 @@ class VLT5(nn.Module):
         lab = dv(labels, torch.int64)
         cate = dv(cate, torch.float32)
         ques = dv(ques, torch.float32)
+        dec = dv(dec_ids, torch.int64)
         B, Lt = ids.shape
         N = feats.shape[1]
         assert feats.shape == (B, N, self.config.feat_dim), f"vis_feats {tuple(feats.shape)}"
         assert bx.shape == (B, N, 4), f"boxes {tuple(bx.shape)}"          # modeling_t5_our.py:105
-        T = lab.shape[1] if lab is not None else 1
+        T = lab.shape[1] if lab is not None else (dec.shape[1] if dec is not None else 1)
+        if dec is not None and lab is not None:
+            assert dec.shape == lab.shape, "decoder_input_ids and labels must have the same shape"
         if cate is not None:
             assert cate.shape == (B, self.config.n_cate_classes) and ques.shape == (B, self.config.n_ques_classes)
-        keep = (ids, feats, bx, lab, cate, ques)
-        cb = Engine.make_batch(B, Lt, N, T, feats, bx, ids, lab, cate, ques)
+        keep = (ids, feats, bx, lab, cate, ques, dec)
+        cb = Engine.make_batch(B, Lt, N, T, feats, bx, ids, lab, cate, ques, dec)
         return cb, keep, (B, Lt, N, T)
 
     def _proto_state(self, proto_update, task_id=0, alpha=0.0, beta=0.0, memory=False):
@@ -652,9 +655,10 @@ class VLT5(nn.Module):
         """VLT5.forward (modeling_t5_our.py:514-713) for the teacher-forced call the reference makes (labels given).
         Returns per-row CE (`reduction='none'`, or the mean over valid rows with reduce_loss=True), bf16 logits (a view
         of engine memory: valid until the next backward / forward), encoder_hidden_states and the [B, L+N+2] memory mask."""
-        if labels is None:
-            raise NotImplementedError("forward() without labels: use generate() for decoding (KV-cached native loop)")
-        for nm, v in (("encoder_outputs", encoder_outputs), ("decoder_input_ids", decoder_input_ids),
+        if labels is None and decoder_input_ids is None:
+            raise NotImplementedError("forward() needs labels (teacher forcing) or decoder_input_ids (logits of a given prefix); "
+                                      "for decoding use generate() (KV-cached native loop)")
+        for nm, v in (("encoder_outputs", encoder_outputs),
                       ("past_key_values", past_key_values), ("inputs_embeds", inputs_embeds),
                       ("decoder_inputs_embeds", decoder_inputs_embeds), ("head_mask", head_mask),
                       ("attention_mask", attention_mask), ("vis_attention_mask", vis_attention_mask),
@@ -667,11 +671,15 @@ class VLT5(nn.Module):
         memory = bool(kwargs.get("memory")) and proto_update
         cb, keep, shape = self._stage_batch(input_ids, vis_inputs[0], vis_inputs[1], labels,
                                             kwargs.get("cate_labels") if proto_update else None,
-                                            kwargs.get("ques_labels") if proto_update else None)
+                                            kwargs.get("ques_labels") if proto_update else None, decoder_input_ids)
         self._forward_native(cb, shape, proto_update, kwargs.get("current_task_id", 0), kwargs.get("proto_alpha"),
                              kwargs.get("proto_beta"), self.training, memory)
         self._keep = keep
         out = self._collect_outputs(shape, keep[0])
+        if labels is None:
+            # decoder_input_ids without labels (modeling_t5_our.py:617-629, 659-671): logits of the given prefix, no loss. The
+            # decoder re-runs on the whole prefix (no past_key_values); for greedy decoding generate() is the cached native loop.
+            return out
         rows = self._engine.ws_tensor("loss_rows", torch.float32, (shape[0] * shape[3],))
         if memory:
             mem2 = self._engine.ws_tensor("loss_memory", torch.float32, (2,))
