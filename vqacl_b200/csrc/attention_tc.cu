@@ -166,12 +166,6 @@ attn_enc_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     int n = 0;
     for (int it = it0; it < nitems; it += gs, ++n) {
       if (it + 2 * gs < nitems) hdr_fetch(it + 2 * gs);      // in flight while lane 0 waits below
-      if (lane == 0 && it + 3 * gs < nitems) {                // L2 prefetch of the item after that: its TMA load then hits L2
-        const int it3 = it + 3 * gs, b3 = it3 / hp, h3 = (it3 - b3 * hp) * 2, row3 = b3 * p.S;
-        tma_prefetch_2d(&tmQ, h3 * 64, row3); tma_prefetch_2d(&tmQ, (h3 + 1) * 64, row3);
-        tma_prefetch_2d(&tmK, h3 * 64, row3); tma_prefetch_2d(&tmK, (h3 + 1) * 64, row3);
-        tma_prefetch_2d(&tmV, h3 * 64, row3); tma_prefetch_2d(&tmV, (h3 + 1) * 64, row3);
-      }
       if (lane == 0) {
         const uint32_t sq = smem_u32(smem + (n & 1) * TCF_STAGE_BYTES), sv = sq + 32768;
         if (it + gs < nitems) {

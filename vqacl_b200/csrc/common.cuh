@@ -179,13 +179,6 @@ VQ_DEVINL void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, 
       : "memory");
 }
 
-// same box, but only into L2 (no shared-memory destination, no barrier): hides DRAM latency of a load that cannot be issued
-// yet because its shared-memory stage is still in use
-VQ_DEVINL void tma_prefetch_2d(const CUtensorMap* m, int c0, int c1) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1)
-               : "memory");
-}
-
 // ---------------------------------------------------------------------------------------------
 // tcgen05 / TMEM
 // ---------------------------------------------------------------------------------------------
