@@ -312,7 +312,10 @@ attn_enc_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 constexpr int TCB_STAGE_BYTES = 4 * 16384;          // Q2 | K2 | V2 | dO2
 constexpr int TCB_HDR_FLOATS = 64 + 2 * 128 + 128;  // kmask[64] | bias[2][128] | lse[128] (stacked rows; +inf beyond S)
 constexpr int TCB_DTAB_FLOATS = 64 * 16;            // [bucket][head] accumulation table (H <= 16)
-constexpr int TCB_SMEM_BYTES = 1024 + 2 * TCB_STAGE_BYTES + 2 * TC_P_BYTES + 2 * TCB_HDR_FLOATS * 4 + TCB_DTAB_FLOATS * 4 + 256;
+constexpr int TCB_DX_FLOATS = 2 * 4 * 128;          // row-sum quarters exchanged between the 4 threads of a row, per item parity
+constexpr int TCB_ROW_WARPS = 16;                   // FOUR threads per stacked query row (16 of its 64 columns each)
+constexpr int TCB_THREADS = (TCB_ROW_WARPS + 2) * 32;   // + warp 16: header + TMA producer, warp 17: MMA issuer + TMEM owner
+constexpr int TCB_SMEM_BYTES = 1024 + 2 * TCB_STAGE_BYTES + 2 * TC_P_BYTES + (2 * TCB_HDR_FLOATS + TCB_DTAB_FLOATS + TCB_DX_FLOATS) * 4 + 256;
 
 struct AttnTcBwdArgs {
   __nv_bfloat16 *dq, *dk, *dv; int lddq, lddk, lddv;
@@ -323,19 +326,22 @@ struct AttnTcBwdArgs {
   uint32_t drop_thr; float drop_inv_keep; uint32_t seed;
 };
 
-VQ_DEVINL void store_row64(__nv_bfloat16* dst, const uint32_t (&a)[32], const uint32_t (&b)[32]) {
+VQ_DEVINL void store_row16(__nv_bfloat16* dst, const uint32_t (&a)[16]) {
   uint4* d4 = reinterpret_cast<uint4*>(dst);
 #pragma unroll
-  for (int c = 0; c < 4; ++c)
+  for (int c = 0; c < 2; ++c)
     d4[c] = make_uint4(pack_bf16(__uint_as_float(a[8 * c]), __uint_as_float(a[8 * c + 1])), pack_bf16(__uint_as_float(a[8 * c + 2]), __uint_as_float(a[8 * c + 3])),
                        pack_bf16(__uint_as_float(a[8 * c + 4]), __uint_as_float(a[8 * c + 5])), pack_bf16(__uint_as_float(a[8 * c + 6]), __uint_as_float(a[8 * c + 7])));
-#pragma unroll
-  for (int c = 0; c < 4; ++c)
-    d4[4 + c] = make_uint4(pack_bf16(__uint_as_float(b[8 * c]), __uint_as_float(b[8 * c + 1])), pack_bf16(__uint_as_float(b[8 * c + 2]), __uint_as_float(b[8 * c + 3])),
-                           pack_bf16(__uint_as_float(b[8 * c + 4]), __uint_as_float(b[8 * c + 5])), pack_bf16(__uint_as_float(b[8 * c + 6]), __uint_as_float(b[8 * c + 7])));
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// Structure (second version; the first — one thread per row, 4 row warps, epilogue in line — was correct but took 99.5 us
+// against the mma.sync kernel's 91 us): everything the forward kernel needed to reach parity, applied here. One CTA per SM
+// (two 64 KB stages + the P and dS tiles), so the warps come from FOUR threads per row: 16 row warps, each thread holds 16
+// scores and 16 dP values, the row's D = sum_j P dP is exchanged between its four threads through shared memory (128-thread
+// named barrier per TMEM lane quarter). S and dP of item n+1 are issued as soon as the rows hold item n's in registers; the
+// dQ / dK / dV rows of item n are stored while item n+1 is being computed (deferred epilogue); the per-item header (key mask,
+// bias, log-sum-exp) is prefetched into registers an item early so the TMA loads start the moment a stage frees.
+__global__ void __launch_bounds__(TCB_THREADS, 1)
 attn_enc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO, const AttnTcBwdArgs p,
                        const __grid_constant__ AttnBuckets bk) {
@@ -347,34 +353,36 @@ attn_enc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   uint8_t* sdS = sP + TC_P_BYTES;
   float* hdr = reinterpret_cast<float*>(sdS + TC_P_BYTES);
   float* dtab = hdr + 2 * TCB_HDR_FLOATS;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(dtab + TCB_DTAB_FLOATS);
-  uint64_t* full_bar = bars;            // [2]
-  uint64_t* empty_bar = bars + 2;       // [2]
+  float* dx = dtab + TCB_DTAB_FLOATS;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(dx + TCB_DX_FLOATS);
+  uint64_t* full_bar = bars;            // [2] TMA bytes landed (+ header written)
+  uint64_t* empty_bar = bars + 2;       // [2] the item's last MMAs are complete: its stage is free
   uint64_t* sfull_bar = bars + 4;       // S and dP accumulators complete
-  uint64_t* sempty_bar = bars + 5;      // ... read by the 4 row warps
-  uint64_t* pfull_bar = bars + 6;       // P and dS tiles written
+  uint64_t* sread_bar = bars + 5;       // ... held in registers by the 16 row warps
+  uint64_t* pfull_bar = bars + 6;       // P and dS tiles written (and the previous item's outputs read)
   uint64_t* ofull_bar = bars + 7;       // dQ, dK, dV accumulators complete
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int hp = p.H >> 1;
   const int nitems = p.B * hp;
+  const int it0 = blockIdx.x, gs = gridDim.x;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == TCB_ROW_WARPS && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
     mbar_init(sfull_bar, 1);
-    mbar_init(sempty_bar, 4);
-    mbar_init(pfull_bar, 4);
+    mbar_init(sread_bar, TCB_ROW_WARPS);
+    mbar_init(pfull_bar, TCB_ROW_WARPS);
     mbar_init(ofull_bar, 1);
     mbar_fence_init();
   }
-  if (warp == 5) tmem_alloc(tmem_holder, TC_TMEM_COLS);
-  for (int i = threadIdx.x; i < 2 * TC_P_BYTES / 16; i += TC_THREADS) reinterpret_cast<uint4*>(sP)[i] = make_uint4(0, 0, 0, 0);   // P and dS tiles
-  for (int i = threadIdx.x; i < TCB_DTAB_FLOATS; i += TC_THREADS) dtab[i] = 0.f;
+  if (warp == TCB_ROW_WARPS + 1) tmem_alloc(tmem_holder, TC_TMEM_COLS);
+  for (int i = threadIdx.x; i < 2 * TC_P_BYTES / 16; i += TCB_THREADS) reinterpret_cast<uint4*>(sP)[i] = make_uint4(0, 0, 0, 0);   // P and dS tiles
+  for (int i = threadIdx.x; i < TCB_DTAB_FLOATS; i += TCB_THREADS) dtab[i] = 0.f;
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -383,23 +391,41 @@ attn_enc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   // TMEM columns: S [0,128) | dP [128,256) | dQ [256,320) | dK [320,384) | dV [384,448)
   vq_pdl_wait();
 
-  if (warp == 4) {
-    int n = 0;
-    for (int it = blockIdx.x; it < nitems; it += gridDim.x, ++n) {
-      const int stage = n & 1;
-      const uint32_t ph = (n >> 1) & 1;
+  if (warp == TCB_ROW_WARPS) {
+    // ------------------------------------------------ header + TMA producer ------------------------------------------------
+    float hk[2], hb[8], hl[4];
+    auto hdr_fetch = [&](int it) {
       const int b = it / hp, h = (it - b * hp) * 2;
-      mbar_wait(&empty_bar[stage], ph ^ 1);
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int j = lane + 32 * u;
+        hk[u] = j < p.S ? (p.keymask ? p.keymask[(size_t)b * p.S + j] : 0.f) : -INFINITY;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int r = lane + 32 * u, hd = r >> 7, rel = r & 127;
+        hb[u] = rel < 127 ? p.rel_table[(int)bk.b[rel] * p.H + h + hd] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = lane + 32 * u, hd = r >> 6, q = r & 63;
+        hl[u] = q < p.S ? p.lse[((size_t)b * p.H + h + hd) * p.S + q] : INFINITY;     // rows >= S: P = dS = 0
+      }
+    };
+    int n = 0;
+    if (it0 < nitems) hdr_fetch(it0);
+    for (int it = it0; it < nitems; it += gs, ++n) {
+      const int stage = n & 1;
+      const int b = it / hp, h = (it - b * hp) * 2;
+      if (lane == 0) mbar_wait(&empty_bar[stage], ((n >> 1) & 1) ^ 1);
+      __syncwarp();
       float* hs = hdr + stage * TCB_HDR_FLOATS;
-      for (int j = lane; j < 64; j += 32) hs[j] = j < p.S ? (p.keymask ? p.keymask[(size_t)b * p.S + j] : 0.f) : -INFINITY;
-      for (int r = lane; r < 2 * 128; r += 32) {
-        const int hd = r >> 7, rel = r & 127;
-        hs[64 + r] = rel < 127 ? p.rel_table[(int)bk.b[rel] * p.H + h + hd] : 0.f;
-      }
-      for (int r = lane; r < 128; r += 32) {
-        const int hd = r >> 6, q = r & 63;
-        hs[64 + 256 + r] = q < p.S ? p.lse[((size_t)b * p.H + h + hd) * p.S + q] : INFINITY;     // rows >= S: P = dS = 0
-      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) hs[lane + 32 * u] = hk[u];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) hs[64 + lane + 32 * u] = hb[u];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) hs[64 + 256 + lane + 32 * u] = hl[u];
       __syncwarp();
       if (lane == 0) {
         uint8_t* st = smem + stage * TCB_STAGE_BYTES;
@@ -414,17 +440,18 @@ attn_enc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         tma_load_2d(st + 49152, &tmdO, &full_bar[stage], h * 64, row);
         tma_load_2d(st + 49152 + 8192, &tmdO, &full_bar[stage], (h + 1) * 64, row);
       }
+      if (it + gs < nitems) hdr_fetch(it + gs);       // in flight while this warp waits for the next stage to free
     }
-  } else if (warp == 5) {
+  } else if (warp == TCB_ROW_WARPS + 1) {
+    // ------------------------------------------------ MMA issuer ------------------------------------------------
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);     // S, dP: both operands K-major
       constexpr uint32_t idesc_t = umma_idesc_bf16(128, 64, true, true);        // dV, dK: A = tile^T (MN-major), B MN-major
       constexpr uint32_t idesc_q = umma_idesc_bf16(128, 64, false, true);       // dQ: A = dS tile K-major, B MN-major
       const uint32_t sP_u32 = smem_u32(sP), sdS_u32 = smem_u32(sdS);
-      auto issue_sdp = [&](int n) {
-        const int stage = n & 1;
-        mbar_wait(&full_bar[stage], (n >> 1) & 1);
-        mbar_wait(sempty_bar, (n & 1) ^ 1);
+      auto issue_sdp = [&](int m) {
+        const int stage = m & 1;
+        mbar_wait(&full_bar[stage], (m >> 1) & 1);
         tc_fence_after();
         const uint32_t sq = smem_u32(smem + stage * TCB_STAGE_BYTES), sk = sq + 16384, sv = sq + 32768, sdo = sq + 49152;
 #pragma unroll
@@ -436,10 +463,14 @@ attn_enc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         umma_commit(sfull_bar);
       };
       int n = 0;
-      if ((int)blockIdx.x < nitems) issue_sdp(0);
-      for (int it = blockIdx.x; it < nitems; it += gridDim.x, ++n) {
+      if (it0 < nitems) issue_sdp(0);
+      for (int it = it0; it < nitems; it += gs, ++n) {
         const int stage = n & 1;
-        mbar_wait(pfull_bar, n & 1);
+        if (it + gs < nitems) {
+          mbar_wait(sread_bar, n & 1);          // the rows hold S / dP of item n in registers
+          issue_sdp(n + 1);
+        }
+        mbar_wait(pfull_bar, n & 1);            // P / dS tiles of item n written; outputs of item n-1 read
         tc_fence_after();
         const uint32_t sq = smem_u32(smem + stage * TCB_STAGE_BYTES), sk = sq + 16384, sdo = sq + 49152;
 #pragma unroll
@@ -455,97 +486,118 @@ attn_enc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                    umma_smem_desc_sw128(sk + kk * 2048, 8192, 1024), idesc_q, kk > 0 ? 1u : 0u);                          // dQ = dS K
         umma_commit(ofull_bar);
         umma_commit(&empty_bar[stage]);
-        // the next item's S / dP: its stage is loaded and the row threads have long read this item's S / dP
-        if (it + (int)gridDim.x < nitems) issue_sdp(n + 1);
       }
     }
   } else {
-    const int r = threadIdx.x;
+    // ------------------------------------------------ row threads: 4 per stacked row ------------------------------------------------
+    const int rw = warp & 3, cq = warp >> 2;    // TMEM lane quarter | column quarter
+    const int r = rw * 32 + lane;
     const int hsel = r >> 6, q = r & 63;
-    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
-    const uint32_t row_off = hsel * 16384 + r * 128;
-    const uint32_t sP_row = smem_u32(sP) + row_off, sdS_row = smem_u32(sdS) + row_off;
+    const uint32_t lane_addr = (uint32_t)(rw * 32) << 16;
+    const uint32_t row_off = hsel * 16384 + r * 128, zero_off = (hsel ^ 1) * 16384 + r * 128;
+    const uint32_t sP_u = smem_u32(sP), sdS_u = smem_u32(sdS);
     const int sw = r & 7;
+    const int bar_id = 1 + rw;                   // the four warps that share TMEM lane quarter rw
+    float* dxr = dx + r;                         // [parity][column quarter][row]
+    int b_prev = 0, h_prev = 0;
+    auto epilogue = [&](int m) {                 // dQ / dK / dV columns [16 cq, 16 cq + 16) of this row for item m
+      mbar_wait(ofull_bar, m & 1);
+      tc_fence_after();
+      const bool ok = q < p.S;
+      const size_t grow = (size_t)b_prev * p.S + q;
+      const int col = (h_prev + hsel) * 64 + cq * 16;
+      uint32_t o[16];
+      tmem_ld_32x16(tmem_base + 256 + cq * 16 + lane_addr, o);
+      tmem_ld_wait();
+      if (ok) store_row16(p.dq + grow * p.lddq + col, o);
+      tmem_ld_32x16(tmem_base + 320 + cq * 16 + lane_addr, o);
+      tmem_ld_wait();
+      if (ok) store_row16(p.dk + grow * p.lddk + col, o);
+      tmem_ld_32x16(tmem_base + 384 + cq * 16 + lane_addr, o);
+      tmem_ld_wait();
+      if (ok) store_row16(p.dv + grow * p.lddv + col, o);
+      tc_fence_before();
+    };
     int n = 0;
-    for (int it = blockIdx.x; it < nitems; it += gridDim.x, ++n) {
+    for (int it = it0; it < nitems; it += gs, ++n) {
       const int stage = n & 1;
       const int b = it / hp, h = (it - b * hp) * 2;
-      mbar_wait(&full_bar[stage], (n >> 1) & 1);
+      mbar_wait(&full_bar[stage], (n >> 1) & 1);     // header visible
       mbar_wait(sfull_bar, n & 1);
       tc_fence_after();
-      float s[64], dp[64];
+      float s[16], dp[16];
       {
-        uint32_t t0[32], t1[32];
-        const uint32_t ta = tmem_base + hsel * 64 + lane_addr;
-        tmem_ld_32x32(ta, t0);
-        tmem_ld_32x32(ta + 32, t1);
+        uint32_t t0[16], t1[16];
+        const uint32_t ta = tmem_base + hsel * 64 + cq * 16 + lane_addr;
+        tmem_ld_32x16(ta, t0);
+        tmem_ld_32x16(ta + 128, t1);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) { s[j] = __uint_as_float(t0[j]); s[32 + j] = __uint_as_float(t1[j]); }
-        tmem_ld_32x32(ta + 128, t0);
-        tmem_ld_32x32(ta + 128 + 32, t1);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) { dp[j] = __uint_as_float(t0[j]); dp[32 + j] = __uint_as_float(t1[j]); }
+        for (int j = 0; j < 16; ++j) { s[j] = __uint_as_float(t0[j]); dp[j] = __uint_as_float(t1[j]); }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(sempty_bar);
+      if (lane == 0) mbar_arrive(sread_bar);
       const float* hs = hdr + stage * TCB_HDR_FLOATS;
       const float lse = hs[64 + 256 + r];
 #pragma unroll
-      for (int j4 = 0; j4 < 16; ++j4) {
-        const float4 km = *reinterpret_cast<const float4*>(hs + 4 * j4);
+      for (int j4 = 0; j4 < 4; ++j4) {
+        const float4 km = *reinterpret_cast<const float4*>(hs + cq * 16 + 4 * j4);
         s[4 * j4] += km.x; s[4 * j4 + 1] += km.y; s[4 * j4 + 2] += km.z; s[4 * j4 + 3] += km.w;
       }
-      if (q < p.Lt) {
-        const float* bp = hs + 64 + hsel * 128 + (AT_S_TC - 1) - q;
+      if (q < p.Lt && cq * 16 < p.Lt) {
+        const float* bp = hs + 64 + hsel * 128 + (AT_S_TC - 1) - q + cq * 16;
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j < p.Lt) s[j] += bp[j];
+        for (int j = 0; j < 16; ++j)
+          if (cq * 16 + j < p.Lt) s[j] += bp[j];
       }
-      uint32_t keep_lo = 0xFFFFFFFFu, keep_hi = 0xFFFFFFFFu;     // bit j: probability j survived dropout
+      uint32_t keep = 0xFFFFu;                     // bit j: probability (q, 16 cq + j) survived dropout
       if (p.drop_thr) {
-        keep_lo = keep_hi = 0u;
-        const uint32_t pi0 = attn_pair_idx((uint32_t)(b * p.H + h + hsel), q, 0);
+        keep = 0u;
+        const uint32_t pi0 = attn_pair_idx((uint32_t)(b * p.H + h + hsel), q, cq * 16);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
+        for (int j = 0; j < 8; ++j) {
           const uint32_t hsh = vq_hash_pair(p.seed, pi0 + j);
-          const uint32_t k0 = (hsh & 0xFFFFu) >= p.drop_thr ? 1u : 0u, k1 = (hsh >> 16) >= p.drop_thr ? 1u : 0u;
-          if (j < 16) keep_lo |= (k0 << (2 * j)) | (k1 << (2 * j + 1));
-          else keep_hi |= (k0 << (2 * j - 32)) | (k1 << (2 * j - 31));
+          keep |= ((hsh & 0xFFFFu) >= p.drop_thr ? 1u : 0u) << (2 * j);
+          keep |= ((hsh >> 16) >= p.drop_thr ? 1u : 0u) << (2 * j + 1);
         }
       }
       const float ik = p.drop_thr ? p.drop_inv_keep : 1.f;
-      float dsum = 0.f;
+      float dpart = 0.f;
 #pragma unroll
-      for (int j = 0; j < 64; ++j) {
-        const bool kept = ((j < 32 ? keep_lo >> j : keep_hi >> (j - 32)) & 1u) != 0u;
+      for (int j = 0; j < 16; ++j) {
         s[j] = __expf(s[j] - lse);                 // exp(-inf) = 0: masked keys, rows beyond S (lse = +inf)
-        dp[j] = kept ? dp[j] * ik : 0.f;           // dP through the dropout
-        dsum += s[j] * dp[j];
+        dp[j] = ((keep >> j) & 1u) ? dp[j] * ik : 0.f;
+        dpart += s[j] * dp[j];
       }
+      dxr[(n & 1) * 512 + cq * 128] = dpart;
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+      const float* dxp = dxr + (n & 1) * 512;
+      const float dsum = (dxp[0] + dxp[128]) + (dxp[256] + dxp[384]);
+      uint32_t pw[8], dw[8];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        uint32_t pw[4], dw[4];
-#pragma unroll
-        for (int x = 0; x < 4; ++x) {
-          const int j = 8 * c + 2 * x;
-          const bool k0 = ((j < 32 ? keep_lo >> j : keep_hi >> (j - 32)) & 1u) != 0u;
-          const bool k1 = ((j + 1 < 32 ? keep_lo >> (j + 1) : keep_hi >> (j + 1 - 32)) & 1u) != 0u;
-          pw[x] = pack_bf16(k0 ? s[j] * ik : 0.f, k1 ? s[j + 1] * ik : 0.f);
-          dw[x] = pack_bf16(s[j] * (dp[j] - dsum), s[j + 1] * (dp[j + 1] - dsum));
-        }
-        const uint32_t off = (uint32_t)(c ^ sw) << 4;
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sP_row + off), "r"(pw[0]), "r"(pw[1]), "r"(pw[2]), "r"(pw[3]) : "memory");
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sdS_row + off), "r"(dw[0]), "r"(dw[1]), "r"(dw[2]), "r"(dw[3]) : "memory");
+      for (int x = 0; x < 8; ++x) {
+        const int j = 2 * x;
+        pw[x] = pack_bf16(((keep >> j) & 1u) ? s[j] * ik : 0.f, ((keep >> (j + 1)) & 1u) ? s[j + 1] * ik : 0.f);
+        dw[x] = pack_bf16(s[j] * (dp[j] - dsum), s[j + 1] * (dp[j + 1] - dsum));
       }
+      // the previous item's output rows: its MMAs finished long ago; reading them here frees the dQ / dK / dV accumulators and
+      // guarantees the P / dS tiles have been consumed before they are overwritten below
+      if (n > 0) epilogue(n - 1);
+      b_prev = b; h_prev = h;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const uint32_t off = (uint32_t)((cq * 2 + c) ^ sw) << 4;
+        sts128_u(sP_u + row_off + off, pw[4 * c], pw[4 * c + 1], pw[4 * c + 2], pw[4 * c + 3]);
+        sts128_u(sdS_u + row_off + off, dw[4 * c], dw[4 * c + 1], dw[4 * c + 2], dw[4 * c + 3]);
+      }
+      (void)zero_off;                              // the off-diagonal halves were zeroed once and are never written
       fence_proxy_async();
       if (p.d_rel_table) {
-        // bias-table gradient: thread (head hsel, diagonal q) sums dS along its diagonal of the text x text corner
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        // bias-table gradient: sums of dS along the diagonals of the text x text corner, one thread per (head, diagonal)
+        asm volatile("bar.sync 5, %0;" ::"n"(TCB_ROW_WARPS * 32) : "memory");
         const int ndiag = 2 * p.Lt - 1;
-        if (q < ndiag) {
+        if (cq == 0 && q < ndiag) {
           const int rel = q - (p.Lt - 1);             // key - query
           const int q_lo = max(0, -rel), q_hi = min(p.Lt, p.Lt - rel);
           float acc = 0.f;
@@ -559,32 +611,11 @@ attn_enc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(pfull_bar);
-      // ---- outputs of this item
-      mbar_wait(ofull_bar, n & 1);
-      tc_fence_after();
-      {
-        uint32_t o0[32], o1[32];
-        const bool ok = q < p.S;
-        const size_t grow = (size_t)b * p.S + q;
-        const int col = (h + hsel) * 64;
-        tmem_ld_32x32(tmem_base + 256 + lane_addr, o0);
-        tmem_ld_32x32(tmem_base + 256 + 32 + lane_addr, o1);
-        tmem_ld_wait();
-        if (ok) store_row64(p.dq + grow * p.lddq + col, o0, o1);
-        tmem_ld_32x32(tmem_base + 320 + lane_addr, o0);
-        tmem_ld_32x32(tmem_base + 320 + 32 + lane_addr, o1);
-        tmem_ld_wait();
-        if (ok) store_row64(p.dk + grow * p.lddk + col, o0, o1);
-        tmem_ld_32x32(tmem_base + 384 + lane_addr, o0);
-        tmem_ld_32x32(tmem_base + 384 + 32 + lane_addr, o1);
-        tmem_ld_wait();
-        if (ok) store_row64(p.dv + grow * p.lddv + col, o0, o1);
-      }
-      tc_fence_before();
     }
+    if (n > 0) epilogue(n - 1);
     if (p.d_rel_table) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int i = r; i < 64 * 16; i += 128) {
+      asm volatile("bar.sync 5, %0;" ::"n"(TCB_ROW_WARPS * 32) : "memory");
+      for (int i = threadIdx.x; i < 64 * 16; i += TCB_ROW_WARPS * 32) {
         const float v = dtab[i];
         const int bucket = i >> 4, head = i & 15;
         if (v != 0.f && head < p.H) atomicAdd(&p.d_rel_table[bucket * p.H + head], v);
@@ -594,7 +625,7 @@ attn_enc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == TCB_ROW_WARPS + 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TC_TMEM_COLS);
   }
@@ -660,7 +691,7 @@ int attn_enc_bwd_tc(const AttnArgs& a, const AttnBuckets& bk, cudaStream_t strea
   p.drop_thr = a.drop_thr; p.drop_inv_keep = a.drop_inv_keep; p.seed = a.seed;
   const int items = a.B * (a.H / 2);
   const int grid = items < num_sms() ? items : num_sms();
-  (void)vq_launch(attn_enc_bwd_tc_kernel, dim3(grid), dim3(TC_THREADS), (size_t)TCB_SMEM_BYTES, stream, tq, tk, tv, tdo, p, bk);
+  (void)vq_launch(attn_enc_bwd_tc_kernel, dim3(grid), dim3(TCB_THREADS), (size_t)TCB_SMEM_BYTES, stream, tq, tk, tv, tdo, p, bk);
   VQ_LAUNCH_CHECK();
   return 0;
 }
