@@ -46,7 +46,7 @@ def build(verbose=False, force=False):
         o = os.path.join(BUILD, src[:-3] + ".o")
         objs.append(o)
         if force or not os.path.exists(o) or os.path.getmtime(o) < max(os.path.getmtime(s), hm):
-            jobs.append([nvcc, *NVCC_FLAGS, "-c", s, "-o", o])
+            jobs.append([nvcc, *NVCC_FLAGS, *os.environ.get("VQACL_NVCC_EXTRA", "").split(), "-c", s, "-o", o])   # e.g. -DVQ_ATTN_TRACE
 
     def run(cmd):
         if verbose:

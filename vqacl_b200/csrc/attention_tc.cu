@@ -61,6 +61,11 @@ struct AttnTcArgs {
 };
 
 VQ_DEVINL void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+VQ_DEVINL uint4 lds128_u(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
 VQ_DEVINL void sts128_u(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -309,13 +314,31 @@ attn_enc_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 // The bias-table gradient (sums of dS along the diagonals of the text x text corner) is accumulated in a per-CTA shared
 // table across all items and flushed with one global atomic per (bucket, head) at the end of the kernel.
 // =====================================================================================================================
+// -DVQ_ATTN_TRACE (VQACL_NVCC_EXTRA of build.py): CTA 0 stamps clock64() at every hand-off of its first 16 items into a
+// buffer installed with vqacl_debug_attn_trace — tools/attn_trace.py turns the stamps into a per-item timeline.
+#ifdef VQ_ATTN_TRACE
+__device__ long long* g_attn_trace = nullptr;     // [role 0..3][item 0..15][slot 0..7]
+#define VQ_TR(role, n, slot)                                                                                  \
+  do {                                                                                                        \
+    if (blockIdx.x == 0 && (n) < 16 && g_attn_trace) g_attn_trace[((role) * 16 + (n)) * 8 + (slot)] = clock64(); \
+  } while (0)
+#else
+#define VQ_TR(role, n, slot) do { } while (0)
+#endif
+
 constexpr int TCB_STAGE_BYTES = 4 * 16384;          // Q2 | K2 | V2 | dO2
 constexpr int TCB_HDR_FLOATS = 64 + 2 * 128 + 128;  // kmask[64] | bias[2][128] | lse[128] (stacked rows; +inf beyond S)
-constexpr int TCB_DTAB_FLOATS = 64 * 16;            // [bucket][head] accumulation table (H <= 16)
+constexpr int TCB_DTAB_FLOATS = 32 * 16;            // [bucket][head] accumulation table (32 buckets, H <= 16)
 constexpr int TCB_DX_FLOATS = 2 * 4 * 128;          // row-sum quarters exchanged between the 4 threads of a row, per item parity
 constexpr int TCB_ROW_WARPS = 16;                   // FOUR threads per stacked query row (16 of its 64 columns each)
-constexpr int TCB_THREADS = (TCB_ROW_WARPS + 2) * 32;   // + warp 16: header + TMA producer, warp 17: MMA issuer + TMEM owner
-constexpr int TCB_SMEM_BYTES = 1024 + 2 * TCB_STAGE_BYTES + 2 * TC_P_BYTES + (2 * TCB_HDR_FLOATS + TCB_DTAB_FLOATS + TCB_DX_FLOATS) * 4 + 256;
+constexpr int TCB_THREADS = (TCB_ROW_WARPS + 2) * 32;   // warp 0: header + TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-17: rows.
+                                                        // The two single-thread warps come FIRST: as the youngest warps of their
+                                                        // schedulers (warps 16 / 17) they were starved by the row warps' spin loops —
+                                                        // 2 us from "stage free" to "TMA issued", 50 ns per tcgen05.mma issued.
+constexpr int TCB_PRODUCER_WARP = 0, TCB_ISSUER_WARP = 1, TCB_FIRST_ROW_WARP = 2;
+constexpr int TCB_OUT_TILE = 2048;                  // output staging: 32 rows x 64 bytes per epilogue warp (12 of the 16 row warps)
+constexpr int TCB_SMEM_BYTES = 1024 + 2 * TCB_STAGE_BYTES + 2 * TC_P_BYTES + (2 * TCB_HDR_FLOATS + TCB_DTAB_FLOATS + TCB_DX_FLOATS) * 4 + 12 * TCB_OUT_TILE + 256;
+static_assert(TCB_SMEM_BYTES <= 232448, "attention backward: shared memory");
 
 struct AttnTcBwdArgs {
   __nv_bfloat16 *dq, *dk, *dv; int lddq, lddk, lddv;
@@ -354,21 +377,23 @@ attn_enc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   float* hdr = reinterpret_cast<float*>(sdS + TC_P_BYTES);
   float* dtab = hdr + 2 * TCB_HDR_FLOATS;
   float* dx = dtab + TCB_DTAB_FLOATS;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(dx + TCB_DX_FLOATS);
+  uint8_t* ostage = reinterpret_cast<uint8_t*>(dx + TCB_DX_FLOATS);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ostage + 12 * TCB_OUT_TILE);
   uint64_t* full_bar = bars;            // [2] TMA bytes landed (+ header written)
   uint64_t* empty_bar = bars + 2;       // [2] the item's last MMAs are complete: its stage is free
   uint64_t* sfull_bar = bars + 4;       // S and dP accumulators complete
   uint64_t* sread_bar = bars + 5;       // ... held in registers by the 16 row warps
-  uint64_t* pfull_bar = bars + 6;       // P and dS tiles written (and the previous item's outputs read)
-  uint64_t* ofull_bar = bars + 7;       // dQ, dK, dV accumulators complete
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* pfull_bar = bars + 6;       // [2, by stage] P and dS tiles written (and the previous item's outputs read): also "the rows are
+                                        // done with this stage's header", which is what the producer waits for before rewriting it
+  uint64_t* ofull_bar = bars + 8;       // dQ, dK, dV accumulators complete
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 9);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int hp = p.H >> 1;
   const int nitems = p.B * hp;
   const int it0 = blockIdx.x, gs = gridDim.x;
 
-  if (warp == TCB_ROW_WARPS && lane == 0) {
+  if (warp == TCB_PRODUCER_WARP && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&full_bar[i], 1);
@@ -376,11 +401,12 @@ attn_enc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     }
     mbar_init(sfull_bar, 1);
     mbar_init(sread_bar, TCB_ROW_WARPS);
-    mbar_init(pfull_bar, TCB_ROW_WARPS);
+    mbar_init(&pfull_bar[0], TCB_ROW_WARPS);
+    mbar_init(&pfull_bar[1], TCB_ROW_WARPS);
     mbar_init(ofull_bar, 1);
     mbar_fence_init();
   }
-  if (warp == TCB_ROW_WARPS + 1) tmem_alloc(tmem_holder, TC_TMEM_COLS);
+  if (warp == TCB_ISSUER_WARP) tmem_alloc(tmem_holder, TC_TMEM_COLS);
   for (int i = threadIdx.x; i < 2 * TC_P_BYTES / 16; i += TCB_THREADS) reinterpret_cast<uint4*>(sP)[i] = make_uint4(0, 0, 0, 0);   // P and dS tiles
   for (int i = threadIdx.x; i < TCB_DTAB_FLOATS; i += TCB_THREADS) dtab[i] = 0.f;
   fence_proxy_async();
@@ -391,7 +417,7 @@ attn_enc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   // TMEM columns: S [0,128) | dP [128,256) | dQ [256,320) | dK [320,384) | dV [384,448)
   vq_pdl_wait();
 
-  if (warp == TCB_ROW_WARPS) {
+  if (warp == TCB_PRODUCER_WARP) {
     // ------------------------------------------------ header + TMA producer ------------------------------------------------
     float hk[2], hb[8], hl[4];
     auto hdr_fetch = [&](int it) {
@@ -417,7 +443,11 @@ attn_enc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     for (int it = it0; it < nitems; it += gs, ++n) {
       const int stage = n & 1;
       const int b = it / hp, h = (it - b * hp) * 2;
-      if (lane == 0) mbar_wait(&empty_bar[stage], ((n >> 1) & 1) ^ 1);
+      // Header first, as soon as the ROWS are done with this stage's previous header (their pfull arrival — the gradient MMAs of
+      // that item, whose completion frees the operand half of the stage, are only being issued now): measured, the 14 STS of this
+      // warp take 1.6-2.4 us under MIO throttle while the tensor pipe and 16 row warps are busy, and they used to sit between
+      // "stage free" and "TMA issued", i.e. on the loop that sets the period of the whole pipeline.
+      if (lane == 0) { VQ_TR(0, n, 0); if (n >= 2) mbar_wait(&pfull_bar[stage], ((n >> 1) & 1) ^ 1); }
       __syncwarp();
       float* hs = hdr + stage * TCB_HDR_FLOATS;
 #pragma unroll
@@ -427,22 +457,30 @@ attn_enc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 #pragma unroll
       for (int u = 0; u < 4; ++u) hs[64 + 256 + lane + 32 * u] = hl[u];
       __syncwarp();
+      if (lane == 0) VQ_TR(0, n, 3);
+      if (it + gs < nitems) hdr_fetch(it + gs);      // the next item's header: in flight across the wait below and the whole next item
+      if (lane == 0) { mbar_wait(&empty_bar[stage], ((n >> 1) & 1) ^ 1); VQ_TR(0, n, 1); }
+      __syncwarp();
       if (lane == 0) {
         uint8_t* st = smem + stage * TCB_STAGE_BYTES;
+        VQ_TR(0, n, 4);
         mbar_expect_tx(&full_bar[stage], TCB_STAGE_BYTES);
         const int row = b * p.S;
         tma_load_2d(st, &tmQ, &full_bar[stage], h * 64, row);
         tma_load_2d(st + 8192, &tmQ, &full_bar[stage], (h + 1) * 64, row);
+        VQ_TR(0, n, 5);
         tma_load_2d(st + 16384, &tmK, &full_bar[stage], h * 64, row);
         tma_load_2d(st + 16384 + 8192, &tmK, &full_bar[stage], (h + 1) * 64, row);
+        VQ_TR(0, n, 6);
         tma_load_2d(st + 32768, &tmV, &full_bar[stage], h * 64, row);
         tma_load_2d(st + 32768 + 8192, &tmV, &full_bar[stage], (h + 1) * 64, row);
+        VQ_TR(0, n, 7);
         tma_load_2d(st + 49152, &tmdO, &full_bar[stage], h * 64, row);
         tma_load_2d(st + 49152 + 8192, &tmdO, &full_bar[stage], (h + 1) * 64, row);
+        VQ_TR(0, n, 2);
       }
-      if (it + gs < nitems) hdr_fetch(it + gs);       // in flight while this warp waits for the next stage to free
     }
-  } else if (warp == TCB_ROW_WARPS + 1) {
+  } else if (warp == TCB_ISSUER_WARP) {
     // ------------------------------------------------ MMA issuer ------------------------------------------------
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);     // S, dP: both operands K-major
@@ -451,7 +489,7 @@ attn_enc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       const uint32_t sP_u32 = smem_u32(sP), sdS_u32 = smem_u32(sdS);
       auto issue_sdp = [&](int m) {
         const int stage = m & 1;
-        mbar_wait(&full_bar[stage], (m >> 1) & 1);
+        VQ_TR(1, m, 1);
         tc_fence_after();
         const uint32_t sq = smem_u32(smem + stage * TCB_STAGE_BYTES), sk = sq + 16384, sv = sq + 32768, sdo = sq + 49152;
 #pragma unroll
@@ -461,16 +499,10 @@ attn_enc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         for (int k = 0; k < 4; ++k)
           umma_f16(tmem_base + 128, umma_smem_desc_sw128(sdo + k * 32, 16, 1024), umma_smem_desc_sw128(sv + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
         umma_commit(sfull_bar);
+        VQ_TR(1, m, 2);
       };
-      int n = 0;
-      if (it0 < nitems) issue_sdp(0);
-      for (int it = it0; it < nitems; it += gs, ++n) {
+      auto issue_grads = [&](int n) {
         const int stage = n & 1;
-        if (it + gs < nitems) {
-          mbar_wait(sread_bar, n & 1);          // the rows hold S / dP of item n in registers
-          issue_sdp(n + 1);
-        }
-        mbar_wait(pfull_bar, n & 1);            // P / dS tiles of item n written; outputs of item n-1 read
         tc_fence_after();
         const uint32_t sq = smem_u32(smem + stage * TCB_STAGE_BYTES), sk = sq + 16384, sdo = sq + 49152;
 #pragma unroll
@@ -486,11 +518,38 @@ attn_enc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                    umma_smem_desc_sw128(sk + kk * 2048, 8192, 1024), idesc_q, kk > 0 ? 1u : 0u);                          // dQ = dS K
         umma_commit(ofull_bar);
         umma_commit(&empty_bar[stage]);
+        VQ_TR(1, n, 5);
+      };
+      // Two independent event streams share this thread: "S / dP of item m may be issued" (the rows hold item m-1 in registers
+      // AND item m's operands have landed) and "dV / dK / dQ of item n may be issued" (its P / dS tiles are written). Issuing in
+      // program order made the gradient MMAs of item n — whose completion frees the stage the item after next is loaded into —
+      // wait for the TMA of item n+1 (measured: the period of the whole pipeline); poll both and issue whichever is ready.
+      const int my_items = it0 < nitems ? (nitems - it0 + gs - 1) / gs : 0;
+      int m = 0, n = 0;                                  // next S/dP item, next gradient item
+      uint32_t spins = 0;
+      while (n < my_items) {
+        bool progressed = false;
+        if (m < my_items && (m == 0 || mbar_try_wait(sread_bar, (m - 1) & 1)) && mbar_try_wait(&full_bar[m & 1], (m >> 1) & 1)) {
+          issue_sdp(m);
+          ++m;
+          progressed = true;
+        }
+        if (n < m && mbar_try_wait(&pfull_bar[n & 1], (n >> 1) & 1)) {
+          VQ_TR(1, n, 4);
+          issue_grads(n);
+          ++n;
+          progressed = true;
+        }
+        if (progressed) spins = 0;
+        else if (++spins > VQ_MBAR_SPIN_LIMIT) {
+          printf("vqacl_b200: attention backward issuer timed out (block %d)\n", blockIdx.x);
+          __trap();
+        }
       }
     }
   } else {
     // ------------------------------------------------ row threads: 4 per stacked row ------------------------------------------------
-    const int rw = warp & 3, cq = warp >> 2;    // TMEM lane quarter | column quarter
+    const int rw = warp & 3, cq = (warp - TCB_FIRST_ROW_WARP) >> 2;    // TMEM lane quarter (fixed by the warp id) | column quarter
     const int r = rw * 32 + lane;
     const int hsel = r >> 6, q = r & 63;
     const uint32_t lane_addr = (uint32_t)(rw * 32) << 16;
@@ -500,30 +559,80 @@ attn_enc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const int bar_id = 1 + rw;                   // the four warps that share TMEM lane quarter rw
     float* dxr = dx + r;                         // [parity][column quarter][row]
     int b_prev = 0, h_prev = 0;
-    auto epilogue = [&](int m) {                 // dQ / dK / dV columns [16 cq, 16 cq + 16) of this row for item m
+    const int trole = warp == TCB_FIRST_ROW_WARP ? 2 : 3;         // trace: first and last row warp
+    const bool tron = (warp == TCB_FIRST_ROW_WARP || warp == TCB_FIRST_ROW_WARP + TCB_ROW_WARPS - 1) && lane == 0;
+    (void)trole; (void)tron;
+#define VQ_TRR(n, slot) do { if (tron) VQ_TR(trole, n, slot); } while (0)
+    // Epilogue roles: the warps of column quarter 0 / 1 / 2 store dQ / dK / dV (thread = row, all 64 columns of the head, in two
+    // halves of 32); column quarter 3 sums the bias-gradient diagonals instead. A thread-per-row store is 32 row-strided 16-byte
+    // requests per instruction (3 072 per item: measured 2.5 us of the item's 6.7), so each half is transposed through a private
+    // XOR-swizzled 32 x 64 B tile and leaves as 8 rows x 64 contiguous bytes per instruction.
+    const int rr0 = lane >> 2, piece = lane & 3;                       // readback role: row inside an 8-row group, 16-byte piece
+    const uint32_t stg = smem_u32(ostage) + (uint32_t)((cq < 3 ? cq * 4 + rw : 0) * TCB_OUT_TILE);
+    const uint32_t sts_base = stg + lane * 64 + (((lane >> 1) & 3) << 4);
+    const uint32_t lds_base = stg + rr0 * 64 + ((piece ^ ((rr0 >> 1) & 3)) << 4);
+    const int qb = (rw & 1) * 32;                                       // first row (inside its head) of this warp's 32-row slab
+    __nv_bfloat16* const outp = cq == 0 ? p.dq : (cq == 1 ? p.dk : p.dv);
+    const int outld = cq == 0 ? p.lddq : (cq == 1 ? p.lddk : p.lddv);
+    // Bias-table gradient of the item whose dS tile is in shared memory: sums along the diagonals of the text x text corner, one
+    // thread per (head, diagonal), by the four warps (column quarter 3) that have no output rows to store — they do it while the
+    // other twelve run the epilogue of the same item, so it is off the rows -> MMA critical path. Named barrier 5 = "every warp
+    // has written its part of the dS tile" (arrive: quarters 0-2, sync: quarter 3), barrier 6 = "the diagonals are summed" (the
+    // other way round; waited for before the tile is rewritten).
+    auto diagonals = [&]() {
+      asm volatile("bar.sync 5, %0;" ::"n"(TCB_ROW_WARPS * 32) : "memory");
+      const int ndiag = 2 * p.Lt - 1;
+      if (q < ndiag) {
+        const int rel = q - (p.Lt - 1);             // key - query
+        const int q_lo = max(0, -rel), q_hi = min(p.Lt, p.Lt - rel);
+        float acc = 0.f;
+        const uint8_t* tile = sdS + hsel * 16384;
+#pragma unroll 4
+        for (int qi = q_lo; qi < q_hi; ++qi) {
+          const int row = hsel * 64 + qi, j = qi + rel;
+          acc += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(tile + row * 128 + (((j >> 3) ^ (row & 7)) << 4) + (j & 7) * 2));
+        }
+        atomicAdd(&dtab[(int)bk.b[rel + (AT_S_TC - 1)] * 16 + h_prev + hsel], acc);
+      }
+    };
+    auto epilogue = [&](int m) {
       mbar_wait(ofull_bar, m & 1);
+      VQ_TRR(m + 1, 4);
       tc_fence_after();
-      const bool ok = q < p.S;
-      const size_t grow = (size_t)b_prev * p.S + q;
-      const int col = (h_prev + hsel) * 64 + cq * 16;
-      uint32_t o[16];
-      tmem_ld_32x16(tmem_base + 256 + cq * 16 + lane_addr, o);
-      tmem_ld_wait();
-      if (ok) store_row16(p.dq + grow * p.lddq + col, o);
-      tmem_ld_32x16(tmem_base + 320 + cq * 16 + lane_addr, o);
-      tmem_ld_wait();
-      if (ok) store_row16(p.dk + grow * p.lddk + col, o);
-      tmem_ld_32x16(tmem_base + 384 + cq * 16 + lane_addr, o);
-      tmem_ld_wait();
-      if (ok) store_row16(p.dv + grow * p.lddv + col, o);
+      if (cq < 3) {
+        char* gp = reinterpret_cast<char*>(outp + ((size_t)b_prev * p.S + qb + rr0) * outld + (h_prev + hsel) * 64 + piece * 8);
+        const size_t gstep = (size_t)8 * outld * 2;
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          uint32_t o[32];
+          tmem_ld_32x32(tmem_base + 256 + cq * 64 + half * 32 + lane_addr, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            sts128_u(sts_base ^ (j << 4), pack_bf16(__uint_as_float(o[8 * j]), __uint_as_float(o[8 * j + 1])),
+                     pack_bf16(__uint_as_float(o[8 * j + 2]), __uint_as_float(o[8 * j + 3])),
+                     pack_bf16(__uint_as_float(o[8 * j + 4]), __uint_as_float(o[8 * j + 5])),
+                     pack_bf16(__uint_as_float(o[8 * j + 6]), __uint_as_float(o[8 * j + 7])));
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint4 u = lds128_u(lds_base + i * 512);
+            if (qb + rr0 + 8 * i < p.S) *reinterpret_cast<uint4*>(gp + i * gstep + half * 64) = u;
+          }
+          __syncwarp();
+        }
+      }
       tc_fence_before();
     };
     int n = 0;
     for (int it = it0; it < nitems; it += gs, ++n) {
       const int stage = n & 1;
       const int b = it / hp, h = (it - b * hp) * 2;
+      VQ_TRR(n, 0);
       mbar_wait(&full_bar[stage], (n >> 1) & 1);     // header visible
+      VQ_TRR(n, 1);
       mbar_wait(sfull_bar, n & 1);
+      VQ_TRR(n, 2);
       tc_fence_after();
       float s[16], dp[16];
       {
@@ -572,6 +681,7 @@ attn_enc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       }
       dxr[(n & 1) * 512 + cq * 128] = dpart;
       asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+      VQ_TRR(n, 3);
       const float* dxp = dxr + (n & 1) * 512;
       const float dsum = (dxp[0] + dxp[128]) + (dxp[256] + dxp[384]);
       uint32_t pw[8], dw[8];
@@ -583,7 +693,18 @@ attn_enc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       }
       // the previous item's output rows: its MMAs finished long ago; reading them here frees the dQ / dK / dV accumulators and
       // guarantees the P / dS tiles have been consumed before they are overwritten below
-      if (n > 0) epilogue(n - 1);
+      if (n > 0) {
+        epilogue(n - 1);
+        if (p.d_rel_table) {
+          if (cq == 3) {
+            diagonals();
+            asm volatile("bar.arrive 6, %0;" ::"n"(TCB_ROW_WARPS * 32) : "memory");
+          } else {
+            asm volatile("bar.sync 6, %0;" ::"n"(TCB_ROW_WARPS * 32) : "memory");     // the dS tile may be rewritten
+          }
+        }
+      }
+      VQ_TRR(n, 5);
       b_prev = b; h_prev = h;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
@@ -593,29 +714,17 @@ attn_enc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       }
       (void)zero_off;                              // the off-diagonal halves were zeroed once and are never written
       fence_proxy_async();
-      if (p.d_rel_table) {
-        // bias-table gradient: sums of dS along the diagonals of the text x text corner, one thread per (head, diagonal)
-        asm volatile("bar.sync 5, %0;" ::"n"(TCB_ROW_WARPS * 32) : "memory");
-        const int ndiag = 2 * p.Lt - 1;
-        if (cq == 0 && q < ndiag) {
-          const int rel = q - (p.Lt - 1);             // key - query
-          const int q_lo = max(0, -rel), q_hi = min(p.Lt, p.Lt - rel);
-          float acc = 0.f;
-          const uint8_t* tile = sdS + hsel * 16384;
-          for (int qi = q_lo; qi < q_hi; ++qi) {
-            const int row = hsel * 64 + qi, j = qi + rel;
-            acc += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(tile + row * 128 + (((j >> 3) ^ (row & 7)) << 4) + (j & 7) * 2));
-          }
-          atomicAdd(&dtab[(int)bk.b[rel + (AT_S_TC - 1)] * 16 + h + hsel], acc);
-        }
-      }
+      VQ_TRR(n, 6);
       __syncwarp();
-      if (lane == 0) mbar_arrive(pfull_bar);
+      if (lane == 0) mbar_arrive(&pfull_bar[stage]);
+      VQ_TRR(n, 7);
+      if (p.d_rel_table && cq < 3) asm volatile("bar.arrive 5, %0;" ::"n"(TCB_ROW_WARPS * 32) : "memory");   // dS tile of item n: this warp's part is written
     }
     if (n > 0) epilogue(n - 1);
     if (p.d_rel_table) {
-      asm volatile("bar.sync 5, %0;" ::"n"(TCB_ROW_WARPS * 32) : "memory");
-      for (int i = threadIdx.x; i < 64 * 16; i += TCB_ROW_WARPS * 32) {
+      if (n > 0 && cq == 3) diagonals();
+      asm volatile("bar.sync 7, %0;" ::"n"(TCB_ROW_WARPS * 32) : "memory");
+      for (int i = threadIdx.x - TCB_FIRST_ROW_WARP * 32; i < TCB_DTAB_FLOATS; i += TCB_ROW_WARPS * 32) {
         const float v = dtab[i];
         const int bucket = i >> 4, head = i & 15;
         if (v != 0.f && head < p.H) atomicAdd(&p.d_rel_table[bucket * p.H + head], v);
@@ -625,7 +734,7 @@ attn_enc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 
   tc_fence_before();
   __syncthreads();
-  if (warp == TCB_ROW_WARPS + 1) {
+  if (warp == TCB_ISSUER_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TC_TMEM_COLS);
   }
@@ -697,3 +806,11 @@ int attn_enc_bwd_tc(const AttnArgs& a, const AttnBuckets& bk, cudaStream_t strea
 }
 
 }  // namespace vq
+
+#ifdef VQ_ATTN_TRACE
+// debug builds only (not declared in include/vqacl_b200.h): installs the device buffer [4][16][8] of int64 clock stamps
+extern "C" int vqacl_debug_attn_trace(void* buf) {
+  VQ_CUDA(cudaMemcpyToSymbol(vq::g_attn_trace, &buf, sizeof(buf)));
+  return 0;
+}
+#endif
