@@ -204,7 +204,15 @@ attn_enc_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     // O2 row of the item with running index m (its row sum halves are in xsum, parity m & 1): scale, convert, store
     float m_prev = 0.f;
     int b_prev = 0, h_prev = 0;
-    auto epilogue = [&](int m) {
+    // A thread-per-row store is 32 row-strided 16-byte requests per instruction (measured on the backward kernel: 2.5 us of a
+    // 6.7 us item). The 64 bytes of each row are therefore transposed through shared memory and leave as 8 rows x 64 contiguous
+    // bytes per instruction. The staging needs no memory of its own: a thread parks its row in the four 16-byte slots of the
+    // OTHER head's key atom that it zeroes for the block-diagonal P tile anyway (stage `st_stage`: operands consumed, P tile not
+    // yet written) — slots only this warp ever touches, read back by the warp's own lanes after a __syncwarp.
+    const int rr0 = lane >> 2, piece = lane & 3;
+    const uint32_t zslot_rd0 = smem_u32(smem) + (hsel ^ 1) * 16384 + (rw * 32 + rr0) * 128 + (((ch * 4 + piece) ^ rr0) << 4);
+    const int qb = (rw & 1) * 32;
+    auto epilogue = [&](int m, int st_stage) {
       mbar_wait(ofull_bar, m & 1);
       tc_fence_after();
       const float l = xsum[(m & 1) * 512] + xsum[(m & 1) * 512 + 128];
@@ -213,16 +221,25 @@ attn_enc_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       uint32_t o0[32];
       tmem_ld_32x32(tmem_base + 128 + lane_addr + ch * 32, o0);
       tmem_ld_wait();
-      if (q < p.S) {
-        uint4* dst = reinterpret_cast<uint4*>(p.o + ((size_t)b_prev * p.S + q) * p.ldo + (h_prev + hsel) * 64 + ch * 32);
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          dst[c] = make_uint4(pack_bf16(__uint_as_float(o0[8 * c]) * osc, __uint_as_float(o0[8 * c + 1]) * osc),
-                              pack_bf16(__uint_as_float(o0[8 * c + 2]) * osc, __uint_as_float(o0[8 * c + 3]) * osc),
-                              pack_bf16(__uint_as_float(o0[8 * c + 4]) * osc, __uint_as_float(o0[8 * c + 5]) * osc),
-                              pack_bf16(__uint_as_float(o0[8 * c + 6]) * osc, __uint_as_float(o0[8 * c + 7]) * osc));
-      }
       tc_fence_before();
+      const uint32_t zw = sZ_row0 + st_stage * TCF_STAGE_BYTES;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        sts128_u(zw + ((uint32_t)((ch * 4 + c) ^ sw) << 4),
+                 pack_bf16(__uint_as_float(o0[8 * c]) * osc, __uint_as_float(o0[8 * c + 1]) * osc),
+                 pack_bf16(__uint_as_float(o0[8 * c + 2]) * osc, __uint_as_float(o0[8 * c + 3]) * osc),
+                 pack_bf16(__uint_as_float(o0[8 * c + 4]) * osc, __uint_as_float(o0[8 * c + 5]) * osc),
+                 pack_bf16(__uint_as_float(o0[8 * c + 6]) * osc, __uint_as_float(o0[8 * c + 7]) * osc));
+      __syncwarp();
+      char* gp = reinterpret_cast<char*>(p.o + ((size_t)b_prev * p.S + qb + rr0) * p.ldo + (h_prev + hsel) * 64 + ch * 32 + piece * 8);
+      const size_t gstep = (size_t)8 * p.ldo * 2;
+      const uint32_t zr = zslot_rd0 + st_stage * TCF_STAGE_BYTES;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint4 u = lds128_u(zr + i * 1024);
+        if (qb + rr0 + 8 * i < p.S) *reinterpret_cast<uint4*>(gp + i * gstep) = u;
+      }
+      __syncwarp();
     };
     int n = 0;
     for (int it = blockIdx.x; it < nitems; it += gridDim.x, ++n) {
@@ -280,7 +297,7 @@ attn_enc_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       }
       // the previous item's O row: its MMA finished long ago (nobody waits here), and reading it now frees the O accumulator
       // before this item's P tile is released to the MMA warp
-      if (n > 0) epilogue(n - 1);
+      if (n > 0) epilogue(n - 1, n & 1);
       xsum[(n & 1) * 512 + ch * 128] = (l4[0] + l4[1]) + (l4[2] + l4[3]);
       m_prev = m; b_prev = b; h_prev = h;
 #pragma unroll
@@ -293,7 +310,7 @@ attn_enc_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");     // the partner's half of the row sum is visible to the next epilogue
       if (lane == 0) mbar_arrive(pfull_bar);
     }
-    if (n > 0) epilogue(n - 1);
+    if (n > 0) epilogue(n - 1, (n - 1) & 1);       // its own stage: the O MMA the epilogue waits for was the last reader
   }
 
   tc_fence_before();
@@ -774,7 +791,7 @@ int attn_enc_fwd_tc(const AttnArgs& a, const AttnBuckets& bk, cudaStream_t strea
 }
 
 bool attn_tc_bwd_eligible(const AttnArgs& a) {
-  static const int on = [] { const char* e = getenv("VQACL_ATTN_TC_BWD"); return (e && e[0] == '1') ? 1 : 0; }();
+  static const int on = [] { const char* e = getenv("VQACL_ATTN_TC_BWD"); return (e && e[0] == '0') ? 0 : 1; }();   // =0: mma.sync backward (A/B)
   return on && a.rel_mode == 1 && a.Sq == a.Sk && a.Sq > 32 && a.Sq <= 64 && a.Lt <= 32 && (a.H & 1) == 0 && !a.causal && a.ldq % 8 == 0 &&
          a.ldk % 8 == 0 && a.ldv % 8 == 0 && a.ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(a.q) & 15) == 0 &&
          (reinterpret_cast<uintptr_t>(a.k) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.v) & 15) == 0 && a.H <= 16 && a.lddq % 8 == 0 && a.lddk % 8 == 0 && a.lddv % 8 == 0 &&
