@@ -27,7 +27,23 @@ dO = torch.randn(B * Sq, 768, device="cuda").bfloat16()
 def fwd(): return cabi.attention_fwd(q, k, v, B, H, Sq, Sk, **kw)
 o, lse = fwd()
 def bwd(): return cabi.attention_bwd(q, k, v, dO, lse, B, H, Sq, Sk, o_saved=(o if mode == 'cross' else None), **kw)
+def graph_us(fn, reps=20):
+    """`reps` launches replayed from one CUDA graph: a ctypes launch costs ~9 us from Python, more than the small kernels take"""
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        for _ in range(3): fn()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=st):
+            for _ in range(reps): fn()
+        g.replay(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st); g.replay(); e1.record(st); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e3 / reps
 for fn, nm in ((fwd, "fwd"), (bwd, "bwd")):
+    if os.environ.get("GRAPH", "0") == "1":
+        print(f"attn {mode} {nm} B={B}: {graph_us(fn):.1f} us (graph replay)")
+        continue
     for _ in range(3): fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

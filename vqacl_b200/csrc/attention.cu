@@ -634,7 +634,7 @@ VQ_DEVINL float* ks_partial_row(__nv_bfloat16 (*k)[AT_P], __nv_bfloat16 (*v)[AT_
 // Every warp runs a complete softmax over ITS 16 keys (own maximum m_w, own sum l_w, un-normalised partial O_w = P_w V_w) and
 // parks the partial in shared memory; the partials are merged flash-decoding style, O = sum_w e^(m_w - M) O_w / sum_w e^(m_w - M) l_w
 // with M = max_w m_w: one barrier after the loads and one before the merge, no shared atomics (fp32 shared atomicAdd is a CAS loop).
-__global__ void __launch_bounds__(KS_WARPS * 32, 6) attn_ks_fwd_kernel(const AttnArgs p) {
+__global__ void __launch_bounds__(KS_WARPS * 32, 8) attn_ks_fwd_kernel(const AttnArgs p) {
   vq_pdl_trigger();
   vq_pdl_wait();
   extern __shared__ __align__(16) uint8_t at_smem_base[];
@@ -774,7 +774,7 @@ struct KsSmemBwd {
 };
 static inline int ks_bwd_smem(int Sq) { return (int)sizeof(KsSmemBwd) + KS_WARPS * Sq * KS_OP * 4; }
 
-__global__ void __launch_bounds__(KS_WARPS * 32, 5) attn_ks_bwd_kernel(const AttnArgs p) {
+__global__ void __launch_bounds__(KS_WARPS * 32, 6) attn_ks_bwd_kernel(const AttnArgs p) {
   vq_pdl_trigger();
   vq_pdl_wait();
   extern __shared__ __align__(16) uint8_t at_smem_base[];
