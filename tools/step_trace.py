@@ -68,3 +68,19 @@ for s, d in sorted(streams.items(), key=lambda kv: -kv[1]):
 print("per step: us  count  avg_us  kernel")
 for n, (c, d) in sorted(per.items(), key=lambda kv: -kv[1][1]):
     print(f"{d / steps:10.1f} {c / steps:6.0f} {d / c:8.1f}  {n}")
+
+# timeline excerpt of the last profiled step: N kernels starting at a named one (default: the LM-head backward, i.e. the decoder
+# backward chain):  python tools/step_trace.py 320 3 ce_bwd_kernel 120
+if len(sys.argv) > 3:
+    start_name, count = sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else 100
+    idx = [i for i, e in enumerate(ev) if start_name in e["name"]]
+    if idx:
+        i0 = idx[-1]
+        base = ev[i0]["ts"]
+        print(f"--- timeline from the last {start_name} (us: start, end, duration | stream | kernel)")
+        prev_end = {}
+        for e in ev[i0:i0 + count]:
+            st = e["args"].get("stream")
+            gap = e["ts"] - prev_end.get(st, e["ts"])
+            prev_end[st] = e["ts"] + e["dur"]
+            print(f"{e['ts'] - base:9.1f} {e['ts'] + e['dur'] - base:9.1f} {e['dur']:7.1f} gap {gap:6.1f} | {st} | {e['name'].split('(')[0][:60]}")

@@ -254,7 +254,11 @@ int64_t engine_carve(Engine& e, uint8_t* base, int B, int L, int N, int T) {
 // --------------------------------------------------------------------------------------------------- GEMM helpers
 // dX[rows, n_in] = dY[rows, n_out] * W[n_out, n_in]      (W stored row-major -> MN-major B operand)
 // split-K factor of the decoder's deep dX GEMMs (VQACL_DEC_DX_SPLITS=1 restores the single-pass bf16 form for A/B runs)
-static int g_dec_dx_splits = [] { const char* ev = getenv("VQACL_DEC_DX_SPLITS"); return ev && atoi(ev) > 0 ? atoi(ev) : 3; }();
+// SMs the decoder's weight-gradient GEMMs (side stream) may occupy while the latency-bound dX / attention / norm chain runs on
+// the main stream. Default 0 = no limit: 48 / 64 / 96 SMs measured 2.69 / 2.42 / 2.34 ms for the decoder-layer backward against
+// 2.36-2.40 ms unlimited (the side stream then falls behind and the chain waits for it at the two-layer lag) — kept as a switch
+static int g_dec_dw_sms = [] { const char* ev = getenv("VQACL_DEC_DW_SMS"); return ev ? atoi(ev) : 0; }();
+static int g_dec_dx_splits = [] { const char* ev = getenv("VQACL_DEC_DX_SPLITS"); return ev && atoi(ev) > 0 ? atoi(ev) : 1; }();
 static int gemm_dx(const bf16* dY, int lddy, const bf16* Wt, int n_out, int n_in, void* C, int ldc, int rows, int epi, cudaStream_t st,
                    const void* R = nullptr, int ldr = 0, float alpha = 1.f, int splits = 1) {
   GemmArgs g{};
@@ -262,9 +266,10 @@ static int gemm_dx(const bf16* dY, int lddy, const bf16* Wt, int n_out, int n_in
   return gemm_bf16(GemmOperand{dY, lddy, false}, GemmOperand{Wt, n_in, true}, g, 0, st);
 }
 // dW[n_out, n_in] += dY[rows, n_out]^T * X[rows, n_in]    (both operands MN-major, split-K over rows, fp32 red.add)
-static int gemm_dw(const bf16* dY, int lddy, const bf16* X, int ldx, float* dWt, int n_out, int n_in, int rows, cudaStream_t st) {
+static int gemm_dw(const bf16* dY, int lddy, const bf16* X, int ldx, float* dWt, int n_out, int n_in, int rows, cudaStream_t st,
+                   int sm_limit = 0) {
   GemmArgs g{};
-  g.epi = EPI_ATOMIC_F32; g.M = n_out; g.N = n_in; g.K = rows; g.C = dWt; g.ldc = n_in; g.alpha = 1.f;
+  g.epi = EPI_ATOMIC_F32; g.M = n_out; g.N = n_in; g.K = rows; g.C = dWt; g.ldc = n_in; g.alpha = 1.f; g.sm_limit = sm_limit;
   const int tiles = ((n_out + 127) / 128) * ((n_in + 255) / 256);
   const int kblocks = (rows + 63) / 64;
   int splits = (2 * num_sms()) / (tiles > 0 ? tiles : 1);
@@ -648,10 +653,10 @@ static int backward(Engine& e, const float* w_rows, const float* gscale, int acc
     e.gdb_i = (e.gdb_i + 3) % (3 * RING);
     // FFN
     VQ_TRY(fork());
-    VQ_TRY(gemm_dw(gdb_in, d, w.dh[l], f, e.G + P.wo, d, f, Md, sd));
+    VQ_TRY(gemm_dw(gdb_in, d, w.dh[l], f, e.G + P.wo, d, f, Md, sd, g_dec_dw_sms));
     VQ_TRY(gemm_dx(gdb_in, d, e.W + P.wo, d, f, w.t_dh[ri], f, Md, EPI_RELUBWD_BF16, st, w.dhmask[l], (f + 31) / 32, e.drop(site_dec(l, 4)).inv_keep));
     VQ_TRY(fork());
-    VQ_TRY(gemm_dw(w.t_dh[ri], f, w.dn3[l], d, e.G + P.wi, f, d, Md, sd));
+    VQ_TRY(gemm_dw(w.t_dh[ri], f, w.dn3[l], d, e.G + P.wi, f, d, Md, sd, g_dec_dw_sms));
     // The deep contractions of the chain (dX of wi: K = d_ff, dX of qkv: K = 3 d) are split-K: with M = B*T rows there are only
     // 39-78 output tiles, and a CTA's operand stream is bound by its SM's ~120 GB/s L2 port (measured: 3.2 us + 0.27 us per 32 KB
     // k-block, tools/gemm_small_sweep.py) — three K slices per tile engage 126 SMs instead of 42. The slices meet in an fp32
@@ -666,7 +671,7 @@ static int backward(Engine& e, const float* w_rows, const float* gscale, int acc
     VQ_TRY(rmsnorm_bwd(q, st));
     // cross attention
     VQ_TRY(fork());
-    VQ_TRY(gemm_dw(gdb_1, d, w.cao[l], d, e.G + P.co, d, d, Md, sd));
+    VQ_TRY(gemm_dw(gdb_1, d, w.cao[l], d, e.G + P.co, d, d, Md, sd, g_dec_dw_sms));
     VQ_TRY(gemm_dx(gdb_1, d, e.W + P.co, d, d, w.t_d768, d, Md, EPI_BF16, st));
     AttnArgs x{};
     x.q = w.cq[l]; x.ldq = d; x.k = w.kv_all + (size_t)l * 2 * d; x.v = x.k + d; x.ldk = x.ldv = ldkv;
@@ -677,14 +682,14 @@ static int backward(Engine& e, const float* w_rows, const float* gscale, int acc
     x.dO = w.t_d768; x.dq = w.t_dcq[ri]; x.lddq = d; x.dk = w.dkv_all + (size_t)l * 2 * d; x.dv = x.dk + d; x.lddk = x.lddv = ldkv;
     VQ_TRY(attn_bwd(x, st));
     VQ_TRY(fork());
-    VQ_TRY(gemm_dw(w.t_dcq[ri], d, w.dn2[l], d, e.G + P.cq, d, d, Md, sd));
+    VQ_TRY(gemm_dw(w.t_dcq[ri], d, w.dn2[l], d, e.G + P.cq, d, d, Md, sd, g_dec_dw_sms));
     VQ_TRY(gemm_dx(w.t_dcq[ri], d, e.W + P.cq, d, d, w.t_d768, d, Md, EPI_BF16, st));
     q.x = w.y[3 * l + 1]; q.w = e.P + P.ln1; q.dw = e.G + P.ln1; q.consumer = e.drop(site_dec(l, 1)); q.gb_out = gdb_2;
     q.dn_f32 = nullptr; q.dn_zero = 0;       // dX of cq (K = d) stays a bf16 single pass
     VQ_TRY(rmsnorm_bwd(q, st));
     // self attention
     VQ_TRY(fork());
-    VQ_TRY(gemm_dw(gdb_2, d, w.dao[l], d, e.G + P.o, d, d, Md, sd));
+    VQ_TRY(gemm_dw(gdb_2, d, w.dao[l], d, e.G + P.o, d, d, Md, sd, g_dec_dw_sms));
     VQ_TRY(gemm_dx(gdb_2, d, e.W + P.o, d, d, w.t_d768, d, Md, EPI_BF16, st));
     AttnArgs a{};
     a.q = w.dqkv[l]; a.k = w.dqkv[l] + d; a.v = w.dqkv[l] + 2 * d; a.ldq = a.ldk = a.ldv = 3 * d;
@@ -696,7 +701,7 @@ static int backward(Engine& e, const float* w_rows, const float* gscale, int acc
     a.d_rel_table = e.G + e.o_dec_rel;
     VQ_TRY(attn_bwd(a, st));
     VQ_TRY(fork());
-    VQ_TRY(gemm_dw(w.t_dqkv[ri], 3 * d, w.dn1[l], d, e.G + P.qkv, 3 * d, d, Md, sd));
+    VQ_TRY(gemm_dw(w.t_dqkv[ri], 3 * d, w.dn1[l], d, e.G + P.qkv, 3 * d, d, Md, sd, g_dec_dw_sms));
     if (dsplit > 1) VQ_TRY(gemm_dx(w.t_dqkv[ri], 3 * d, e.W + P.qkv, 3 * d, d, w.t_d768_f32, d, Md, EPI_ATOMIC_F32, st, nullptr, 0, 1.f, dsplit));
     else VQ_TRY(gemm_dx(w.t_dqkv[ri], 3 * d, e.W + P.qkv, 3 * d, d, w.t_d768, d, Md, EPI_BF16, st));
     if (dsplit > 1) { q.dn_f32 = w.t_d768_f32; q.dn_zero = 1; }

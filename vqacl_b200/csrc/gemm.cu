@@ -120,7 +120,7 @@ static int g_row_tail_off = [] { const char* e = getenv("VQACL_GEMM_ROW_TAIL"); 
 // shared memory (vqacl_set_gemm_sm_limit).
 static int g_sm_limit = 0;
 static int g_num_sms = 0;
-static int gemm_sms();
+static int gemm_sms(int call_limit = 0);
 int num_sms() {
   if (g_num_sms == 0) {
     int dev = 0;
@@ -133,9 +133,11 @@ int num_sms() {
   return g_num_sms;
 }
 
-static int gemm_sms() {
-  const int n = num_sms();
-  return (g_sm_limit > 0 && g_sm_limit < n) ? g_sm_limit : n;
+static int gemm_sms(int call_limit) {
+  int n = num_sms();
+  if (g_sm_limit > 0 && g_sm_limit < n) n = g_sm_limit;
+  if (call_limit > 0 && call_limit < n) n = call_limit & ~1;   // even: the CTA-pair kernel launches clusters of two
+  return n;
 }
 // Is folding a row tail into an M-row GEMM with 768 output columns a good deal? In the tail mode a CTA pair owns whole 256-row
 // blocks, so the kernel's parallelism is ceil(M / 256) pairs instead of 3x as many tiles: only when the blocks fill the pairs
@@ -170,7 +172,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& 
     attr_set = true;
   }
   const int tiles = ((args.M + GEMM_BM - 1) / GEMM_BM) * ((args.N + BN - 1) / BN) * args.splits;
-  const int grid = tiles < gemm_sms() ? tiles : gemm_sms();
+  const int grid = tiles < gemm_sms(args.sm_limit) ? tiles : gemm_sms(args.sm_limit);
   (void)vq_launch(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, ta, tb, args);
   VQ_LAUNCH_CHECK();
   return 0;
@@ -206,7 +208,7 @@ static int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmA
     attr_set = true;
   }
   const int work = ((args.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM)) * ((args.N + GEMM2_BN - 1) / GEMM2_BN) * args.splits;
-  const int max_pairs = gemm_sms() / 2;
+  const int max_pairs = gemm_sms(args.sm_limit) / 2;
   const int pairs = work < max_pairs ? work : max_pairs;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * pairs);
@@ -299,7 +301,7 @@ int gemm_bf16(const GemmOperand& A, const GemmOperand& B, GemmArgs args, int for
     //   256 x 256 CTA-pair tile (bn = 512): 4 MMAs at the full rate on two SMs.
     const int tiles_m = (args.M + GEMM_BM - 1) / GEMM_BM;
     (void)num_sms();
-    const int sms = gemm_sms();
+    const int sms = gemm_sms(args.sm_limit);
     const int kb_split = (kblocks + args.splits - 1) / args.splits;
     const int cand[3] = {256, 128, 64};
     const int cyc[3] = {768, 400, 240};

@@ -63,6 +63,10 @@ struct GemmArgs {
   void* tail_out;
   int tail_ld;          // elements
   float tail_eps;
+  int sm_limit;         // host side only: launch on at most this many SMs (0 = all). The decoder's weight-gradient GEMMs run on a
+                        // second stream beside a chain of small latency-bound kernels; a persistent 148-CTA launch with 225 KB of
+                        // shared memory per CTA holds EVERY SM until it ends, and the chain's next GEMM waits for it (measured:
+                        // 10 us per cross-attention backward, profiles/r02_step_trace_decoder.txt)
   uint32_t* sched;      // CTA-pair kernel only: {next work item, pairs finished} counters of a DYNAMIC tile schedule (null = static
                         // round robin). A pair that becomes resident late — its SMs were held by a collective's CTAs or by another
                         // stream's kernel — then finds the work list drained instead of running its whole static share afterwards.
