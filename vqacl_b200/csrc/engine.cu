@@ -252,13 +252,15 @@ int64_t engine_carve(Engine& e, uint8_t* base, int B, int L, int N, int T) {
 }
 
 // --------------------------------------------------------------------------------------------------- GEMM helpers
-// dX[rows, n_in] = dY[rows, n_out] * W[n_out, n_in]      (W stored row-major -> MN-major B operand)
-// split-K factor of the decoder's deep dX GEMMs (VQACL_DEC_DX_SPLITS=1 restores the single-pass bf16 form for A/B runs)
 // SMs the decoder's weight-gradient GEMMs (side stream) may occupy while the latency-bound dX / attention / norm chain runs on
 // the main stream. Default 0 = no limit: 48 / 64 / 96 SMs measured 2.69 / 2.42 / 2.34 ms for the decoder-layer backward against
 // 2.36-2.40 ms unlimited (the side stream then falls behind and the chain waits for it at the two-layer lag) — kept as a switch
 static int g_dec_dw_sms = [] { const char* ev = getenv("VQACL_DEC_DW_SMS"); return ev ? atoi(ev) : 0; }();
+// split-K factor of the decoder's deep dX GEMMs (wi: K = d_ff, qkv: K = 3 d) into an fp32 buffer the RMSNorm backward reads and
+// clears. Default 1 = single-pass bf16: 3 slices make the two GEMMs 2x faster alone (126 instead of 42 CTAs streaming operands)
+// but the step 0.1-0.2 ms slower — they then compete with the side stream's dW GEMMs for the same SMs
 static int g_dec_dx_splits = [] { const char* ev = getenv("VQACL_DEC_DX_SPLITS"); return ev && atoi(ev) > 0 ? atoi(ev) : 1; }();
+// dX[rows, n_in] = dY[rows, n_out] * W[n_out, n_in]      (W stored row-major -> MN-major B operand)
 static int gemm_dx(const bf16* dY, int lddy, const bf16* Wt, int n_out, int n_in, void* C, int ldc, int rows, int epi, cudaStream_t st,
                    const void* R = nullptr, int ldr = 0, float alpha = 1.f, int splits = 1) {
   GemmArgs g{};
