@@ -386,6 +386,43 @@ def test_gemm_fused_argmax_epilogue_first_max(bn):
     torch.testing.assert_close(v, ref.max(dim=1).values, rtol=1e-4, atol=1e-4)
 
 
+@pytest.mark.parametrize("S,Lt,B,masked", [(33, 20, 3, True), (40, 1, 7, False), (64, 32, 4, True), (56, 20, 200, True), (47, 9, 26, False)])
+def test_attention_tcgen05_shapes_vs_torch(S, Lt, B, masked):
+    """The whole shape range the tcgen05 encoder kernels accept (33..64 positions, 1..32 text tokens, fewer and more items than
+    SMs, with and without masked keys): forward, dQ / dK / dV and the bias-table gradient against the fp32 torch formulation."""
+    from vqacl_b200.engine import rel_bucket_table
+    torch.manual_seed(S * 100 + Lt)
+    H = 12
+    q = (torch.randn(B * S, H * 64, device=DEV) * 0.3).bfloat16().requires_grad_()
+    k = (torch.randn(B * S, H * 64, device=DEV) * 0.3).bfloat16().requires_grad_()
+    v = torch.randn(B * S, H * 64, device=DEV).bfloat16().requires_grad_()
+    table = (torch.randn(32, H, device=DEV) * 0.5)
+    att = O.T5Attention(O.VLT5Config(), False, True).to(DEV)
+    att.relative_attention_bias.weight = torch.nn.Parameter(table.clone())
+    full = torch.zeros(1, H, S, S, device=DEV)
+    full[:, :, :Lt, :Lt] = att.compute_bias(Lt, Lt)
+    pad = torch.zeros(B, S, device=DEV)
+    if masked:
+        pad[B // 2, max(1, Lt // 2):Lt] = -10000.0
+        pad[B - 1, Lt - 1:Lt] = -10000.0
+    bias = full + pad[:, None, None, :]
+    kw = dict(rel_table=table, rel_bucket=rel_bucket_table(True), rel_mode=1, Lt=Lt, keymask=pad.contiguous() if masked else None)
+    ref = _attn_ref(q, k, v, B, H, S, S, bias)
+    o, lse = cabi.attention_fwd(q.detach(), k.detach(), v.detach(), B, H, S, S, **kw)
+    assert rel_err(o, ref.detach()) < 1e-2
+    ps = torch.softmax((q.float().view(B, S, H, 64).transpose(1, 2) @ k.float().view(B, S, H, 64).transpose(1, 2).transpose(2, 3) + bias).detach(), -1)
+    lse_ref = torch.logsumexp((q.float().view(B, S, H, 64).transpose(1, 2) @ k.float().view(B, S, H, 64).transpose(1, 2).transpose(2, 3) + bias).detach(), -1)
+    assert (lse.view(B, H, S) - lse_ref).abs().max() < 2e-2 and ps.isfinite().all()
+    dO = torch.randn_like(ref).bfloat16()
+    ref.backward(dO.float())
+    dq, dk, dv, dtab = cabi.attention_bwd(q.detach(), k.detach(), v.detach(), dO, lse, B, H, S, S, **kw)
+    for mine, theirs, nm in ((dq, q.grad, "dq"), (dk, k.grad, "dk"), (dv, v.grad, "dv")):
+        assert mine.float().isfinite().all(), nm
+        assert cos(mine, theirs) > 0.999 and rel_err(mine, theirs) < 2e-2, nm
+    tg = att.relative_attention_bias.weight.grad
+    assert cos(dtab, tg) > 0.999 and rel_err(dtab, tg) < 2e-2
+
+
 @pytest.mark.parametrize("Sq,Sk,mode", [(150, 150, "enc"), (100, 200, "plain"), (5, 152, "cross"), (256, 256, "enc"), (70, 33, "plain")])
 def test_attention_multi_tile_fwd_bwd_vs_torch(Sq, Sk, mode):
     """The generic multi-tile kernels (Sq or Sk > 64): encoder form (text x text bias corner + key padding mask), a plain
