@@ -162,6 +162,12 @@ long long vqacl_launch_count(void);
  * 6 fused row argmax (no C matrix: C = float [M, ldc] per-tile maxima, R = int32 [M, ldr] their columns, slot = 2 * (column / 256)
  * + epilogue-warp group; first maximum = lowest index among equals; 256-wide tiles only).
  * force_bn: 0 = cost model, 64/128/256 = single-CTA tile width, 512 = 256x256 CTA-pair tile (cta_group::2).                 */
+/* Several weight gradients in ONE launch (the decoder's six dW = dY^T X per layer, each too small to fill the machine: replaces
+ * the autograd-generated per-Linear sgemm calls of T5Attention / T5DenseReluDense backward, hf modeling_t5.py via
+ * modeling_t5_our.py:659-671): problem i is C[i][M[i], N[i]] (+)= A[i]^T B[i] with A[i] stored [K, M[i]] and B[i] stored [K, N[i]]
+ * (bf16, pitches lda / ldb), C fp32 with pitch ldc[i]; n <= 8; epi 3 = accumulate (red.global.add), 5 = store.                */
+int vqacl_gemm_bf16_grouped_mn(int n, const void* const* A, const int* lda, const void* const* B, const int* ldb, void* const* C,
+                               const int* ldc, const int* M, const int* N, int K, int epi, float alpha, void* stream);
 int vqacl_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major, void* C, int ldc,
                     const void* R, int ldr, int M, int N, int K, int epi, float alpha, int splits, int force_bn, void* stream);
 /* same with the dropout that nn.Dropout applies after the activation / before the residual add (HF T5LayerFF / T5LayerSelfAttention)

@@ -180,3 +180,20 @@ def visual_embed_fused(feats_bf16, Wf_bf16, boxes, bf, wf, Wp, bp, wp, img, shar
     check(_L().vqacl_visual_embed_fused(ptr(feats_bf16), ptr(Wf_bf16), Fd, ptr(boxes), ptr(bf), ptr(wf), ptr(Wp), ptr(bp), ptr(wp), ptr(img),
                                         ptr(shared), shared.shape[0], B, N, N, 0, eps, ptr(featpre), ptr(x), cur_stream()))
     return x, featpre
+
+
+def gemm_grouped_mn(As, Bs, Cs, epi=3, alpha=1.0):
+    """Problem i: Cs[i][M_i, N_i] (+)= As[i]^T @ Bs[i] with As[i] stored [K, M_i], Bs[i] stored [K, N_i] (bf16); one launch."""
+    n = len(As)
+    K = As[0].shape[0]
+    VP = ctypes.c_void_p * n
+    IP = ctypes.c_int * n
+    L = _L()
+    L.vqacl_gemm_bf16_grouped_mn.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_void_p),
+                                             ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int),
+                                             ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                                             ctypes.c_void_p]
+    check(L.vqacl_gemm_bf16_grouped_mn(n, VP(*[a.data_ptr() for a in As]), IP(*[a.stride(0) for a in As]), VP(*[b.data_ptr() for b in Bs]),
+                                       IP(*[b.stride(0) for b in Bs]), VP(*[c.data_ptr() for c in Cs]), IP(*[c.stride(0) for c in Cs]),
+                                       IP(*[a.shape[1] for a in As]), IP(*[b.shape[1] for b in Bs]), K, epi, ctypes.c_float(alpha), cur_stream()))
+    return Cs

@@ -386,6 +386,27 @@ def test_gemm_fused_argmax_epilogue_first_max(bn):
     torch.testing.assert_close(v, ref.max(dim=1).values, rtol=1e-4, atol=1e-4)
 
 
+@pytest.mark.parametrize("K,epi", [(1600, 3), (1600, 5), (333 * 8, 3), (64, 5)])
+def test_gemm_grouped_weight_gradients_vs_torch(K, epi):
+    """Several dW = dY^T X problems in one CTA-pair launch (the decoder's six per layer, plus ragged sizes): every problem's tiles
+    land in its own output, accumulate (epi 3) adds to what is there, store (epi 5) overwrites."""
+    torch.manual_seed(K + epi)
+    shapes = [(768, 3072), (3072, 768), (768, 768), (2304, 768), (200, 520), (768, 768), (8, 8)]
+    As = [(torch.randn(K, m, device=DEV) * 0.5).bfloat16() for m, _ in shapes]
+    Bs = [(torch.randn(K, n, device=DEV) * 0.5).bfloat16() for _, n in shapes]
+    Cs = [torch.randn(m, n, device=DEV) for m, n in shapes]
+    before = [c.clone() for c in Cs]
+    guard = [torch.full((m + 3, n + 8), 7.0, device=DEV) for m, n in shapes]     # the outputs live inside larger buffers: nothing outside is touched
+    for gbuf, c in zip(guard, Cs):
+        gbuf[:c.shape[0], :c.shape[1]] = c
+    views = [gbuf[:c.shape[0], :c.shape[1]] for gbuf, c in zip(guard, Cs)]
+    cabi.gemm_grouped_mn(As, Bs, views, epi=epi, alpha=0.5)
+    for i, (a, b) in enumerate(zip(As, Bs)):
+        ref = 0.5 * (a.float().t() @ b.float()) + (before[i] if epi == 3 else 0.0)
+        assert rel_err(views[i], ref) < 2e-3, (i, shapes[i])
+        assert (guard[i][shapes[i][0]:, :] == 7.0).all() and (guard[i][:, shapes[i][1]:] == 7.0).all(), i
+
+
 @pytest.mark.parametrize("S,Lt,B,masked", [(33, 20, 3, True), (40, 1, 7, False), (64, 32, 4, True), (56, 20, 200, True), (47, 9, 26, False)])
 def test_attention_tcgen05_shapes_vs_torch(S, Lt, B, masked):
     """The whole shape range the tcgen05 encoder kernels accept (33..64 positions, 1..32 text tokens, fewer and more items than

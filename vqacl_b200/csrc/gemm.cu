@@ -229,6 +229,58 @@ static int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmA
   return 0;
 }
 
+int gemm_bf16_grouped_mn(const GemmGroupProblem* probs, int n, int K, int epi, float alpha, int sm_limit, cudaStream_t stream) {
+  VQ_CHECK(n >= 1 && n <= GEMM_GROUP_MAX, "gemm_grouped: %d problems (1..%d)", n, GEMM_GROUP_MAX);
+  VQ_CHECK(epi == EPI_ATOMIC_F32 || epi == EPI_F32, "gemm_grouped: fp32 store / accumulate epilogues only");
+  VQ_CHECK(K > 0, "gemm_grouped: empty contraction");
+  (void)num_sms();
+  VQ_CHECK(g_pair_enabled, "gemm_grouped: needs the CTA-pair kernel");
+  GemmGroupMaps maps;
+  GemmGroup grp{};
+  grp.n = n;
+  int total = 0;
+  for (int i = 0; i < n; ++i) {
+    const GemmGroupProblem& q = probs[i];
+    VQ_CHECK(q.M > 0 && q.N > 0 && q.N % 8 == 0 && q.ldc % 8 == 0 && q.A && q.B && q.C, "gemm_grouped: bad problem %d (%d x %d)", i, q.M, q.N);
+    if (make_tmap(&maps.a[i], q.A, q.M, K, q.lda, 64, GEMM_BK)) return 1;
+    if (make_tmap(&maps.b[i], q.B, q.N, K, q.ldb, 64, GEMM_BK)) return 1;
+    grp.M[i] = q.M; grp.N[i] = q.N; grp.ldc[i] = q.ldc; grp.C[i] = q.C;
+    grp.tiles_n[i] = (q.N + GEMM2_BN - 1) / GEMM2_BN;
+    grp.tile_start[i] = total;
+    total += ((q.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM)) * grp.tiles_n[i];
+  }
+  for (int i = n; i <= GEMM_GROUP_MAX; ++i) grp.tile_start[i] = total;
+  for (int i = n; i < GEMM_GROUP_MAX; ++i) { maps.a[i] = maps.a[0]; maps.b[i] = maps.b[0]; }
+  GemmArgs args{};
+  args.epi = epi; args.K = K; args.alpha = alpha; args.splits = 1;
+  args.M = probs[0].M; args.N = probs[0].N; args.C = probs[0].C; args.ldc = probs[0].ldc;   // unused by the grouped body
+  auto kern = gemm_bf16_tcgen05_2cta_grouped_kernel<true, true>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int max_pairs = gemm_sms(sm_limit) / 2;
+  const int pairs = total < max_pairs ? total : max_pairs;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Gemm2Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = g_vq_pdl;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  VQ_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, args, grp));
+  ++g_vq_launches;
+  return 0;
+}
+
 static int dispatch_pair(const GemmOperand& A, const GemmOperand& B, const GemmArgs& args, cudaStream_t stream) {
   CUtensorMap ta, tb;
   if (!A.mn_major) {
@@ -334,6 +386,15 @@ int gemm_bf16(const GemmOperand& A, const GemmOperand& B, GemmArgs args, int for
 // ------------------------------------------------------------------------------------------
 // C-ABI entry (see include/vqacl_b200.h)
 // ------------------------------------------------------------------------------------------
+/* grouped weight-gradient GEMM: problem i is C[i][M[i], N[i]] (+)= A[i]^T-stored [K, M[i]] x B[i] stored [K, N[i]] */
+extern "C" int vqacl_gemm_bf16_grouped_mn(int n, const void* const* A, const int* lda, const void* const* B, const int* ldb, void* const* C,
+                                          const int* ldc, const int* M, const int* N, int K, int epi, float alpha, void* stream) {
+  VQ_CHECK(n >= 1 && n <= vq::GEMM_GROUP_MAX, "gemm_grouped: %d problems", n);
+  vq::GemmGroupProblem pr[vq::GEMM_GROUP_MAX];
+  for (int i = 0; i < n; ++i) pr[i] = vq::GemmGroupProblem{A[i], lda[i], B[i], ldb[i], C[i], ldc[i], M[i], N[i]};
+  return vq::gemm_bf16_grouped_mn(pr, n, K, epi, alpha, 0, reinterpret_cast<cudaStream_t>(stream));
+}
+
 extern "C" int vqacl_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int ldb, int b_mn_major, void* C,
                                int ldc, const void* R, int ldr, int M, int N, int K, int epi, float alpha, int splits,
                                int force_bn, void* stream) {

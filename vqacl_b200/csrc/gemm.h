@@ -12,6 +12,15 @@ struct GemmOperand {
 
 // C[M,N] (+)= A[M,K] * B[N,K]^T with the epilogue in args.epi. force_bn = 0 picks the N tile by occupancy.
 int gemm_bf16(const GemmOperand& A, const GemmOperand& B, GemmArgs args, int force_bn, cudaStream_t stream);
+// n <= GEMM_GROUP_MAX independent weight-gradient problems C_i[M_i, N_i] += A_i[M_i, K] * B_i[N_i, K]^T (both operands MN-major,
+// shared K) as ONE launch of the CTA-pair kernel; epi = EPI_ATOMIC_F32 (accumulate) or EPI_F32 (store)
+struct GemmGroupProblem {
+  const void* A; int lda;     // stored [K, M]
+  const void* B; int ldb;     // stored [K, N]
+  void* C; int ldc;           // fp32 [M, N]
+  int M, N;
+};
+int gemm_bf16_grouped_mn(const GemmGroupProblem* probs, int n, int K, int epi, float alpha, int sm_limit, cudaStream_t stream);
 bool gemm_vis_tail_on();        // VisualEmbedding as ONE launch (GEMM + row tail 2); VQACL_VIS_FUSED=0 keeps GEMM + vis_embed_fwd_kernel
 bool gemm_row_tail_ok(int M);   // fold a row-wise follow-up (RMSNorm) into a GEMM with 768 output columns? (see gemm.cu)
 void gemm_tmap_cache_clear();

@@ -72,6 +72,20 @@ struct GemmArgs {
                         // stream's kernel — then finds the work list drained instead of running its whole static share afterwards.
 };
 
+// A group of up to GEMM_GROUP_MAX independent problems that share K, the operand majors and the epilogue, computed by ONE launch
+// of the CTA-pair kernel (its work list is the concatenation of the problems' 256 x 256 tiles; no split-K, no row tail).
+// Made for the decoder's weight gradients: six dW = dY^T X per layer with K = B*T = 1 600 rows, 18-72 tiles each — alone each
+// is a launch whose pipeline fill and drain outweigh its 25 k-blocks (25 % of the tensor peak, measured), together they are
+// 126 pair tiles = 1.7 waves of one persistent launch.
+constexpr int GEMM_GROUP_MAX = 8;
+struct GemmGroup {
+  int n;
+  int M[GEMM_GROUP_MAX], N[GEMM_GROUP_MAX], ldc[GEMM_GROUP_MAX], tiles_n[GEMM_GROUP_MAX];
+  int tile_start[GEMM_GROUP_MAX + 1];     // prefix sums of the problems' pair-tile counts
+  void* C[GEMM_GROUP_MAX];
+};
+struct GemmGroupMaps { CUtensorMap a[GEMM_GROUP_MAX], b[GEMM_GROUP_MAX]; };
+
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 #ifndef GEMM_EPI_WARPS_N
@@ -566,9 +580,8 @@ struct Gemm2Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + GEMM_EPI_WARPS * EPI_TILE_BYTES;
 };
 
-template <bool A_MN, bool B_MN>
-__global__ void __maxnreg__(GEMM_MAXREG)
-gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs p) {
+template <bool A_MN, bool B_MN, bool GROUPED>
+VQ_DEVINL void gemm_pair_body(const CUtensorMap* tmA_, const CUtensorMap* tmB_, const GemmArgs& p, const GemmGroup* grp) {
   vq_pdl_trigger();
   using Cfg = Gemm2Cfg;
   constexpr int STAGES = Cfg::STAGES;
@@ -596,15 +609,34 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
   const int tiles_m = (p.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
   const int tiles_n = (p.N + BN - 1) / BN;
   const int kblocks = (p.K + GEMM_BK - 1) / GEMM_BK;
-  const int kb_per_split = (kblocks + p.splits - 1) / p.splits;
-  const int tiles_mn = tiles_m * tiles_n;
-  // work items: one (split, m, n) tile each — or, with a row tail, one 256-row block each = `run` consecutive tiles (n fastest)
-  const int run = p.tail ? tiles_n : 1;
-  const int total_work = p.tail ? tiles_m : tiles_mn * p.splits;
+  const int kb_per_split = GROUPED ? kblocks : (kblocks + p.splits - 1) / p.splits;
+  const int tiles_mn = GROUPED ? grp->tile_start[grp->n] : tiles_m * tiles_n;
+  // work items: one (split, m, n) tile each — or, with a row tail, one 256-row block each = `run` consecutive tiles (n fastest);
+  // grouped: one tile of one problem each
+  const int run = (!GROUPED && p.tail) ? tiles_n : 1;
+  const int total_work = GROUPED ? tiles_mn : (p.tail ? tiles_m : tiles_mn * p.splits);
+  // work index -> (problem, split, tile coordinates)
+  auto decode = [&](int w, int& g, int& split, int& m_blk, int& n_blk) {
+    if (GROUPED) {
+      g = 0;
+      while (w >= grp->tile_start[g + 1]) ++g;
+      const int t = w - grp->tile_start[g];
+      m_blk = t / grp->tiles_n[g]; n_blk = t - m_blk * grp->tiles_n[g];
+      split = 0;
+    } else {
+      g = 0;
+      split = w / tiles_mn;
+      const int t = w - split * tiles_mn;
+      m_blk = t / tiles_n; n_blk = t - m_blk * tiles_n;
+    }
+  };
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
+    const int nmaps = GROUPED ? grp->n : 1;
+    for (int g = 0; g < nmaps; ++g) {
+      tma_prefetch_desc(tmA_ + g);
+      tma_prefetch_desc(tmB_ + g);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -627,7 +659,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
   vq_pdl_wait();
-  const bool dyn = p.sched != nullptr;
+  const bool dyn = !GROUPED && p.sched != nullptr;
   // next work item of a consumer role (anything but the leader's producer lane): read the ring slot, release it on the leader
   auto next_work = [&](int& it) -> int {
     const int slot = it % SCHED_DEPTH;
@@ -665,9 +697,10 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
       };
       for (int wi = dyn ? fetch() : pair; wi < total_work; wi = dyn ? fetch() : wi + npairs)
       for (int w = wi * run; w < wi * run + run; ++w) {
-        const int split = w / tiles_mn;
-        const int t = w - split * tiles_mn;
-        const int m_blk = t / tiles_n, n_blk = t - m_blk * tiles_n;
+        int g, split, m_blk, n_blk;
+        decode(w, g, split, m_blk, n_blk);
+        const CUtensorMap& tmA = tmA_[g];
+        const CUtensorMap& tmB = tmB_[g];
         const int m0 = m_blk * 2 * GEMM_BM + (int)rank * GEMM_BM;        // this CTA's 128 rows of the 256-row tile
         const int n0 = n_blk * BN + (int)rank * (BN / 2);                // this CTA's half of the B tile
         const int kb0 = split * kb_per_split;
@@ -716,7 +749,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
       int it = 0;
       for (int wi = dyn ? next_work(it) : pair; wi < total_work; wi = dyn ? next_work(it) : wi + npairs)
       for (int w = wi * run; w < wi * run + run; ++w) {
-        const int split = w / tiles_mn;
+        const int split = GROUPED ? 0 : w / tiles_mn;
         const int kb0 = split * kb_per_split;
         const int kb1 = min(kblocks, kb0 + kb_per_split);
         mbar_wait(&tempty_bar[astage], aphase ^ 1);
@@ -758,13 +791,18 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
     };
     for (int wi = dyn ? warp_next() : pair; wi < total_work; wi = dyn ? warp_next() : wi + npairs) {
     for (int w = wi * run; w < wi * run + run; ++w) {
-      const int split = w / tiles_mn;
-      const int t = w - split * tiles_mn;
-      const int m_blk = t / tiles_n, n_blk = t - m_blk * tiles_n;
+      int g, split, m_blk, n_blk;
+      decode(w, g, split, m_blk, n_blk);
       const bool has_k = split * kb_per_split < kblocks;
       const int row_base = m_blk * 2 * GEMM_BM + (int)rank * GEMM_BM + q * 32;
       const uint32_t t_base = tmem_base + astage * BN + ((uint32_t)(q * 32) << 16);
       uint64_t* tf = &tfull_bar[astage];
+      if constexpr (GROUPED) {
+        GemmArgs pg = p;                 // the epilogue is inlined: only the fields it reads exist
+        pg.M = grp->M[g]; pg.N = grp->N[g]; pg.C = grp->C[g]; pg.ldc = grp->ldc[g];
+        if (p.epi == EPI_ATOMIC_F32) gemm_epilogue_tile<EPI_ATOMIC_F32, BN>(pg, t_base, stg, row_base, n_blk * BN, half, lane, has_k, tf, aphase);
+        else gemm_epilogue_tile<EPI_F32, BN>(pg, t_base, stg, row_base, n_blk * BN, half, lane, has_k, tf, aphase);
+      } else
       switch (p.epi) {
         case EPI_BF16: gemm_epilogue_tile<EPI_BF16, BN>(p, t_base, stg, row_base, n_blk * BN, half, lane, has_k, tf, aphase); break;
         case EPI_RELU_BF16: gemm_epilogue_tile<EPI_RELU_BF16, BN>(p, t_base, stg, row_base, n_blk * BN, half, lane, has_k, tf, aphase); break;
@@ -779,7 +817,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
       if (lane == 0) mbar_arrive_cluster(&tempty_bar[astage], 0);   // the leader's MMA lane owns accumulator reuse
       if (++astage == 2) { astage = 0; aphase ^= 1; }
     }
-    if (p.tail) {
+    if (!GROUPED && p.tail) {
       // ---- row tail: this CTA's 128 rows of block wi are complete in C (written by these 8 warps) and still in L2
       asm volatile("bar.sync 1, %0;" ::"n"(GEMM_EPI_WARPS * 32) : "memory");
       const int row0 = wi * 2 * GEMM_BM + (int)rank * GEMM_BM;
@@ -795,6 +833,18 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
     tc_fence_after();
     tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
   }
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __maxnreg__(GEMM_MAXREG)
+gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs p) {
+  gemm_pair_body<A_MN, B_MN, false>(&tmA, &tmB, p, nullptr);
+}
+// grouped form: GemmArgs carries K, the epilogue and alpha; M / N / C / ldc come from the group table
+template <bool A_MN, bool B_MN>
+__global__ void __maxnreg__(GEMM_MAXREG)
+gemm_bf16_tcgen05_2cta_grouped_kernel(const __grid_constant__ GemmGroupMaps maps, const GemmArgs p, const __grid_constant__ GemmGroup grp) {
+  gemm_pair_body<A_MN, B_MN, true>(maps.a, maps.b, p, &grp);
 }
 
 }  // namespace vq
