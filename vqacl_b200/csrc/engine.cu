@@ -259,6 +259,9 @@ static int g_dec_dw_sms = [] { const char* ev = getenv("VQACL_DEC_DW_SMS"); retu
 // split-K factor of the decoder's deep dX GEMMs (wi: K = d_ff, qkv: K = 3 d) into an fp32 buffer the RMSNorm backward reads and
 // clears. Default 1 = single-pass bf16: 3 slices make the two GEMMs 2x faster alone (126 instead of 42 CTAs streaming operands)
 // but the step 0.1-0.2 ms slower — they then compete with the side stream's dW GEMMs for the same SMs
+// the decoder's six weight gradients of a layer as ONE grouped launch at the end of the layer (VQACL_DEC_DW_GROUPED=0: one launch
+// each, right after the kernel that produced its dY)
+static int g_dec_dw_grouped = [] { const char* ev = getenv("VQACL_DEC_DW_GROUPED"); return ev ? atoi(ev) : 1; }();   // 2: on the main stream
 static int g_dec_dx_splits = [] { const char* ev = getenv("VQACL_DEC_DX_SPLITS"); return ev && atoi(ev) > 0 ? atoi(ev) : 1; }();
 // dX[rows, n_in] = dY[rows, n_out] * W[n_out, n_in]      (W stored row-major -> MN-major B operand)
 static int gemm_dx(const bf16* dY, int lddy, const bf16* Wt, int n_out, int n_in, void* C, int ldc, int rows, int epi, cudaStream_t st,
@@ -653,12 +656,25 @@ static int backward(Engine& e, const float* w_rows, const float* gscale, int acc
     bf16* gdb_2 = w.gdb_ring[(e.gdb_i + 2) % (3 * RING)];
     bf16* gdb_out = w.gdb_ring[(e.gdb_i + 3) % (3 * RING)];
     e.gdb_i = (e.gdb_i + 3) % (3 * RING);
+    // Weight gradients: with M = B*T rows of contraction each of the six dW GEMMs is a launch of 18-72 tiles whose pipeline fill
+    // and drain outweigh its 25 k-blocks, and whose persistent CTAs (225 KB of shared memory) keep the chain's next kernel off
+    // the SMs they hold. Grouped: the six problems are queued here and go out as ONE launch of 126 CTA-pair tiles on the side
+    // stream at the end of the layer (their dY operands live in rings three layers deep).
+    const bool grouped = g_dec_dw_grouped != 0;
+    GemmGroupProblem dwq[6];
+    int ndw = 0;
+    auto dw = [&](const bf16* dY, int lddy, const bf16* X, int ldx, float* dWt, int n_out, int n_in) -> int {
+      if (grouped) {
+        dwq[ndw++] = GemmGroupProblem{dY, lddy, X, ldx, dWt, n_in, n_out, n_in};
+        return 0;
+      }
+      VQ_TRY(fork());
+      return gemm_dw(dY, lddy, X, ldx, dWt, n_out, n_in, Md, sd, g_dec_dw_sms);
+    };
     // FFN
-    VQ_TRY(fork());
-    VQ_TRY(gemm_dw(gdb_in, d, w.dh[l], f, e.G + P.wo, d, f, Md, sd, g_dec_dw_sms));
+    VQ_TRY(dw(gdb_in, d, w.dh[l], f, e.G + P.wo, d, f));
     VQ_TRY(gemm_dx(gdb_in, d, e.W + P.wo, d, f, w.t_dh[ri], f, Md, EPI_RELUBWD_BF16, st, w.dhmask[l], (f + 31) / 32, e.drop(site_dec(l, 4)).inv_keep));
-    VQ_TRY(fork());
-    VQ_TRY(gemm_dw(w.t_dh[ri], f, w.dn3[l], d, e.G + P.wi, f, d, Md, sd, g_dec_dw_sms));
+    VQ_TRY(dw(w.t_dh[ri], f, w.dn3[l], d, e.G + P.wi, f, d));
     // The deep contractions of the chain (dX of wi: K = d_ff, dX of qkv: K = 3 d) are split-K: with M = B*T rows there are only
     // 39-78 output tiles, and a CTA's operand stream is bound by its SM's ~120 GB/s L2 port (measured: 3.2 us + 0.27 us per 32 KB
     // k-block, tools/gemm_small_sweep.py) — three K slices per tile engage 126 SMs instead of 42. The slices meet in an fp32
@@ -672,8 +688,7 @@ static int backward(Engine& e, const float* w_rows, const float* gscale, int acc
     q.dw = e.G + P.ln2; q.M = Md; q.eps = c.eps; q.scale = 1.f; q.consumer = e.drop(site_dec(l, 3)); q.consumer_cols = d;
     VQ_TRY(rmsnorm_bwd(q, st));
     // cross attention
-    VQ_TRY(fork());
-    VQ_TRY(gemm_dw(gdb_1, d, w.cao[l], d, e.G + P.co, d, d, Md, sd, g_dec_dw_sms));
+    VQ_TRY(dw(gdb_1, d, w.cao[l], d, e.G + P.co, d, d));
     VQ_TRY(gemm_dx(gdb_1, d, e.W + P.co, d, d, w.t_d768, d, Md, EPI_BF16, st));
     AttnArgs x{};
     x.q = w.cq[l]; x.ldq = d; x.k = w.kv_all + (size_t)l * 2 * d; x.v = x.k + d; x.ldk = x.ldv = ldkv;
@@ -683,15 +698,13 @@ static int backward(Engine& e, const float* w_rows, const float* gscale, int acc
     x.o_saved = w.cao[l];
     x.dO = w.t_d768; x.dq = w.t_dcq[ri]; x.lddq = d; x.dk = w.dkv_all + (size_t)l * 2 * d; x.dv = x.dk + d; x.lddk = x.lddv = ldkv;
     VQ_TRY(attn_bwd(x, st));
-    VQ_TRY(fork());
-    VQ_TRY(gemm_dw(w.t_dcq[ri], d, w.dn2[l], d, e.G + P.cq, d, d, Md, sd, g_dec_dw_sms));
+    VQ_TRY(dw(w.t_dcq[ri], d, w.dn2[l], d, e.G + P.cq, d, d));
     VQ_TRY(gemm_dx(w.t_dcq[ri], d, e.W + P.cq, d, d, w.t_d768, d, Md, EPI_BF16, st));
     q.x = w.y[3 * l + 1]; q.w = e.P + P.ln1; q.dw = e.G + P.ln1; q.consumer = e.drop(site_dec(l, 1)); q.gb_out = gdb_2;
     q.dn_f32 = nullptr; q.dn_zero = 0;       // dX of cq (K = d) stays a bf16 single pass
     VQ_TRY(rmsnorm_bwd(q, st));
     // self attention
-    VQ_TRY(fork());
-    VQ_TRY(gemm_dw(gdb_2, d, w.dao[l], d, e.G + P.o, d, d, Md, sd, g_dec_dw_sms));
+    VQ_TRY(dw(gdb_2, d, w.dao[l], d, e.G + P.o, d, d));
     VQ_TRY(gemm_dx(gdb_2, d, e.W + P.o, d, d, w.t_d768, d, Md, EPI_BF16, st));
     AttnArgs a{};
     a.q = w.dqkv[l]; a.k = w.dqkv[l] + d; a.v = w.dqkv[l] + 2 * d; a.ldq = a.ldk = a.ldv = 3 * d;
@@ -702,14 +715,19 @@ static int backward(Engine& e, const float* w_rows, const float* gscale, int acc
     a.dO = w.t_d768; a.dq = w.t_dqkv[ri]; a.dk = w.t_dqkv[ri] + d; a.dv = w.t_dqkv[ri] + 2 * d; a.lddq = a.lddk = a.lddv = 3 * d;
     a.d_rel_table = e.G + e.o_dec_rel;
     VQ_TRY(attn_bwd(a, st));
-    VQ_TRY(fork());
-    VQ_TRY(gemm_dw(w.t_dqkv[ri], 3 * d, w.dn1[l], d, e.G + P.qkv, 3 * d, d, Md, sd, g_dec_dw_sms));
+    VQ_TRY(dw(w.t_dqkv[ri], 3 * d, w.dn1[l], d, e.G + P.qkv, 3 * d, d));
     if (dsplit > 1) VQ_TRY(gemm_dx(w.t_dqkv[ri], 3 * d, e.W + P.qkv, 3 * d, d, w.t_d768_f32, d, Md, EPI_ATOMIC_F32, st, nullptr, 0, 1.f, dsplit));
     else VQ_TRY(gemm_dx(w.t_dqkv[ri], 3 * d, e.W + P.qkv, 3 * d, d, w.t_d768, d, Md, EPI_BF16, st));
     if (dsplit > 1) { q.dn_f32 = w.t_d768_f32; q.dn_zero = 1; }
     q.x = w.y[3 * l]; q.w = e.P + P.ln0; q.dw = e.G + P.ln0; q.gb_out = gdb_out;
     q.consumer = l > 0 ? e.drop(site_dec(l - 1, 5)) : Dropout();
     VQ_TRY(rmsnorm_bwd(q, st));
+    if (grouped && g_dec_dw_grouped == 2) {
+      VQ_TRY(gemm_bf16_grouped_mn(dwq, ndw, Md, EPI_ATOMIC_F32, 1.f, g_dec_dw_sms, st));
+    } else if (grouped) {
+      VQ_TRY(fork());       // every dY of the layer has been produced
+      VQ_TRY(gemm_bf16_grouped_mn(dwq, ndw, Md, EPI_ATOMIC_F32, 1.f, g_dec_dw_sms, sd));
+    }
     VQ_TRY(layer_end());
     VQ_TRY(stage_done(Ld - l));
   }
