@@ -249,23 +249,42 @@ VQ_DEVINL void scores_tile(float (&s)[NKT][4], const __nv_bfloat16 (*sq)[AT_P], 
   }
 }
 
+// Bias / key-mask header of a problem in two halves: `fetch` issues every global load into registers, `store` writes them to
+// shared memory. The tile loads go BETWEEN the two: a gather that feeds a shared store directly (the single-function form this
+// replaces) stalls the thread for one memory round trip per loop iteration — with one warp per problem that was 6 dependent
+// round trips before the first tile load was even issued (ncu: stall_long_sb on every STS of the header).
 template <int NW>
-VQ_DEVINL void load_bias_mask(float* sbias, float* skmask, const AttnArgs& p, const AttnBuckets& bk, int b, int h, int tid) {
-  constexpr int T = NW * 32;
-  if (p.rel_mode) {
+struct BiasMaskRegs {
+  static constexpr int T = NW * 32, NB = (2 * AT_S + T - 1) / T, NK = (AT_S + T - 1) / T;
+  float bias[NB], kmask[NK];
+  VQ_DEVINL void fetch(const AttnArgs& p, const AttnBuckets& bk, int b, int h, int tid) {
 #pragma unroll
-    for (int it = 0; it < (2 * AT_S + T - 1) / T; ++it) {
+    for (int it = 0; it < NB; ++it) {
       const int r = it * T + tid;
-      if (r < 2 * AT_S - 1) sbias[r] = p.rel_table[(int)bk.b[r] * p.H + h];
+      bias[it] = (p.rel_mode && r < 2 * AT_S - 1) ? p.rel_table[(int)bk.b[r] * p.H + h] : 0.f;
+    }
+    // key-side additive term: padding mask for existing keys, -inf beyond Sk
+#pragma unroll
+    for (int it = 0; it < NK; ++it) {
+      const int j = it * T + tid;
+      kmask[it] = j < p.Sk ? (p.keymask ? p.keymask[(size_t)b * p.Sk + j] : 0.f) : -INFINITY;
     }
   }
-  // key-side additive term: padding mask for existing keys, -inf beyond Sk
+  VQ_DEVINL void store(float* sbias, float* skmask, const AttnArgs& p, int tid) const {
+    if (p.rel_mode) {
 #pragma unroll
-  for (int it = 0; it < (AT_S + T - 1) / T; ++it) {
-    const int j = it * T + tid;
-    if (j < AT_S) skmask[j] = j < p.Sk ? (p.keymask ? p.keymask[(size_t)b * p.Sk + j] : 0.f) : -INFINITY;
+      for (int it = 0; it < NB; ++it) {
+        const int r = it * T + tid;
+        if (r < 2 * AT_S - 1) sbias[r] = bias[it];
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < NK; ++it) {
+      const int j = it * T + tid;
+      if (j < AT_S) skmask[j] = kmask[it];
+    }
   }
-}
+};
 
 struct AttnSmemF { float* bias; float* kmask; AttnTile q, k, v; };
 VQ_DEVINL AttnSmemF attn_carve_fwd(uint8_t* raw, int qrows, int krows) {
@@ -413,8 +432,10 @@ __global__ void __launch_bounds__(NW * 32 * HPC, NW == 4 ? 3 : 16 / (NW * HPC)) 
       const int ld[3] = {p.ldq, p.ldk, p.ldv};
       const int rows[3] = {p.Sq, p.Sk, p.Sk};
       const int fill[3] = {rows16(p.Sq), NKT * 8, NKT * 8};
-      load_bias_mask<NW>(sm.bias, sm.kmask, p, bk, b, h, tid);
+      BiasMaskRegs<NW> hdr;
+      hdr.fetch(p, bk, b, h, tid);
       load_heads<NW, 3>(dst, src, ld, rows, fill, tid);
+      hdr.store(sm.bias, sm.kmask, p, tid);
     }
     if (NW == 1) __syncwarp(); else __syncthreads();
     attn_fwd_compute<NW, NKT>(p, sm, vblk, b, h, warp, lane);
@@ -600,8 +621,10 @@ __global__ void __launch_bounds__(NW * 32 * HPC, NW == 4 ? 4 : 8 / HPC) attn_bwd
       const int ld[4] = {p.ldq, p.ldk, p.ldv, p.ldo};
       const int rows[4] = {p.Sq, p.Sk, p.Sk, p.Sq};
       const int fill[4] = {rows16(p.Sq), NKT * 8, NKT * 8, rows16(p.Sq)};
-      load_bias_mask<NW>(sm.bias, sm.kmask, p, bk, b, h, tid);
+      BiasMaskRegs<NW> hdr;
+      hdr.fetch(p, bk, b, h, tid);
       load_heads<NW, 4>(dst, src, ld, rows, fill, tid);
+      hdr.store(sm.bias, sm.kmask, p, tid);
     }
     for (int i = tid; i < 64; i += NW * 32) sm.dbucket[i] = 0.f;
     if (NW == 1) __syncwarp(); else __syncthreads();
@@ -649,8 +672,12 @@ __global__ void __launch_bounds__(KS_WARPS * 32, 8) attn_ks_fwd_kernel(const Att
     const int ld[3] = {p.ldq, p.ldk, p.ldv};
     const int rows[3] = {p.Sq, p.Sk, p.Sk};
     const int fill[3] = {16, AT_S, AT_S};
-    if (tid < AT_S) sm.kmask[tid] = tid < p.Sk ? (p.keymask ? p.keymask[(size_t)b * p.Sk + tid] : 0.f) : -INFINITY;
+    // the key-mask value is loaded into a register first and stored after the tile loads have been issued: a load feeding a
+    // shared store directly would stall this thread for a DRAM round trip before its tile loads even start
+    float kmv = -INFINITY;
+    if (tid < p.Sk) kmv = p.keymask ? p.keymask[(size_t)b * p.Sk + tid] : 0.f;
     load_heads<KS_WARPS, 3>(dst, src, ld, rows, fill, tid);
+    if (tid < AT_S) sm.kmask[tid] = kmv;
   }
   __syncthreads();
   const int k0 = warp * 16;   // this warp's keys
@@ -789,30 +816,36 @@ __global__ void __launch_bounds__(KS_WARPS * 32, 6) attn_ks_bwd_kernel(const Att
     const int ld[4] = {p.ldq, p.ldo, p.ldk, p.ldv};
     const int rows[4] = {p.Sq, p.Sq, p.Sk, p.Sk};
     const int fill[4] = {16, 16, AT_S, AT_S};
-    if (tid < AT_S) sm.kmask[tid] = tid < p.Sk ? (p.keymask ? p.keymask[(size_t)b * p.Sk + tid] : 0.f) : -INFINITY;
-    // D[q] = sum_d dO[q][d] * O[q][d]: 8 threads per query row, 8 columns each
+    float kmv = -INFINITY;
+    if (tid < p.Sk) kmv = p.keymask ? p.keymask[(size_t)b * p.Sk + tid] : 0.f;
+    // D[q] = sum_d dO[q][d] * O[q][d]: 8 threads per query row, 8 columns each. Its two loads are issued BEFORE the tile loads
+    // and consumed after them: one DRAM round trip for everything instead of two in a row at the head of a 7 us CTA.
+    const int qi = tid >> 3, c0 = (tid & 7) * 8;
+    uint4 da = make_uint4(0, 0, 0, 0), oa = make_uint4(0, 0, 0, 0);
+    float lse_q = INFINITY;                                                                    // rows >= Sq -> P = 0
+    if (qi < p.Sq) {
+      da = *reinterpret_cast<const uint4*>(p.dO + ((size_t)b * p.Sq + qi) * p.ldo + h * AT_D + c0);
+      oa = *reinterpret_cast<const uint4*>(p.o_saved + ((size_t)b * p.Sq + qi) * p.ldo + h * AT_D + c0);
+      if ((tid & 7) == 0) lse_q = p.lse[((size_t)b * p.H + h) * p.Sq + qi];
+    }
+    load_heads<KS_WARPS, 4>(dst, src, ld, rows, fill, tid);
+    if (tid < AT_S) sm.kmask[tid] = kmv;
     {
-      const int qi = tid >> 3, c0 = (tid & 7) * 8;
       float acc = 0.f;
-      if (qi < p.Sq) {
-        const uint4 a = *reinterpret_cast<const uint4*>(p.dO + ((size_t)b * p.Sq + qi) * p.ldo + h * AT_D + c0);
-        const uint4 o = *reinterpret_cast<const uint4*>(p.o_saved + ((size_t)b * p.Sq + qi) * p.ldo + h * AT_D + c0);
-        const uint32_t aa[4] = {a.x, a.y, a.z, a.w}, oo[4] = {o.x, o.y, o.z, o.w};
+      const uint32_t aa[4] = {da.x, da.y, da.z, da.w}, oo[4] = {oa.x, oa.y, oa.z, oa.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 x = unpack_bf16(aa[j]), y = unpack_bf16(oo[j]);
-          acc += x.x * y.x + x.y * y.y;
-        }
+      for (int j = 0; j < 4; ++j) {
+        const float2 x = unpack_bf16(aa[j]), y = unpack_bf16(oo[j]);
+        acc += x.x * y.x + x.y * y.y;
       }
       acc += __shfl_xor_sync(0xffffffffu, acc, 1);
       acc += __shfl_xor_sync(0xffffffffu, acc, 2);
       acc += __shfl_xor_sync(0xffffffffu, acc, 4);
       if ((tid & 7) == 0) {
         sm.D[qi] = acc;
-        sm.lse[qi] = qi < p.Sq ? p.lse[((size_t)b * p.H + h) * p.Sq + qi] : INFINITY;   // rows >= Sq -> P = 0
+        sm.lse[qi] = lse_q;
       }
     }
-    load_heads<KS_WARPS, 4>(dst, src, ld, rows, fill, tid);
   }
   __syncthreads();
   const int k0 = warp * 16;
