@@ -445,8 +445,11 @@ __global__ void __launch_bounds__(NW * 32 * HPC, NW == 4 ? 3 : 16 / (NW * HPC)) 
 struct AttnSmemB { float* bias; float* kmask; float* dbucket; AttnTile q, dO, P, dS, k, v; };
 
 // backward of one problem whose q / dO / k / v tiles (and bias header, zeroed dbucket) are in sm; P and dS are scratch tiles
+// lse_pre: the saved log-sum-exp of this lane's two query rows (rows m0 + g and m0 + g + 8 of its warp's block; +inf beyond
+// Sq), fetched by the caller together with the tile loads so that no global round trip sits in the middle of the math
 template <int NW, int NKT>
-VQ_DEVINL void attn_bwd_compute(const AttnArgs& p, const AttnBuckets& bk, const AttnSmemB& sm, int vblk, int b, int h, int tid) {
+VQ_DEVINL void attn_bwd_compute(const AttnArgs& p, const AttnBuckets& bk, const AttnSmemB& sm, int vblk, int b, int h, int tid,
+                                const float (&lse_pre)[2]) {
   const int warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   const int nqk = (p.Sq + 15) >> 4;   // query blocks of 16
@@ -455,12 +458,7 @@ VQ_DEVINL void attn_bwd_compute(const AttnArgs& p, const AttnBuckets& bk, const 
   if (m0 < p.Sq) {
     float s[NKT][4];
     scores_tile<NKT>(s, sm.q, sm.k, sm.bias, sm.kmask, p, m0, lane);
-    float lse[2];
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const int qi = m0 + g + r * 8;
-      lse[r] = qi < p.Sq ? p.lse[((size_t)b * p.H + h) * p.Sq + qi] : INFINITY;  // rows >= Sq -> P = 0
-    }
+    const float lse[2] = {lse_pre[0], lse_pre[1]};                               // rows >= Sq: +inf -> P = 0
     // dPd = dO V^T
     float dp[NKT][4];
 #pragma unroll
@@ -614,6 +612,7 @@ __global__ void __launch_bounds__(NW * 32 * HPC, NW == 4 ? 4 : 8 / HPC) attn_bwd
     sm.k = sm.dS + rows16(p.Sq);
     sm.v = sm.k + NKT * 8;
     const int b = vblk / p.H, h = vblk % p.H;
+    float lse_pre[2];
     {
       const AttnTile dst[4] = {sm.q, sm.k, sm.v, sm.dO};
       const __nv_bfloat16* const src[4] = {p.q + (size_t)b * p.Sq * p.ldq + h * AT_D, p.k + (size_t)b * p.Sk * p.ldk + h * AT_D,
@@ -623,12 +622,17 @@ __global__ void __launch_bounds__(NW * 32 * HPC, NW == 4 ? 4 : 8 / HPC) attn_bwd
       const int fill[4] = {rows16(p.Sq), NKT * 8, NKT * 8, rows16(p.Sq)};
       BiasMaskRegs<NW> hdr;
       hdr.fetch(p, bk, b, h, tid);
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int qi = (tid >> 5) * 16 + ((tid & 31) >> 2) + r * 8;
+        lse_pre[r] = qi < p.Sq ? p.lse[((size_t)b * p.H + h) * p.Sq + qi] : INFINITY;
+      }
       load_heads<NW, 4>(dst, src, ld, rows, fill, tid);
       hdr.store(sm.bias, sm.kmask, p, tid);
     }
     for (int i = tid; i < 64; i += NW * 32) sm.dbucket[i] = 0.f;
     if (NW == 1) __syncwarp(); else __syncthreads();
-    attn_bwd_compute<NW, NKT>(p, bk, sm, vblk, b, h, tid);
+    attn_bwd_compute<NW, NKT>(p, bk, sm, vblk, b, h, tid, lse_pre);
   }
 }
 
