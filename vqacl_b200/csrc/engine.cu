@@ -660,7 +660,7 @@ static int backward(Engine& e, const float* w_rows, const float* gscale, int acc
     // and drain outweigh its 25 k-blocks, and whose persistent CTAs (225 KB of shared memory) keep the chain's next kernel off
     // the SMs they hold. Grouped: the six problems are queued here and go out as ONE launch of 126 CTA-pair tiles on the side
     // stream at the end of the layer (their dY operands live in rings three layers deep).
-    const bool grouped = g_dec_dw_grouped != 0;
+    const bool grouped = g_dec_dw_grouped != 0 && gemm_pair_on();
     GemmGroupProblem dwq[6];
     int ndw = 0;
     auto dw = [&](const bf16* dY, int lddy, const bf16* X, int ldx, float* dWt, int n_out, int n_in) -> int {

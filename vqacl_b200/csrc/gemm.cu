@@ -142,6 +142,10 @@ static int gemm_sms(int call_limit) {
 // Is folding a row tail into an M-row GEMM with 768 output columns a good deal? In the tail mode a CTA pair owns whole 256-row
 // blocks, so the kernel's parallelism is ceil(M / 256) pairs instead of 3x as many tiles: only when the blocks fill the pairs
 // about as well as the tiles would (B = 320: 70 blocks on 74 pairs either way).
+bool gemm_pair_on() {
+  (void)num_sms();
+  return g_pair_enabled != 0;
+}
 bool gemm_vis_tail_on() {
   static const int on = [] { const char* e = getenv("VQACL_VIS_FUSED"); return (e && e[0] == '0') ? 0 : 1; }();
   (void)num_sms();

@@ -21,6 +21,7 @@ struct GemmGroupProblem {
   int M, N;
 };
 int gemm_bf16_grouped_mn(const GemmGroupProblem* probs, int n, int K, int epi, float alpha, int sm_limit, cudaStream_t stream);
+bool gemm_pair_on();            // CTA-pair kernel available (VQACL_GEMM_PAIR=0 turns it off for A/B runs): needed by the grouped form
 bool gemm_vis_tail_on();        // VisualEmbedding as ONE launch (GEMM + row tail 2); VQACL_VIS_FUSED=0 keeps GEMM + vis_embed_fwd_kernel
 bool gemm_row_tail_ok(int M);   // fold a row-wise follow-up (RMSNorm) into a GEMM with 768 output columns? (see gemm.cu)
 void gemm_tmap_cache_clear();
