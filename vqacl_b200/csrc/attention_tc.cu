@@ -28,7 +28,6 @@ namespace vq {
 
 constexpr int AT_S_TC = 64;                          // positions per head tile
 constexpr int TC_P_BYTES = 2 * 16384;               // two K-atoms (keys of head h | keys of head h+1), each 128 rows x 128 B
-constexpr int TC_THREADS = 192;                     // backward kernel: warps 0-3 rows, 4 producer, 5 MMA
 constexpr int TC_TMEM_COLS = 512;
 
 // ---- forward: small CTAs (2 x 48 KB of shared memory, 128 TMEM columns, <= 128 registers) so that TWO are resident per SM;
@@ -366,21 +365,16 @@ struct AttnTcBwdArgs {
   uint32_t drop_thr; float drop_inv_keep; uint32_t seed;
 };
 
-VQ_DEVINL void store_row16(__nv_bfloat16* dst, const uint32_t (&a)[16]) {
-  uint4* d4 = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-  for (int c = 0; c < 2; ++c)
-    d4[c] = make_uint4(pack_bf16(__uint_as_float(a[8 * c]), __uint_as_float(a[8 * c + 1])), pack_bf16(__uint_as_float(a[8 * c + 2]), __uint_as_float(a[8 * c + 3])),
-                       pack_bf16(__uint_as_float(a[8 * c + 4]), __uint_as_float(a[8 * c + 5])), pack_bf16(__uint_as_float(a[8 * c + 6]), __uint_as_float(a[8 * c + 7])));
-}
-
-// Structure (second version; the first — one thread per row, 4 row warps, epilogue in line — was correct but took 99.5 us
-// against the mma.sync kernel's 91 us): everything the forward kernel needed to reach parity, applied here. One CTA per SM
-// (two 64 KB stages + the P and dS tiles), so the warps come from FOUR threads per row: 16 row warps, each thread holds 16
-// scores and 16 dP values, the row's D = sum_j P dP is exchanged between its four threads through shared memory (128-thread
-// named barrier per TMEM lane quarter). S and dP of item n+1 are issued as soon as the rows hold item n's in registers; the
-// dQ / dK / dV rows of item n are stored while item n+1 is being computed (deferred epilogue); the per-item header (key mask,
-// bias, log-sum-exp) is prefetched into registers an item early so the TMA loads start the moment a stage frees.
+// Structure (history with timings and traces: profiles/r02_attention_tc.md; 99.5 us -> 69.9 us, mma.sync kernel: 91 us).
+// One CTA per SM (two 64 KB stages + the P and dS tiles), so the warps come from FOUR threads per row: 16 row warps, each
+// thread holds 16 scores and 16 dP values, the row's D = sum_j P dP is exchanged between its four threads through shared
+// memory (128-thread named barrier per TMEM lane quarter). S and dP of item n+1 are issued as soon as the rows hold item n's
+// in registers and its operands have landed; the gradient MMAs of item n as soon as its P / dS tiles are written — one issuer
+// thread polls both conditions. The dQ / dK / dV rows of item n are stored while item n+1 is being computed (deferred
+// epilogue), through per-warp swizzled staging tiles so that a store instruction covers 8 rows x 64 contiguous bytes; the
+// four warps without an output sum the bias-gradient diagonals meanwhile. The per-item header (key mask, bias, log-sum-exp)
+// is prefetched into registers an item early and written to shared memory when the rows release the slot, so that only the
+// TMA issue itself sits between "stage free" and "loads in flight".
 __global__ void __launch_bounds__(TCB_THREADS, 1)
 attn_enc_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO, const AttnTcBwdArgs p,
