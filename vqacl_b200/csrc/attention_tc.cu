@@ -15,10 +15,11 @@
 //   softmax rows -> P2[128 x 128] bf16 in shared memory, block diagonal (the off-diagonal halves are zeroed once and never
 //                                                 written), in the K-major 128-byte-swizzle operand layout
 //   O2[128 x 64]  = P2[128 x 128] V2[128 x 64]    V2 = the two heads' V slices stacked along the key axis (MN-major operand)
-// Roles: warps 0-3 softmax + epilogue (thread r = TMEM lane r = stacked query row r), warp 4 TMA producer (+ the per-item
-// bias / key-mask header), warp 5 MMA issuer and TMEM owner. Two shared-memory stages and two S accumulators let the loads
-// and the S MMA of item i+1 run under the softmax of item i; the O epilogue of item i-1 is folded into item i's softmax
-// phase so the softmax warps never wait for the O MMA.
+// Roles (forward): warps 0-7 softmax + epilogue, TWO threads per stacked query row (TMEM lane = row; each thread holds 32 of
+// the row's 64 scores), warp 8 per-item header + TMA producer + MMA issuer + TMEM owner; two shared-memory stages, two CTAs per
+// SM; the S MMA of item i+1 runs under the softmax of item i and the O epilogue of item i-1 is folded into item i's softmax
+// phase, so the softmax warps never wait for an MMA. O rows leave as 8 rows x 64 contiguous bytes per store instruction,
+// transposed through shared-memory slots the thread owns anyway. The backward kernel (further down) has its own role layout.
 #include "gemm.h"
 #include "ops.h"
 
