@@ -121,8 +121,16 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) rmsnorm_bwd_kernel(const RmsBw
     float x[RW_CHUNKS][4], dy[RW_CHUNKS][4];
     load_row_f32(x, a.x + (size_t)r * DM, lane);
     const int rd = out_row_of(r, a.in_rpb, a.out_rpb);
-    if (a.dn_f32) load_row_f32(dy, a.dn_f32 + (size_t)rd * a.ld_dn, lane);
-    else load_row_bf16(dy, a.dn + (size_t)rd * a.ld_dn, lane);
+    if (a.dn_f32) {
+      load_row_f32(dy, a.dn_f32 + (size_t)rd * a.ld_dn, lane);
+      if (a.dn_zero) {
+        float* zp = const_cast<float*>(a.dn_f32) + (size_t)rd * a.ld_dn;
+#pragma unroll
+        for (int j = 0; j < RW_CHUNKS; ++j) *reinterpret_cast<float4*>(zp + (lane + 32 * j) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    } else {
+      load_row_bf16(dy, a.dn + (size_t)rd * a.ld_dn, lane);
+    }
     if (a.dn2) {
       float d2[RW_CHUNKS][4];
       load_row_bf16(d2, a.dn2 + (size_t)rd * a.ld_dn2, lane);

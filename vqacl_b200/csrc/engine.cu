@@ -256,9 +256,15 @@ int64_t engine_carve(Engine& e, uint8_t* base, int B, int L, int N, int T) {
 // the main stream. Default 0 = no limit: 48 / 64 / 96 SMs measured 2.69 / 2.42 / 2.34 ms for the decoder-layer backward against
 // 2.36-2.40 ms unlimited (the side stream then falls behind and the chain waits for it at the two-layer lag) — kept as a switch
 static int g_dec_dw_sms = [] { const char* ev = getenv("VQACL_DEC_DW_SMS"); return ev ? atoi(ev) : 0; }();
+// split-K factor of the decoder's deep dX GEMMs (wi: K = d_ff, qkv: K = 3 d) into an fp32 buffer the RMSNorm backward reads and
+// clears (VQACL_DEC_DX_SPLITS=1: single-pass bf16). Three slices make the two GEMMs 2x faster alone (126 instead of 42 CTAs
+// streaming operands). Measured twice: with six separate dW launches on the side stream the step got 0.1-0.2 ms SLOWER (the
+// wide dX launches and the dW launches fought for SMs); with the dW GEMMs grouped into one launch per layer the decoder-layer
+// backward drops from 2.22-2.25 to 2.10-2.14 ms
 // the decoder's six weight gradients of a layer as ONE grouped launch at the end of the layer (VQACL_DEC_DW_GROUPED=0: one launch
 // each, right after the kernel that produced its dY)
 static int g_dec_dw_grouped = [] { const char* ev = getenv("VQACL_DEC_DW_GROUPED"); return (ev && ev[0] == '0') ? 0 : 1; }();
+static int g_dec_dx_splits = [] { const char* ev = getenv("VQACL_DEC_DX_SPLITS"); return ev && atoi(ev) > 0 ? atoi(ev) : 3; }();
 // dX[rows, n_in] = dY[rows, n_out] * W[n_out, n_in]      (W stored row-major -> MN-major B operand)
 static int gemm_dx(const bf16* dY, int lddy, const bf16* Wt, int n_out, int n_in, void* C, int ldc, int rows, int epi, cudaStream_t st,
                    const void* R = nullptr, int ldr = 0, float alpha = 1.f, int splits = 1) {
@@ -635,7 +641,7 @@ static int backward(Engine& e, const float* w_rows, const float* gscale, int acc
     }
     e.gdb_i = 0;
     RmsBwdArgs r{};
-    r.dn_f32 = w.t_d768_f32; r.ld_dn = d; r.x = w.y[3 * Ld]; r.w = e.P + e.o_dec_final; r.g_in = nullptr; r.g_out = w.gd;
+    r.dn_f32 = w.t_d768_f32; r.dn_zero = 1; r.ld_dn = d; r.x = w.y[3 * Ld]; r.w = e.P + e.o_dec_final; r.g_in = nullptr; r.g_out = w.gd;
     r.gb_out = w.gdb_ring[e.gdb_i];
     r.dw = e.G + e.o_dec_final; r.M = Md; r.eps = c.eps; r.scale = 1.f / sqrtf((float)d); r.own = e.drop(SITE_DEC_FINAL);
     r.consumer = e.drop(site_dec(Ld - 1, 5)); r.consumer_cols = d;
@@ -671,10 +677,16 @@ static int backward(Engine& e, const float* w_rows, const float* gscale, int acc
     VQ_TRY(dw(gdb_in, d, w.dh[l], f, e.G + P.wo, d, f));
     VQ_TRY(gemm_dx(gdb_in, d, e.W + P.wo, d, f, w.t_dh[ri], f, Md, EPI_RELUBWD_BF16, st, w.dhmask[l], (f + 31) / 32, e.drop(site_dec(l, 4)).inv_keep));
     VQ_TRY(dw(w.t_dh[ri], f, w.dn3[l], d, e.G + P.wi, f, d));
-    VQ_TRY(gemm_dx(w.t_dh[ri], f, e.W + P.wi, f, d, w.t_d768, d, Md, EPI_BF16, st));
+    // The deep contractions of the chain (dX of wi: K = d_ff, dX of qkv: K = 3 d) are split-K: with M = B*T rows there are only
+    // 39-78 output tiles, and a CTA's operand stream is bound by its SM's ~120 GB/s L2 port (measured: 3.2 us + 0.27 us per 32 KB
+    // k-block, tools/gemm_small_sweep.py) — three K slices per tile engage 126 SMs instead of 42. The slices meet in an fp32
+    // buffer (red.global.add) that the RMSNorm backward reads — and clears for the next user — instead of a bf16 dX.
+    const int dsplit = g_dec_dx_splits;
+    if (dsplit > 1) VQ_TRY(gemm_dx(w.t_dh[ri], f, e.W + P.wi, f, d, w.t_d768_f32, d, Md, EPI_ATOMIC_F32, st, nullptr, 0, 1.f, dsplit));
+    else VQ_TRY(gemm_dx(w.t_dh[ri], f, e.W + P.wi, f, d, w.t_d768, d, Md, EPI_BF16, st));
     RmsBwdArgs q{};
     q.dn = w.t_d768; q.ld_dn = d; q.x = w.y[3 * l + 2];
-    q.w = e.P + P.ln2; q.g_in = w.gd; q.g_out = w.gd; q.gb_out = gdb_1;
+    if (dsplit > 1) { q.dn_f32 = w.t_d768_f32; q.dn_zero = 1; } q.w = e.P + P.ln2; q.g_in = w.gd; q.g_out = w.gd; q.gb_out = gdb_1;
     q.dw = e.G + P.ln2; q.M = Md; q.eps = c.eps; q.scale = 1.f; q.consumer = e.drop(site_dec(l, 3)); q.consumer_cols = d;
     VQ_TRY(rmsnorm_bwd(q, st));
     // cross attention
@@ -691,6 +703,7 @@ static int backward(Engine& e, const float* w_rows, const float* gscale, int acc
     VQ_TRY(dw(w.t_dcq[ri], d, w.dn2[l], d, e.G + P.cq, d, d));
     VQ_TRY(gemm_dx(w.t_dcq[ri], d, e.W + P.cq, d, d, w.t_d768, d, Md, EPI_BF16, st));
     q.x = w.y[3 * l + 1]; q.w = e.P + P.ln1; q.dw = e.G + P.ln1; q.consumer = e.drop(site_dec(l, 1)); q.gb_out = gdb_2;
+    q.dn_f32 = nullptr; q.dn_zero = 0;       // dX of cq (K = d) stays a bf16 single pass
     VQ_TRY(rmsnorm_bwd(q, st));
     // self attention
     VQ_TRY(dw(gdb_2, d, w.dao[l], d, e.G + P.o, d, d));
@@ -705,7 +718,9 @@ static int backward(Engine& e, const float* w_rows, const float* gscale, int acc
     a.d_rel_table = e.G + e.o_dec_rel;
     VQ_TRY(attn_bwd(a, st));
     VQ_TRY(dw(w.t_dqkv[ri], 3 * d, w.dn1[l], d, e.G + P.qkv, 3 * d, d));
-    VQ_TRY(gemm_dx(w.t_dqkv[ri], 3 * d, e.W + P.qkv, 3 * d, d, w.t_d768, d, Md, EPI_BF16, st));
+    if (dsplit > 1) VQ_TRY(gemm_dx(w.t_dqkv[ri], 3 * d, e.W + P.qkv, 3 * d, d, w.t_d768_f32, d, Md, EPI_ATOMIC_F32, st, nullptr, 0, 1.f, dsplit));
+    else VQ_TRY(gemm_dx(w.t_dqkv[ri], 3 * d, e.W + P.qkv, 3 * d, d, w.t_d768, d, Md, EPI_BF16, st));
+    if (dsplit > 1) { q.dn_f32 = w.t_d768_f32; q.dn_zero = 1; }
     q.x = w.y[3 * l]; q.w = e.P + P.ln0; q.dw = e.G + P.ln0; q.gb_out = gdb_out;
     q.consumer = l > 0 ? e.drop(site_dec(l - 1, 5)) : Dropout();
     VQ_TRY(rmsnorm_bwd(q, st));

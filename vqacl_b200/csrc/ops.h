@@ -77,6 +77,8 @@ int rmsnorm_fwd(const RmsFwdArgs& a, cudaStream_t stream);
 struct RmsBwdArgs {
   const __nv_bfloat16* dn; int ld_dn;   // upstream gradient (bf16)
   const float* dn_f32;                  // ... or fp32 (same pitch ld_dn), used when non-null
+  int dn_zero;                          // fp32 form only: write zeros back after reading — dn_f32 is a split-K accumulation target
+                                        // (red.global.add) that the next GEMM expects cleared, and this kernel is its only reader
   const __nv_bfloat16* dn2; int ld_dn2; // optional second upstream gradient added to dn (bf16), same row map
   int in_rpb, out_rpb;                  // row map applied to dn/dn2 rows (see RmsFwdArgs), identity if in_rpb == 0
   const float* x; const float* w;
