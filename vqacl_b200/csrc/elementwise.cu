@@ -86,7 +86,26 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) rmsnorm_fwd_kernel(const RmsFw
   const int r = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   if (r >= a.M) return;
   float v[RW_CHUNKS][4], w[RW_CHUNKS][4];
-  load_row_f32(v, a.x + (size_t)r * DM, lane);
+  if (a.parts) {
+    float t[RW_CHUNKS][4];
+    load_row_f32(v, a.parts + (size_t)r * DM, lane);
+    for (int s = 1; s < a.n_parts; ++s) {
+      load_row_f32(t, a.parts + (size_t)s * a.part_stride + (size_t)r * DM, lane);
+#pragma unroll
+      for (int j = 0; j < RW_CHUNKS; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[j][i] += t[j][i];
+    }
+    apply_dropout(v, a.resid_drop, (uint64_t)r * DM, lane);
+    load_row_f32(t, a.resid + (size_t)r * DM, lane);
+#pragma unroll
+    for (int j = 0; j < RW_CHUNKS; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[j][i] += t[j][i];
+    store_row_f32(a.x_out + (size_t)r * DM, v, lane);
+  } else {
+    load_row_f32(v, a.x + (size_t)r * DM, lane);
+  }
   load_row_f32(w, a.w, lane);
   const float rstd = rsqrtf(row_sumsq(v) / DM + a.eps) * a.scale;
 #pragma unroll

@@ -222,6 +222,7 @@ int64_t engine_carve(Engine& e, uint8_t* base, int B, int L, int N, int T) {
   for (auto& p : w.gdb_ring) p = bp.take<bf16>(Md * d);
   w.t_d768 = bp.take<bf16>(Md * d);
   w.t_d768_f32 = bp.take<float>(Md * d);
+  w.t_parts = bp.take<float>((size_t)3 * Md * d);
   for (int i = 0; i < Workspace::RING; ++i) {
     w.t_dqkv[i] = bp.take<bf16>(Md * 3 * d);
     w.t_dh[i] = bp.take<bf16>(Md * f);
@@ -455,11 +456,22 @@ static int decoder_forward(Engine& e, const vqacl_batch* b, cudaStream_t st) {
   VQ_TRY(embed_fwd(w.dec_ids, B, T, e.P + e.o_shared, w.y[0], T, 0, e.drop(SITE_DEC_EMB), c.vocab_size, e.err_flags(), st));
   // cross-attention K/V of every decoder layer in one GEMM over the decoder memory
   VQ_TRY(gemm_fwd(w.mem, d, e.W + e.o_ckv, d, w.kv_all, ldkv, M2, ldkv, EPI_BF16, st));
+  // FFN-out (K = d_ff = 3072 against 39-78 output tiles at M = B*T rows) as a 3-way split-K: three times the CTAs stream the
+  // operands (a CTA's stream is bound by its SM's L2 port: 17.9 -> ~9 us), each slice stores an fp32 slab, and the NEXT norm
+  // kernel forms y[3l+3] = y[3l+2] + dropout(slab0 + slab1 + slab2) in that fixed order before normalising — deterministic,
+  // unlike an atomic meeting point. VQACL_DEC_FFN_SPLITS=1 restores the single-pass residual epilogue.
+  static const int fsplit = [] { const char* ev = getenv("VQACL_DEC_FFN_SPLITS"); const int v = ev ? atoi(ev) : 3; return v >= 1 && v <= 3 ? v : 3; }();
+  auto ffn_out_pending = [&](RmsFwdArgs& r, int l_prev) {     // make r's norm consume the slabs of layer l_prev's FFN-out GEMM
+    r.parts = w.t_parts; r.n_parts = fsplit; r.part_stride = (long long)Md * d;
+    r.resid = w.y[3 * l_prev + 2]; r.x_out = w.y[3 * l_prev + 3]; r.resid_drop = e.drop(site_dec(l_prev, 5));
+  };
   for (int l = 0; l < Ld; ++l) {
     const DecLayer& P = e.dec[l];
     RmsFwdArgs r{};
     r.x = w.y[3 * l]; r.w = e.P + P.ln0; r.y_bf16 = w.dn1[l]; r.ld_bf16 = d; r.M = Md; r.eps = c.eps; r.scale = 1.f;
+    if (fsplit > 1 && l > 0) ffn_out_pending(r, l - 1);
     VQ_TRY(rmsnorm_fwd(r, st));
+    r.parts = nullptr;
     VQ_TRY(gemm_fwd(w.dn1[l], d, e.W + P.qkv, d, w.dqkv[l], 3 * d, Md, 3 * d, EPI_BF16, st));
     AttnArgs a{};
     a.q = w.dqkv[l]; a.k = w.dqkv[l] + d; a.v = w.dqkv[l] + 2 * d; a.ldq = a.ldk = a.ldv = 3 * d;
@@ -484,12 +496,20 @@ static int decoder_forward(Engine& e, const vqacl_batch* b, cudaStream_t st) {
     r.x = w.y[3 * l + 2]; r.w = e.P + P.ln2; r.y_bf16 = w.dn3[l];
     VQ_TRY(rmsnorm_fwd(r, st));
     VQ_TRY(gemm_fwd(w.dn3[l], d, e.W + P.wi, d, w.dh[l], f, Md, f, EPI_RELU_BF16, st, w.dhmask[l], (f + 31) / 32, e.drop(site_dec(l, 4))));
-    VQ_TRY(gemm_fwd(w.dh[l], f, e.W + P.wo, f, w.y[3 * l + 3], d, Md, d, EPI_RESID_F32, st, w.y[3 * l + 2], d, e.drop(site_dec(l, 5))));
+    if (fsplit > 1) {
+      GemmArgs g{};
+      g.epi = EPI_F32; g.M = Md; g.N = d; g.K = f; g.C = w.t_parts; g.ldc = d; g.alpha = 1.f; g.splits = fsplit;
+      g.split_stride = (long long)Md * d;
+      VQ_TRY(gemm_bf16(GemmOperand{w.dh[l], f, false}, GemmOperand{e.W + P.wo, f, false}, g, 0, st));
+    } else {
+      VQ_TRY(gemm_fwd(w.dh[l], f, e.W + P.wo, f, w.y[3 * l + 3], d, Md, d, EPI_RESID_F32, st, w.y[3 * l + 2], d, e.drop(site_dec(l, 5))));
+    }
   }
   // final norm, dropout, x d^-1/2 (:666), tied LM head (:671), CE with reduction='none' (:683-686)
   RmsFwdArgs r{};
   r.x = w.y[3 * Ld]; r.w = e.P + e.o_dec_final; r.y_bf16 = w.yfin; r.ld_bf16 = d; r.M = Md; r.eps = c.eps;
   r.scale = 1.f / sqrtf((float)d); r.drop = e.drop(SITE_DEC_FINAL);
+  if (fsplit > 1) ffn_out_pending(r, Ld - 1);
   VQ_TRY(rmsnorm_fwd(r, st));
   VQ_TRY(gemm_fwd(w.yfin, d, e.W + e.o_shared, d, w.logits, e.ldv, Md, c.vocab_size, EPI_BF16, st));
   if (b->labels) VQ_TRY(ce_fwd(w.logits, e.ldv, Md, c.vocab_size, b->labels, w.lse_ce, w.loss_rows, st));

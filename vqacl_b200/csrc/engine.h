@@ -55,6 +55,7 @@ struct Workspace {
   bf16 *t_dqkv[RING], *t_dh[RING], *t_dcq[RING];          // decoder dY temporaries
   bf16 *t_eqkv[RING], *t_eh[RING];                        // encoder dY temporaries
   bf16 *t_d768, *t_e768;                                  // main-stream-only temporaries
+  float* t_parts;                                         // [3][Md, d] fp32 slabs of the decoder FFN-out split-K GEMM
   float* t_d768_f32;                                      // split-K target of the LM-head dX GEMM
   bf16* dkv_all; bf16* dmem; bf16* dfeatpre;
   float* vis_partials;            // [num_sms, 10*768] per-CTA column sums of the visual-embedding backward

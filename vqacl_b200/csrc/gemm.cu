@@ -327,7 +327,9 @@ int gemm_bf16(const GemmOperand& A, const GemmOperand& B, GemmArgs args, int for
   VQ_CHECK(args.N % 8 == 0, "gemm: N=%d must be a multiple of 8", args.N);
   VQ_CHECK(args.ldc % 8 == 0, "gemm: ldc=%d must be a multiple of 8", args.ldc);
   if (args.splits < 1) args.splits = 1;
-  VQ_CHECK(args.splits == 1 || args.epi == EPI_ATOMIC_F32, "gemm: split-K needs the atomic epilogue");
+  VQ_CHECK(args.splits == 1 || args.epi == EPI_ATOMIC_F32 || (args.epi == EPI_F32 && args.split_stride >= (long long)args.M * args.ldc),
+           "gemm: split-K needs the atomic epilogue, or the fp32 one with a slab stride");
+  if (args.splits == 1) args.split_stride = 0;
   if (args.tail) {
     VQ_CHECK((args.tail == 1 || args.tail == 2) && args.N == 768 && args.splits == 1 && (args.epi == EPI_RESID_F32 || args.epi == EPI_F32) &&
                  !A.mn_major && g_pair_enabled,

@@ -47,7 +47,11 @@ struct GemmArgs {
   const void* R;
   int ldr;            // elements
   float alpha;
-  int splits;         // split-K factor (EPI_ATOMIC_F32 only)
+  int splits;         // split-K factor: EPI_ATOMIC_F32 (the slices meet in C through red.global.add), or EPI_F32 with
+                      // split_stride > 0: slice s stores its partial product to C + s * split_stride (elements) and the
+                      // consumer adds the slabs in a fixed order — the deterministic form, used where the sum is a forward
+                      // activation (decoder FFN-out: the next RMSNorm kernel forms residual + dropout(sum of slabs))
+  long long split_stride;
   uint32_t drop_thr;  // 16-bit keep threshold (0 = no dropout), see vq_dropout_pair
   float drop_inv_keep;
   uint32_t seed, site;  // seed = per-launch dropout key (already mixed with the site id); site is informational
@@ -432,6 +436,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const int row_base = m_blk * GEMM_BM + q * 32;
       const uint32_t t_base = tmem_base + astage * BN + ((uint32_t)(q * 32) << 16);
       uint64_t* tf = &tfull_bar[astage];
+      if (p.epi == EPI_F32 && p.split_stride) {
+        GemmArgs pg = p;
+        pg.C = reinterpret_cast<float*>(p.C) + (size_t)split * p.split_stride;
+        gemm_epilogue_tile<EPI_F32, BN>(pg, t_base, stg, row_base, n_blk * BN, half, lane, has_k, tf, aphase);
+      } else
       switch (p.epi) {
         case EPI_BF16: gemm_epilogue_tile<EPI_BF16, BN>(p, t_base, stg, row_base, n_blk * BN, half, lane, has_k, tf, aphase); break;
         case EPI_RELU_BF16: gemm_epilogue_tile<EPI_RELU_BF16, BN>(p, t_base, stg, row_base, n_blk * BN, half, lane, has_k, tf, aphase); break;
@@ -802,6 +811,11 @@ VQ_DEVINL void gemm_pair_body(const CUtensorMap* tmA_, const CUtensorMap* tmB_, 
         pg.M = grp->M[g]; pg.N = grp->N[g]; pg.C = grp->C[g]; pg.ldc = grp->ldc[g];
         if (p.epi == EPI_ATOMIC_F32) gemm_epilogue_tile<EPI_ATOMIC_F32, BN>(pg, t_base, stg, row_base, n_blk * BN, half, lane, has_k, tf, aphase);
         else gemm_epilogue_tile<EPI_F32, BN>(pg, t_base, stg, row_base, n_blk * BN, half, lane, has_k, tf, aphase);
+      } else
+      if (p.epi == EPI_F32 && p.split_stride) {
+        GemmArgs pg = p;
+        pg.C = reinterpret_cast<float*>(p.C) + (size_t)split * p.split_stride;
+        gemm_epilogue_tile<EPI_F32, BN>(pg, t_base, stg, row_base, n_blk * BN, half, lane, has_k, tf, aphase);
       } else
       switch (p.epi) {
         case EPI_BF16: gemm_epilogue_tile<EPI_BF16, BN>(p, t_base, stg, row_base, n_blk * BN, half, lane, has_k, tf, aphase); break;

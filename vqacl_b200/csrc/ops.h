@@ -68,6 +68,10 @@ struct RmsFwdArgs {
   int M; float eps; float scale;
   int in_rpb, out_rpb;
   Dropout drop;
+  // optional: the input row is formed here, x = resid + dropout_r(sum over n_parts slabs of parts, fixed order), and also
+  // written to x_out (fp32 [M, 768]) — the deterministic meeting point of a split-K GEMM whose result is a residual update
+  const float* parts; int n_parts; long long part_stride;
+  const float* resid; float* x_out; Dropout resid_drop;
 };
 int rmsnorm_fwd(const RmsFwdArgs& a, cudaStream_t stream);
 
