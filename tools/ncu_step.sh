@@ -4,7 +4,7 @@
 P=${1:-gpurun_out/r02}
 ARGS="bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-kernel-roofline"
 SKIP=${SKIP:-1900}
-COUNT=${COUNT:-640}
+COUNT=${COUNT:-540}   # launches of one steady-state step = gpu_launches / steps of a bench.py line
 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip $SKIP -c $COUNT --csv --log-file ${P}_launches_bench_step.csv python $ARGS > /dev/null 2>&1
 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --launch-skip $SKIP -c $COUNT --csv --log-file ${P}_dram_bench_step.csv python $ARGS > /dev/null 2>&1
 python tools/launch_summary.py ${P}_launches_bench_step.csv > ${P}_launch_summary.txt 2>&1
