@@ -401,8 +401,8 @@ def run_decode(args):
                 "config": {"workload": f"configs[4]: eval-only greedy answer generation, batch {B} per GPU, 12+12 layers, vocab 32200, random init "
                                        f"(no EOS: all {ntok // max(1, args.steps)} decode steps run), frozen SI prototype banks",
                            "global_batch": B * world,
-                       "parallelism": f"dp{world}" + (" (gradients reduce-scattered, optimizer state sharded, bf16 weights all-gathered)"
-                                                       if getattr(opt, "shard", False) else ""), "l2": f"{pool} distinct batches rotate; K/V + weights per token step {per_tok / 1e6:.0f} MB > 126 MB L2"},
+                           "parallelism": f"dp{world} (independent replicas: evaluation has no exchange step)",
+                           "l2": f"{pool} distinct batches rotate; K/V + weights per token step {per_tok / 1e6:.0f} MB > 126 MB L2"},
                 "e2e": {"value": world * B * args.steps / (ms_e2e / 1e3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": B * 20 * 8, "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(launches), "clocks": ck,

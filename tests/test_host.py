@@ -210,3 +210,54 @@ def test_rehearsal_memory_matches_reference_fixture():
     mem2 = RehearsalMemory({}, 0)
     mem2.load_state_dict(json.loads(json.dumps(mem.state_dict())))
     assert [x["question_id"] for x in mem2.all_examplars()] == d["steps"][-1]["all_examplar"]
+
+
+def test_no_undefined_global_names_in_entry_points():
+    """bench.py / __graft_entry__.py / the package / the tools run on GPU boxes only, so a NameError in a rarely taken branch
+    (bench.py --mode decode once referenced the training arm's optimizer, a local of another function) would not show up in the
+    CPU suite: every name a FUNCTION loads as a global must be a builtin, an import or a module-level binding."""
+    import ast, builtins, dis, glob
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = [os.path.join(root, "bench.py"), os.path.join(root, "__graft_entry__.py")]
+    files += sorted(glob.glob(os.path.join(root, "vqacl_b200", "*.py"))) + sorted(glob.glob(os.path.join(root, "tools", "*.py")))
+
+    def module_bindings(node, out):
+        """names bound at module scope: do not descend into function / class / lambda bodies"""
+        for ch in ast.iter_child_nodes(node):
+            if isinstance(ch, (ast.FunctionDef, ast.AsyncFunctionDef, ast.ClassDef)):
+                out.add(ch.name)
+                continue
+            if isinstance(ch, ast.Lambda):
+                continue
+            if isinstance(ch, (ast.Import, ast.ImportFrom)):
+                out |= {(a.asname or a.name).split(".")[0] for a in ch.names}
+            elif isinstance(ch, ast.Name) and isinstance(ch.ctx, (ast.Store, ast.Del)):
+                out.add(ch.id)
+            elif isinstance(ch, ast.ExceptHandler) and ch.name:
+                out.add(ch.name)
+            module_bindings(ch, out)
+
+    def function_globals(co, in_function):
+        out = set()
+        if in_function:
+            out = {i.argval for i in dis.get_instructions(co) if i.opname == "LOAD_GLOBAL"}
+        for c in co.co_consts:
+            if hasattr(c, "co_code"):
+                out |= function_globals(c, True)
+        return out
+
+    problems = []
+    for path in files:
+        src = open(path).read()
+        tree = ast.parse(src)
+        known = set(dir(builtins)) | {"__file__", "__name__", "__doc__", "__spec__", "__package__", "__builtins__", "__annotations__"}
+        module_bindings(tree, known)
+        for n in ast.walk(tree):                  # `global x` inside a function makes x a module-level binding
+            if isinstance(n, ast.Global):
+                known |= set(n.names)
+            elif isinstance(n, (ast.Import, ast.ImportFrom)):      # function-local imports are LOAD_FAST, harmless to allow
+                known |= {(a.asname or a.name).split(".")[0] for a in n.names}
+        undefined = sorted(function_globals(compile(src, path, "exec"), False) - known)
+        if undefined:
+            problems.append((os.path.relpath(path, root), undefined))
+    assert not problems, problems
